@@ -1,0 +1,199 @@
+/*
+ * rnb_b200.h — C ABI of the Blackwell-native NeuS2 / RNb-NeuS2 training inner loop.
+ *
+ * The reference (RobinBruneau/RNb-NeuS2) has no plugin/FFI seam on this path: L2–L0 are C++ templates linked into
+ * ./build/testbed (CMakeLists.txt:322-333).  This header introduces the seam at the Testbed -> step boundary.
+ * Every entry point names the reference interface it replaces (file:line in the reference tree).
+ *
+ * Conventions
+ *   - plain C types only; no C++ exceptions cross the boundary.  Every call returns 0 on success or a negative
+ *     rnb_status; rnb_last_error() returns a thread-local message (reference behaviour: CUDA_CHECK_THROW ->
+ *     std::runtime_error; the caller turns non-zero into a throw).
+ *   - `stream` arguments are cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - device pointers are marked _dev, host pointers _host.
+ *   - one rnb_ctx per CUDA device / process; calls on one ctx must come from one host thread at a time
+ *     (the reference drives training from a single host thread, src/testbed.cu:2776).
+ */
+#ifndef RNB_B200_H
+#define RNB_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNB_ABI_VERSION 1
+
+typedef enum rnb_status {
+	RNB_OK = 0,
+	RNB_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+	RNB_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+	RNB_ERR_STATE = -3,       /* call order violated (e.g. training without a dataset) */
+	RNB_ERR_NOMEM = -4
+} rnb_status;
+
+typedef struct rnb_ctx rnb_ctx;
+
+/* Network / optimizer / sampling configuration: the values of configs/nerf/base.json (:5-80) plus the Testbed
+ * constants that reach the step (include/neural-graphics-primitives/testbed.h:237,550,633; src/testbed.cu:2256). */
+typedef struct rnb_config {
+	uint32_t abi_version;           /* RNB_ABI_VERSION */
+	/* encoding: configs/nerf/base.json:30-40, src/testbed.cu:2300-2325 */
+	uint32_t n_levels;              /* 14 */
+	uint32_t log2_hashmap_size;     /* 19 */
+	uint32_t base_resolution;       /* 16 */
+	float    per_level_scale;       /* <=0: derive from top_resolution like src/testbed.cu:2321 */
+	float    top_resolution;        /* 2048 */
+	float    base_valid_level_scale;/* 0.2  (progressive levels, grid.h:1430-1437) */
+	float    valid_level_scale;     /* 0.02 */
+	uint32_t base_training_step;    /* 100 */
+	/* MLPs: base.json:41-48,64-70 — FullyFusedMLP, ReLU, no output activation, no bias */
+	uint32_t sdf_n_neurons;         /* 64 (32 supported) */
+	uint32_t sdf_n_hidden_layers;   /* 1 */
+	uint32_t rgb_n_neurons;         /* 64 (32 supported) */
+	uint32_t rgb_n_hidden_layers;   /* 2 (1 supported) */
+	float    sdf_bias;              /* -0.1 */
+	/* optimizer: base.json:5-29 */
+	float    learning_rate;         /* 1e-3 */
+	float    beta1, beta2, epsilon; /* 0.9, 0.99, 1e-15 */
+	float    l2_reg;                /* 1e-6 (MLP weights only) */
+	float    ema_decay;             /* 0.95 */
+	uint32_t lr_decay_start;        /* 20000 */
+	uint32_t lr_decay_interval;     /* 10000 */
+	float    lr_decay_base;         /* 0.33 */
+	float    loss_scale;            /* 128 (testbed.h:237) */
+	/* sampling / batching */
+	uint32_t target_batch_size;     /* 1<<18 (src/testbed.cu:2256) */
+	uint32_t rays_per_batch;        /* 4096 initial (testbed.h:633) */
+	uint32_t pin_rays_per_batch;    /* 1 = benchmark knob: disable the controller of testbed_nerf.cu:3554-3555 */
+	uint32_t seed;                  /* 1337 (testbed.h:550) */
+	float    density_grid_decay;    /* 0.95 (testbed.h:671) */
+	/* data parallelism: rays i with i % world_size == rank are processed by this ctx */
+	uint32_t world_size;            /* 1 */
+	uint32_t rank;                  /* 0 */
+} rnb_config;
+
+/* Loss / shading switches: Testbed::m_apply_* etc. (testbed.h:490-521), passed by value to
+ * compute_loss_kernel_train_nerf (src/testbed_nerf.cu:4030-4039). */
+typedef struct rnb_flags {
+	int32_t apply_L2;               /* 1 unless --lone */
+	int32_t apply_supernormal;      /* --supernormal: identity light basis */
+	int32_t apply_rgbplus;          /* 1 unless --no-rgbplus */
+	int32_t apply_relu;
+	int32_t apply_bce;
+	int32_t light_opti;             /* --opti-lights */
+	int32_t no_albedo;              /* --no-albedo */
+	float   mask_loss_weight;       /* 1.0 */
+	float   ek_loss_weight;         /* 0.01 */
+	float   cos_anneal_ratio;       /* 1.0 (anneal_end == 0) */
+	int32_t light_mode;             /* -1: hashed per (ray, step) [the reference uses curand_init(clock64())]; 0..2 pinned */
+	int32_t only_sdf_training;      /* Optimizer::only_sdf_training (src/testbed.cu:1886-1895) */
+} rnb_flags;
+
+/* One training view = TrainingImageMetadata + TrainingXForm (nerf_loader.h:32-49, common.h:171-174).
+ * Pixels are uint16 RGBA, 8 bytes per pixel, as uploaded by src/nerf_loader.cu and read by read_rgba
+ * (common_device.cuh:665-700). */
+typedef struct rnb_view {
+	const void* normal_px;          /* device (rnb_set_dataset) or host (rnb_upload_dataset) pointer */
+	const void* albedo_px;          /* may be NULL: alpha of the normal map is used as the colour mask */
+	int32_t w, h;
+	float fx, fy;                   /* focal length in pixels */
+	float cx, cy;                   /* principal point / resolution */
+	float xform[12];                /* 3x4 camera-to-world in the NGP frame, column-major (nerf_matrix_to_ngp applied) */
+} rnb_view;
+
+/* Per-step read-back: Counters::update_after_training (src/testbed_nerf.cu:3532-3558) and m_loss_scalar & co. */
+typedef struct rnb_step_stats {
+	float    loss, ek_loss, mask_loss;
+	uint32_t n_rays;                /* rays_per_batch used by this step (global, all ranks) */
+	uint32_t n_rays_kept;           /* rays that produced samples (this rank) */
+	uint32_t n_samples;             /* samples before compaction  = numsteps_counter */
+	uint32_t n_samples_compacted;   /* samples after compaction   = numsteps_counter_compacted */
+	uint32_t n_samples_trained;     /* min(compacted, target_batch_size) */
+	uint32_t rays_per_batch_next;
+	uint32_t training_step;         /* value after the step */
+	uint32_t density_grid_updated;  /* 1 if training_prep_nerf ran inside this call */
+} rnb_step_stats;
+
+const char* rnb_last_error(void);
+uint32_t    rnb_abi_version(void);
+
+/* replaces Testbed::reset_network (src/testbed.cu:2220-2485): builds encoding tables, allocates
+ * [fp32 | fp16 | fp16 ema | grads | adam state] (trainer.h:72-109) and all step scratch on the current device. */
+int rnb_create(const rnb_config* cfg, rnb_ctx** out);
+int rnb_destroy(rnb_ctx* ctx);
+void rnb_default_config(rnb_config* cfg);
+void rnb_default_flags(rnb_flags* f);
+
+/* parameter layout (same order as NerfNetwork::set_params, nerf_network.h:539-583):
+ * [sdf mlp | rgb mlp | hash grid | variance(4)].  out[0..4] = off_sdf, off_rgb, off_grid, off_var, n_params */
+int rnb_param_layout(rnb_ctx* ctx, uint64_t out[5]);
+
+/* replaces Trainer::initialize_params + NerfNetwork::initialize_params (trainer.h:72-109, nerf_network.h:625-694).
+ * sdf_init_host: contents of utils/mlp_weights*.txt (geometric initialisation, nerf_network.h:585-623) or NULL for
+ * the built-in sphere initialisation. */
+int rnb_init_params(rnb_ctx* ctx, const float* sdf_init_host, size_t n_sdf_init);
+int rnb_set_params_fp32(rnb_ctx* ctx, const float* params_host, size_t n);
+int rnb_get_params_fp32(rnb_ctx* ctx, float* params_host, size_t n);
+
+/* snapshot hand-off: Trainer::serialize / deserialize (trainer.h:263-304), src/testbed.cu:3280-3390.
+ * fp16 views use IEEE binary16 bit patterns. use_ema selects the inference (EMA) copy. */
+int rnb_export_params_fp16(rnb_ctx* ctx, uint16_t* host, size_t n, int use_ema);
+int rnb_import_params_fp16(rnb_ctx* ctx, const uint16_t* host, size_t n);
+int rnb_export_density_grid(rnb_ctx* ctx, float* host, size_t n /* 128^3 */, uint32_t* ema_step);
+int rnb_import_density_grid(rnb_ctx* ctx, const float* host, size_t n, uint32_t ema_step);
+int rnb_get_bitfield(rnb_ctx* ctx, uint8_t* host, size_t n /* 128^3 (8 mips x 128^3 bits) */);
+int rnb_set_bitfield(rnb_ctx* ctx, const uint8_t* host, size_t n);
+int rnb_get_train_state(rnb_ctx* ctx, uint32_t out[4] /* training_step, rays_per_batch, n_rays_total, measured_before_compaction */);
+int rnb_set_train_state(rnb_ctx* ctx, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before_compaction);
+int rnb_get_rng(rnb_ctx* ctx, uint64_t out[4] /* m_rng state, inc, density_grid_rng state, inc */);
+int rnb_set_rng(rnb_ctx* ctx, const uint64_t in[4]);
+
+/* replaces Testbed::load_nerf's device-side result (metadata_normal_gpu / metadata_albedo_gpu / transforms_gpu,
+ * testbed.h:591-592).  rnb_set_dataset: pixel pointers are device pointers owned by the caller;
+ * rnb_upload_dataset: pixel pointers are host pointers, copied into device memory owned by ctx. */
+int rnb_set_dataset(rnb_ctx* ctx, const rnb_view* views_host, uint32_t n_views);
+int rnb_upload_dataset(rnb_ctx* ctx, const rnb_view* views_host, uint32_t n_views);
+int rnb_set_flags(rnb_ctx* ctx, const rnb_flags* flags);
+
+/* replaces Testbed::training_prep_nerf (src/testbed_nerf.cu:4125-4138): one occupancy-grid refresh. */
+int rnb_prep(rnb_ctx* ctx, void* stream);
+/* replaces Testbed::train_nerf (src/testbed_nerf.cu:3560-3668): generate samples, forward, loss, backward,
+ * optimizer step, counters.  stats may be NULL (no host synchronisation). */
+int rnb_train_step(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
+/* replaces Testbed::train (src/testbed.cu:2776-2872): progressive-level update, prep cadence, train_nerf. */
+int rnb_train(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
+
+/* data-parallel split of rnb_train_step: [begin: everything up to and including backward] -> the caller all-reduces
+ * rnb_grad_buffer (sum, fp32, n_params elements) and rnb_counter_buffer (sum, uint32 x 8 / float) over its communicator
+ * -> [end: optimizer + controller].  The reference has no collective; this is where one goes (trainer.h:78-84). */
+int rnb_train_step_begin(rnb_ctx* ctx, void* stream);
+int rnb_train_step_end(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
+int rnb_grad_buffer(rnb_ctx* ctx, float** grads_dev, uint64_t* n);
+int rnb_stat_buffer(rnb_ctx* ctx, float** stats_dev, uint64_t* n);
+
+/* replaces NerfNetwork::sdf / density (nerf_network.h:454-537) used by marching cubes (src/testbed_nerf.cu:4252)
+ * and the grid refresh.  xyz_dev: n x 3 floats in [0,1]^3; outputs may be NULL. */
+int rnb_eval_sdf(rnb_ctx* ctx, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream);
+
+/* ---- stage-level entry points (host buffers; parity tests and micro-benchmarks) --------------------------------
+ * Each mirrors one reference kernel / call; see DESIGN.md for the mapping. */
+/* generate_training_samples_nerf (src/testbed_nerf.cu:1216-1387) */
+int rnb_stage_generate(rnb_ctx* ctx, uint32_t n_rays, uint32_t n_rays_total, uint32_t max_samples,
+                       uint32_t* ray_indices_host, float* rays_host /*6/ray*/, uint32_t* numsteps_host /*2/ray*/, float* coords_host /*7/sample*/, uint32_t counters_host[2]);
+/* NerfNetwork::forward_impl / inference_mixed_precision (nerf_network.h:87-253): coords 7 floats/sample -> 16 binary16 as float */
+int rnb_stage_forward(rnb_ctx* ctx, const float* coords_host, size_t n, int use_ema, float* out16_host, float* normal_host);
+/* compute_loss_kernel_train_nerf (src/testbed_nerf.cu:1396-2097) on the samples produced by rnb_stage_generate */
+int rnb_stage_loss(rnb_ctx* ctx, const float* out16_compacted_host, const uint32_t* ray_indices_host, const uint32_t* n_fwd, const uint32_t* cbase, const uint32_t* n_emit,
+                   uint32_t n_kept, uint32_t n_rays, uint32_t n_rays_total, float* dout16_host, float* loss_host, float* ek_host, float* mask_host);
+/* NerfNetwork::forward + backward (nerf_network.h:257-452): gradients (x loss scale) into the fp32 gradient buffer */
+int rnb_stage_backward(rnb_ctx* ctx, const float* coords_host, const float* dout16_host, size_t n, uint32_t n_in_rollover, float* grads_host);
+/* Trainer::optimizer_step (trainer.h:170; adam.h:51-202, ema.h:116-152, exponential_decay.h:61-72) on given gradients */
+int rnb_stage_optimizer(rnb_ctx* ctx, const float* grads_host /* NULL: use the device gradient buffer */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNB_B200_H */

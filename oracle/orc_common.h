@@ -27,10 +27,13 @@ typedef _Float16 half_t;
 // round-to-nearest-even through IEEE binary16 and back
 static inline float hq(float x) { return (float)(half_t)x; }
 static inline float hq_d(double x) { return (float)(half_t)x; }
-// binary16 arithmetic with a single rounding (operands are already binary16 values)
-static inline float hadd(float a, float b) { return hq_d((double)a + (double)b); }
-static inline float hsub(float a, float b) { return hq_d((double)a - (double)b); }
-static inline float hmul(float a, float b) { return hq_d((double)a * (double)b); }
+// binary16 arithmetic on operands that are already binary16 values.  The product of two 11-bit significands is exact
+// in fp32; a sum is exact in fp32 unless the exponents differ by more than 12, in which case the fp32 result is
+// already within a quarter binary16-ulp of the larger operand — so rounding fp32 -> binary16 (hardware F16C) gives the
+// correctly rounded result except on measure-zero ties.
+static inline float hadd(float a, float b) { return hq(a + b); }
+static inline float hsub(float a, float b) { return hq(a - b); }
+static inline float hmul(float a, float b) { return hq(a * b); }
 
 static inline uint16_t half_bits(float x) { half_t h = (half_t)x; uint16_t u; std::memcpy(&u, &h, 2); return u; }
 static inline float half_from_bits(uint16_t u) { half_t h; std::memcpy(&h, &u, 2); return (float)h; }

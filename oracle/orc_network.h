@@ -91,7 +91,7 @@ static const int MAXL = 16;   // max hash levels
 template <bool Q>
 struct Net {
 	typedef typename std::conditional<Q, float, double>::type real;
-	static inline real h(real x) { return Q ? (real)hq_d((double)x) : x; }
+	static inline real h(real x) { return Q ? (real)hq((float)x) : x; }
 
 	const ModelDesc& m;
 	const real* P;            // parameters as values (Q: the fp16 copy widened to float)
@@ -153,7 +153,7 @@ struct Net {
 		const real scale = (real)m.scale[l];
 		const uint32_t res = m.res[l];
 		for (int d = 0; d < 3; ++d) {          // pos_fract: common_device.h:415-424
-			real p = xyz[d] * scale + (real)0.5;
+			real p = std::fma(xyz[d], scale, (real)0.5);   // FMA: see orc_render.h ray_setup
 			int t = (int)std::floor(p);
 			c.pg[l][d] = (uint32_t)t;
 			c.frac[l][d] = p - (real)t;

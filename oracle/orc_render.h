@@ -134,17 +134,19 @@ static inline void ray_setup(uint32_t i, uint32_t n_rays, uint32_t n_rays_total,
 	(void)rng.next_float();                                       // motion-blur time (unused)
 	float dc[3] = {(r.xy[0] - v.cx) * (float)v.w / v.fx, (r.xy[1] - v.cy) * (float)v.h / v.fy, 1.0f};
 	const float* X = v.xform;
-	for (int k = 0; k < 3; ++k) { r.d_un[k] = X[0 + k] * dc[0] + X[3 + k] * dc[1] + X[6 + k] * dc[2]; r.o[k] = X[9 + k]; }
-	float nrm = std::sqrt(r.d_un[0] * r.d_un[0] + r.d_un[1] * r.d_un[1] + r.d_un[2] * r.d_un[2]);
+	// nvcc contracts a*b+c into FMA by default (-fmad=true); the restatement spells the fused form out so that sample
+	// positions — and therefore occupancy cell indices — are bit-identical to the CUDA path.
+	for (int k = 0; k < 3; ++k) { r.d_un[k] = std::fma(X[6 + k], dc[2], std::fma(X[3 + k], dc[1], X[0 + k] * dc[0])); r.o[k] = X[9 + k]; }
+	float nrm = std::sqrt(std::fma(r.d_un[2], r.d_un[2], std::fma(r.d_un[1], r.d_un[1], r.d_un[0] * r.d_un[0])));
 	for (int k = 0; k < 3; ++k) r.dir[k] = r.d_un[k] / nrm;
 	float tmin, tmax; ray_unit_cube(r.o, r.dir, tmin, tmax);
 	tmin = std::max(tmin, 0.0f);
-	r.startt = tmin + MIN_STEP() * rng.next_float();
+	r.startt = std::fma(MIN_STEP(), rng.next_float(), tmin);
 	r.img = img;
 	float idir[3] = {1.0f / r.dir[0], 1.0f / r.dir[1], 1.0f / r.dir[2]};
 	uint32_t j = 0; float t = r.startt; float pos[3];
 	for (;;) {
-		for (int k = 0; k < 3; ++k) pos[k] = r.o[k] + t * r.dir[k];
+		for (int k = 0; k < 3; ++k) pos[k] = std::fma(t, r.dir[k], r.o[k]);
 		if (!in_unit_cube(pos) || j >= NSTEPS) break;
 		float dt = MIN_STEP();
 		uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
@@ -162,7 +164,7 @@ static inline void ray_emit(const RayGen& r, const uint8_t* bitfield, float* coo
 	float max_step = MIN_STEP() * (1 << (CASCADES - 1));
 	uint32_t j = 0; float t = r.startt; float pos[3];
 	for (;;) {
-		for (int k = 0; k < 3; ++k) pos[k] = r.o[k] + t * r.dir[k];
+		for (int k = 0; k < 3; ++k) pos[k] = std::fma(t, r.dir[k], r.o[k]);
 		if (!in_unit_cube(pos) || j >= r.numsteps) break;
 		float dt = MIN_STEP();
 		uint32_t mip = (uint32_t)mip_from_dt(dt, pos);

@@ -451,3 +451,8 @@ void orc_backward_f64(Oracle* o, const double* params, const float* coords, cons
 }
 
 } // extern "C"
+
+extern "C" void orc_pcg32_seq(uint64_t seed, uint64_t seq, int64_t advance, uint32_t n, uint32_t* out_u) {
+	orc::Pcg32 r(seed, seq); r.advance(advance);
+	for (uint32_t i = 0; i < n; ++i) out_u[i] = r.next_uint();
+}

@@ -1,0 +1,295 @@
+"""rnb-neus2_b200 — host-side mirror of the reference Testbed training interface over the C ABI of librnb_b200.so.
+
+The product is the CUDA library (csrc/, include/rnb_b200.h).  This module is the thin Python host layer used by
+tests/ and bench.py: it mirrors the names of the reference's C++ host interface for this path
+(Testbed::train / training_prep_nerf / train_nerf, Trainer::optimizer_step, NerfNetwork::sdf — reference
+src/testbed.cu:2776-2872, src/testbed_nerf.cu:3560-3668,4125-4138).
+
+The directory name contains a hyphen, so import it with `load_package()` from `rnb_loader.py` (repo root) or
+importlib.  There is NO CPU fallback: if the CUDA library is missing or no GPU is present, calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_DIR, "librnb_b200.so")
+GRID_CELLS = 128 ** 3
+
+
+class RnbError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("n_levels", C.c_uint32), ("log2_hashmap_size", C.c_uint32), ("base_resolution", C.c_uint32),
+                ("per_level_scale", C.c_float), ("top_resolution", C.c_float), ("base_valid_level_scale", C.c_float), ("valid_level_scale", C.c_float),
+                ("base_training_step", C.c_uint32), ("sdf_n_neurons", C.c_uint32), ("sdf_n_hidden_layers", C.c_uint32), ("rgb_n_neurons", C.c_uint32),
+                ("rgb_n_hidden_layers", C.c_uint32), ("sdf_bias", C.c_float), ("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("epsilon", C.c_float), ("l2_reg", C.c_float), ("ema_decay", C.c_float), ("lr_decay_start", C.c_uint32), ("lr_decay_interval", C.c_uint32),
+                ("lr_decay_base", C.c_float), ("loss_scale", C.c_float), ("target_batch_size", C.c_uint32), ("rays_per_batch", C.c_uint32),
+                ("pin_rays_per_batch", C.c_uint32), ("seed", C.c_uint32), ("density_grid_decay", C.c_float), ("world_size", C.c_uint32), ("rank", C.c_uint32)]
+
+
+class Flags(C.Structure):
+    _fields_ = [("apply_L2", C.c_int32), ("apply_supernormal", C.c_int32), ("apply_rgbplus", C.c_int32), ("apply_relu", C.c_int32), ("apply_bce", C.c_int32),
+                ("light_opti", C.c_int32), ("no_albedo", C.c_int32), ("mask_loss_weight", C.c_float), ("ek_loss_weight", C.c_float), ("cos_anneal_ratio", C.c_float),
+                ("light_mode", C.c_int32), ("only_sdf_training", C.c_int32)]
+
+
+class View(C.Structure):
+    _fields_ = [("normal_px", C.c_void_p), ("albedo_px", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12)]
+
+
+class StepStats(C.Structure):
+    _fields_ = [("loss", C.c_float), ("ek_loss", C.c_float), ("mask_loss", C.c_float), ("n_rays", C.c_uint32), ("n_rays_kept", C.c_uint32),
+                ("n_samples", C.c_uint32), ("n_samples_compacted", C.c_uint32), ("n_samples_trained", C.c_uint32), ("rays_per_batch_next", C.c_uint32),
+                ("training_step", C.c_uint32), ("density_grid_updated", C.c_uint32)]
+
+
+EXPORTED_SYMBOLS = [
+    "rnb_last_error", "rnb_abi_version", "rnb_create", "rnb_destroy", "rnb_default_config", "rnb_default_flags", "rnb_param_layout", "rnb_init_params",
+    "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
+    "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
+    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_eval_sdf",
+    "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
+]
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into librnb_b200.so (in-tree)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_DIR, "csrc"), "-j8"], stdout=out)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built — there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise RnbError("librnb_b200.so is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        L = C.CDLL(_SO)
+        L.rnb_last_error.restype = C.c_char_p
+        L.rnb_abi_version.restype = C.c_uint32
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def default_config(**kw):
+    c = Config()
+    lib().rnb_default_config(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def default_flags(**kw):
+    f = Flags()
+    lib().rnb_default_flags(C.byref(f))
+    for k, v in kw.items():
+        setattr(f, k, v)
+    return f
+
+
+def small_config(**kw):
+    """BASELINE configs[0]: L=8, T=2^14, base 16 -> top 2048, 32-wide MLPs with one hidden layer each."""
+    base = dict(n_levels=8, log2_hashmap_size=14, base_resolution=16, top_resolution=2048.0, sdf_n_neurons=32, rgb_n_neurons=32, rgb_n_hidden_layers=1)
+    base.update(kw)
+    return default_config(**base)
+
+
+class Testbed:
+    """Mirror of the reference Testbed's training surface for the NeuS2 step."""
+
+    def __init__(self, config=None, flags=None):
+        self.L = lib()
+        self.cfg = config if config is not None else default_config()
+        self.h = C.c_void_p()
+        self._chk(self.L.rnb_create(C.byref(self.cfg), C.byref(self.h)))
+        lay = (C.c_uint64 * 5)()
+        self._chk(self.L.rnb_param_layout(self.h, lay))
+        self.off_sdf, self.off_rgb, self.off_grid, self.off_var, self.n_params = [int(x) for x in lay]
+        self._keep = []
+        if flags is not None:
+            self.set_flags(flags)
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RnbError("rnb error %d: %s" % (rc, self.L.rnb_last_error().decode()))
+
+    def close(self):
+        if self.h:
+            self.L.rnb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- parameters / snapshot (Trainer::initialize_params, serialize, deserialize) ---
+    def init_params(self, sdf_init=None):
+        if sdf_init is None:
+            self._chk(self.L.rnb_init_params(self.h, None, C.c_size_t(0)))
+        else:
+            a = np.ascontiguousarray(sdf_init, np.float32)
+            self._chk(self.L.rnb_init_params(self.h, _p(a, C.c_float), C.c_size_t(a.size)))
+
+    def set_params(self, p):
+        p = np.ascontiguousarray(p, np.float32)
+        self._chk(self.L.rnb_set_params_fp32(self.h, _p(p, C.c_float), C.c_size_t(p.size)))
+
+    def get_params(self):
+        p = np.zeros(self.n_params, np.float32)
+        self._chk(self.L.rnb_get_params_fp32(self.h, _p(p, C.c_float), C.c_size_t(p.size)))
+        return p
+
+    def export_params_fp16(self, use_ema=False):
+        p = np.zeros(self.n_params, np.uint16)
+        self._chk(self.L.rnb_export_params_fp16(self.h, _p(p, C.c_uint16), C.c_size_t(p.size), int(use_ema)))
+        return p.view(np.float16)
+
+    def import_params_fp16(self, p):
+        p = np.ascontiguousarray(p, np.float16).view(np.uint16)
+        self._chk(self.L.rnb_import_params_fp16(self.h, _p(p, C.c_uint16), C.c_size_t(p.size)))
+
+    def export_density_grid(self):
+        g = np.zeros(GRID_CELLS, np.float32); st = C.c_uint32()
+        self._chk(self.L.rnb_export_density_grid(self.h, _p(g, C.c_float), C.c_size_t(g.size), C.byref(st)))
+        return g, int(st.value)
+
+    def import_density_grid(self, g, ema_step):
+        g = np.ascontiguousarray(g, np.float32)
+        self._chk(self.L.rnb_import_density_grid(self.h, _p(g, C.c_float), C.c_size_t(g.size), ema_step))
+
+    def get_bitfield(self):
+        b = np.zeros(GRID_CELLS, np.uint8)
+        self._chk(self.L.rnb_get_bitfield(self.h, _p(b, C.c_uint8), C.c_size_t(b.size)))
+        return b
+
+    def set_bitfield(self, b):
+        b = np.ascontiguousarray(b, np.uint8)
+        self._chk(self.L.rnb_set_bitfield(self.h, _p(b, C.c_uint8), C.c_size_t(b.size)))
+
+    def get_train_state(self):
+        o = (C.c_uint32 * 4)(); self._chk(self.L.rnb_get_train_state(self.h, o)); return [int(x) for x in o]
+
+    def set_train_state(self, training_step, rays_per_batch, n_rays_total=0, measured_before=0):
+        self._chk(self.L.rnb_set_train_state(self.h, training_step, rays_per_batch, n_rays_total, measured_before))
+
+    def get_rng(self):
+        o = (C.c_uint64 * 4)(); self._chk(self.L.rnb_get_rng(self.h, o)); return [int(x) for x in o]
+
+    def set_rng(self, vals):
+        a = (C.c_uint64 * 4)(*vals); self._chk(self.L.rnb_set_rng(self.h, a))
+
+    # --- dataset (Testbed::load_training_data result) ---
+    def _views(self, views, device_ptrs):
+        arr = (View * len(views))()
+        self._keep = []
+        for i, v in enumerate(views):
+            if device_ptrs:
+                arr[i].normal_px = int(v["normal"]); arr[i].albedo_px = int(v["albedo"]) if v.get("albedo") else None
+                arr[i].w, arr[i].h = v["w"], v["h"]
+            else:
+                n = np.ascontiguousarray(v["normal"], np.uint16); self._keep.append(n)
+                arr[i].normal_px = n.ctypes.data
+                if v.get("albedo") is not None:
+                    a = np.ascontiguousarray(v["albedo"], np.uint16); self._keep.append(a); arr[i].albedo_px = a.ctypes.data
+                arr[i].h, arr[i].w = n.shape[0], n.shape[1]
+            arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = v["fx"], v["fy"], v["cx"], v["cy"]
+            for k in range(12):
+                arr[i].xform[k] = float(v["xform"][k])
+        return arr
+
+    def load_training_data(self, views):
+        """views: list of dict(normal=uint16[h,w,4], albedo=uint16[h,w,4]|None, fx, fy, cx, cy, xform[12]) in host memory."""
+        arr = self._views(views, False)
+        self._chk(self.L.rnb_upload_dataset(self.h, arr, len(views)))
+        self._keep = []
+
+    def set_dataset_device(self, views):
+        arr = self._views(views, True)
+        self._chk(self.L.rnb_set_dataset(self.h, arr, len(views)))
+
+    def set_flags(self, flags):
+        self.flags = flags
+        self._chk(self.L.rnb_set_flags(self.h, C.byref(flags)))
+
+    # --- training (Testbed::train / training_prep_nerf / train_nerf) ---
+    def training_prep_nerf(self, stream=None):
+        self._chk(self.L.rnb_prep(self.h, C.c_void_p(stream)))
+
+    def train_nerf(self, stream=None, want_stats=True):
+        st = StepStats()
+        self._chk(self.L.rnb_train_step(self.h, C.c_void_p(stream), C.byref(st) if want_stats else None))
+        return st
+
+    def train(self, stream=None, want_stats=True):
+        st = StepStats()
+        self._chk(self.L.rnb_train(self.h, C.c_void_p(stream), C.byref(st) if want_stats else None))
+        return st
+
+    def train_step_begin(self, stream=None):
+        self._chk(self.L.rnb_train_step_begin(self.h, C.c_void_p(stream)))
+
+    def train_step_end(self, stream=None):
+        st = StepStats()
+        self._chk(self.L.rnb_train_step_end(self.h, C.c_void_p(stream), C.byref(st)))
+        return st
+
+    def grad_buffer(self):
+        p = C.POINTER(C.c_float)(); n = C.c_uint64()
+        self._chk(self.L.rnb_grad_buffer(self.h, C.byref(p), C.byref(n)))
+        return C.cast(p, C.c_void_p).value, int(n.value)
+
+    def stat_buffer(self):
+        p = C.POINTER(C.c_float)(); n = C.c_uint64()
+        self._chk(self.L.rnb_stat_buffer(self.h, C.byref(p), C.byref(n)))
+        return C.cast(p, C.c_void_p).value, int(n.value)
+
+    def eval_sdf_device(self, xyz_dev_ptr, n, sdf_ptr=None, normal_ptr=None, density_ptr=None, use_ema=True, stream=None):
+        self._chk(self.L.rnb_eval_sdf(self.h, C.c_void_p(xyz_dev_ptr), C.c_size_t(n), C.c_void_p(sdf_ptr), C.c_void_p(normal_ptr), C.c_void_p(density_ptr), int(use_ema), C.c_void_p(stream)))
+
+    # --- stage-level calls (host buffers) ---
+    def stage_generate(self, n_rays, n_rays_total, max_samples):
+        ri = np.zeros(n_rays, np.uint32); rays = np.zeros((n_rays, 6), np.float32); ns = np.zeros((n_rays, 2), np.uint32)
+        coords = np.zeros((max_samples, 7), np.float32); cnt = (C.c_uint32 * 2)()
+        self._chk(self.L.rnb_stage_generate(self.h, n_rays, n_rays_total, max_samples, _p(ri, C.c_uint32), _p(rays, C.c_float), _p(ns, C.c_uint32), _p(coords, C.c_float), cnt))
+        k = int(cnt[0])
+        return dict(ray_indices=ri[:k], rays=rays[:k], numsteps=ns[:k], coords=coords, n_kept=k, n_samples=int(cnt[1]))
+
+    def stage_forward(self, coords, use_ema=False, want_normal=True):
+        coords = np.ascontiguousarray(coords, np.float32); n = coords.shape[0]
+        out = np.zeros((n, 16), np.float32); nrm = np.zeros((n, 3), np.float32) if want_normal else None
+        self._chk(self.L.rnb_stage_forward(self.h, _p(coords, C.c_float), C.c_size_t(n), int(use_ema), _p(out, C.c_float), _p(nrm, C.c_float)))
+        return out, nrm
+
+    def stage_loss(self, out_c, ray_indices, n_fwd, cbase, n_emit, n_rays, n_rays_total):
+        out_c = np.ascontiguousarray(out_c, np.float32); k = len(ray_indices)
+        dout = np.zeros_like(out_c); lo = np.zeros(k, np.float32); ek = np.zeros(k, np.float32); ml = np.zeros(k, np.float32)
+        a = [np.ascontiguousarray(x, np.uint32) for x in (ray_indices, n_fwd, cbase, n_emit)]
+        self._chk(self.L.rnb_stage_loss(self.h, _p(out_c, C.c_float), _p(a[0], C.c_uint32), _p(a[1], C.c_uint32), _p(a[2], C.c_uint32), _p(a[3], C.c_uint32), k, n_rays, n_rays_total,
+                                        _p(dout, C.c_float), _p(lo, C.c_float), _p(ek, C.c_float), _p(ml, C.c_float)))
+        return dout, lo, ek, ml
+
+    def stage_backward(self, coords, dout, n_in_rollover):
+        coords = np.ascontiguousarray(coords, np.float32); dout = np.ascontiguousarray(dout, np.float32)
+        g = np.zeros(self.n_params, np.float32)
+        self._chk(self.L.rnb_stage_backward(self.h, _p(coords, C.c_float), _p(dout, C.c_float), C.c_size_t(coords.shape[0]), n_in_rollover, _p(g, C.c_float)))
+        return g
+
+    def stage_optimizer(self, grads=None):
+        g = np.ascontiguousarray(grads, np.float32) if grads is not None else None
+        self._chk(self.L.rnb_stage_optimizer(self.h, _p(g, C.c_float)))

@@ -1,0 +1,621 @@
+// rnb_api.cu — context object and C ABI (include/rnb_b200.h).  Host-side orchestration of one training step:
+// the B200-native counterpart of Testbed::train / training_prep_nerf / train_nerf / train_nerf_step
+// (reference src/testbed.cu:2776-2872, src/testbed_nerf.cu:3424-3668,3844-4138) and Trainer::optimizer_step.
+//
+// Differences in structure (not in results): no per-step host synchronisation (sample counts stay on the device and
+// kernels read them there; the reference copies counters to the host and reduces the variance gradient through the
+// host every step), one scratch arena allocated up front, ordered scans instead of atomicAdd slot hand-out.
+#include "rnb_common.cuh"
+#include <vector>
+#include <string>
+#include <random>
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <algorithm>
+
+namespace rnb {
+// rnb_march.cu
+void launch_march(cudaStream_t, uint32_t, uint32_t, uint32_t, uint32_t, Pcg32, const ViewDev*, uint32_t, const uint8_t*, uint32_t*, float*, float*);
+void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, uint32_t*, uint32_t*, uint32_t*);
+void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, const float*, const float*, float4*);
+// rnb_network_simt.cu
+void launch_forward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, int, const float4*, const uint32_t*, uint32_t, const float*, __half*, float*, float*, float*);
+void launch_backward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, const uint32_t*, const uint32_t*, float*, __half*, float*);
+size_t backward_simt_scratch_halfs(const ModelDev&);
+// rnb_loss.cu
+void launch_ray_dirw(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const float*, float*);
+void launch_compact_count(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const __half*, const float*, const __half*, uint32_t, float, uint32_t*);
+void launch_scan_compact(cudaStream_t, uint32_t*, uint32_t, const uint32_t*, uint32_t*, uint32_t*);
+void launch_gather_compacted(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const float4*, float4*);
+void launch_loss(cudaStream_t, uint32_t, const rnb_flags&, uint32_t, uint32_t, uint32_t, float, const uint32_t*, Pcg32, const ViewDev*, uint32_t, const uint32_t*, const float*,
+                 const uint32_t*, const uint32_t*, const uint32_t*, const __half*, __half*, float*, float*);
+// rnb_optim.cu
+struct AdamParams {
+	float base_lr, beta1, beta2, eps, l2, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
+	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf;
+};
+void launch_adam_ema(cudaStream_t, const AdamParams&, float*, __half*, __half*, float*, float*, float*, uint32_t*);
+void launch_cast_params(cudaStream_t, uint32_t, const float*, __half*);
+void launch_widen_params(cudaStream_t, uint32_t, const __half*, float*);
+void launch_init_grid(cudaStream_t, Pcg32, uint64_t, float*);
+void launch_grid_samples(cudaStream_t, uint32_t, Pcg32, uint32_t, const float*, float4*, uint32_t*, float);
+void launch_grid_finish(cudaStream_t, uint32_t, const uint32_t*, const float*, float, float*, float*, double*, float*, uint8_t*);
+}
+
+using namespace rnb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(RNB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct rnb_ctx {
+	rnb_config cfg; rnb_flags flags; ModelDev M;
+	uint32_t off_sdf = 0, off_rgb = 0;
+	// parameters / optimizer state
+	float* master = nullptr; __half* params = nullptr; __half* ema = nullptr; float* grads = nullptr; float* m1 = nullptr; float* m2 = nullptr; uint32_t* steps = nullptr;
+	uint32_t opt_step = 0; float lr_factor = 1.f;
+	// occupancy
+	float* density_grid = nullptr; float* density_tmp = nullptr; uint8_t* bitfield = nullptr; double* mean_acc = nullptr; float* mean = nullptr;
+	float4* gpos = nullptr; uint32_t* gidx = nullptr; float* gdens = nullptr;
+	uint32_t density_ema_step = 0;
+	// dataset
+	ViewDev* views_dev = nullptr; uint32_t n_views = 0; std::vector<void*> owned;
+	// step scratch
+	uint32_t cap_rays = 0, max_samples = 0, cap_compact = 0;
+	uint32_t *ray_n = nullptr, *ray_indices = nullptr, *numsteps = nullptr, *counters = nullptr, *n_fwd = nullptr, *cbase = nullptr, *n_emit = nullptr;
+	float *ray_geom = nullptr, *ts = nullptr, *ray_dirw = nullptr, *loss_out = nullptr, *stats = nullptr;
+	float4 *pos4 = nullptr, *cpos4 = nullptr;
+	__half *outA = nullptr, *out16 = nullptr, *dout16 = nullptr, *bw_scratch = nullptr; float* bw_front = nullptr;
+	uint32_t* counters_host = nullptr; float* stats_host = nullptr;   // pinned
+	// training state
+	Pcg32 rng, density_rng;
+	uint32_t training_step = 0, rays_per_batch = 4096, n_rays_total = 0, measured_before = 0, measured = 0;
+	uint32_t step_R = 0, step_nrt = 0; bool in_step = false;
+};
+
+static uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
+
+static uint32_t valid_level_for_step(const rnb_ctx* c, int step) {   // grid.h:1430-1437
+	if (step <= 0) return c->cfg.n_levels;
+	float v = c->cfg.base_valid_level_scale * (float)c->cfg.n_levels + c->cfg.valid_level_scale * (float)std::max(0, (int)((uint32_t)step - c->cfg.base_training_step));
+	return std::min(c->cfg.n_levels, (uint32_t)std::ceil(v));
+}
+
+static int ensure_ray_capacity(rnb_ctx* c, uint32_t R) {
+	if (R <= c->cap_rays) return 0;
+	uint32_t cap = std::max(R, 4096u);
+	cudaFree(c->ray_n); cudaFree(c->ray_indices); cudaFree(c->numsteps); cudaFree(c->n_fwd); cudaFree(c->cbase); cudaFree(c->n_emit);
+	cudaFree(c->ray_geom); cudaFree(c->ts); cudaFree(c->ray_dirw); cudaFree(c->loss_out);
+	CU(cudaMalloc(&c->ray_n, cap * 4)); CU(cudaMalloc(&c->ray_indices, cap * 4)); CU(cudaMalloc(&c->numsteps, cap * 8));
+	CU(cudaMalloc(&c->n_fwd, cap * 4)); CU(cudaMalloc(&c->cbase, cap * 4)); CU(cudaMalloc(&c->n_emit, cap * 4));
+	CU(cudaMalloc(&c->ray_geom, (size_t)cap * 9 * 4));
+	const uint32_t local = (cap + c->cfg.world_size - 1) / c->cfg.world_size;
+	CU(cudaMalloc(&c->ts, (size_t)local * MAX_STEPS * 4));
+	CU(cudaMalloc(&c->ray_dirw, (size_t)cap * 3 * 4)); CU(cudaMalloc(&c->loss_out, (size_t)cap * 3 * 4));
+	CU(cudaMemset(c->ray_n, 0, cap * 4));
+	c->cap_rays = cap;
+	return 0;
+}
+
+extern "C" {
+
+const char* rnb_last_error(void) { return g_err.c_str(); }
+uint32_t rnb_abi_version(void) { return RNB_ABI_VERSION; }
+
+void rnb_default_config(rnb_config* c) {
+	memset(c, 0, sizeof(*c));
+	c->abi_version = RNB_ABI_VERSION;
+	c->n_levels = 14; c->log2_hashmap_size = 19; c->base_resolution = 16; c->per_level_scale = 0.f; c->top_resolution = 2048.f;
+	c->base_valid_level_scale = 0.2f; c->valid_level_scale = 0.02f; c->base_training_step = 100;
+	c->sdf_n_neurons = 64; c->sdf_n_hidden_layers = 1; c->rgb_n_neurons = 64; c->rgb_n_hidden_layers = 2; c->sdf_bias = -0.1f;
+	c->learning_rate = 1e-3f; c->beta1 = 0.9f; c->beta2 = 0.99f; c->epsilon = 1e-15f; c->l2_reg = 1e-6f; c->ema_decay = 0.95f;
+	c->lr_decay_start = 20000; c->lr_decay_interval = 10000; c->lr_decay_base = 0.33f; c->loss_scale = 128.f;
+	c->target_batch_size = 1u << 18; c->rays_per_batch = 4096; c->pin_rays_per_batch = 1; c->seed = 1337; c->density_grid_decay = 0.95f;
+	c->world_size = 1; c->rank = 0;
+}
+void rnb_default_flags(rnb_flags* f) {
+	memset(f, 0, sizeof(*f));
+	f->apply_L2 = 1; f->apply_rgbplus = 1; f->no_albedo = 1; f->mask_loss_weight = 1.0f; f->ek_loss_weight = 0.01f; f->cos_anneal_ratio = 1.0f; f->light_mode = -1;
+}
+
+int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
+	if (!cfg || !out) return fail(RNB_ERR_INVALID, "null argument");
+	if (cfg->abi_version != RNB_ABI_VERSION) return fail(RNB_ERR_INVALID, "ABI version mismatch");
+	if (cfg->n_levels < 1 || cfg->n_levels > 14) return fail(RNB_ERR_INVALID, "n_levels must be in 1..14 (SDF-MLP input width must be 32 or 48, nerf_network.h:594-604)");
+	if (cfg->sdf_n_hidden_layers != 1) return fail(RNB_ERR_INVALID, "sdf network: exactly 1 hidden layer is supported (geometric initialisation file covers 1 layer)");
+	if (cfg->rgb_n_hidden_layers < 1 || cfg->rgb_n_hidden_layers > 2) return fail(RNB_ERR_INVALID, "rgb network: 1 or 2 hidden layers");
+	if ((cfg->sdf_n_neurons != 32 && cfg->sdf_n_neurons != 64) || (cfg->rgb_n_neurons != 32 && cfg->rgb_n_neurons != 64)) return fail(RNB_ERR_INVALID, "n_neurons must be 32 or 64");
+	if (cfg->world_size < 1 || cfg->rank >= cfg->world_size) return fail(RNB_ERR_INVALID, "bad rank / world_size");
+	int dev = 0; CU(cudaGetDevice(&dev));
+	rnb_ctx* c = new rnb_ctx();
+	c->cfg = *cfg; rnb_default_flags(&c->flags);
+	if (c->cfg.per_level_scale <= 0.f && c->cfg.n_levels > 1)
+		c->cfg.per_level_scale = std::exp(std::log(c->cfg.top_resolution * 1.0f / (float)c->cfg.base_resolution) / (c->cfg.n_levels - 1));   // src/testbed.cu:2321
+	ModelDev& M = c->M; memset(&M, 0, sizeof(M));
+	M.n_levels = cfg->n_levels; M.n_enc = 2 * cfg->n_levels; M.sdf_width = cfg->sdf_n_neurons; M.rgb_width = cfg->rgb_n_neurons; M.sdf_bias = cfg->sdf_bias;
+	uint32_t offset = 0;
+	for (uint32_t i = 0; i < M.n_levels; ++i) {      // grid.h:977-1013
+		const float s = exp2f(i * std::log2(c->cfg.per_level_scale)) * c->cfg.base_resolution - 1.0f;
+		const uint32_t r = (uint32_t)(ceilf(s)) + 1;
+		M.scale[i] = (float)(r - 1); M.res[i] = r;
+		uint32_t max_params = 0xFFFFFFFFu / 2;
+		uint32_t pil = std::pow((float)r, 3.f) > (float)max_params ? max_params : r * r * r;
+		pil = next_multiple(pil, 8u);
+		pil = std::min(pil, 1u << cfg->log2_hashmap_size);
+		M.offsets[i] = offset; offset += pil;
+	}
+	M.offsets[M.n_levels] = offset;
+	M.sdf_in = next_multiple(3 + M.n_enc, 16u); M.rgb_in = next_multiple(3 + 3 + 16 + 16, 16u);
+	uint32_t off = 0; c->off_sdf = 0;
+	auto add = [&](LayerDesc* ls, uint32_t& nl, uint32_t in, uint32_t width, uint32_t hidden) {
+		nl = 0; ls[nl++] = {width, in, off}; off += width * in;
+		for (uint32_t h = 1; h < hidden; ++h) { ls[nl++] = {width, width, off}; off += width * width; }
+		ls[nl++] = {16, width, off}; off += 16 * width;
+	};
+	add(M.sdf_layers, M.n_sdf_layers, M.sdf_in, M.sdf_width, cfg->sdf_n_hidden_layers);
+	c->off_rgb = off;
+	add(M.rgb_layers, M.n_rgb_layers, M.rgb_in, M.rgb_width, cfg->rgb_n_hidden_layers);
+	M.off_grid = off; off += offset * 2; M.off_var = off; off += 4; M.n_params = off;
+	const size_t np = M.n_params;
+	CU(cudaMalloc(&c->master, np * 4)); CU(cudaMalloc(&c->params, np * 2)); CU(cudaMalloc(&c->ema, np * 2)); CU(cudaMalloc(&c->grads, np * 4));
+	CU(cudaMalloc(&c->m1, np * 4)); CU(cudaMalloc(&c->m2, np * 4)); CU(cudaMalloc(&c->steps, np * 4));
+	CU(cudaMemset(c->master, 0, np * 4)); CU(cudaMemset(c->params, 0, np * 2)); CU(cudaMemset(c->ema, 0, np * 2)); CU(cudaMemset(c->grads, 0, np * 4));
+	CU(cudaMemset(c->m1, 0, np * 4)); CU(cudaMemset(c->m2, 0, np * 4)); CU(cudaMemset(c->steps, 0, np * 4));
+	CU(cudaMalloc(&c->density_grid, GRID_CELLS * 4)); CU(cudaMalloc(&c->density_tmp, GRID_CELLS * 4)); CU(cudaMalloc(&c->bitfield, GRID_CELLS));
+	CU(cudaMalloc(&c->mean_acc, 8)); CU(cudaMalloc(&c->mean, 4));
+	CU(cudaMemset(c->density_grid, 0, GRID_CELLS * 4)); CU(cudaMemset(c->density_tmp, 0, GRID_CELLS * 4)); CU(cudaMemset(c->bitfield, 0, GRID_CELLS)); CU(cudaMemset(c->mean, 0, 4));
+	CU(cudaMalloc(&c->gpos, (size_t)GRID_CELLS * 16)); CU(cudaMalloc(&c->gidx, (size_t)GRID_CELLS * 4)); CU(cudaMalloc(&c->gdens, (size_t)GRID_CELLS * 4));
+	c->max_samples = cfg->target_batch_size * 16;                 // testbed_nerf.cu:3846
+	c->cap_compact = cfg->target_batch_size + MAX_STEPS;          // the straddling ray is forwarded in full
+	CU(cudaMalloc(&c->pos4, (size_t)c->max_samples * 16)); CU(cudaMalloc(&c->outA, (size_t)c->max_samples * 8));
+	CU(cudaMalloc(&c->cpos4, (size_t)c->cap_compact * 16)); CU(cudaMalloc(&c->out16, (size_t)c->cap_compact * 32)); CU(cudaMalloc(&c->dout16, (size_t)c->cap_compact * 32));
+	CU(cudaMemset(c->dout16, 0, (size_t)c->cap_compact * 32));
+	CU(cudaMalloc(&c->bw_scratch, (size_t)cfg->target_batch_size * backward_simt_scratch_halfs(M) * 2)); CU(cudaMalloc(&c->bw_front, (size_t)cfg->target_batch_size * M.sdf_width * 4));
+	CU(cudaMalloc(&c->counters, 16 * 4)); CU(cudaMemset(c->counters, 0, 16 * 4));
+	CU(cudaMalloc(&c->stats, 8 * 4)); CU(cudaMemset(c->stats, 0, 8 * 4));
+	CU(cudaMallocHost(&c->counters_host, 16 * 4)); CU(cudaMallocHost(&c->stats_host, 8 * 4));
+	c->rays_per_batch = cfg->rays_per_batch;
+	int rc = ensure_ray_capacity(c, c->rays_per_batch); if (rc) return rc;
+	c->rng = Pcg32(cfg->seed);
+	{ Pcg32 t = c->rng; c->density_rng = Pcg32(t.next_uint()); }     // src/testbed.cu:2223,2236,2490
+	*out = c;
+	return RNB_OK;
+}
+
+int rnb_destroy(rnb_ctx* c) {
+	if (!c) return RNB_OK;
+	void* ptrs[] = {c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps, c->density_grid, c->density_tmp, c->bitfield, c->mean_acc, c->mean, c->gpos, c->gidx, c->gdens,
+	                c->views_dev, c->ray_n, c->ray_indices, c->numsteps, c->counters, c->n_fwd, c->cbase, c->n_emit, c->ray_geom, c->ts, c->ray_dirw, c->loss_out, c->stats,
+	                c->pos4, c->cpos4, c->outA, c->out16, c->dout16, c->bw_scratch, c->bw_front};
+	for (void* p : ptrs) cudaFree(p);
+	for (void* p : c->owned) cudaFree(p);
+	cudaFreeHost(c->counters_host); cudaFreeHost(c->stats_host);
+	delete c;
+	return RNB_OK;
+}
+
+int rnb_param_layout(rnb_ctx* c, uint64_t out[5]) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	out[0] = c->off_sdf; out[1] = c->off_rgb; out[2] = c->M.off_grid; out[3] = c->M.off_var; out[4] = c->M.n_params;
+	return RNB_OK;
+}
+
+// Built-in geometric initialisation used when the reference's utils/mlp_weights*.txt is not supplied: a bias-free
+// one-hidden-layer ReLU network whose output 0 approximates |x - 0.5| * k (sum of ReLUs over random directions).
+static void builtin_sphere_init(const rnb_ctx* c, std::vector<float>& w) {
+	const ModelDev& M = c->M;
+	const uint32_t W = M.sdf_width, IN = M.sdf_in;
+	w.assign((size_t)W * IN + 16 * W, 0.f);
+	Pcg32 r(c->cfg.seed + 7);
+	for (uint32_t i = 0; i < W; ++i) {
+		float x, y, z, n;
+		do { x = r.next_float() * 2 - 1; y = r.next_float() * 2 - 1; z = r.next_float() * 2 - 1; n = std::sqrt(x * x + y * y + z * z); } while (n < 1e-3f || n > 1.f);
+		w[(size_t)i * IN + 0] = x / n; w[(size_t)i * IN + 1] = y / n; w[(size_t)i * IN + 2] = z / n;
+		for (uint32_t k = 3; k < 3 + M.n_enc; ++k) w[(size_t)i * IN + k] = (r.next_float() * 2 - 1) * 0.05f;
+	}
+	// E[relu(w.x)] = |x|/4 over the unit sphere; radius 0.25 in the unit cube with the -0.1 bias: k*0.25 = 0.1
+	const float k = -c->cfg.sdf_bias / 0.25f;
+	for (uint32_t i = 0; i < W; ++i) w[(size_t)W * IN + i] = k * 4.0f / (float)W;
+	for (uint32_t o = 1; o < 16; ++o) for (uint32_t i = 0; i < W; ++i) w[(size_t)W * IN + (size_t)o * W + i] = (r.next_float() * 2 - 1) * 0.1f;
+}
+
+int rnb_init_params(rnb_ctx* c, const float* sdf_init, size_t n_sdf_init) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	const ModelDev& M = c->M;
+	std::seed_seq seq{c->cfg.seed};                 // trainer.h:54-60
+	std::vector<uint32_t> seeds(2); seq.generate(seeds.begin(), seeds.end());
+	Pcg32 rnd(seeds.front());
+	std::vector<float> mlp(M.off_grid, 0.f);
+	auto xavier = [&](const LayerDesc* ls, uint32_t nl) {   // gpu_matrix.h:292-304
+		for (uint32_t l = 0; l < nl; ++l) {
+			const float scale = std::sqrt(6.0f / (float)(ls[l].cols + ls[l].rows));
+			for (size_t i = 0; i < (size_t)ls[l].rows * ls[l].cols; ++i) mlp[ls[l].off + i] = rnd.next_float() * 2.0f * scale - scale;
+		}
+	};
+	xavier(M.sdf_layers, M.n_sdf_layers);
+	const size_t n_sdf = c->off_rgb - c->off_sdf;
+	std::vector<float> builtin;
+	if (!sdf_init) { builtin_sphere_init(c, builtin); sdf_init = builtin.data(); n_sdf_init = builtin.size(); }
+	for (size_t i = 0; i < n_sdf; ++i) mlp[c->off_sdf + i] = i < n_sdf_init ? sdf_init[i] : 0.f;
+	xavier(M.rgb_layers, M.n_rgb_layers);
+	CU(cudaMemcpy(c->master, mlp.data(), mlp.size() * 4, cudaMemcpyHostToDevice));
+	const uint64_t n_grid = (uint64_t)M.off_var - M.off_grid;
+	launch_init_grid(0, rnd, n_grid, c->master + M.off_grid);
+	rnd.advance((int64_t)n_grid);
+	const float var[4] = {0.3f, 0.3f, 0.3f, 0.3f};
+	CU(cudaMemcpy(c->master + M.off_var, var, 16, cudaMemcpyHostToDevice));
+	launch_cast_params(0, M.n_params, c->master, c->params);
+	CU(cudaMemset(c->ema, 0, (size_t)M.n_params * 2)); CU(cudaMemset(c->m1, 0, (size_t)M.n_params * 4)); CU(cudaMemset(c->m2, 0, (size_t)M.n_params * 4));
+	CU(cudaMemset(c->steps, 0, (size_t)M.n_params * 4)); CU(cudaMemset(c->grads, 0, (size_t)M.n_params * 4));
+	c->opt_step = 0; c->lr_factor = 1.f;
+	CU(cudaDeviceSynchronize());
+	return RNB_OK;
+}
+
+int rnb_set_params_fp32(rnb_ctx* c, const float* p, size_t n) {
+	if (!c || !p || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
+	CU(cudaMemcpy(c->master, p, n * 4, cudaMemcpyHostToDevice));
+	launch_cast_params(0, c->M.n_params, c->master, c->params);
+	CU(cudaDeviceSynchronize());
+	return RNB_OK;
+}
+int rnb_get_params_fp32(rnb_ctx* c, float* p, size_t n) {
+	if (!c || !p || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
+	CU(cudaMemcpy(p, c->master, n * 4, cudaMemcpyDeviceToHost));
+	return RNB_OK;
+}
+int rnb_export_params_fp16(rnb_ctx* c, uint16_t* host, size_t n, int use_ema) {
+	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
+	CU(cudaMemcpy(host, use_ema ? c->ema : c->params, n * 2, cudaMemcpyDeviceToHost));
+	return RNB_OK;
+}
+// Trainer::deserialize (trainer.h:263-275): fp16 params in, fp32 master re-derived, optimizer moments restart
+int rnb_import_params_fp16(rnb_ctx* c, const uint16_t* host, size_t n) {
+	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
+	CU(cudaMemcpy(c->params, host, n * 2, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->ema, host, n * 2, cudaMemcpyHostToDevice));
+	launch_widen_params(0, c->M.n_params, c->params, c->master);
+	CU(cudaMemset(c->m1, 0, n * 4)); CU(cudaMemset(c->m2, 0, n * 4)); CU(cudaMemset(c->steps, 0, n * 4));
+	c->opt_step = 0; c->lr_factor = 1.f;
+	CU(cudaDeviceSynchronize());
+	return RNB_OK;
+}
+int rnb_export_density_grid(rnb_ctx* c, float* host, size_t n, uint32_t* ema_step) {
+	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "density grid is 128^3 floats");
+	CU(cudaMemcpy(host, c->density_grid, n * 4, cudaMemcpyDeviceToHost));
+	if (ema_step) *ema_step = c->density_ema_step;
+	return RNB_OK;
+}
+int rnb_get_bitfield(rnb_ctx* c, uint8_t* host, size_t n) {
+	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "bitfield is 128^3 bytes");
+	CU(cudaMemcpy(host, c->bitfield, n, cudaMemcpyDeviceToHost));
+	return RNB_OK;
+}
+int rnb_set_bitfield(rnb_ctx* c, const uint8_t* host, size_t n) {
+	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "bitfield is 128^3 bytes");
+	CU(cudaMemcpy(c->bitfield, host, n, cudaMemcpyHostToDevice));
+	return RNB_OK;
+}
+int rnb_get_train_state(rnb_ctx* c, uint32_t out[4]) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	out[0] = c->training_step; out[1] = c->rays_per_batch; out[2] = c->n_rays_total; out[3] = c->measured_before;
+	return RNB_OK;
+}
+int rnb_set_train_state(rnb_ctx* c, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) {
+	if (!c || rays_per_batch == 0 || rays_per_batch > (1u << 18)) return fail(RNB_ERR_INVALID, "bad train state");
+	c->training_step = training_step; c->rays_per_batch = rays_per_batch; c->n_rays_total = n_rays_total; c->measured_before = measured_before;
+	return ensure_ray_capacity(c, rays_per_batch);
+}
+int rnb_get_rng(rnb_ctx* c, uint64_t out[4]) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	out[0] = c->rng.state; out[1] = c->rng.inc; out[2] = c->density_rng.state; out[3] = c->density_rng.inc; return RNB_OK;
+}
+int rnb_set_rng(rnb_ctx* c, const uint64_t in[4]) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	c->rng.state = in[0]; c->rng.inc = in[1]; c->density_rng.state = in[2]; c->density_rng.inc = in[3]; return RNB_OK;
+}
+
+static int set_views(rnb_ctx* c, const rnb_view* views, uint32_t n, bool upload) {
+	if (!c || !views || n == 0) return fail(RNB_ERR_INVALID, "no views");
+	for (void* p : c->owned) cudaFree(p);
+	c->owned.clear();
+	std::vector<ViewDev> vd(n);
+	for (uint32_t i = 0; i < n; ++i) {
+		const rnb_view& v = views[i];
+		if (!v.normal_px || v.w <= 0 || v.h <= 0) return fail(RNB_ERR_INVALID, "view without normal map");
+		const size_t bytes = (size_t)v.w * v.h * 8;
+		const void* np = v.normal_px; const void* ap = v.albedo_px;
+		if (upload) {
+			void* d = nullptr; CU(cudaMalloc(&d, bytes)); c->owned.push_back(d); CU(cudaMemcpy(d, v.normal_px, bytes, cudaMemcpyHostToDevice)); np = d;
+			if (v.albedo_px) { void* a = nullptr; CU(cudaMalloc(&a, bytes)); c->owned.push_back(a); CU(cudaMemcpy(a, v.albedo_px, bytes, cudaMemcpyHostToDevice)); ap = a; }
+		}
+		vd[i].normal_px = (const uint2*)np; vd[i].albedo_px = (const uint2*)ap; vd[i].w = v.w; vd[i].h = v.h;
+		vd[i].fx = v.fx; vd[i].fy = v.fy; vd[i].cx = v.cx; vd[i].cy = v.cy;
+		memcpy(vd[i].xform, v.xform, sizeof(v.xform));
+	}
+	cudaFree(c->views_dev); c->views_dev = nullptr;
+	CU(cudaMalloc(&c->views_dev, n * sizeof(ViewDev)));
+	CU(cudaMemcpy(c->views_dev, vd.data(), n * sizeof(ViewDev), cudaMemcpyHostToDevice));
+	c->n_views = n;
+	return RNB_OK;
+}
+int rnb_set_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { return set_views(c, v, n, false); }
+int rnb_upload_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { return set_views(c, v, n, true); }
+int rnb_set_flags(rnb_ctx* c, const rnb_flags* f) { if (!c || !f) return fail(RNB_ERR_INVALID, "null argument"); c->flags = *f; return RNB_OK; }
+
+int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t ema_step) {
+	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "density grid is 128^3 floats");
+	CU(cudaMemcpy(c->density_grid, host, n * 4, cudaMemcpyHostToDevice));
+	c->density_ema_step = ema_step;
+	// update_density_grid_mean_and_bitfield (testbed_nerf.cu:3497-3517): bitfield follows the imported grid
+	CU(cudaMemset(c->density_tmp, 0, GRID_CELLS * 4));
+	launch_grid_finish(0, 0, c->gidx, c->gdens, 1.0f, c->density_grid, c->density_tmp, c->mean_acc, c->mean, c->bitfield);
+	CU(cudaDeviceSynchronize());
+	return RNB_OK;
+}
+
+// ---- occupancy refresh: training_prep_nerf / update_density_grid_nerf --------------------------------------------
+static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint32_t n_nonuniform) {
+	if (c->training_step == 0) {
+		c->density_ema_step = 0;
+		CU(cudaMemsetAsync(c->density_grid, 0, GRID_CELLS * 4, st));
+	}
+	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
+	launch_grid_samples(st, n_uniform, c->density_rng, c->density_ema_step, c->density_grid, c->gpos, c->gidx, -0.01f);
+	c->density_rng.advance();
+	launch_grid_samples(st, n_nonuniform, c->density_rng, c->density_ema_step, c->density_grid, c->gpos + n_uniform, c->gidx + n_uniform, MIN_OPTICAL_THICKNESS);
+	c->density_rng.advance();
+	const uint32_t n = n_uniform + n_nonuniform;
+	launch_forward_simt(st, c->M, c->params, vl, 2, c->gpos, nullptr, n, nullptr, nullptr, nullptr, nullptr, c->gdens);
+	launch_grid_finish(st, n, c->gidx, c->gdens, c->cfg.density_grid_decay, c->density_grid, c->density_tmp, c->mean_acc, c->mean, c->bitfield);
+	++c->density_ema_step;
+	CU(cudaGetLastError());
+	return RNB_OK;
+}
+int rnb_prep(rnb_ctx* c, void* stream) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (c->training_step < 256) return density_update(c, (cudaStream_t)stream, GRID_CELLS, 0);
+	return density_update(c, (cudaStream_t)stream, GRID_CELLS / 4, GRID_CELLS / 4);
+}
+
+// ---- one training step ----------------------------------------------------------------------------------------------
+// counters (device, uint32): [0] kept rays  [1] samples before compaction  [2] compacted (untruncated)  [3] trained = min([2], target)
+//                            [4] samples forwarded in pass B  [5] samples before compaction of the previous step
+static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt, uint32_t max_inference) {
+	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
+	const ModelDev& M = c->M;
+	launch_march(st, R, c->cfg.world_size, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts);
+	launch_scan_rays(st, R, max_inference, c->ray_n, c->ray_indices, c->numsteps, c->counters);
+	launch_emit(st, R, c->counters, c->cfg.world_size, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4);
+	launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw);
+	launch_forward_simt(st, M, c->params, vl, 0, c->pos4, c->counters + 1, max_inference, c->ray_dirw, c->outA, nullptr, nullptr, nullptr);
+	launch_compact_count(st, R, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd);
+	launch_scan_compact(st, c->counters, c->cfg.target_batch_size, c->n_fwd, c->cbase, c->n_emit);
+	launch_gather_compacted(st, R, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4);
+	launch_forward_simt(st, M, c->params, vl, 1, c->cpos4, c->counters + 4, c->cap_compact, c->ray_dirw, c->out16, nullptr, nullptr, nullptr);
+	launch_loss(st, R, c->flags, R, nrt, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
+	            c->out16, c->dout16, c->loss_out, c->stats);
+	launch_backward_simt(st, M, c->params, vl, c->cpos4, c->dout16, c->counters + 3, c->cfg.target_batch_size, c->cfg.target_batch_size, c->counters + 3, nullptr, c->grads, c->bw_scratch, c->bw_front);
+	CU(cudaGetLastError());
+	return RNB_OK;
+}
+
+static int optimizer_step(rnb_ctx* c, cudaStream_t st) {
+	if (c->opt_step == 0) c->lr_factor = 1.0f;      // exponential_decay.h:61-72
+	if (c->opt_step >= c->cfg.lr_decay_start && c->cfg.lr_decay_interval && (c->opt_step - c->cfg.lr_decay_start) % c->cfg.lr_decay_interval == 0) c->lr_factor *= c->cfg.lr_decay_base;
+	++c->opt_step;
+	AdamParams A;
+	A.base_lr = c->cfg.learning_rate * c->lr_factor; A.beta1 = c->cfg.beta1; A.beta2 = c->cfg.beta2; A.eps = c->cfg.epsilon; A.l2 = c->cfg.l2_reg; A.loss_scale = c->cfg.loss_scale;
+	A.ema_decay = c->cfg.ema_decay;
+	A.ema_debias_old = 1 - (float)std::pow(c->cfg.ema_decay, c->opt_step - 1);       // ema.h:121-122
+	A.ema_debias_new = 1.0f / (1 - (float)std::pow(c->cfg.ema_decay, c->opt_step));
+	A.n_params = c->M.n_params; A.n_matrix = c->M.off_grid; A.rgb_begin = c->off_rgb; A.rgb_end = c->M.off_grid; A.only_sdf = c->flags.only_sdf_training;
+	launch_adam_ema(st, A, c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps);
+	CU(cudaGetLastError());
+	return RNB_OK;
+}
+
+int rnb_train_step_begin(rnb_ctx* c, void* stream) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (!c->views_dev) return fail(RNB_ERR_STATE, "no dataset: call rnb_set_dataset / rnb_upload_dataset first");
+	if (c->in_step) return fail(RNB_ERR_STATE, "rnb_train_step_begin called twice");
+	cudaStream_t st = (cudaStream_t)stream;
+	const uint32_t R = c->rays_per_batch;
+	int rc = ensure_ray_capacity(c, R); if (rc) return rc;
+	uint32_t max_inference;                                         // testbed_nerf.cu:3891-3896
+	if (c->measured_before == 0) { c->measured_before = max_inference = c->max_samples; }
+	else max_inference = next_multiple(std::min(c->measured_before, c->max_samples), 128u);
+	if (c->training_step == 0) c->n_rays_total = 0;                 // :3906-3911
+	const uint32_t nrt = c->n_rays_total; c->n_rays_total += R;
+	c->step_R = R; c->step_nrt = nrt;
+	rc = step_front(c, st, R, nrt, max_inference); if (rc) return rc;
+	c->rng.advance();                                               // :4118
+	c->in_step = true;
+	return RNB_OK;
+}
+
+int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (!c->in_step) return fail(RNB_ERR_STATE, "rnb_train_step_end without begin");
+	cudaStream_t st = (cudaStream_t)stream;
+	int rc = optimizer_step(c, st); if (rc) return rc;
+	++c->training_step;
+	c->in_step = false;
+	// Counters::update_after_training (:3532-3558).  The sample counts are needed on the host for next step's
+	// max_inference and for the batch-size controller; they are small and copied asynchronously.
+	CU(cudaMemcpyAsync(c->counters_host, c->counters, 8 * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(c->stats_host, c->stats, 8 * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const uint32_t total = c->counters_host[2];
+	c->measured_before = c->counters_host[1]; c->measured = total;
+	const uint32_t R = c->step_R;
+	if (!c->cfg.pin_rays_per_batch && total > 0) {
+		uint32_t r = (uint32_t)((float)R * (float)c->cfg.target_batch_size / (float)total);
+		c->rays_per_batch = std::min(next_multiple(r, 128u), 1u << 18);
+	}
+	if (stats) {
+		const float f = (float)total / (float)c->cfg.target_batch_size;
+		stats->loss = c->stats_host[0] * f; stats->ek_loss = c->stats_host[1] * f; stats->mask_loss = c->stats_host[2] * f;
+		stats->n_rays = R; stats->n_rays_kept = c->counters_host[0]; stats->n_samples = c->counters_host[1]; stats->n_samples_compacted = total;
+		stats->n_samples_trained = c->counters_host[3]; stats->rays_per_batch_next = c->rays_per_batch; stats->training_step = c->training_step; stats->density_grid_updated = 0;
+	}
+	return RNB_OK;
+}
+
+int rnb_train_step(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
+	int rc = rnb_train_step_begin(c, stream); if (rc) return rc;
+	return rnb_train_step_end(c, stream, stats);
+}
+
+int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	const uint32_t skip = std::min(std::max(c->training_step / 16u, 1u), 16u);     // src/testbed.cu:2805-2806
+	uint32_t updated = 0;
+	if (c->training_step % skip == 0) { int rc = rnb_prep(c, stream); if (rc) return rc; updated = 1; }
+	int rc = rnb_train_step(c, stream, stats);
+	if (!rc && stats) stats->density_grid_updated = updated;
+	return rc;
+}
+
+int rnb_grad_buffer(rnb_ctx* c, float** g, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *g = c->grads; *n = c->M.n_params; return RNB_OK; }
+int rnb_stat_buffer(rnb_ctx* c, float** s, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *s = c->stats; *n = 8; return RNB_OK; }
+
+int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream) {
+	if (!c || !xyz_dev) return fail(RNB_ERR_INVALID, "null argument");
+	cudaStream_t st = (cudaStream_t)stream;
+	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
+	float4* tmp = nullptr;
+	const size_t CH = 1u << 20;
+	CU(cudaMallocAsync(&tmp, CH * 16, st));
+	for (size_t o = 0; o < n; o += CH) {
+		const size_t m = std::min(CH, n - o);
+		CU(cudaMemcpy2DAsync(tmp, 16, xyz_dev + o * 3, 12, 12, m, cudaMemcpyDeviceToDevice, st));
+		launch_forward_simt(st, c->M, use_ema ? c->ema : c->params, vl, 2, tmp, nullptr, (uint32_t)m, nullptr, nullptr, sdf_dev ? sdf_dev + o : nullptr, normal_dev ? normal_dev + o * 3 : nullptr, density_dev ? density_dev + o : nullptr);
+	}
+	CU(cudaFreeAsync(tmp, st));
+	CU(cudaGetLastError());
+	return RNB_OK;
+}
+
+// ---- stage-level entry points (host buffers) ------------------------------------------------------------------------
+int rnb_stage_generate(rnb_ctx* c, uint32_t n_rays, uint32_t n_rays_total, uint32_t max_samples, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t counters[2]) {
+	if (!c || !c->views_dev) return fail(RNB_ERR_STATE, "no dataset");
+	if (max_samples > c->max_samples) return fail(RNB_ERR_INVALID, "max_samples exceeds capacity");
+	int rc = ensure_ray_capacity(c, n_rays); if (rc) return rc;
+	launch_march(0, n_rays, c->cfg.world_size, c->cfg.rank, n_rays_total, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts);
+	launch_scan_rays(0, n_rays, max_samples, c->ray_n, c->ray_indices, c->numsteps, c->counters);
+	launch_emit(0, n_rays, c->counters, c->cfg.world_size, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4);
+	CU(cudaDeviceSynchronize());
+	uint32_t cnt[2]; CU(cudaMemcpy(cnt, c->counters, 8, cudaMemcpyDeviceToHost));
+	counters[0] = cnt[0]; counters[1] = cnt[1];
+	const uint32_t K = cnt[0];
+	std::vector<float> geom((size_t)n_rays * 9);
+	CU(cudaMemcpy(ray_indices, c->ray_indices, K * 4, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(numsteps, c->numsteps, K * 8, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(geom.data(), c->ray_geom, geom.size() * 4, cudaMemcpyDeviceToHost));
+	uint32_t n_emitted = 0;
+	for (uint32_t k = 0; k < K; ++k) n_emitted = std::max(n_emitted, numsteps[2 * k] + numsteps[2 * k + 1]);
+	std::vector<float4> p4(n_emitted);
+	CU(cudaMemcpy(p4.data(), c->pos4, (size_t)n_emitted * 16, cudaMemcpyDeviceToHost));
+	for (uint32_t k = 0; k < K; ++k) {
+		const float* g = &geom[(size_t)ray_indices[k] * 9];
+		for (int q = 0; q < 6; ++q) rays[k * 6 + q] = g[q];
+		for (uint32_t j = 0; j < numsteps[2 * k]; ++j) {
+			const size_t s = numsteps[2 * k + 1] + j;
+			float* o = coords + s * 7;
+			o[0] = p4[s].x; o[1] = p4[s].y; o[2] = p4[s].z; o[3] = 0.f;
+			o[4] = (g[6] + 1.0f) * 0.5f; o[5] = (g[7] + 1.0f) * 0.5f; o[6] = (g[8] + 1.0f) * 0.5f;
+		}
+	}
+	return RNB_OK;
+}
+
+static int upload_coords(rnb_ctx* c, const float* coords, size_t n, float4* dst_pos, float** dirw_out) {
+	std::vector<float4> p4(n); std::vector<float> dw(n * 3);
+	for (size_t i = 0; i < n; ++i) {
+		uint32_t slot = (uint32_t)i; float w; memcpy(&w, &slot, 4);
+		p4[i] = make_float4(coords[i * 7], coords[i * 7 + 1], coords[i * 7 + 2], w);
+		dw[i * 3] = coords[i * 7 + 4]; dw[i * 3 + 1] = coords[i * 7 + 5]; dw[i * 3 + 2] = coords[i * 7 + 6];
+	}
+	CU(cudaMemcpy(dst_pos, p4.data(), n * 16, cudaMemcpyHostToDevice));
+	float* d = nullptr; CU(cudaMalloc(&d, std::max<size_t>(n, 1) * 12));
+	CU(cudaMemcpy(d, dw.data(), n * 12, cudaMemcpyHostToDevice));
+	*dirw_out = d;
+	return RNB_OK;
+}
+
+int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, float* out16, float* normal) {
+	if (!c || !coords || !out16) return fail(RNB_ERR_INVALID, "null argument");
+	if (n > c->cap_compact) return fail(RNB_ERR_INVALID, "too many samples for one stage call");
+	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
+	float* dirw = nullptr;
+	int rc = upload_coords(c, coords, n, c->cpos4, &dirw); if (rc) return rc;
+	const __half* P = use_ema ? c->ema : c->params;
+	launch_forward_simt(0, c->M, P, vl, 1, c->cpos4, nullptr, (uint32_t)n, dirw, c->out16, nullptr, nullptr, nullptr);
+	float* nrm_dev = nullptr;
+	if (normal) { CU(cudaMalloc(&nrm_dev, std::max<size_t>(n, 1) * 12)); launch_forward_simt(0, c->M, P, vl, 2, c->cpos4, nullptr, (uint32_t)n, nullptr, nullptr, nullptr, nrm_dev, nullptr); }
+	CU(cudaDeviceSynchronize());
+	std::vector<__half> h(n * 16);
+	CU(cudaMemcpy(h.data(), c->out16, n * 32, cudaMemcpyDeviceToHost));
+	for (size_t i = 0; i < n * 16; ++i) out16[i] = __half2float(h[i]);
+	if (normal) { CU(cudaMemcpy(normal, nrm_dev, n * 12, cudaMemcpyDeviceToHost)); cudaFree(nrm_dev); }
+	cudaFree(dirw);
+	return RNB_OK;
+}
+
+int rnb_stage_loss(rnb_ctx* c, const float* out16_c, const uint32_t* ray_indices, const uint32_t* n_fwd, const uint32_t* cbase, const uint32_t* n_emit,
+                   uint32_t K, uint32_t n_rays, uint32_t n_rays_total, float* dout16, float* loss, float* ek, float* mask) {
+	if (!c || !c->views_dev) return fail(RNB_ERR_STATE, "no dataset");
+	int rc = ensure_ray_capacity(c, std::max(K, n_rays)); if (rc) return rc;
+	size_t total = 0; for (uint32_t k = 0; k < K; ++k) total = std::max<size_t>(total, (size_t)cbase[k] + n_fwd[k]);
+	if (total > c->cap_compact) return fail(RNB_ERR_INVALID, "too many compacted samples");
+	std::vector<__half> h(total * 16); std::vector<float> dirw((size_t)K * 3);
+	for (size_t i = 0; i < total * 16; ++i) h[i] = __float2half_rn(out16_c[i]);
+	for (uint32_t k = 0; k < K; ++k) for (int d = 0; d < 3; ++d) dirw[k * 3 + d] = out16_c[(size_t)cbase[k] * 16 + 8 + d];   // already binary16 values
+	CU(cudaMemcpy(c->out16, h.data(), total * 32, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->ray_dirw, dirw.data(), (size_t)K * 12, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->ray_indices, ray_indices, K * 4, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->n_fwd, n_fwd, K * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(c->cbase, cbase, K * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(c->n_emit, n_emit, K * 4, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->counters, &K, 4, cudaMemcpyHostToDevice));
+	CU(cudaMemset(c->dout16, 0, total * 32));
+	launch_loss(0, K, c->flags, n_rays, n_rays_total, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
+	            c->out16, c->dout16, c->loss_out, nullptr);
+	CU(cudaDeviceSynchronize());
+	CU(cudaMemcpy(h.data(), c->dout16, total * 32, cudaMemcpyDeviceToHost));
+	for (size_t i = 0; i < total * 16; ++i) dout16[i] = __half2float(h[i]);
+	std::vector<float> lo((size_t)K * 3);
+	CU(cudaMemcpy(lo.data(), c->loss_out, (size_t)K * 12, cudaMemcpyDeviceToHost));
+	for (uint32_t k = 0; k < K; ++k) { loss[k] = lo[3 * k]; ek[k] = lo[3 * k + 1]; mask[k] = lo[3 * k + 2]; }
+	return RNB_OK;
+}
+
+int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, size_t n, uint32_t n_in_rollover, float* grads) {
+	if (!c || !coords || !dout16 || !grads) return fail(RNB_ERR_INVALID, "null argument");
+	if (n > c->cfg.target_batch_size) return fail(RNB_ERR_INVALID, "too many samples");
+	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
+	float* dirw = nullptr;
+	int rc = upload_coords(c, coords, n, c->cpos4, &dirw); if (rc) return rc;
+	std::vector<__half> h(n * 16);
+	for (size_t i = 0; i < n * 16; ++i) h[i] = __float2half_rn(dout16[i]);
+	CU(cudaMemcpy(c->dout16, h.data(), n * 32, cudaMemcpyHostToDevice));
+	CU(cudaMemset(c->grads, 0, (size_t)c->M.n_params * 4));
+	uint32_t* nin = nullptr; CU(cudaMalloc(&nin, 4)); CU(cudaMemcpy(nin, &n_in_rollover, 4, cudaMemcpyHostToDevice));
+	launch_backward_simt(0, c->M, c->params, vl, c->cpos4, c->dout16, nullptr, (uint32_t)n, c->cfg.target_batch_size, nin, nullptr, c->grads, c->bw_scratch, c->bw_front);
+	CU(cudaDeviceSynchronize());
+	CU(cudaMemcpy(grads, c->grads, (size_t)c->M.n_params * 4, cudaMemcpyDeviceToHost));
+	CU(cudaMemset(c->grads, 0, (size_t)c->M.n_params * 4));
+	cudaFree(nin); cudaFree(dirw);
+	return RNB_OK;
+}
+
+int rnb_stage_optimizer(rnb_ctx* c, const float* grads_host) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (grads_host) CU(cudaMemcpy(c->grads, grads_host, (size_t)c->M.n_params * 4, cudaMemcpyHostToDevice));
+	int rc = optimizer_step(c, 0); if (rc) return rc;
+	CU(cudaDeviceSynchronize());
+	return RNB_OK;
+}
+
+} // extern "C"

