@@ -174,6 +174,12 @@ int rnb_train_step_end(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
 int rnb_grad_buffer(rnb_ctx* ctx, float** grads_dev, uint64_t* n);
 int rnb_stat_buffer(rnb_ctx* ctx, float** stats_dev, uint64_t* n);
 
+/* instrumentation for bench.py: per-stage CUDA-event timing (events recorded on the caller's stream around each stage of
+ * the step; resolved at the end of rnb_train_step_end) and a count of kernels launched by this ctx. */
+int rnb_profile_enable(rnb_ctx* ctx, int on);
+int rnb_profile_read(rnb_ctx* ctx, char* names_buf, size_t names_cap, double* ms, uint64_t* calls, uint32_t* n);
+int rnb_launch_count(rnb_ctx* ctx, uint64_t* out);
+
 /* replaces NerfNetwork::sdf / density (nerf_network.h:454-537) used by marching cubes (src/testbed_nerf.cu:4252)
  * and the grid refresh.  xyz_dev: n x 3 floats in [0,1]^3; outputs may be NULL. */
 int rnb_eval_sdf(rnb_ctx* ctx, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream);

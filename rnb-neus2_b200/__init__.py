@@ -53,7 +53,7 @@ EXPORTED_SYMBOLS = [
     "rnb_last_error", "rnb_abi_version", "rnb_create", "rnb_destroy", "rnb_default_config", "rnb_default_flags", "rnb_param_layout", "rnb_init_params",
     "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
     "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
-    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_eval_sdf",
+    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
 ]
 
@@ -258,6 +258,18 @@ class Testbed:
         p = C.POINTER(C.c_float)(); n = C.c_uint64()
         self._chk(self.L.rnb_stat_buffer(self.h, C.byref(p), C.byref(n)))
         return C.cast(p, C.c_void_p).value, int(n.value)
+
+    def profile_enable(self, on=True):
+        self._chk(self.L.rnb_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        buf = C.create_string_buffer(1024); ms = (C.c_double * 32)(); calls = (C.c_uint64 * 32)(); n = C.c_uint32(32)
+        self._chk(self.L.rnb_profile_read(self.h, buf, C.c_size_t(1024), ms, calls, C.byref(n)))
+        names = buf.value.decode().split(";")[:n.value]
+        return {names[i]: (float(ms[i]), int(calls[i])) for i in range(n.value)}
+
+    def launch_count(self):
+        v = C.c_uint64(); self._chk(self.L.rnb_launch_count(self.h, C.byref(v))); return int(v.value)
 
     def eval_sdf_device(self, xyz_dev_ptr, n, sdf_ptr=None, normal_ptr=None, density_ptr=None, use_ema=True, stream=None):
         self._chk(self.L.rnb_eval_sdf(self.h, C.c_void_p(xyz_dev_ptr), C.c_size_t(n), C.c_void_p(sdf_ptr), C.c_void_p(normal_ptr), C.c_void_p(density_ptr), int(use_ema), C.c_void_p(stream)))

@@ -22,12 +22,12 @@ void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, uint32_
 void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, const float*, const float*, float4*);
 // rnb_network_simt.cu
 void launch_forward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, int, const float4*, const uint32_t*, uint32_t, const float*, __half*, float*, float*, float*);
-void launch_backward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, const uint32_t*, const uint32_t*, float*, __half*, float*);
+void launch_backward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, float*, __half*, float*);
 size_t backward_simt_scratch_halfs(const ModelDev&);
 // rnb_loss.cu
 void launch_ray_dirw(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const float*, float*);
 void launch_compact_count(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const __half*, const float*, const __half*, uint32_t, float, uint32_t*);
-void launch_scan_compact(cudaStream_t, uint32_t*, uint32_t, const uint32_t*, uint32_t*, uint32_t*);
+void launch_scan_compact(cudaStream_t, uint32_t*, uint32_t, const uint32_t*, uint32_t*, uint32_t*, float*);
 void launch_gather_compacted(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const float4*, float4*);
 void launch_loss(cudaStream_t, uint32_t, const rnb_flags&, uint32_t, uint32_t, uint32_t, float, const uint32_t*, Pcg32, const ViewDev*, uint32_t, const uint32_t*, const float*,
                  const uint32_t*, const uint32_t*, const uint32_t*, const __half*, __half*, float*, float*);
@@ -73,7 +73,33 @@ struct rnb_ctx {
 	Pcg32 rng, density_rng;
 	uint32_t training_step = 0, rays_per_batch = 4096, n_rays_total = 0, measured_before = 0, measured = 0;
 	uint32_t step_R = 0, step_nrt = 0; bool in_step = false;
+	// instrumentation: kernel launch counter and optional per-stage CUDA-event timing (bench.py roofline)
+	uint64_t launches = 0;
+	bool prof = false;
+	struct ProfAcc { std::string name; double ms = 0; uint64_t calls = 0; };
+	struct ProfPending { int acc; cudaEvent_t e0, e1; };
+	std::vector<ProfAcc> prof_acc; std::vector<ProfPending> prof_pending; std::vector<cudaEvent_t> ev_pool;
 };
+
+static void prof_begin(rnb_ctx* c, cudaStream_t st, const char* name) {
+	if (!c->prof) return;
+	int a = -1;
+	for (size_t i = 0; i < c->prof_acc.size(); ++i) if (c->prof_acc[i].name == name) { a = (int)i; break; }
+	if (a < 0) { c->prof_acc.push_back({name, 0, 0}); a = (int)c->prof_acc.size() - 1; }
+	cudaEvent_t e[2];
+	for (int k = 0; k < 2; ++k) { if (c->ev_pool.empty()) cudaEventCreate(&e[k]); else { e[k] = c->ev_pool.back(); c->ev_pool.pop_back(); } }
+	cudaEventRecord(e[0], st);
+	c->prof_pending.push_back({a, e[0], e[1]});
+}
+static void prof_end(rnb_ctx* c, cudaStream_t st) { if (c->prof) cudaEventRecord(c->prof_pending.back().e1, st); }
+static void prof_resolve(rnb_ctx* c) {      // call after the stream has been synchronised
+	for (auto& p : c->prof_pending) {
+		float ms = 0; if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { c->prof_acc[p.acc].ms += ms; c->prof_acc[p.acc].calls++; }
+		c->ev_pool.push_back(p.e0); c->ev_pool.push_back(p.e1);
+	}
+	c->prof_pending.clear();
+}
+#define KT(name, nk, call) do { prof_begin(c, st, name); call; prof_end(c, st); c->launches += (nk); } while (0)
 
 static uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
 
@@ -363,13 +389,13 @@ static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint3
 		CU(cudaMemsetAsync(c->density_grid, 0, GRID_CELLS * 4, st));
 	}
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
-	launch_grid_samples(st, n_uniform, c->density_rng, c->density_ema_step, c->density_grid, c->gpos, c->gidx, -0.01f);
-	c->density_rng.advance();
-	launch_grid_samples(st, n_nonuniform, c->density_rng, c->density_ema_step, c->density_grid, c->gpos + n_uniform, c->gidx + n_uniform, MIN_OPTICAL_THICKNESS);
-	c->density_rng.advance();
 	const uint32_t n = n_uniform + n_nonuniform;
-	launch_forward_simt(st, c->M, c->params, vl, 2, c->gpos, nullptr, n, nullptr, nullptr, nullptr, nullptr, c->gdens);
-	launch_grid_finish(st, n, c->gidx, c->gdens, c->cfg.density_grid_decay, c->density_grid, c->density_tmp, c->mean_acc, c->mean, c->bitfield);
+	KT("grid_update", 14, (launch_grid_samples(st, n_uniform, c->density_rng, c->density_ema_step, c->density_grid, c->gpos, c->gidx, -0.01f),
+	    c->density_rng.advance(),
+	    launch_grid_samples(st, n_nonuniform, c->density_rng, c->density_ema_step, c->density_grid, c->gpos + n_uniform, c->gidx + n_uniform, MIN_OPTICAL_THICKNESS),
+	    c->density_rng.advance(),
+	    launch_forward_simt(st, c->M, c->params, vl, 2, c->gpos, nullptr, n, nullptr, nullptr, nullptr, nullptr, c->gdens),
+	    launch_grid_finish(st, n, c->gidx, c->gdens, c->cfg.density_grid_decay, c->density_grid, c->density_tmp, c->mean_acc, c->mean, c->bitfield)));
 	++c->density_ema_step;
 	CU(cudaGetLastError());
 	return RNB_OK;
@@ -386,18 +412,19 @@ int rnb_prep(rnb_ctx* c, void* stream) {
 static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt, uint32_t max_inference) {
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
 	const ModelDev& M = c->M;
-	launch_march(st, R, c->cfg.world_size, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts);
-	launch_scan_rays(st, R, max_inference, c->ray_n, c->ray_indices, c->numsteps, c->counters);
-	launch_emit(st, R, c->counters, c->cfg.world_size, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4);
-	launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw);
-	launch_forward_simt(st, M, c->params, vl, 0, c->pos4, c->counters + 1, max_inference, c->ray_dirw, c->outA, nullptr, nullptr, nullptr);
-	launch_compact_count(st, R, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd);
-	launch_scan_compact(st, c->counters, c->cfg.target_batch_size, c->n_fwd, c->cbase, c->n_emit);
-	launch_gather_compacted(st, R, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4);
-	launch_forward_simt(st, M, c->params, vl, 1, c->cpos4, c->counters + 4, c->cap_compact, c->ray_dirw, c->out16, nullptr, nullptr, nullptr);
-	launch_loss(st, R, c->flags, R, nrt, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
-	            c->out16, c->dout16, c->loss_out, c->stats);
-	launch_backward_simt(st, M, c->params, vl, c->cpos4, c->dout16, c->counters + 3, c->cfg.target_batch_size, c->cfg.target_batch_size, c->counters + 3, nullptr, c->grads, c->bw_scratch, c->bw_front);
+	const uint32_t G = c->cfg.world_size, local_target = c->cfg.target_batch_size / G;
+	KT("march", 1, launch_march(st, R, G, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts));
+	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->ray_n, c->ray_indices, c->numsteps, c->counters),
+	                   launch_emit(st, R, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4),
+	                   launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw)));
+	KT("pass_a_sdf_normal", 1, launch_forward_simt(st, M, c->params, vl, 0, c->pos4, c->counters + 1, max_inference, c->ray_dirw, c->outA, nullptr, nullptr, nullptr));
+	KT("compact", 3, (launch_compact_count(st, R, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd),
+	                 launch_scan_compact(st, c->counters, local_target, c->n_fwd, c->cbase, c->n_emit, c->stats),
+	                 launch_gather_compacted(st, R, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4)));
+	KT("pass_b_forward", 1, launch_forward_simt(st, M, c->params, vl, 1, c->cpos4, c->counters + 4, c->cap_compact, c->ray_dirw, c->out16, nullptr, nullptr, nullptr));
+	KT("loss", 2, launch_loss(st, R, c->flags, R, nrt, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
+	            c->out16, c->dout16, c->loss_out, c->stats));
+	KT("backward", 9, launch_backward_simt(st, M, c->params, vl, c->cpos4, c->dout16, c->counters + 3, local_target, c->cfg.target_batch_size, local_target, c->counters + 3, nullptr, c->grads, c->bw_scratch, c->bw_front));
 	CU(cudaGetLastError());
 	return RNB_OK;
 }
@@ -412,7 +439,7 @@ static int optimizer_step(rnb_ctx* c, cudaStream_t st) {
 	A.ema_debias_old = 1 - (float)std::pow(c->cfg.ema_decay, c->opt_step - 1);       // ema.h:121-122
 	A.ema_debias_new = 1.0f / (1 - (float)std::pow(c->cfg.ema_decay, c->opt_step));
 	A.n_params = c->M.n_params; A.n_matrix = c->M.off_grid; A.rgb_begin = c->off_rgb; A.rgb_end = c->M.off_grid; A.only_sdf = c->flags.only_sdf_training;
-	launch_adam_ema(st, A, c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps);
+	KT("adam_ema", 1, launch_adam_ema(st, A, c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps));
 	CU(cudaGetLastError());
 	return RNB_OK;
 }
@@ -448,6 +475,7 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
 	CU(cudaMemcpyAsync(c->counters_host, c->counters, 8 * 4, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(c->stats_host, c->stats, 8 * 4, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	prof_resolve(c);
 	const uint32_t total = c->counters_host[2];
 	c->measured_before = c->counters_host[1]; c->measured = total;
 	const uint32_t R = c->step_R;
@@ -456,7 +484,8 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
 		c->rays_per_batch = std::min(next_multiple(r, 128u), 1u << 18);
 	}
 	if (stats) {
-		const float f = (float)total / (float)c->cfg.target_batch_size;
+		// stats_host[3] = compacted sample count as float: summed over ranks together with the losses when data-parallel
+		const float f = c->stats_host[3] / (float)c->cfg.target_batch_size;
 		stats->loss = c->stats_host[0] * f; stats->ek_loss = c->stats_host[1] * f; stats->mask_loss = c->stats_host[2] * f;
 		stats->n_rays = R; stats->n_rays_kept = c->counters_host[0]; stats->n_samples = c->counters_host[1]; stats->n_samples_compacted = total;
 		stats->n_samples_trained = c->counters_host[3]; stats->rays_per_batch_next = c->rays_per_batch; stats->training_step = c->training_step; stats->density_grid_updated = 0;
@@ -478,6 +507,23 @@ int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
 	if (!rc && stats) stats->density_grid_updated = updated;
 	return rc;
 }
+
+int rnb_profile_enable(rnb_ctx* c, int on) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	c->prof = on != 0;
+	if (on) { for (auto& a : c->prof_acc) { a.ms = 0; a.calls = 0; } }
+	return RNB_OK;
+}
+// names_buf receives ';'-separated stage names; ms / calls are parallel arrays of capacity *n (in) and count (out)
+int rnb_profile_read(rnb_ctx* c, char* names_buf, size_t names_cap, double* ms, uint64_t* calls, uint32_t* n) {
+	if (!c || !n) return fail(RNB_ERR_INVALID, "null argument");
+	std::string names; uint32_t k = 0;
+	for (auto& a : c->prof_acc) { if (k >= *n) break; names += a.name; names += ';'; ms[k] = a.ms; calls[k] = a.calls; ++k; }
+	*n = k;
+	if (names_buf && names_cap) { strncpy(names_buf, names.c_str(), names_cap - 1); names_buf[names_cap - 1] = 0; }
+	return RNB_OK;
+}
+int rnb_launch_count(rnb_ctx* c, uint64_t* out) { if (!c || !out) return fail(RNB_ERR_INVALID, "null argument"); *out = c->launches; return RNB_OK; }
 
 int rnb_grad_buffer(rnb_ctx* c, float** g, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *g = c->grads; *n = c->M.n_params; return RNB_OK; }
 int rnb_stat_buffer(rnb_ctx* c, float** s, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *s = c->stats; *n = 8; return RNB_OK; }
@@ -602,7 +648,7 @@ int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, siz
 	CU(cudaMemcpy(c->dout16, h.data(), n * 32, cudaMemcpyHostToDevice));
 	CU(cudaMemset(c->grads, 0, (size_t)c->M.n_params * 4));
 	uint32_t* nin = nullptr; CU(cudaMalloc(&nin, 4)); CU(cudaMemcpy(nin, &n_in_rollover, 4, cudaMemcpyHostToDevice));
-	launch_backward_simt(0, c->M, c->params, vl, c->cpos4, c->dout16, nullptr, (uint32_t)n, c->cfg.target_batch_size, nin, nullptr, c->grads, c->bw_scratch, c->bw_front);
+	launch_backward_simt(0, c->M, c->params, vl, c->cpos4, c->dout16, nullptr, (uint32_t)n, c->cfg.target_batch_size, c->cfg.target_batch_size, nin, nullptr, c->grads, c->bw_scratch, c->bw_front);
 	CU(cudaDeviceSynchronize());
 	CU(cudaMemcpy(grads, c->grads, (size_t)c->M.n_params * 4, cudaMemcpyDeviceToHost));
 	CU(cudaMemset(c->grads, 0, (size_t)c->M.n_params * 4));

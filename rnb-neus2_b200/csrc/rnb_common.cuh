@@ -99,7 +99,8 @@ __device__ __forceinline__ uint32_t grid_entry(uint32_t hsz, uint32_t res, uint3
 }
 
 __device__ __forceinline__ float hq(float x) { return __half2float(__float2half_rn(x)); }
-__device__ __forceinline__ float logisticf(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// tcnn::logistic (common_device.h:52-54): full-precision expf — the reference is not built with --use_fast_math
+__device__ __forceinline__ float logisticf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // image_idx — testbed_nerf.cu:1194-1214 (uint32 wrap-around intended)
 __host__ __device__ inline uint32_t image_idx(uint32_t base, uint32_t n_rays, uint32_t n_rays_total, uint32_t n_images) {

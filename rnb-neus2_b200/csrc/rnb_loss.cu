@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_compact_count(const uint32_t* __restric
 // totals.  counters: [2] = compacted total (untruncated), [3] = trained samples min(total, max), [4] = samples to forward.
 // ext_base (optional, data-parallel): global compacted index of each kept ray's first sample.
 __global__ void __launch_bounds__(1024) k_scan_compact(uint32_t* __restrict__ counters, uint32_t max_compacted, const uint32_t* __restrict__ n_fwd,
-                                                       uint32_t* __restrict__ cbase, uint32_t* __restrict__ n_emit) {
+                                                       uint32_t* __restrict__ cbase, uint32_t* __restrict__ n_emit, float* __restrict__ stats) {
 	__shared__ uint32_t s_a[32];
 	__shared__ uint32_t carry, fwd_end;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(1024) k_scan_compact(uint32_t* __restrict__ co
 		if (tid == 1023) carry = incl;
 		__syncthreads();
 	}
-	if (tid == 0) { counters[2] = carry; counters[3] = min(carry, max_compacted); counters[4] = fwd_end; }
+	if (tid == 0) {
+		counters[2] = carry; counters[3] = min(carry, max_compacted); counters[4] = fwd_end;
+		if (stats) { stats[3] = (float)carry; stats[4] = (float)counters[1]; stats[5] = (float)K; }   // float copies: summed across ranks with the losses
+	}
 }
 
 // Gather compacted samples: cpos4[cbase + j] = pos4[base + j] for j < n_fwd, rays with n_emit > 0 only.
@@ -317,8 +320,8 @@ void launch_ray_dirw(cudaStream_t st, uint32_t n_upper, const uint32_t* counters
 void launch_compact_count(cudaStream_t st, uint32_t n_upper, const uint32_t* counters, const uint32_t* numsteps, const __half* outA, const float* ray_dirw, const __half* P, uint32_t off_var, float car, uint32_t* n_fwd) {
 	if (n_upper) k_compact_count<<<(n_upper * 32 + 255) / 256, 256, 0, st>>>(counters, numsteps, outA, ray_dirw, P, off_var, car, n_fwd);
 }
-void launch_scan_compact(cudaStream_t st, uint32_t* counters, uint32_t max_compacted, const uint32_t* n_fwd, uint32_t* cbase, uint32_t* n_emit) {
-	k_scan_compact<<<1, 1024, 0, st>>>(counters, max_compacted, n_fwd, cbase, n_emit);
+void launch_scan_compact(cudaStream_t st, uint32_t* counters, uint32_t max_compacted, const uint32_t* n_fwd, uint32_t* cbase, uint32_t* n_emit, float* stats) {
+	k_scan_compact<<<1, 1024, 0, st>>>(counters, max_compacted, n_fwd, cbase, n_emit, stats);
 }
 void launch_gather_compacted(cudaStream_t st, uint32_t n_upper, const uint32_t* counters, const uint32_t* numsteps, const uint32_t* n_fwd, const uint32_t* cbase, const uint32_t* n_emit, const float4* pos4, float4* cpos4) {
 	if (n_upper) k_gather_compacted<<<(n_upper * 32 + 255) / 256, 256, 0, st>>>(counters, numsteps, n_fwd, cbase, n_emit, pos4, cpos4);

@@ -180,7 +180,7 @@ struct BwdScratch { __half *dc, *h2, *dh2, *h1, *dh1, *rin, *dy, *hs, *dhs, *u, 
 // second-order hash-grid scatter, operands for the weight-gradient GEMMs.
 __global__ void __launch_bounds__(128) k_backward_simt(ModelDev M, const __half* __restrict__ P, uint32_t valid_level,
                                                        const float4* __restrict__ pos4, const __half* __restrict__ dout16, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
-                                                       uint32_t n_batch, const uint32_t* __restrict__ n_in_ptr, const uint32_t* __restrict__ gidx /*global compacted index per sample or null*/,
+                                                       uint32_t n_roll /*roll-over batch (target / world)*/, uint32_t n_batch /*Eikonal divisor (global target)*/, const uint32_t* __restrict__ n_in_ptr, const uint32_t* __restrict__ gidx,
                                                        float* __restrict__ G, BwdScratch B) {
 	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) k_backward_simt(ModelDev M, const __half*
 	else matvec(P + L[1].off, L[1].rows, L[1].cols, h1, c, false);
 	// incoming gradient, scaled by the roll-over multiplicity (fill_rollover_and_rescale, common_device.h:525-535)
 	const uint32_t n_in = n_in_ptr ? *n_in_ptr : n;
-	const float w = rollover_weight(gidx ? gidx[i] : i, min(n_in, n_batch), n_batch);
+	const float w = rollover_weight(gidx ? gidx[i] : i, min(n_in, n_roll), n_roll);
 	float dout[16];
 	{
 		__align__(16) __half hraw[16];
@@ -312,7 +312,7 @@ void launch_forward_simt(cudaStream_t st, const ModelDev& M, const __half* P, ui
 }
 
 void launch_backward_simt(cudaStream_t st, const ModelDev& M, const __half* P, uint32_t valid_level, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
-                          uint32_t n_batch, const uint32_t* n_in_ptr, const uint32_t* gidx, float* G, __half* scratch_h, float* scratch_f) {
+                          uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, const uint32_t* gidx, float* G, __half* scratch_h, float* scratch_f) {
 	if (!n_max) return;
 	BwdScratch B;
 	size_t o = 0; const size_t N = n_max;
@@ -320,7 +320,7 @@ void launch_backward_simt(cudaStream_t st, const ModelDev& M, const __half* P, u
 	B.dc = take(16); B.h2 = take(M.rgb_width); B.dh2 = take(M.rgb_width); B.h1 = take(M.rgb_width); B.dh1 = take(M.rgb_width); B.rin = take(M.rgb_in);
 	B.dy = take(16); B.hs = take(M.sdf_width); B.dhs = take(M.sdf_width); B.u = take(M.sdf_in); B.tm = take(M.sdf_width); B.v = take(M.sdf_in);
 	B.front1 = scratch_f;
-	k_backward_simt<<<min((n_max + 127) / 128, 148u * 16u), 128, 0, st>>>(M, P, valid_level, pos4, dout16, n_ptr, n_max, n_batch, n_in_ptr, gidx, G, B);
+	k_backward_simt<<<min((n_max + 127) / 128, 148u * 16u), 128, 0, st>>>(M, P, valid_level, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, gidx, G, B);
 	const uint32_t nb = (n_max + 1023) / 1024;
 	const LayerDesc* L = M.rgb_layers;
 	const bool three = M.n_rgb_layers == 3;
