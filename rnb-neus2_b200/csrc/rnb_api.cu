@@ -24,6 +24,10 @@ void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32
 void launch_forward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, int, const float4*, const uint32_t*, uint32_t, const float*, __half*, float*, float*, float*);
 void launch_backward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, float*, __half*, float*);
 size_t backward_simt_scratch_halfs(const ModelDev&);
+// rnb_network_mma.cu
+bool mma_supported(const ModelDev&);
+size_t mma_pack_u32(const ModelDev&);
+void launch_mma(int, cudaStream_t, const ModelDev&, const __half*, uint32_t*, uint32_t, const float4*, const uint32_t*, uint32_t, const float*, __half*, const __half*, uint32_t, uint32_t, const uint32_t*, float*, int);
 // rnb_loss.cu
 void launch_ray_dirw(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const float*, float*);
 void launch_compact_count(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const __half*, const float*, const __half*, uint32_t, float, uint32_t*);
@@ -73,6 +77,7 @@ struct rnb_ctx {
 	Pcg32 rng, density_rng;
 	uint32_t training_step = 0, rays_per_batch = 4096, n_rays_total = 0, measured_before = 0, measured = 0;
 	uint32_t step_R = 0, step_nrt = 0; bool in_step = false;
+	bool use_mma = false; uint32_t* wpack = nullptr; int n_sm = 148;
 	// instrumentation: kernel launch counter and optional per-stage CUDA-event timing (bench.py roofline)
 	uint64_t launches = 0;
 	bool prof = false;
@@ -202,6 +207,12 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 	CU(cudaMalloc(&c->counters, 16 * 4)); CU(cudaMemset(c->counters, 0, 16 * 4));
 	CU(cudaMalloc(&c->stats, 8 * 4)); CU(cudaMemset(c->stats, 0, 8 * 4));
 	CU(cudaMallocHost(&c->counters_host, 16 * 4)); CU(cudaMallocHost(&c->stats_host, 8 * 4));
+	{
+		cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev)); c->n_sm = prop.multiProcessorCount;
+		const char* e = getenv("RNB_NETWORK");        // "simt" selects the CUDA-core kernels (cross-check path)
+		c->use_mma = mma_supported(M) && !(e && std::string(e) == "simt");
+		CU(cudaMalloc(&c->wpack, mma_pack_u32(M) * 4)); CU(cudaMemset(c->wpack, 0, mma_pack_u32(M) * 4));
+	}
 	c->rays_per_batch = cfg->rays_per_batch;
 	int rc = ensure_ray_capacity(c, c->rays_per_batch); if (rc) return rc;
 	c->rng = Pcg32(cfg->seed);
@@ -214,7 +225,7 @@ int rnb_destroy(rnb_ctx* c) {
 	if (!c) return RNB_OK;
 	void* ptrs[] = {c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps, c->density_grid, c->density_tmp, c->bitfield, c->mean_acc, c->mean, c->gpos, c->gidx, c->gdens,
 	                c->views_dev, c->ray_n, c->ray_indices, c->numsteps, c->counters, c->n_fwd, c->cbase, c->n_emit, c->ray_geom, c->ts, c->ray_dirw, c->loss_out, c->stats,
-	                c->pos4, c->cpos4, c->outA, c->out16, c->dout16, c->bw_scratch, c->bw_front};
+	                c->pos4, c->cpos4, c->outA, c->out16, c->dout16, c->bw_scratch, c->bw_front, c->wpack};
 	for (void* p : ptrs) cudaFree(p);
 	for (void* p : c->owned) cudaFree(p);
 	cudaFreeHost(c->counters_host); cudaFreeHost(c->stats_host);
@@ -406,6 +417,21 @@ int rnb_prep(rnb_ctx* c, void* stream) {
 	return density_update(c, (cudaStream_t)stream, GRID_CELLS / 4, GRID_CELLS / 4);
 }
 
+// network stage dispatch: tensor-core tile kernels (default) or the CUDA-core kernels
+static void net_pack(rnb_ctx* c, cudaStream_t st, const __half* P) { if (c->use_mma) launch_mma(0, st, c->M, P, c->wpack, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, c->n_sm); }
+static void net_pass_a(rnb_ctx* c, cudaStream_t st, uint32_t vl, const float4* pos, const uint32_t* n_ptr, uint32_t n_max) {
+	if (c->use_mma) launch_mma(1, st, c->M, c->params, c->wpack, vl, pos, n_ptr, n_max, nullptr, c->outA, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
+	else launch_forward_simt(st, c->M, c->params, vl, 0, pos, n_ptr, n_max, c->ray_dirw, c->outA, nullptr, nullptr, nullptr);
+}
+static void net_pass_b(rnb_ctx* c, cudaStream_t st, const __half* P, uint32_t vl, const float4* pos, const uint32_t* n_ptr, uint32_t n_max, const float* dirw) {
+	if (c->use_mma) launch_mma(2, st, c->M, P, c->wpack, vl, pos, n_ptr, n_max, dirw, c->out16, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
+	else launch_forward_simt(st, c->M, P, vl, 1, pos, n_ptr, n_max, dirw, c->out16, nullptr, nullptr, nullptr);
+}
+static void net_backward(rnb_ctx* c, cudaStream_t st, uint32_t vl, const uint32_t* n_ptr, uint32_t n_max, uint32_t n_roll, const uint32_t* n_in_ptr) {
+	if (c->use_mma) launch_mma(3, st, c->M, c->params, c->wpack, vl, c->cpos4, n_ptr, n_max, nullptr, nullptr, c->dout16, n_roll, c->cfg.target_batch_size, n_in_ptr, c->grads, c->n_sm);
+	else launch_backward_simt(st, c->M, c->params, vl, c->cpos4, c->dout16, n_ptr, n_max, n_roll, c->cfg.target_batch_size, n_in_ptr, nullptr, c->grads, c->bw_scratch, c->bw_front);
+}
+
 // ---- one training step ----------------------------------------------------------------------------------------------
 // counters (device, uint32): [0] kept rays  [1] samples before compaction  [2] compacted (untruncated)  [3] trained = min([2], target)
 //                            [4] samples forwarded in pass B  [5] samples before compaction of the previous step
@@ -417,14 +443,14 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt, uin
 	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->ray_n, c->ray_indices, c->numsteps, c->counters),
 	                   launch_emit(st, R, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4),
 	                   launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw)));
-	KT("pass_a_sdf_normal", 1, launch_forward_simt(st, M, c->params, vl, 0, c->pos4, c->counters + 1, max_inference, c->ray_dirw, c->outA, nullptr, nullptr, nullptr));
+	KT("pass_a_sdf_normal", 2, (net_pack(c, st, c->params), net_pass_a(c, st, vl, c->pos4, c->counters + 1, max_inference)));
 	KT("compact", 3, (launch_compact_count(st, R, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd),
 	                 launch_scan_compact(st, c->counters, local_target, c->n_fwd, c->cbase, c->n_emit, c->stats),
 	                 launch_gather_compacted(st, R, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4)));
-	KT("pass_b_forward", 1, launch_forward_simt(st, M, c->params, vl, 1, c->cpos4, c->counters + 4, c->cap_compact, c->ray_dirw, c->out16, nullptr, nullptr, nullptr));
+	KT("pass_b_forward", 1, net_pass_b(c, st, c->params, vl, c->cpos4, c->counters + 4, c->cap_compact, c->ray_dirw));
 	KT("loss", 2, launch_loss(st, R, c->flags, R, nrt, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
 	            c->out16, c->dout16, c->loss_out, c->stats));
-	KT("backward", 9, launch_backward_simt(st, M, c->params, vl, c->cpos4, c->dout16, c->counters + 3, local_target, c->cfg.target_batch_size, local_target, c->counters + 3, nullptr, c->grads, c->bw_scratch, c->bw_front));
+	KT("backward", c->use_mma ? 1 : 9, net_backward(c, st, vl, c->counters + 3, local_target, local_target, c->counters + 3));
 	CU(cudaGetLastError());
 	return RNB_OK;
 }
@@ -599,7 +625,8 @@ int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, fl
 	float* dirw = nullptr;
 	int rc = upload_coords(c, coords, n, c->cpos4, &dirw); if (rc) return rc;
 	const __half* P = use_ema ? c->ema : c->params;
-	launch_forward_simt(0, c->M, P, vl, 1, c->cpos4, nullptr, (uint32_t)n, dirw, c->out16, nullptr, nullptr, nullptr);
+	net_pack(c, 0, P);
+	net_pass_b(c, 0, P, vl, c->cpos4, nullptr, (uint32_t)n, dirw);
 	float* nrm_dev = nullptr;
 	if (normal) { CU(cudaMalloc(&nrm_dev, std::max<size_t>(n, 1) * 12)); launch_forward_simt(0, c->M, P, vl, 2, c->cpos4, nullptr, (uint32_t)n, nullptr, nullptr, nullptr, nrm_dev, nullptr); }
 	CU(cudaDeviceSynchronize());
@@ -648,7 +675,8 @@ int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, siz
 	CU(cudaMemcpy(c->dout16, h.data(), n * 32, cudaMemcpyHostToDevice));
 	CU(cudaMemset(c->grads, 0, (size_t)c->M.n_params * 4));
 	uint32_t* nin = nullptr; CU(cudaMalloc(&nin, 4)); CU(cudaMemcpy(nin, &n_in_rollover, 4, cudaMemcpyHostToDevice));
-	launch_backward_simt(0, c->M, c->params, vl, c->cpos4, c->dout16, nullptr, (uint32_t)n, c->cfg.target_batch_size, c->cfg.target_batch_size, nin, nullptr, c->grads, c->bw_scratch, c->bw_front);
+	net_pack(c, 0, c->params);
+	net_backward(c, 0, vl, nullptr, (uint32_t)n, c->cfg.target_batch_size, nin);
 	CU(cudaDeviceSynchronize());
 	CU(cudaMemcpy(grads, c->grads, (size_t)c->M.n_params * 4, cudaMemcpyDeviceToHost));
 	CU(cudaMemset(c->grads, 0, (size_t)c->M.n_params * 4));

@@ -1,0 +1,706 @@
+// rnb_network_mma.cu — fused hash-encode + SDF MLP + analytic normal + colour MLP (forward and backward) on tensor cores.
+//
+// One warp owns a 16-sample tile.  The encodings are produced directly in the A-fragment layout of
+// mma.sync.m16n8k16 (lane (g,t) owns samples g, g+8 and the feature pairs 2t,2t+1 of every 8-column block, i.e. whole
+// hash levels), every layer's D fragments are re-packed in registers into the next layer's A fragments, and the
+// analytic normal / second-order terms are reduced inside the lane quad.  Activations never touch shared or global memory
+// in the forward kernels.  Weights live in shared memory pre-packed in B-fragment order (loaded with one bulk async copy).
+//
+// Replaces NerfNetwork::forward_impl / backward_impl (reference include/neural-graphics-primitives/nerf_network.h:97-452):
+// 19 + ~30 kernel launches, ~10 CUTLASS GEMMs and ~15 global temporaries per step in the reference.
+//
+// Column orders inside the kernels (weights are permuted when packed, gradients un-permuted when flushed):
+//   SDF-MLP input   u'  = [enc(2L) | x-0.5 (3) | 0...]  (reference: [x-0.5 | enc | 0], nerf_network.h:149-155)
+//   colour input    r'  = [sdf-MLP out (16) | x (3) | normal (3) | 0 (10)]  (reference columns 0-15 and 32-47; 16-31 are the
+//                                                                            compiled-out view-direction encoding = zeros)
+#include "rnb_encode.cuh"
+
+namespace rnb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// packed weight blob (uint32 = half2 units)
+// ------------------------------------------------------------------------------------------------------------------
+template <int SW, int RW, bool RGB3>
+struct Pack {
+	static constexpr int F1 = 0;                                 // W1'   fwd : KB=2,      NB=SW/8
+	static constexpr int F1T = F1 + 2 * (SW / 8) * 64;           // W1'   trn : KB=SW/16,  NB=4
+	static constexpr int F2 = F1T + (SW / 16) * 4 * 64;          // W2    fwd : KB=SW/16,  NB=2
+	static constexpr int F2T = F2 + (SW / 16) * 2 * 64;          // W2    trn : KB=1,      NB=SW/8
+	static constexpr int W2R0 = F2T + (SW / 8) * 64;             // W2 row 0 as halfs (SW/2 uint32)
+	static constexpr int SDF_END = W2R0 + SW / 2;
+	static constexpr int C1 = SDF_END;                           // Wc1'  fwd : KB=2,      NB=RW/8
+	static constexpr int C1T = C1 + 2 * (RW / 8) * 64;           // Wc1'  trn : KB=RW/16,  NB=3 (cols 0-23)
+	static constexpr int C2 = C1T + (RW / 16) * 3 * 64;          // Wc2   fwd : KB=RW/16,  NB=RW/8
+	static constexpr int C2T = C2 + (RGB3 ? (RW / 16) * (RW / 8) * 64 : 0);
+	static constexpr int C3 = C2T + (RGB3 ? (RW / 16) * (RW / 8) * 64 : 0);   // Wc_out fwd : KB=RW/16, NB=2
+	static constexpr int C3T = C3 + (RW / 16) * 2 * 64;          // Wc_out trn : KB=1,     NB=RW/8
+	static constexpr int END = C3T + (RW / 8) * 64;
+};
+
+struct PackSrc { const __half* W; int rows, cols, kind; };   // kind 0: plain, 1: sdf layer 0 (u' permutation), 2: rgb layer 0 (r' permutation)
+
+__device__ __forceinline__ __half w_elem(const PackSrc& S, int n_enc, int n, int k) {
+	if (n >= S.rows) return __float2half_rn(0.f);
+	int kc = k;
+	if (S.kind == 1) { kc = k < n_enc ? 3 + k : (k < n_enc + 3 ? k - n_enc : -1); }
+	else if (S.kind == 2) { kc = k < 16 ? k : 16 + k; }
+	if (kc < 0 || kc >= S.cols) return __float2half_rn(0.f);
+	return S.W[(size_t)n * S.cols + kc];
+}
+// forward set: B[k][n] = W'[n][k];  transposed set: B[k][n] = W'[k][n]
+__device__ __forceinline__ void pack_set(uint32_t* out, const PackSrc& S, int n_enc, int KB, int NB, bool trn, int tid, int nthreads) {
+	for (int i = tid; i < KB * NB * 64; i += nthreads) {
+		const int r = i & 1, lane = (i >> 1) & 31, blk = i >> 6, nb = blk % NB, kb = blk / NB;
+		const int g = lane >> 2, t = lane & 3;
+		const int k0 = 16 * kb + 8 * r + 2 * t, n = 8 * nb + g;
+		__half a, b;
+		if (!trn) { a = w_elem(S, n_enc, n, k0); b = w_elem(S, n_enc, n, k0 + 1); }
+		else { a = w_elem(S, n_enc, k0, n); b = w_elem(S, n_enc, k0 + 1, n); }
+		__half2 h = __halves2half2(a, b);
+		out[i] = *reinterpret_cast<uint32_t*>(&h);
+	}
+}
+
+template <int SW, int RW, bool RGB3>
+__global__ void __launch_bounds__(256) k_pack_weights(ModelDev M, const __half* __restrict__ P, uint32_t* __restrict__ out) {
+	using PK = Pack<SW, RW, RGB3>;
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+	const int ne = (int)M.n_enc;
+	PackSrc s0{P + M.sdf_layers[0].off, (int)M.sdf_layers[0].rows, (int)M.sdf_layers[0].cols, 1};
+	PackSrc s1{P + M.sdf_layers[1].off, 16, (int)M.sdf_layers[1].cols, 0};
+	PackSrc c0{P + M.rgb_layers[0].off, (int)M.rgb_layers[0].rows, (int)M.rgb_layers[0].cols, 2};
+	PackSrc cl{P + M.rgb_layers[M.n_rgb_layers - 1].off, 16, (int)M.rgb_layers[M.n_rgb_layers - 1].cols, 0};
+	pack_set(out + PK::F1, s0, ne, 2, SW / 8, false, tid, nt);
+	pack_set(out + PK::F1T, s0, ne, SW / 16, 4, true, tid, nt);
+	pack_set(out + PK::F2, s1, ne, SW / 16, 2, false, tid, nt);
+	pack_set(out + PK::F2T, s1, ne, 1, SW / 8, true, tid, nt);
+	for (int i = tid; i < SW / 2; i += nt) { __half2 h = __halves2half2(s1.W[2 * i], s1.W[2 * i + 1]); out[PK::W2R0 + i] = *reinterpret_cast<uint32_t*>(&h); }
+	pack_set(out + PK::C1, c0, ne, 2, RW / 8, false, tid, nt);
+	pack_set(out + PK::C1T, c0, ne, RW / 16, 3, true, tid, nt);
+	if constexpr (RGB3) {
+		PackSrc c1{P + M.rgb_layers[1].off, (int)M.rgb_layers[1].rows, (int)M.rgb_layers[1].cols, 0};
+		pack_set(out + PK::C2, c1, ne, RW / 16, RW / 8, false, tid, nt);
+		pack_set(out + PK::C2T, c1, ne, RW / 16, RW / 8, true, tid, nt);
+	}
+	pack_set(out + PK::C3, cl, ne, RW / 16, 2, false, tid, nt);
+	pack_set(out + PK::C3T, cl, ne, 1, RW / 8, true, tid, nt);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fragment helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+	             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+
+// D[16 x 8NB] = A[16 x 16KB] * B, B fragments from shared memory in packed order
+template <int NB, int KB>
+__device__ __forceinline__ void layer(float (&acc)[NB][4], const uint32_t (&a)[KB][4], const uint32_t* __restrict__ wp, int lane) {
+	const uint2* w2 = reinterpret_cast<const uint2*>(wp);
+	#pragma unroll
+	for (int nb = 0; nb < NB; ++nb) {
+		acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+		#pragma unroll
+		for (int kb = 0; kb < KB; ++kb) {
+			const uint2 b = w2[(kb * NB + nb) * 32 + lane];
+			mma16816(acc[nb], a[kb], b.x, b.y);
+		}
+	}
+}
+// D fragments -> next layer's A fragments (binary16 rounding at the layer output), optional ReLU
+template <int NB, bool RELU>
+__device__ __forceinline__ void to_afrag(uint32_t (&a)[NB / 2][4], const float (&acc)[NB][4]) {
+	#pragma unroll
+	for (int kb = 0; kb < NB / 2; ++kb) {
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int nb = 2 * kb + (q >> 1), i = (q & 1) * 2;
+			float v0 = acc[nb][i], v1 = acc[nb][i + 1];
+			if (RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+			a[kb][q] = pack_h2(v0, v1);
+		}
+	}
+}
+// dX = relu'(H) .* acc  -> A fragments; H given as A fragments of the forward activation
+template <int NB>
+__device__ __forceinline__ void to_afrag_masked(uint32_t (&a)[NB / 2][4], const float (&acc)[NB][4], const uint32_t (&h)[NB / 2][4]) {
+	#pragma unroll
+	for (int kb = 0; kb < NB / 2; ++kb) {
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int nb = 2 * kb + (q >> 1), i = (q & 1) * 2;
+			const float2 hv = unpack_h2(h[kb][q]);
+			a[kb][q] = pack_h2(hv.x > 0.f ? acc[nb][i] : 0.f, hv.y > 0.f ? acc[nb][i + 1] : 0.f);
+		}
+	}
+}
+__device__ __forceinline__ float quad_sum(float v) { v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); return v; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// per-warp 16-sample tile: SDF branch
+// ------------------------------------------------------------------------------------------------------------------
+template <int SW>
+struct SdfTile {
+	uint32_t U[2][4];            // u' as A fragments
+	uint32_t H[SW / 16][4];      // hidden activation (binary16) as A fragments
+	float Y[2][4];               // SDF-MLP output (fp32 accumulators; rounded on use)
+	float G[4][4];               // d sdf / d u' (binary16-rounded values), D-fragment layout == the lane's slots
+	float dy[4][2][6];           // dy/dx of the lane's level slots [slot][row][feature*3+dim]
+	float nrm[2][3];             // analytic normal of rows g, g+8 (identical in the 4 lanes of a quad)
+	float px[2], py[2], pz[2];
+};
+
+// slot s = 2*kb + hi covers columns c0 = 16kb + 8hi + 2t, c0+1 of u'
+template <int SW, bool WITH_DY>
+__device__ __forceinline__ void sdf_tile(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, const uint32_t* __restrict__ sw /*packed sdf weights*/,
+                                         int lane, SdfTile<SW>& T) {
+	const int t = lane & 3;
+	const int ne = (int)M.n_enc;
+	#pragma unroll
+	for (int s = 0; s < 4; ++s) {
+		const int c0 = 16 * (s >> 1) + 8 * (s & 1) + 2 * t;
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			uint32_t val = 0u;
+			if (c0 < ne) {
+				const uint32_t l = (uint32_t)c0 >> 1;
+				if (l <= valid_level) {
+					__half2 e = encode_level_packed(M, P, l, T.px[r], T.py[r], T.pz[r], WITH_DY ? T.dy[s][r] : nullptr);
+					val = *reinterpret_cast<uint32_t*>(&e);
+				} else if (WITH_DY) {
+					#pragma unroll
+					for (int q = 0; q < 6; ++q) T.dy[s][r][q] = 0.f;
+				}
+			} else {
+				const int d0 = c0 - ne;
+				const float pc[3] = {T.px[r], T.py[r], T.pz[r]};
+				__half a = __float2half_rn(0.f), b = a;
+				if (d0 < 3) a = __hsub(__float2half_rn(pc[d0]), __float2half_rn(0.5f));          // fill_positions_view_with_fixed_offset
+				if (d0 + 1 < 3) b = __hsub(__float2half_rn(pc[d0 + 1]), __float2half_rn(0.5f));
+				__half2 e = __halves2half2(a, b);
+				val = *reinterpret_cast<uint32_t*>(&e);
+			}
+			T.U[s >> 1][(s & 1) * 2 + r] = val;
+		}
+	}
+	float acc[SW / 8][4];
+	layer<SW / 8, 2>(acc, T.U, sw + 0 /*F1*/, lane);
+	to_afrag<SW / 8, true>(T.H, acc);
+	constexpr int F1T = 2 * (SW / 8) * 64, F2 = F1T + (SW / 16) * 4 * 64, F2T = F2 + (SW / 16) * 2 * 64, W2R0 = F2T + (SW / 8) * 64;
+	layer<2, SW / 16>(T.Y, T.H, sw + F2, lane);
+	// one-hot back chain: tm = relu'(H) .* W2[0,:]  ->  G = tm * W1'
+	uint32_t TM[SW / 16][4];
+	#pragma unroll
+	for (int kb = 0; kb < SW / 16; ++kb) {
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int col = 16 * kb + 8 * (q >> 1) + 2 * t;
+			const float2 w = unpack_h2(sw[W2R0 + (col >> 1)]);
+			const float2 hv = unpack_h2(T.H[kb][q]);
+			TM[kb][q] = pack_h2(hv.x > 0.f ? w.x : 0.f, hv.y > 0.f ? w.y : 0.f);
+		}
+	}
+	layer<4, SW / 16>(T.G, TM, sw + F1T, lane);
+	#pragma unroll
+	for (int s = 0; s < 4; ++s) {
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) T.G[s][q] = hq(T.G[s][q]);
+	}
+	// analytic normal: sum over the lane's slots, then over the quad
+	#pragma unroll
+	for (int r = 0; r < 2; ++r) {
+		float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+		#pragma unroll
+		for (int s = 0; s < 4; ++s) {
+			const int c0 = 16 * (s >> 1) + 8 * (s & 1) + 2 * t;
+			const float g0 = T.G[s][2 * r], g1 = T.G[s][2 * r + 1];
+			if (c0 < ne) {
+				if (WITH_DY) {
+					n0 = fmaf(g0, T.dy[s][r][0], n0); n1 = fmaf(g0, T.dy[s][r][1], n1); n2 = fmaf(g0, T.dy[s][r][2], n2);
+					n0 = fmaf(g1, T.dy[s][r][3], n0); n1 = fmaf(g1, T.dy[s][r][4], n1); n2 = fmaf(g1, T.dy[s][r][5], n2);
+				}
+			} else {
+				const int d0 = c0 - ne;
+				if (d0 == 0) { n0 += g0; n1 += g1; } else if (d0 == 1) { n1 += g0; n2 += g1; } else if (d0 == 2) { n2 += g0; }
+			}
+		}
+		T.nrm[r][0] = quad_sum(n0); T.nrm[r][1] = quad_sum(n1); T.nrm[r][2] = quad_sum(n2);
+	}
+}
+
+__device__ __forceinline__ void load_weights_bulk(uint32_t* smem_dst, const uint32_t* __restrict__ gsrc, int n_u32, uint64_t* bar) {
+	// one elected thread issues a bulk async copy (TMA engine, cp.async.bulk) and everyone waits on the mbarrier
+	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar), dst_s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+	const uint32_t bytes = (uint32_t)n_u32 * 4u;
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(gsrc), "r"(bytes), "r"(bar_s) : "memory");
+	}
+	uint32_t done = 0;
+	while (!done) {
+		asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_s), "r"(0u) : "memory");
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pass A: sdf + normal for every marched sample (the transmittance cut needs nothing else)
+// ------------------------------------------------------------------------------------------------------------------
+template <int SW, int RW, bool RGB3>
+__global__ void __launch_bounds__(256, 2) k_pass_a_mma(ModelDev M, const __half* __restrict__ P, const uint32_t* __restrict__ wpack, uint32_t valid_level,
+                                                       const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max, __half* __restrict__ outA) {
+	using PK = Pack<SW, RW, RGB3>;
+	__shared__ __align__(128) uint32_t sw[PK::SDF_END];
+	__shared__ __align__(8) uint64_t bar;
+	load_weights_bulk(sw, wpack, PK::SDF_END, &bar);
+	const uint32_t n = min(*n_ptr, n_max);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+	const uint32_t n_tiles = (n + 15) / 16;
+	for (uint32_t tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += gridDim.x * 8) {
+		SdfTile<SW> T;
+		uint32_t row[2];
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			row[r] = tile * 16 + g + 8 * r;
+			const float4 p = pos4[min(row[r], n - 1)];
+			T.px[r] = p.x; T.py[r] = p.y; T.pz[r] = p.z;
+		}
+		sdf_tile<SW, true>(M, P, valid_level, sw, lane, T);
+		const int src = lane & ~3;
+		const float y0 = __shfl_sync(0xffffffffu, T.Y[0][0], src), y8 = __shfl_sync(0xffffffffu, T.Y[0][2], src);
+		if (t < 2) {
+			const int r = t;
+			if (row[r] < n) {
+				const float sdfb = __half2float(__hadd(__float2half_rn(r ? y8 : y0), __float2half_rn(M.sdf_bias)));
+				uint2 v; v.x = pack_h2(sdfb, T.nrm[r][0]); v.y = pack_h2(T.nrm[r][1], T.nrm[r][2]);
+				reinterpret_cast<uint2*>(outA)[row[r]] = v;
+			}
+		}
+	}
+}
+
+// colour branch forward on top of an SdfTile; returns the final 16-wide output accumulators and keeps activations
+template <int SW, int RW, bool RGB3>
+struct RgbTile {
+	uint32_t R[2][4];                 // r' as A fragments
+	uint32_t H1[RW / 16][4];
+	uint32_t H2[RGB3 ? RW / 16 : 1][4];
+	float C[2][4];
+};
+
+template <int SW, int RW, bool RGB3>
+__device__ __forceinline__ void rgb_tile(const uint32_t* __restrict__ sw, int lane, const SdfTile<SW>& T, RgbTile<SW, RW, RGB3>& Q) {
+	using PK = Pack<SW, RW, RGB3>;
+	const int t = lane & 3;
+	Q.R[0][0] = pack_h2(T.Y[0][0], T.Y[0][1]); Q.R[0][1] = pack_h2(T.Y[0][2], T.Y[0][3]);
+	Q.R[0][2] = pack_h2(T.Y[1][0], T.Y[1][1]); Q.R[0][3] = pack_h2(T.Y[1][2], T.Y[1][3]);
+	#pragma unroll
+	for (int r = 0; r < 2; ++r) {
+		float a = 0.f, b = 0.f;
+		if (t == 0) { a = T.px[r]; b = T.py[r]; } else if (t == 1) { a = T.pz[r]; b = T.nrm[r][0]; } else if (t == 2) { a = T.nrm[r][1]; b = T.nrm[r][2]; }
+		Q.R[1][r] = pack_h2(a, b);
+		Q.R[1][2 + r] = 0u;
+	}
+	float acc[RW / 8][4];
+	layer<RW / 8, 2>(acc, Q.R, sw + PK::C1, lane);
+	to_afrag<RW / 8, true>(Q.H1, acc);
+	if constexpr (RGB3) {
+		layer<RW / 8, RW / 16>(acc, Q.H1, sw + PK::C2, lane);
+		to_afrag<RW / 8, true>(Q.H2, acc);
+		layer<2, RW / 16>(Q.C, Q.H2, sw + PK::C3, lane);
+	} else {
+		layer<2, RW / 16>(Q.C, Q.H1, sw + PK::C3, lane);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pass B: full 16-wide output row for the compacted samples (nerf_network.h:221-250)
+// ------------------------------------------------------------------------------------------------------------------
+template <int SW, int RW, bool RGB3>
+__global__ void __launch_bounds__(256, 1) k_pass_b_mma(ModelDev M, const __half* __restrict__ P, const uint32_t* __restrict__ wpack, uint32_t valid_level,
+                                                       const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
+                                                       const float* __restrict__ ray_dirw, __half* __restrict__ out16) {
+	using PK = Pack<SW, RW, RGB3>;
+	__shared__ __align__(128) uint32_t sw[PK::C3T];
+	__shared__ __align__(8) uint64_t bar;
+	load_weights_bulk(sw, wpack, PK::C3T, &bar);
+	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+	const uint32_t n_tiles = (n + 15) / 16;
+	const float var = __half2float(__ldg(P + M.off_var));
+	for (uint32_t tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += gridDim.x * 8) {
+		SdfTile<SW> T;
+		uint32_t row[2], slot[2];
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			row[r] = tile * 16 + g + 8 * r;
+			const float4 p = pos4[min(row[r], n - 1)];
+			T.px[r] = p.x; T.py[r] = p.y; T.pz[r] = p.z; slot[r] = __float_as_uint(p.w);
+		}
+		sdf_tile<SW, true>(M, P, valid_level, sw, lane, T);
+		RgbTile<SW, RW, RGB3> Q;
+		rgb_tile<SW, RW, RGB3>(sw, lane, T, Q);
+		const int src = lane & ~3;
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const float y0 = __shfl_sync(0xffffffffu, T.Y[0][2 * r], src);
+			const float sdfb = __half2float(__hadd(__float2half_rn(y0), __float2half_rn(M.sdf_bias)));
+			float lo0 = Q.C[0][2 * r], lo1 = Q.C[0][2 * r + 1], hi0 = Q.C[1][2 * r], hi1 = Q.C[1][2 * r + 1];
+			if (t == 1) lo1 = sdfb;
+			else if (t == 2) { lo0 = T.nrm[r][0]; lo1 = T.nrm[r][1]; }
+			else if (t == 3) { lo0 = T.nrm[r][2]; lo1 = var; }
+			if (t == 0) { hi0 = ray_dirw[3 * slot[r]]; hi1 = ray_dirw[3 * slot[r] + 1]; }
+			else if (t == 1) hi0 = ray_dirw[3 * slot[r] + 2];
+			if (row[r] < n) {
+				uint32_t* o = reinterpret_cast<uint32_t*>(out16 + (size_t)row[r] * 16);
+				o[t] = pack_h2(lo0, lo1);
+				o[4 + t] = pack_h2(hi0, hi1);
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward: forward recompute, data gradients in registers, merged hash scatter, weight gradients via staged tiles
+// ------------------------------------------------------------------------------------------------------------------
+// staged row-major tiles [128 rows][stride] (binary16), strides padded by 8 halfs so that ldmatrix rows hit distinct banks
+template <int SW, int RW, bool RGB3>
+struct Stage {
+	static constexpr int S32 = 40, SSW = SW + 8, SRW = RW + 8, S16 = 24;
+	static constexpr int U = 0;
+	static constexpr int H = U + 128 * S32;
+	static constexpr int V = H + 128 * SSW;
+	static constexpr int DH = V + 128 * S32;
+	static constexpr int DY = DH + 128 * SSW;
+	static constexpr int R = DY + 128 * S16;
+	static constexpr int H1 = R + 128 * S32;
+	static constexpr int DH1 = H1 + 128 * SRW;
+	static constexpr int H2 = DH1 + 128 * SRW;
+	static constexpr int DH2 = H2 + (RGB3 ? 128 * SRW : 0);
+	static constexpr int DC = DH2 + (RGB3 ? 128 * SRW : 0);
+	static constexpr int END = DC + 128 * S16;      // halfs
+};
+
+template <int KB>
+__device__ __forceinline__ void stage_afrag(__half* tile, int stride, int row0, int lane, const uint32_t (&a)[KB][4]) {
+	const int g = lane >> 2, t = lane & 3;
+	#pragma unroll
+	for (int kb = 0; kb < KB; ++kb) {
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int r = row0 + g + 8 * (q & 1), c = 16 * kb + 8 * (q >> 1) + 2 * t;
+			*reinterpret_cast<uint32_t*>(tile + r * stride + c) = a[kb][q];
+		}
+	}
+}
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __half* p) {
+	const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+	asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t& r0, uint32_t& r1, const __half* p) {
+	const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+	asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+
+// acc[16 x 8 block at (n0, k0)] += sum_m dY[m][n0..n0+15]^T X[m][k0..k0+7] over the 128 staged rows.
+// MASKW: A = relu'(H) .* wrow[n] (second-order term: tm is rebuilt from the staged activation)
+template <bool MASKW>
+__device__ __forceinline__ void dw_block(float (&acc)[4], const __half* dY, int sdy, int n0, const __half* X, int sx, int k0, int lane, const uint32_t* wrow) {
+	const int mi = lane >> 3, ri = lane & 7;
+	float wlo = 0.f, whi = 0.f;
+	if (MASKW) {
+		const int g = lane >> 2;
+		const uint32_t u0 = wrow[(n0 + g) >> 1], u1 = wrow[(n0 + 8 + g) >> 1];
+		const float2 f0 = unpack_h2(u0), f1 = unpack_h2(u1);
+		wlo = ((n0 + g) & 1) ? f0.y : f0.x; whi = ((n0 + 8 + g) & 1) ? f1.y : f1.x;
+	}
+	#pragma unroll
+	for (int ks = 0; ks < 8; ++ks) {
+		const int m0 = ks * 16;
+		uint32_t a[4], b0, b1;
+		// matrices: 0:(m 0-7, n 0-7) 1:(m 0-7, n 8-15) 2:(m 8-15, n 0-7) 3:(m 8-15, n 8-15)  -> A regs R0,R1,R2,R3
+		ldsm_x4_t(a, dY + (m0 + (mi >> 1) * 8 + ri) * sdy + n0 + (mi & 1) * 8);
+		ldsm_x2_t(b0, b1, X + (m0 + ((lane >> 3) & 1) * 8 + ri) * sx + k0);
+		if (MASKW) {
+			#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const float2 hv = unpack_h2(a[q]);
+				const float w = (q & 1) ? whi : wlo;
+				a[q] = pack_h2(hv.x > 0.f ? w : 0.f, hv.y > 0.f ? w : 0.f);
+			}
+		}
+		mma16816(acc, a, b0, b1);
+	}
+}
+
+template <int SW, int RW, bool RGB3>
+__global__ void __launch_bounds__(256, 1) k_backward_mma(ModelDev M, const __half* __restrict__ P, const uint32_t* __restrict__ wpack, uint32_t valid_level,
+                                                         const float4* __restrict__ pos4, const __half* __restrict__ dout16, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
+                                                         uint32_t n_roll, uint32_t n_batch, const uint32_t* __restrict__ n_in_ptr, float* __restrict__ G) {
+	using PK = Pack<SW, RW, RGB3>;
+	using ST = Stage<SW, RW, RGB3>;
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	uint32_t* sw = reinterpret_cast<uint32_t*>(smem_raw);
+	__half* stg = reinterpret_cast<__half*>(smem_raw + ((PK::END * 4 + 127) / 128) * 128);
+	__shared__ __align__(8) uint64_t bar;
+	load_weights_bulk(sw, wpack, PK::END, &bar);
+	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
+	const uint32_t n_in = n_in_ptr ? *n_in_ptr : n;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+	const int ne = (int)M.n_enc;
+	const uint32_t n_tiles = (n + 127) / 128;
+	const float inv_nb = 1.0f / (float)n_batch;
+	// persistent weight-gradient accumulators (this warp's blocks of every matrix)
+	float aW1[2 * (SW / 64 > 0 ? SW / 64 : 1)][4];      // SW x 32  -> (SW/16)*4 blocks / 8 warps
+	constexpr int NW1 = (SW / 16) * 4 / 8;              // blocks per warp
+	float aW2[(SW / 8 + 7) / 8][4];                     // 16 x SW  -> SW/8 blocks
+	constexpr int NW2 = (SW / 8 + 7) / 8;
+	constexpr int NC1 = (RW / 16) * 4 / 8;
+	float aC1[NC1][4];
+	constexpr int NC2 = RGB3 ? (RW / 16) * (RW / 8) / 8 : 1;
+	float aC2[NC2][4];
+	constexpr int NC3 = (RW / 8 + 7) / 8;
+	float aC3[NC3][4];
+	float f1acc[SW / 8][2];
+	#pragma unroll
+	for (int i = 0; i < NW1; ++i) for (int q = 0; q < 4; ++q) aW1[i][q] = 0.f;
+	#pragma unroll
+	for (int i = 0; i < NW2; ++i) for (int q = 0; q < 4; ++q) aW2[i][q] = 0.f;
+	#pragma unroll
+	for (int i = 0; i < NC1; ++i) for (int q = 0; q < 4; ++q) aC1[i][q] = 0.f;
+	#pragma unroll
+	for (int i = 0; i < NC2; ++i) for (int q = 0; q < 4; ++q) aC2[i][q] = 0.f;
+	#pragma unroll
+	for (int i = 0; i < NC3; ++i) for (int q = 0; q < 4; ++q) aC3[i][q] = 0.f;
+	#pragma unroll
+	for (int i = 0; i < SW / 8; ++i) f1acc[i][0] = f1acc[i][1] = 0.f;
+	float var_acc = 0.f;
+
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		// ---------------- phase 1: per-warp 16-sample tile, everything in registers ----------------
+		SdfTile<SW> T;
+		uint32_t row[2]; bool live[2];
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			row[r] = tile * 128 + warp * 16 + g + 8 * r;
+			live[r] = row[r] < n;
+			const float4 p = pos4[min(row[r], n - 1)];
+			T.px[r] = p.x; T.py[r] = p.y; T.pz[r] = p.z;
+		}
+		sdf_tile<SW, true>(M, P, valid_level, sw, lane, T);
+		RgbTile<SW, RW, RGB3> Q;
+		rgb_tile<SW, RW, RGB3>(sw, lane, T, Q);
+		// incoming gradient in D-fragment layout: lo = cols 2t,2t+1 ; hi = cols 8+2t, 9+2t ; scaled by the roll-over weight
+		float dlo[2][2], dhi[2][2];
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const uint32_t* dp = reinterpret_cast<const uint32_t*>(dout16 + (size_t)min(row[r], n - 1) * 16);
+			const float w = live[r] ? rollover_weight(row[r], min(n_in, n_roll), n_roll) : 0.f;
+			const float2 a = unpack_h2(__ldg(dp + t)), b = unpack_h2(__ldg(dp + 4 + t));
+			dlo[r][0] = hq(a.x * w); dlo[r][1] = hq(a.y * w); dhi[r][0] = hq(b.x * w); dhi[r][1] = hq(b.y * w);
+		}
+		if (t == 3) var_acc += dlo[0][1] + dlo[1][1];
+		// colour MLP backward (data)
+		uint32_t dC[1][4];
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) { dC[0][r] = t == 0 ? pack_h2(dlo[r][0], dlo[r][1]) : (t == 1 ? pack_h2(dlo[r][0], 0.f) : 0u); dC[0][2 + r] = 0u; }
+		float acc[(SW > RW ? SW : RW) / 8][4];
+		uint32_t dH2[RGB3 ? RW / 16 : 1][4], dH1[RW / 16][4];
+		if constexpr (RGB3) {
+			layer<RW / 8, 1>(acc, dC, sw + PK::C3T, lane);
+			to_afrag_masked<RW / 8>(dH2, acc, Q.H2);
+			layer<RW / 8, RW / 16>(acc, dH2, sw + PK::C2T, lane);
+			to_afrag_masked<RW / 8>(dH1, acc, Q.H1);
+		} else {
+			layer<RW / 8, 1>(acc, dC, sw + PK::C3T, lane);
+			to_afrag_masked<RW / 8>(dH1, acc, Q.H1);
+		}
+		float dR[3][4];
+		layer<3, RW / 16>(dR, dH1, sw + PK::C1T, lane);
+		// dL/dy = dL/dr'[0:16] (+ dout[3] on column 0, binary16 add)
+		uint32_t dY[1][4];
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const float d3 = __shfl_sync(0xffffffffu, dlo[r][1], (lane & ~3) | 1);
+			float y0 = hq(dR[0][2 * r]), y1 = hq(dR[0][2 * r + 1]);
+			if (t == 0) y0 = __half2float(__hadd(__float2half_rn(y0), __float2half_rn(d3)));
+			dY[0][r] = pack_h2(y0, y1);
+			dY[0][2 + r] = pack_h2(dR[1][2 * r], dR[1][2 * r + 1]);
+		}
+		uint32_t dH[SW / 16][4];
+		layer<SW / 8, 1>(acc, dY, sw + PK::F2T, lane);
+		to_afrag_masked<SW / 8>(dH, acc, T.H);
+		float dU[4][4];
+		layer<4, SW / 16>(dU, dH, sw + PK::F1T, lane);
+		// g_n = dL/dr'[normal] + dout[4:7]/N + dout[8:11]   (nerf_network.h:343-373); assembled across the quad
+		float gn[2][3];
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+			if (t == 1) a0 += hq(dR[2][2 * r + 1]);
+			if (t == 2) { a1 += hq(dR[2][2 * r]); a2 += hq(dR[2][2 * r + 1]); a0 += dlo[r][0] * inv_nb; a1 += dlo[r][1] * inv_nb; }
+			if (t == 3) a2 += dlo[r][0] * inv_nb;
+			if (t == 0) { a0 += dhi[r][0]; a1 += dhi[r][1]; }
+			if (t == 1) a2 += dhi[r][0];
+			gn[r][0] = quad_sum(a0); gn[r][1] = quad_sum(a1); gn[r][2] = quad_sum(a2);
+		}
+		// second-order input v (fully_fused_mlp.cu:1036-1142 front[0]) and merged hash scatter
+		uint32_t Vf[2][4];
+		#pragma unroll
+		for (int s = 0; s < 4; ++s) {
+			const int c0 = 16 * (s >> 1) + 8 * (s & 1) + 2 * t;
+			#pragma unroll
+			for (int r = 0; r < 2; ++r) {
+				float v0 = 0.f, v1 = 0.f;
+				if (c0 < ne) {
+					const uint32_t l = (uint32_t)c0 >> 1;
+					if (l <= valid_level) {
+						const float* d = T.dy[s][r];
+						v0 = d[0] * gn[r][0] + d[1] * gn[r][1] + d[2] * gn[r][2];
+						v1 = d[3] * gn[r][0] + d[4] * gn[r][1] + d[5] * gn[r][2];
+						if (live[r]) scatter_level(M, G, l, T.px[r], T.py[r], T.pz[r], hq(dU[s][2 * r]), hq(dU[s][2 * r + 1]), T.G[s][2 * r], T.G[s][2 * r + 1], gn[r][0], gn[r][1], gn[r][2]);
+					}
+				} else {
+					const int d0 = c0 - ne;
+					if (d0 < 3) v0 = gn[r][d0];
+					if (d0 + 1 < 3) v1 = gn[r][d0 + 1];
+				}
+				Vf[s >> 1][(s & 1) * 2 + r] = pack_h2(v0, v1);
+			}
+		}
+		// front1 = relu'(H) .* (V W1'^T): only its column sums are needed (gradient of W2 row 0)
+		layer<SW / 8, 2>(acc, Vf, sw + PK::F1, lane);
+		#pragma unroll
+		for (int nb = 0; nb < SW / 8; ++nb) {
+			const float2 h0 = unpack_h2(T.H[nb >> 1][(nb & 1) * 2]), h1 = unpack_h2(T.H[nb >> 1][(nb & 1) * 2 + 1]);
+			f1acc[nb][0] += (h0.x > 0.f ? hq(acc[nb][0]) : 0.f) + (h1.x > 0.f ? hq(acc[nb][2]) : 0.f);
+			f1acc[nb][1] += (h0.y > 0.f ? hq(acc[nb][1]) : 0.f) + (h1.y > 0.f ? hq(acc[nb][3]) : 0.f);
+		}
+		// ---------------- stage operands (rows beyond n contribute zeros through their zero gradients) ----------------
+		const int row0 = warp * 16;
+		stage_afrag<2>(stg + ST::U, ST::S32, row0, lane, T.U);
+		stage_afrag<SW / 16>(stg + ST::H, ST::SSW, row0, lane, T.H);
+		stage_afrag<2>(stg + ST::V, ST::S32, row0, lane, Vf);
+		stage_afrag<SW / 16>(stg + ST::DH, ST::SSW, row0, lane, dH);
+		stage_afrag<1>(stg + ST::DY, ST::S16, row0, lane, dY);
+		stage_afrag<2>(stg + ST::R, ST::S32, row0, lane, Q.R);
+		stage_afrag<RW / 16>(stg + ST::H1, ST::SRW, row0, lane, Q.H1);
+		stage_afrag<RW / 16>(stg + ST::DH1, ST::SRW, row0, lane, dH1);
+		if constexpr (RGB3) { stage_afrag<RW / 16>(stg + ST::H2, ST::SRW, row0, lane, Q.H2); stage_afrag<RW / 16>(stg + ST::DH2, ST::SRW, row0, lane, dH2); }
+		stage_afrag<1>(stg + ST::DC, ST::S16, row0, lane, dC);
+		__syncthreads();
+		// ---------------- phase 2: weight gradients, blocks distributed over the 8 warps ----------------
+		#pragma unroll
+		for (int i = 0; i < NW1; ++i) {             // dW1' [SW x 32]: blocks (mt, nb) ; first order dH^T U + second order tm^T V
+			const int b = warp + 8 * i, mt = b >> 2, nb = b & 3;
+			dw_block<false>(aW1[i], stg + ST::DH, ST::SSW, 16 * mt, stg + ST::U, ST::S32, 8 * nb, lane, nullptr);
+			dw_block<true>(aW1[i], stg + ST::H, ST::SSW, 16 * mt, stg + ST::V, ST::S32, 8 * nb, lane, sw + PK::W2R0);
+		}
+		#pragma unroll
+		for (int i = 0; i < NW2; ++i) {             // dW2 [16 x SW]
+			const int b = warp + 8 * i;
+			if (b < SW / 8) dw_block<false>(aW2[i], stg + ST::DY, ST::S16, 0, stg + ST::H, ST::SSW, 8 * b, lane, nullptr);
+		}
+		#pragma unroll
+		for (int i = 0; i < NC1; ++i) {             // dWc1' [RW x 32]
+			const int b = warp + 8 * i, mt = b >> 2, nb = b & 3;
+			dw_block<false>(aC1[i], stg + ST::DH1, ST::SRW, 16 * mt, stg + ST::R, ST::S32, 8 * nb, lane, nullptr);
+		}
+		if constexpr (RGB3) {
+			#pragma unroll
+			for (int i = 0; i < NC2; ++i) {         // dWc2 [RW x RW]
+				const int b = warp + 8 * i, mt = b / (RW / 8), nb = b % (RW / 8);
+				dw_block<false>(aC2[i], stg + ST::DH2, ST::SRW, 16 * mt, stg + ST::H1, ST::SRW, 8 * nb, lane, nullptr);
+			}
+		}
+		#pragma unroll
+		for (int i = 0; i < NC3; ++i) {             // dWc_out [16 x RW]
+			const int b = warp + 8 * i;
+			if (b < RW / 8) dw_block<false>(aC3[i], stg + ST::DC, ST::S16, 0, RGB3 ? stg + ST::H2 : stg + ST::H1, ST::SRW, 8 * b, lane, nullptr);
+		}
+		__syncthreads();
+	}
+	// ---------------- flush: accumulators -> global gradient buffer (un-permuting the input columns) ----------------
+	auto flush = [&](const float (&a)[4], const LayerDesc& L, int n0, int k0, int kind) {
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int nn = n0 + g + 8 * (q >> 1), kk = k0 + 2 * t + (q & 1);
+			int kc = kk;
+			if (kind == 1) kc = kk < ne ? 3 + kk : (kk < ne + 3 ? kk - ne : -1);
+			else if (kind == 2) kc = kk < 16 ? kk : 16 + kk;
+			if (nn < (int)L.rows && kc >= 0 && kc < (int)L.cols && a[q] != 0.f) atomicAdd(&G[L.off + (size_t)nn * L.cols + kc], a[q]);
+		}
+	};
+	#pragma unroll
+	for (int i = 0; i < NW1; ++i) { const int b = warp + 8 * i; flush(aW1[i], M.sdf_layers[0], 16 * (b >> 2), 8 * (b & 3), 1); }
+	#pragma unroll
+	for (int i = 0; i < NW2; ++i) { const int b = warp + 8 * i; if (b < SW / 8) flush(aW2[i], M.sdf_layers[1], 0, 8 * b, 0); }
+	#pragma unroll
+	for (int i = 0; i < NC1; ++i) { const int b = warp + 8 * i; flush(aC1[i], M.rgb_layers[0], 16 * (b >> 2), 8 * (b & 3), 2); }
+	if constexpr (RGB3) {
+		#pragma unroll
+		for (int i = 0; i < NC2; ++i) { const int b = warp + 8 * i; flush(aC2[i], M.rgb_layers[1], 16 * (b / (RW / 8)), 8 * (b % (RW / 8)), 0); }
+	}
+	#pragma unroll
+	for (int i = 0; i < NC3; ++i) { const int b = warp + 8 * i; if (b < RW / 8) flush(aC3[i], M.rgb_layers[M.n_rgb_layers - 1], 0, 8 * b, 0); }
+	// second-order gradient of W2 row 0: column sums of front1 over the warp's rows
+	#pragma unroll
+	for (int nb = 0; nb < SW / 8; ++nb) {
+		#pragma unroll
+		for (int j = 0; j < 2; ++j) {
+			float v = f1acc[nb][j];
+			v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+			if (g == 0 && v != 0.f) atomicAdd(&G[M.sdf_layers[1].off + 8 * nb + 2 * t + j], v);
+		}
+	}
+	for (int o = 16; o; o >>= 1) var_acc += __shfl_xor_sync(0xffffffffu, var_acc, o);
+	if (lane == 0 && var_acc != 0.f) atomicAdd(&G[M.off_var], var_acc);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------------------------
+template <int SW, int RW, bool RGB3>
+static void launch_all(int what, cudaStream_t st, const ModelDev& M, const __half* P, uint32_t* wpack, uint32_t vl, const float4* pos4, const uint32_t* n_ptr, uint32_t n_max,
+                       const float* ray_dirw, __half* out, const __half* dout16, uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
+	using PK = Pack<SW, RW, RGB3>;
+	using ST = Stage<SW, RW, RGB3>;
+	if (what == 0) { k_pack_weights<SW, RW, RGB3><<<8, 256, 0, st>>>(M, P, wpack); return; }
+	if (!n_max) return;
+	if (what == 1) { k_pass_a_mma<SW, RW, RGB3><<<std::min<uint32_t>((n_max + 127) / 128, (uint32_t)n_sm * 2), 256, 0, st>>>(M, P, wpack, vl, pos4, n_ptr, n_max, out); return; }
+	if (what == 2) { k_pass_b_mma<SW, RW, RGB3><<<std::min<uint32_t>((n_max + 127) / 128, (uint32_t)n_sm * 2), 256, 0, st>>>(M, P, wpack, vl, pos4, n_ptr, n_max, ray_dirw, out); return; }
+	if (what == 3) {
+		const size_t smem = ((PK::END * 4 + 127) / 128) * 128 + (size_t)ST::END * 2;
+		static bool attr_set = false;
+		if (!attr_set) { cudaFuncSetAttribute(k_backward_mma<SW, RW, RGB3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+		k_backward_mma<SW, RW, RGB3><<<std::min<uint32_t>((n_max + 127) / 128, (uint32_t)n_sm), 256, smem, st>>>(M, P, wpack, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+	}
+}
+
+bool mma_supported(const ModelDev& M) {
+	return M.sdf_in == 32 && M.rgb_in == 48 && M.n_sdf_layers == 2 && M.sdf_width == M.rgb_width && (M.sdf_width == 32 || M.sdf_width == 64) && (M.n_rgb_layers == 2 || M.n_rgb_layers == 3);
+}
+size_t mma_pack_u32(const ModelDev& M) { return 32768; }
+
+// what: 0 pack weights, 1 pass A, 2 pass B, 3 backward
+void launch_mma(int what, cudaStream_t st, const ModelDev& M, const __half* P, uint32_t* wpack, uint32_t vl, const float4* pos4, const uint32_t* n_ptr, uint32_t n_max,
+                const float* ray_dirw, __half* out, const __half* dout16, uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
+	const bool three = M.n_rgb_layers == 3;
+	if (M.sdf_width == 64) {
+		if (three) launch_all<64, 64, true>(what, st, M, P, wpack, vl, pos4, n_ptr, n_max, ray_dirw, out, dout16, n_roll, n_batch, n_in_ptr, G, n_sm);
+		else launch_all<64, 64, false>(what, st, M, P, wpack, vl, pos4, n_ptr, n_max, ray_dirw, out, dout16, n_roll, n_batch, n_in_ptr, G, n_sm);
+	} else {
+		if (three) launch_all<32, 32, true>(what, st, M, P, wpack, vl, pos4, n_ptr, n_max, ray_dirw, out, dout16, n_roll, n_batch, n_in_ptr, G, n_sm);
+		else launch_all<32, 32, false>(what, st, M, P, wpack, vl, pos4, n_ptr, n_max, ray_dirw, out, dout16, n_roll, n_batch, n_in_ptr, G, n_sm);
+	}
+}
+
+} // namespace rnb
