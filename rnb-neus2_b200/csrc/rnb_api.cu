@@ -38,7 +38,7 @@ void launch_loss(cudaStream_t, uint32_t, const rnb_flags&, uint32_t, uint32_t, u
 // rnb_optim.cu
 struct AdamParams {
 	float base_lr, beta1, beta2, eps, l2, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
-	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf;
+	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf; float log2_beta1, log2_beta2;
 };
 void launch_adam_ema(cudaStream_t, const AdamParams&, float*, __half*, __half*, float*, float*, float*, uint32_t*);
 void launch_cast_params(cudaStream_t, uint32_t, const float*, __half*);
@@ -393,6 +393,13 @@ int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t em
 	return RNB_OK;
 }
 
+static void net_density(rnb_ctx* c, cudaStream_t st, uint32_t vl, uint32_t n) {
+	if (c->use_mma) {
+		launch_mma(0, st, c->M, c->params, c->wpack, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
+		launch_mma(4, st, c->M, c->params, c->wpack, vl, c->gpos, nullptr, n, nullptr, (__half*)c->gdens, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
+	} else launch_forward_simt(st, c->M, c->params, vl, 2, c->gpos, nullptr, n, nullptr, nullptr, nullptr, nullptr, c->gdens);
+}
+
 // ---- occupancy refresh: training_prep_nerf / update_density_grid_nerf --------------------------------------------
 static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint32_t n_nonuniform) {
 	if (c->training_step == 0) {
@@ -405,7 +412,7 @@ static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint3
 	    c->density_rng.advance(),
 	    launch_grid_samples(st, n_nonuniform, c->density_rng, c->density_ema_step, c->density_grid, c->gpos + n_uniform, c->gidx + n_uniform, MIN_OPTICAL_THICKNESS),
 	    c->density_rng.advance(),
-	    launch_forward_simt(st, c->M, c->params, vl, 2, c->gpos, nullptr, n, nullptr, nullptr, nullptr, nullptr, c->gdens),
+	    net_density(c, st, vl, n),
 	    launch_grid_finish(st, n, c->gidx, c->gdens, c->cfg.density_grid_decay, c->density_grid, c->density_tmp, c->mean_acc, c->mean, c->bitfield)));
 	++c->density_ema_step;
 	CU(cudaGetLastError());
@@ -465,6 +472,7 @@ static int optimizer_step(rnb_ctx* c, cudaStream_t st) {
 	A.ema_debias_old = 1 - (float)std::pow(c->cfg.ema_decay, c->opt_step - 1);       // ema.h:121-122
 	A.ema_debias_new = 1.0f / (1 - (float)std::pow(c->cfg.ema_decay, c->opt_step));
 	A.n_params = c->M.n_params; A.n_matrix = c->M.off_grid; A.rgb_begin = c->off_rgb; A.rgb_end = c->M.off_grid; A.only_sdf = c->flags.only_sdf_training;
+	A.log2_beta1 = (float)std::log2((double)c->cfg.beta1); A.log2_beta2 = (float)std::log2((double)c->cfg.beta2);
 	KT("adam_ema", 1, launch_adam_ema(st, A, c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps));
 	CU(cudaGetLastError());
 	return RNB_OK;

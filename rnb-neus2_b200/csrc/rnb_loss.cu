@@ -130,16 +130,33 @@ __device__ __forceinline__ void load_out16(const __half* p, float* o) {
 	for (int i = 0; i < 16; ++i) o[i] = __half2float(h[i]);
 }
 
-// One thread per kept ray (serial along the ray, like the reference): compositing sweep, losses, gradient sweep.
-__global__ void __launch_bounds__(128) k_loss(LossParams LP, const uint32_t* __restrict__ counters, Pcg32 rng, const ViewDev* __restrict__ views, uint32_t n_views,
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+	return v;
+}
+__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v *= t; }
+	return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+	#pragma unroll
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// One WARP per kept ray (the reference walks each ray serially in one thread): lanes own consecutive samples, the
+// transmittance product and the running colour / weight sums become warp scans, every lane writes its sample's gradient row.
+__global__ void __launch_bounds__(256) k_loss(LossParams LP, const uint32_t* __restrict__ counters, Pcg32 rng, const ViewDev* __restrict__ views, uint32_t n_views,
                                               const uint32_t* __restrict__ ray_indices, const float* __restrict__ ray_dirw,
                                               const uint32_t* __restrict__ n_fwd, const uint32_t* __restrict__ cbase, const uint32_t* __restrict__ n_emit,
                                               const __half* __restrict__ out16, __half* __restrict__ dout16, float* __restrict__ loss_out /*3 per kept ray*/) {
-	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (k >= counters[0]) return;
-	loss_out[3 * k] = loss_out[3 * k + 1] = loss_out[3 * k + 2] = 0.f;
 	const uint32_t ne = n_emit[k];
-	if (ne == 0) return;
+	if (ne == 0) { if (lane < 3) loss_out[3 * k + lane] = 0.f; return; }
 	const uint32_t nf = n_fwd[k], cb = cbase[k];
 	const rnb_flags& F = LP.F;
 	const uint32_t ray_idx = ray_indices[k];
@@ -189,18 +206,29 @@ __global__ void __launch_bounds__(128) k_loss(LossParams LP, const uint32_t* __r
 	const float car = F.cos_anneal_ratio;
 	const __half* op = out16 + (size_t)cb * 16;
 	// ---- sweep 1: composite (testbed_nerf.cu:1608-1697) ----
-	float rgb_ray[4] = {0, 0, 0, 0}, weight_sum = 0.f, T = 1.f;
-	for (uint32_t j = 0; j < nf; ++j) {
-		float o[16]; load_out16(op + (size_t)j * 16, o);
-		const AlphaTerms A = neus_alpha(o[3], o[4], o[5], o[6], __float2half_rn(o[7]), dx, dy, dz, car);
-		float alb[4]; albedo4(o, F, alb);
-		const float w = A.alpha * T;
-		float sh = A.nx * light[0] + A.ny * light[1] + A.nz * light[2];
-		if (F.apply_relu) sh = fmaxf(sh, 0.f);
+	float rgb_ray[4] = {0, 0, 0, 0}, weight_sum = 0.f, Tc = 1.f;
+	for (uint32_t c0 = 0; c0 < nf; c0 += 32) {
+		const uint32_t j = c0 + lane;
+		float om = 1.f, w = 0.f, alb[4] = {0, 0, 0, 0}, sh = 0.f, alpha = 0.f;
+		if (j < nf) {
+			float o[16]; load_out16(op + (size_t)j * 16, o);
+			const AlphaTerms A = neus_alpha(o[3], o[4], o[5], o[6], __float2half_rn(o[7]), dx, dy, dz, car);
+			albedo4(o, F, alb);
+			sh = A.nx * light[0] + A.ny * light[1] + A.nz * light[2];
+			if (F.apply_relu) sh = fmaxf(sh, 0.f);
+			alpha = A.alpha; om = 1.f - alpha;
+		}
+		const float incl = warp_scan_mul(om, lane);
+		float excl = __shfl_up_sync(0xffffffffu, incl, 1); if (lane == 0) excl = 1.f;
+		w = alpha * (Tc * excl);
+		#pragma unroll
 		for (int c = 0; c < 4; ++c) rgb_ray[c] += w * alb[c] * sh;
 		weight_sum += w;
-		T *= (1.f - A.alpha);
+		Tc *= __shfl_sync(0xffffffffu, incl, 31);
 	}
+	#pragma unroll
+	for (int c = 0; c < 4; ++c) rgb_ray[c] = warp_sum(rgb_ray[c]);
+	weight_sum = warp_sum(weight_sum);
 	// ---- losses (testbed_nerf.cu:1737-1798) ----
 	float grad[4], loss = 0.f;
 	for (int c = 0; c < 4; ++c) {
@@ -216,24 +244,39 @@ __global__ void __launch_bounds__(128) k_loss(LossParams LP, const uint32_t* __r
 		const float sg = 1.0f / (1.0f + expf(-weight_sum));
 		gws = F.apply_bce ? ((1 - mask_gt) / (1 - weight_sum) - mask_gt / weight_sum) * F.mask_loss_weight : (sg - mask_gt) * F.mask_loss_weight;
 	}
-	{
+	if (lane == 0) {
 		const float sg = 1.0f / (1.0f + expf(-weight_sum));
 		loss_out[3 * k] = loss / (float)LP.n_rays;
 		loss_out[3 * k + 2] = F.apply_bce ? -(mask_gt * logf(weight_sum) + (1 - mask_gt) * logf(1 - weight_sum)) : -(mask_gt * logf(sg) + (1 - mask_gt) * logf(1 - sg));
 	}
 	// ---- sweep 2: gradients (testbed_nerf.cu:1836-2091) ----
 	const float loss_scale = LP.loss_scale / (float)LP.n_rays;
-	float rgb_ray2[4] = {0, 0, 0, 0}, weight_sum2 = 0.f, ek_acc = 0.f; T = 1.f;
-	for (uint32_t j = 0; j < ne; ++j) {
-		float o[16]; load_out16(op + (size_t)j * 16, o);
+	float c_rgb[4] = {0, 0, 0, 0}, c_w = 0.f, ek_acc = 0.f; Tc = 1.f;
+	for (uint32_t c0 = 0; c0 < ne; c0 += 32) {
+		const uint32_t j = c0 + lane;
+		const bool valid = j < ne;
+		float o[16];
+		#pragma unroll
+		for (int c = 0; c < 16; ++c) o[c] = 0.f;
+		if (valid) load_out16(op + (size_t)j * 16, o);
 		const AlphaTerms A = neus_alpha(o[3], o[4], o[5], o[6], __float2half_rn(o[7]), dx, dy, dz, car);
 		float alb[4]; albedo4(o, F, alb);
-		const float alpha = A.alpha, w = alpha * T;
+		const float alpha = valid ? A.alpha : 0.f;
 		float sh = A.nx * light[0] + A.ny * light[1] + A.nz * light[2];
 		if (F.apply_relu) sh = fmaxf(sh, 0.f);
-		for (int c = 0; c < 4; ++c) rgb_ray2[c] += w * alb[c] * sh;
-		weight_sum2 += w;
-		T *= (1.f - alpha);
+		const float incl = warp_scan_mul(1.f - alpha, lane);
+		float excl = __shfl_up_sync(0xffffffffu, incl, 1); if (lane == 0) excl = 1.f;
+		const float w = alpha * (Tc * excl);
+		const float T = Tc * incl;                               // transmittance after this sample
+		float rgb_ray2[4];
+		#pragma unroll
+		for (int c = 0; c < 4; ++c) rgb_ray2[c] = c_rgb[c] + warp_scan_add(w * alb[c] * sh, lane);
+		const float weight_sum2 = c_w + warp_scan_add(w, lane);
+		#pragma unroll
+		for (int c = 0; c < 4; ++c) c_rgb[c] = __shfl_sync(0xffffffffu, rgb_ray2[c], 31);
+		c_w = __shfl_sync(0xffffffffu, weight_sum2, 31);
+		Tc *= __shfl_sync(0xffffffffu, incl, 31);
+		if (!valid) continue;
 		const float ag = alb[0] * grad[0] + alb[1] * grad[1] + alb[2] * grad[2] + alb[3] * grad[3];
 		float jac3[3] = {0, 0, 0};
 		if (F.apply_rgbplus) {
@@ -287,7 +330,8 @@ __global__ void __launch_bounds__(128) k_loss(LossParams LP, const uint32_t* __r
 		uint4* dst = reinterpret_cast<uint4*>(dout16 + (size_t)(cb + j) * 16);
 		dst[0] = reinterpret_cast<uint4*>(h)[0]; dst[1] = reinterpret_cast<uint4*>(h)[1];
 	}
-	loss_out[3 * k + 1] = ek_acc / ((float)ne * (float)LP.n_rays);
+	ek_acc = warp_sum(ek_acc);
+	if (lane == 0) loss_out[3 * k + 1] = ek_acc / ((float)ne * (float)LP.n_rays);
 }
 
 // Sum per-ray losses into stats[0..2] (reduce_sum, testbed_nerf.cu:3547-3552); one CTA.
@@ -331,7 +375,7 @@ void launch_loss(cudaStream_t st, uint32_t n_upper, const rnb_flags& F, uint32_t
                  const __half* out16, __half* dout16, float* loss_out, float* stats) {
 	if (!n_upper) return;
 	LossParams LP; LP.F = F; LP.n_rays = n_rays; LP.n_rays_total = n_rays_total; LP.step = step; LP.loss_scale = loss_scale;
-	k_loss<<<(n_upper + 127) / 128, 128, 0, st>>>(LP, counters, rng, views, n_views, ray_indices, ray_dirw, n_fwd, cbase, n_emit, out16, dout16, loss_out);
+	k_loss<<<(n_upper * 32 + 255) / 256, 256, 0, st>>>(LP, counters, rng, views, n_views, ray_indices, ray_dirw, n_fwd, cbase, n_emit, out16, dout16, loss_out);
 	if (stats) k_reduce_losses<<<1, 1024, 0, st>>>(counters, loss_out, stats);
 }
 

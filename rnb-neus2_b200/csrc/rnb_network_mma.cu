@@ -154,7 +154,7 @@ struct SdfTile {
 };
 
 // slot s = 2*kb + hi covers columns c0 = 16kb + 8hi + 2t, c0+1 of u'
-template <int SW, bool WITH_DY>
+template <int SW, bool WITH_DY, bool WITH_NORMAL = true>
 __device__ __forceinline__ void sdf_tile(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, const uint32_t* __restrict__ sw /*packed sdf weights*/,
                                          int lane, SdfTile<SW>& T) {
 	const int t = lane & 3;
@@ -191,6 +191,7 @@ __device__ __forceinline__ void sdf_tile(const ModelDev& M, const __half* __rest
 	to_afrag<SW / 8, true>(T.H, acc);
 	constexpr int F1T = 2 * (SW / 8) * 64, F2 = F1T + (SW / 16) * 4 * 64, F2T = F2 + (SW / 16) * 2 * 64, W2R0 = F2T + (SW / 8) * 64;
 	layer<2, SW / 16>(T.Y, T.H, sw + F2, lane);
+	if (!WITH_NORMAL) return;
 	// one-hot back chain: tm = relu'(H) .* W2[0,:]  ->  G = tm * W1'
 	uint32_t TM[SW / 16][4];
 	#pragma unroll
@@ -281,6 +282,44 @@ __global__ void __launch_bounds__(256, 2) k_pass_a_mma(ModelDev M, const __half*
 				const float sdfb = __half2float(__hadd(__float2half_rn(r ? y8 : y0), __float2half_rn(M.sdf_bias)));
 				uint2 v; v.x = pack_h2(sdfb, T.nrm[r][0]); v.y = pack_h2(T.nrm[r][1], T.nrm[r][2]);
 				reinterpret_cast<uint2*>(outA)[row[r]] = v;
+			}
+		}
+	}
+}
+
+// SDF probe for the occupancy-grid refresh and rnb_eval_sdf (NerfNetwork::sdf / ::density, nerf_network.h:454-537):
+// encoding + SDF MLP only.  Outputs are optional.
+template <int SW, int RW, bool RGB3>
+__global__ void __launch_bounds__(256, 2) k_sdf_probe_mma(ModelDev M, const __half* __restrict__ P, const uint32_t* __restrict__ wpack, uint32_t valid_level,
+                                                          const float4* __restrict__ pos4, uint32_t n, float* __restrict__ sdf_out, float* __restrict__ dens_out) {
+	using PK = Pack<SW, RW, RGB3>;
+	__shared__ __align__(128) uint32_t sw[PK::SDF_END];
+	__shared__ __align__(8) uint64_t bar;
+	load_weights_bulk(sw, wpack, PK::SDF_END, &bar);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+	const uint32_t n_tiles = (n + 15) / 16;
+	const __half var = __ldg(P + M.off_var);
+	const __half sc = __float2half_rn(__expf(__half2float(__hmul(var, __float2half_rn(10.0f)))));
+	for (uint32_t tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += gridDim.x * 8) {
+		SdfTile<SW> T;
+		uint32_t row[2];
+		#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			row[r] = tile * 16 + g + 8 * r;
+			const float4 p = pos4[min(row[r], n - 1)];
+			T.px[r] = p.x; T.py[r] = p.y; T.pz[r] = p.z;
+		}
+		sdf_tile<SW, false, false>(M, P, valid_level, sw, lane, T);
+		if (t == 0) {
+			#pragma unroll
+			for (int r = 0; r < 2; ++r) {
+				if (row[r] >= n) continue;
+				const __half sdfb = __hadd(__float2half_rn(T.Y[0][2 * r]), __float2half_rn(M.sdf_bias));
+				if (sdf_out) sdf_out[row[r]] = __half2float(sdfb);
+				if (dens_out) {   // sdf_to_density_variance_buffer, common_operation.cuh:310-328 (binary16 arithmetic)
+					const __half sg = __float2half_rn(1.0f / (1.0f + expf(-__half2float(__hmul(sdfb, sc)))));
+					dens_out[row[r]] = __half2float(__hmul(__hmul(sc, sg), __hsub(__float2half_rn(1.0f), sg)));
+				}
 			}
 		}
 	}
@@ -677,6 +716,7 @@ static void launch_all(int what, cudaStream_t st, const ModelDev& M, const __hal
 	if (!n_max) return;
 	if (what == 1) { k_pass_a_mma<SW, RW, RGB3><<<std::min<uint32_t>((n_max + 127) / 128, (uint32_t)n_sm * 2), 256, 0, st>>>(M, P, wpack, vl, pos4, n_ptr, n_max, out); return; }
 	if (what == 2) { k_pass_b_mma<SW, RW, RGB3><<<std::min<uint32_t>((n_max + 127) / 128, (uint32_t)n_sm * 2), 256, 0, st>>>(M, P, wpack, vl, pos4, n_ptr, n_max, ray_dirw, out); return; }
+	if (what == 4) { k_sdf_probe_mma<SW, RW, RGB3><<<std::min<uint32_t>((n_max + 127) / 128, (uint32_t)n_sm * 4), 256, 0, st>>>(M, P, wpack, vl, pos4, n_max, G /*sdf*/, (float*)out /*density*/); return; }
 	if (what == 3) {
 		const size_t smem = ((PK::END * 4 + 127) / 128) * 128 + (size_t)ST::END * 2;
 		static bool attr_set = false;
@@ -690,7 +730,7 @@ bool mma_supported(const ModelDev& M) {
 }
 size_t mma_pack_u32(const ModelDev& M) { return 32768; }
 
-// what: 0 pack weights, 1 pass A, 2 pass B, 3 backward
+// what: 0 pack weights, 1 pass A, 2 pass B, 3 backward, 4 SDF probe (G = sdf out, out = density out as float*)
 void launch_mma(int what, cudaStream_t st, const ModelDev& M, const __half* P, uint32_t* wpack, uint32_t vl, const float4* pos4, const uint32_t* n_ptr, uint32_t n_max,
                 const float* ray_dirw, __half* out, const __half* dout16, uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
 	const bool three = M.n_rgb_layers == 3;

@@ -14,34 +14,57 @@ namespace rnb {
 
 struct AdamParams {
 	float base_lr, beta1, beta2, eps, l2, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
-	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf;
+	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf; float log2_beta1, log2_beta2;
 };
 
-__global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restrict__ master, __half* __restrict__ params, __half* __restrict__ ema,
-                                                  float* __restrict__ grads, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= A.n_params) return;
-	const float g32 = grads[i];
-	grads[i] = 0.f;                                   // gradient buffer is consumed: ready for the next step's atomics
+// One thread owns 4 consecutive parameters (128-bit gradient load).  Fast path for the common case of an untouched
+// hash-grid quad whose EMA copy has already converged to the weight: nothing to write (the EMA update
+// (ema*d*old + w*(1-d))*new is a fixed point at ema == w because d*old + 1 - d == 1/new).
+__device__ __forceinline__ void adam_one(const AdamParams& A, uint32_t i, float g32, float* __restrict__ master, __half& wh, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
 	float gradient = hq(g32) / A.loss_scale;
 	const bool is_mat = i < A.n_matrix;
 	bool update = is_mat || gradient != 0.f;
 	if (A.only_sdf && i >= A.rgb_begin && i < A.rgb_end) update = false;
-	__half wh = params[i];
-	if (update) {
-		const float w = master[i];
-		if (is_mat) gradient += A.l2 * w;
-		const float fm = m1[i] = A.beta1 * m1[i] + (1 - A.beta1) * gradient;
-		const float sm = m2[i] = A.beta2 * m2[i] + (1 - A.beta2) * (gradient * gradient);
-		const uint32_t cs = ++steps[i];
-		const float lr = A.base_lr * (sqrtf(1 - powf(A.beta2, (float)cs)) / (1 - powf(A.beta1, (float)cs)));
-		const float eff = fminf(fmaxf(lr / (sqrtf(sm) + A.eps), 0.f), 3.402823466e+38f);
-		const float nw = w - eff * fm;
-		master[i] = nw;
-		wh = __float2half_rn(nw);
-		params[i] = wh;
+	if (!update) return;
+	const float w = master[i];
+	if (is_mat) gradient += A.l2 * w;
+	const float fm = m1[i] = A.beta1 * m1[i] + (1 - A.beta1) * gradient;
+	const float sm = m2[i] = A.beta2 * m2[i] + (1 - A.beta2) * (gradient * gradient);
+	const uint32_t cs = ++steps[i];
+	const float lr = A.base_lr * (sqrtf(1 - exp2f((float)cs * A.log2_beta2)) / (1 - exp2f((float)cs * A.log2_beta1)));
+	const float eff = fminf(fmaxf(lr / (sqrtf(sm) + A.eps), 0.f), 3.402823466e+38f);
+	const float nw = w - eff * fm;
+	master[i] = nw;
+	wh = __float2half_rn(nw);
+}
+
+__global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restrict__ master, __half* __restrict__ params, __half* __restrict__ ema,
+                                                  float* __restrict__ grads, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
+	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (i0 >= A.n_params) return;
+	if (i0 + 4 <= A.n_params) {
+		const float4 g = *reinterpret_cast<const float4*>(grads + i0);
+		uint2 pw = *reinterpret_cast<const uint2*>(params + i0), pe = *reinterpret_cast<const uint2*>(ema + i0);
+		const bool anyg = g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f;
+		if (!anyg && i0 >= A.n_matrix && pw.x == pe.x && pw.y == pe.y) return;
+		if (anyg) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);     // consumed: ready for the next step's atomics
+		__half* wh = reinterpret_cast<__half*>(&pw); __half* eh = reinterpret_cast<__half*>(&pe);
+		const float gg[4] = {g.x, g.y, g.z, g.w};
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			adam_one(A, i0 + q, gg[q], master, wh[q], m1, m2, steps);
+			eh[q] = __float2half_rn((__half2float(eh[q]) * A.ema_decay * A.ema_debias_old + __half2float(wh[q]) * (1 - A.ema_decay)) * A.ema_debias_new);
+		}
+		*reinterpret_cast<uint2*>(params + i0) = pw; *reinterpret_cast<uint2*>(ema + i0) = pe;
+	} else {
+		for (uint32_t i = i0; i < A.n_params; ++i) {
+			const float g32 = grads[i]; grads[i] = 0.f;
+			__half wh = params[i];
+			adam_one(A, i, g32, master, wh, m1, m2, steps);
+			params[i] = wh;
+			ema[i] = __float2half_rn((__half2float(ema[i]) * A.ema_decay * A.ema_debias_old + __half2float(wh) * (1 - A.ema_decay)) * A.ema_debias_new);
+		}
 	}
-	ema[i] = __float2half_rn((__half2float(ema[i]) * A.ema_decay * A.ema_debias_old + __half2float(wh) * (1 - A.ema_decay)) * A.ema_debias_new);
 }
 
 __global__ void k_cast_params(uint32_t n, const float* __restrict__ master, __half* __restrict__ params) {
@@ -132,7 +155,7 @@ __global__ void k_bitfield_pool(const uint8_t* __restrict__ prev, uint8_t* __res
 }
 
 void launch_adam_ema(cudaStream_t st, const AdamParams& A, float* master, __half* params, __half* ema, float* grads, float* m1, float* m2, uint32_t* steps) {
-	k_adam_ema<<<(A.n_params + 255) / 256, 256, 0, st>>>(A, master, params, ema, grads, m1, m2, steps);
+	k_adam_ema<<<((A.n_params + 3) / 4 + 255) / 256, 256, 0, st>>>(A, master, params, ema, grads, m1, m2, steps);
 }
 void launch_cast_params(cudaStream_t st, uint32_t n, const float* master, __half* params) { k_cast_params<<<(n + 255) / 256, 256, 0, st>>>(n, master, params); }
 void launch_widen_params(cudaStream_t st, uint32_t n, const __half* params, float* master) { k_widen_params<<<(n + 255) / 256, 256, 0, st>>>(n, params, master); }
