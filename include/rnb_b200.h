@@ -88,7 +88,7 @@ typedef struct rnb_flags {
 	float   mask_loss_weight;       /* 1.0 */
 	float   ek_loss_weight;         /* 0.01 */
 	float   cos_anneal_ratio;       /* 1.0 (anneal_end == 0) */
-	int32_t light_mode;             /* -1: hashed per (ray, step) [the reference uses curand_init(clock64())]; 0..2 pinned */
+	int32_t light_mode;             /* -1: hashed per (ray, step) [the reference uses curand_init(clock64())]; -2: ray index % 3; 0..2 pinned */
 	int32_t only_sdf_training;      /* Optimizer::only_sdf_training (src/testbed.cu:1886-1895) */
 } rnb_flags;
 
@@ -173,6 +173,11 @@ int rnb_train_step_begin(rnb_ctx* ctx, void* stream);
 int rnb_train_step_end(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
 int rnb_grad_buffer(rnb_ctx* ctx, float** grads_dev, uint64_t* n);
 int rnb_stat_buffer(rnb_ctx* ctx, float** stats_dev, uint64_t* n);
+/* host copies for parity checks: gradient accumulators (fp32, loss-scaled; the reference's Trainer::param_gradients(),
+ * trainer.h:240, is the fp16 equivalent) and, per kept ray, its index and (loss, ek_loss, mask_loss) as written by
+ * compute_loss_kernel_train_nerf (src/testbed_nerf.cu:1833-1841) */
+int rnb_get_grads_fp32(rnb_ctx* ctx, float* host, size_t n);
+int rnb_get_ray_losses(rnb_ctx* ctx, uint32_t cap, uint32_t* ray_idx_host, float* loss3_host, uint32_t* n_out);
 
 /* instrumentation for bench.py: per-stage CUDA-event timing (events recorded on the caller's stream around each stage of
  * the step; resolved at the end of rnb_train_step_end) and a count of kernels launched by this ctx. */

@@ -28,7 +28,7 @@ struct View {
 struct Flags {
 	int32_t apply_L2 = 1, apply_supernormal = 0, apply_rgbplus = 1, apply_relu = 0, apply_bce = 0, light_opti = 0, no_albedo = 1;
 	float mask_loss_weight = 1.0f, ek_loss_weight = 0.01f, cos_anneal_ratio = 1.0f;
-	int32_t light_mode = -1;   // -1: hashed per (ray, step); 0..2: pinned light index
+	int32_t light_mode = -1;   // -1: hashed per (ray, step); -2: ray index % 3 (the pin oracle/ref_prelude.h gives the reference); 0..2: pinned light index
 };
 
 static inline float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : std::pow((s + 0.055f) / 1.055f, 2.4f); }
@@ -216,7 +216,7 @@ static inline void ray_target(uint32_t ray_idx, uint32_t n_rays, uint32_t n_rays
 	const float tilt[3] = {(float)(0.0f * M_PI / 180.0f), (float)(120.0f * M_PI / 180.0f), (float)(240.0f * M_PI / 180.0f)};
 	for (int k = 0; k < 3; ++k) { LD[0][k] = -std::sin(slant) * std::cos(tilt[k]); LD[1][k] = -std::sin(slant) * std::sin(tilt[k]); LD[2][k] = -std::cos(slant); }
 	if (F.apply_supernormal) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) LD[a][b] = a == b ? 1.f : 0.f;
-	uint32_t li = F.light_mode >= 0 ? (uint32_t)F.light_mode % 3u : hashed_light(ray_idx, step);
+	uint32_t li = F.light_mode >= 0 ? (uint32_t)F.light_mode % 3u : (F.light_mode == -2 ? ray_idx % 3u : hashed_light(ray_idx, step));
 	if (F.light_opti) {   // Rodrigues alignment to the GT normal: testbed_nerf.cu:1563-1581
 		float k[3] = {-nv[1], nv[0], 0.f};
 		float kn = std::sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2]);

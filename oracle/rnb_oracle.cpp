@@ -42,6 +42,7 @@ struct Oracle {
 	std::vector<View> views;
 	// scratch kept for inspection
 	std::vector<uint32_t> ray_indices, numsteps; std::vector<float> rays, coords;
+	std::vector<float> last_loss, last_ek, last_mask;   // per kept ray, in ray_indices order
 };
 
 static void sync_half(Oracle* o) { for (size_t i = 0; i < o->m.n_params; ++i) o->pv[i] = hq(o->master[i]); }
@@ -419,6 +420,7 @@ void orc_train_step(Oracle* o, OrcStats* st) {
 	}
 	std::vector<float> loss(K), ek(K), ml(K);
 	orc_loss(o, oc.data(), o->ray_indices.data(), n_fwd.data(), cbase.data(), n_emit.data(), K, R, nrt, o->training_step, dout.data(), loss.data(), ek.data(), ml.data());
+	o->last_loss = loss; o->last_ek = ek; o->last_mask = ml; o->ray_indices.resize(K);
 	const uint32_t n_in = std::min(total, o->target_batch);
 	orc_network_backward(o, cc.data(), dout.data(), n_in, n_in, o->target_batch, vl);
 	o->rng.advance();
@@ -433,6 +435,13 @@ void orc_train_step(Oracle* o, OrcStats* st) {
 		o->rays_per_batch = std::min(next_multiple(r, 128u), 1u << 18);
 	}
 	if (st) st->rays_per_batch_next = o->rays_per_batch;
+}
+
+// per-ray loss terms of the last orc_train_step (compute_loss_kernel's loss_output / ek_loss_output / mask_loss_output)
+uint32_t orc_get_last_losses(Oracle* o, uint32_t cap, uint32_t* ray_idx, float* loss, float* ek, float* mask) {
+	const uint32_t K = (uint32_t)std::min<size_t>(cap, o->last_loss.size());
+	for (uint32_t k = 0; k < K; ++k) { ray_idx[k] = o->ray_indices[k]; loss[k] = o->last_loss[k]; ek[k] = o->last_ek[k]; mask[k] = o->last_mask[k]; }
+	return K;
 }
 
 // ---- double-precision (smooth) entry points for finite-difference checks only ----

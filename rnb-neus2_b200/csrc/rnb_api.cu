@@ -176,6 +176,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 		pil = next_multiple(pil, 8u);
 		pil = std::min(pil, 1u << cfg->log2_hashmap_size);
 		M.offsets[i] = offset; offset += pil;
+		if ((uint64_t)r * r * r > (uint64_t)pil) M.hashed_mask |= 1u << i;
 	}
 	M.offsets[M.n_levels] = offset;
 	M.sdf_in = next_multiple(3 + M.n_enc, 16u); M.rgb_in = next_multiple(3 + 3 + 16 + 16, 16u);
@@ -560,6 +561,22 @@ int rnb_profile_read(rnb_ctx* c, char* names_buf, size_t names_cap, double* ms, 
 int rnb_launch_count(rnb_ctx* c, uint64_t* out) { if (!c || !out) return fail(RNB_ERR_INVALID, "null argument"); *out = c->launches; return RNB_OK; }
 
 int rnb_grad_buffer(rnb_ctx* c, float** g, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *g = c->grads; *n = c->M.n_params; return RNB_OK; }
+// host copies for parity tests: the fp32 gradient accumulators (valid between rnb_train_step_begin and _end) and the per-ray
+// loss terms of the last step (loss_output / ek_loss_output / mask_loss_output of compute_loss_kernel, testbed_nerf.cu:1396-2097)
+int rnb_get_grads_fp32(rnb_ctx* c, float* host, size_t n) {
+	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad gradient buffer");
+	CU(cudaMemcpy(host, c->grads, n * 4, cudaMemcpyDeviceToHost));
+	return RNB_OK;
+}
+int rnb_get_ray_losses(rnb_ctx* c, uint32_t cap, uint32_t* ray_idx, float* loss3, uint32_t* n_out) {
+	if (!c || !ray_idx || !loss3 || !n_out) return fail(RNB_ERR_INVALID, "null argument");
+	uint32_t K = 0; CU(cudaMemcpy(&K, c->counters, 4, cudaMemcpyDeviceToHost));
+	K = std::min(K, std::min(cap, c->cap_rays));
+	CU(cudaMemcpy(ray_idx, c->ray_indices, (size_t)K * 4, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(loss3, c->loss_out, (size_t)K * 12, cudaMemcpyDeviceToHost));
+	*n_out = K;
+	return RNB_OK;
+}
 int rnb_stat_buffer(rnb_ctx* c, float** s, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *s = c->stats; *n = 8; return RNB_OK; }
 
 int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream) {

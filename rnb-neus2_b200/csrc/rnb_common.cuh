@@ -29,6 +29,7 @@ struct ModelDev {
 	uint32_t res[MAX_LEVELS];
 	float scale[MAX_LEVELS];
 	uint32_t off_grid, off_var, n_params;
+	uint32_t hashed_mask;                       // bit l: level l is hashed (res^3 > entries), else dense
 	float sdf_bias;
 };
 

@@ -16,38 +16,65 @@ __device__ __forceinline__ LevelGeom level_geom(float scale, float x, float y, f
 	return g;
 }
 
+// The 8 corner entries of one cell, corner c = bx + 2 by + 4 bz.  Same values as grid_entry() (tcnn grid.h:113-148)
+// without its per-corner branches and runtime modulo:
+//  * a hashed level has hsz == 2^log2_hashmap_size, so `% hsz` is a mask and the three products are shared by the corners;
+//  * a dense level has index < res^3 + res^2 + res < 2 hsz, so `% hsz` is one conditional subtraction, and it can only
+//    trigger when the cell touches the upper face of the grid (coordinate + 1 == res).
+__device__ __forceinline__ void corner_entries(bool hashed, uint32_t hsz, uint32_t res, const LevelGeom& g, uint32_t (&e)[8]) {
+	if (hashed) {
+		const uint32_t m = hsz - 1u;
+		const uint32_t x0 = g.gx, x1 = g.gx + 1u;
+		const uint32_t y0 = g.gy * 2654435761u, y1 = y0 + 2654435761u;
+		const uint32_t z0 = g.gz * 805459861u, z1 = z0 + 805459861u;
+		const uint32_t a0 = y0 ^ z0, a1 = y1 ^ z0, a2 = y0 ^ z1, a3 = y1 ^ z1;
+		e[0] = (x0 ^ a0) & m; e[1] = (x1 ^ a0) & m; e[2] = (x0 ^ a1) & m; e[3] = (x1 ^ a1) & m;
+		e[4] = (x0 ^ a2) & m; e[5] = (x1 ^ a2) & m; e[6] = (x0 ^ a3) & m; e[7] = (x1 ^ a3) & m;
+	} else {
+		const uint32_t r2 = res * res;
+		const uint32_t b = g.gx + g.gy * res + g.gz * r2;
+		e[0] = b; e[1] = b + 1u; e[2] = b + res; e[3] = b + res + 1u;
+		e[4] = b + r2; e[5] = b + r2 + 1u; e[6] = b + r2 + res; e[7] = b + r2 + res + 1u;
+		if (max(g.gx, max(g.gy, g.gz)) + 1u >= res || b >= hsz) {
+			#pragma unroll
+			for (int c = 0; c < 8; ++c) e[c] = e[c] % hsz;
+		}
+	}
+}
+
 // One level for one sample: the 8 corners are gathered once (the reference re-gathers them per axis); the encoding is
 // accumulated in binary16 in corner order (grid.h:291-315), dy/dx in fp32 (grid.h:324-363).
 // Returns the two features packed as half2; dy = {d f0/dx, d f0/dy, d f0/dz, d f1/dx, d f1/dy, d f1/dz}.
 __device__ __forceinline__ __half2 encode_level_packed(const ModelDev& M, const __half* __restrict__ P, uint32_t l, float x, float y, float z, float* __restrict__ dy) {
-	const __half2* grid = reinterpret_cast<const __half2*>(P + M.off_grid) + M.offsets[l];
-	const uint32_t hsz = M.offsets[l + 1] - M.offsets[l], res = M.res[l];
+	const uint32_t off = M.offsets[l];
+	const __half2* grid = reinterpret_cast<const __half2*>(P + M.off_grid) + off;
+	const uint32_t hsz = M.offsets[l + 1] - off, res = M.res[l];
 	const float scale = M.scale[l];
 	const LevelGeom g = level_geom(scale, x, y, z);
+	uint32_t e[8];
+	corner_entries((M.hashed_mask >> l) & 1u, hsz, res, g, e);
 	float2 v[8];
 	#pragma unroll
-	for (int c = 0; c < 8; ++c) {
-		const uint32_t e = grid_entry(hsz, res, g.gx + (c & 1), g.gy + ((c >> 1) & 1), g.gz + ((c >> 2) & 1));
-		v[c] = __half22float2(__ldg(&grid[e]));
-	}
+	for (int c = 0; c < 8; ++c) v[c] = __half22float2(__ldg(&grid[e[c]]));
 	const float wx[2] = {1.f - g.fx, g.fx}, wy[2] = {1.f - g.fy, g.fy}, wz[2] = {1.f - g.fz, g.fz};
-	__half r0 = __float2half_rn(0.f), r1 = r0;
+	const float wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
+	__half2 r = __floats2half2_rn(0.f, 0.f);
 	#pragma unroll
 	for (int c = 0; c < 8; ++c) {
-		const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
-		r0 = __hadd(r0, __float2half_rn(w * v[c].x));
-		r1 = __hadd(r1, __float2half_rn(w * v[c].y));
+		const float w = wxy[c & 3] * wz[c >> 2];
+		r = __hadd2(r, __floats2half2_rn(w * v[c].x, w * v[c].y));
 	}
 	if (dy) {
+		const float sx[2] = {scale * wx[0], scale * wx[1]}, sy[2] = {scale * wy[0], scale * wy[1]};
 		#pragma unroll
 		for (int d = 0; d < 3; ++d) {
 			float a0 = 0.f, a1 = 0.f;
 			#pragma unroll
 			for (int idx = 0; idx < 4; ++idx) {
-				int c; float w = scale;
-				if (d == 0) { c = (idx & 1) * 2 + (idx >> 1) * 4; w *= wy[idx & 1]; w *= wz[idx >> 1]; }
-				else if (d == 1) { c = (idx & 1) * 1 + (idx >> 1) * 4; w *= wx[idx & 1]; w *= wz[idx >> 1]; }
-				else { c = (idx & 1) * 1 + (idx >> 1) * 2; w *= wx[idx & 1]; w *= wy[idx >> 1]; }
+				int c; float w;
+				if (d == 0) { c = (idx & 1) * 2 + (idx >> 1) * 4; w = sy[idx & 1] * wz[idx >> 1]; }
+				else if (d == 1) { c = (idx & 1) * 1 + (idx >> 1) * 4; w = sx[idx & 1] * wz[idx >> 1]; }
+				else { c = (idx & 1) * 1 + (idx >> 1) * 2; w = sx[idx & 1] * wy[idx >> 1]; }
 				const int cr = c | (1 << d);
 				a0 += w * (v[cr].x - v[c].x);
 				a1 += w * (v[cr].y - v[c].y);
@@ -55,7 +82,7 @@ __device__ __forceinline__ __half2 encode_level_packed(const ModelDev& M, const 
 			dy[d] = a0; dy[3 + d] = a1;
 		}
 	}
-	return __halves2half2(r0, r1);
+	return r;
 }
 
 // Merged first- and second-order gradient scatter for one (sample, level):
@@ -63,19 +90,30 @@ __device__ __forceinline__ __half2 encode_level_packed(const ModelDev& M, const 
 // (kernel_grid_backward grid.h:366-495 and kernel_grid_backward_input_backward_grid grid.h:556-683 hit the same 8 corners).
 __device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restrict__ G, uint32_t l, float x, float y, float z,
                                               float d10, float d11, float ge0, float ge1, float gnx, float gny, float gnz) {
-	float* gg = G + M.off_grid + (size_t)M.offsets[l] * 2;
-	const uint32_t hsz = M.offsets[l + 1] - M.offsets[l], res = M.res[l];
+	const uint32_t off = M.offsets[l];
+	float* gg = G + M.off_grid + (size_t)off * 2;
+	const uint32_t hsz = M.offsets[l + 1] - off, res = M.res[l];
 	const float scale = M.scale[l];
 	const LevelGeom g = level_geom(scale, x, y, z);
+	uint32_t e[8];
+	corner_entries((M.hashed_mask >> l) & 1u, hsz, res, g, e);
 	const float wx[2] = {1.f - g.fx, g.fx}, wy[2] = {1.f - g.fy, g.fy}, wz[2] = {1.f - g.fz, g.fz};
+	const float sgx = scale * gnx, sgy = scale * gny, sgz = scale * gnz;
+	// w1 = wx wy wz ; w2 = (+-sgx) wy wz + (+-sgy) wx wz + (+-sgz) wx wy   (sign = + on the upper corner of that axis)
+	float ax[4], ay[4], az[4];   // ax[by + 2 bz], ay[bx + 2 bz], az[bx + 2 by]
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		ax[i] = sgx * (wy[i & 1] * wz[i >> 1]);
+		ay[i] = sgy * (wx[i & 1] * wz[i >> 1]);
+		az[i] = sgz * (wx[i & 1] * wy[i >> 1]);
+	}
 	#pragma unroll
 	for (int c = 0; c < 8; ++c) {
 		const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
 		const float w1 = wx[bx] * wy[by] * wz[bz];
-		const float w2 = scale * (gnx * (bx ? 1.f : -1.f) * wy[by] * wz[bz] + gny * (by ? 1.f : -1.f) * wx[bx] * wz[bz] + gnz * (bz ? 1.f : -1.f) * wx[bx] * wy[by]);
-		const uint32_t e = grid_entry(hsz, res, g.gx + bx, g.gy + by, g.gz + bz);
+		const float w2 = (bx ? ax[by + 2 * bz] : -ax[by + 2 * bz]) + (by ? ay[bx + 2 * bz] : -ay[bx + 2 * bz]) + (bz ? az[bx + 2 * by] : -az[bx + 2 * by]);
 		const float v0 = d10 * w1 + ge0 * w2, v1 = d11 * w1 + ge1 * w2;
-		if (v0 != 0.f || v1 != 0.f) atomicAdd(reinterpret_cast<float2*>(gg + 2 * e), make_float2(v0, v1));
+		if (v0 != 0.f || v1 != 0.f) atomicAdd(reinterpret_cast<float2*>(gg + 2 * e[c]), make_float2(v0, v1));
 	}
 }
 

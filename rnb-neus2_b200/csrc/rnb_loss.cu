@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) k_loss(LossParams LP, const uint32_t* __r
 		for (int q = 0; q < 3; ++q) { LD[0][q] = -sinf(slant) * cosf(tilt[q]); LD[1][q] = -sinf(slant) * sinf(tilt[q]); LD[2][q] = -cosf(slant); }
 		if (F.apply_supernormal) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) LD[a][b] = a == b ? 1.f : 0.f;
 	}
-	const uint32_t li = F.light_mode >= 0 ? (uint32_t)F.light_mode % 3u : hashed_light(ray_idx, LP.step);
+	const uint32_t li = F.light_mode >= 0 ? (uint32_t)F.light_mode % 3u : (F.light_mode == -2 ? ray_idx % 3u : hashed_light(ray_idx, LP.step));
 	if (F.light_opti) {
 		float kk[3] = {-nv[1], nv[0], 0.f};
 		const float kn = sqrtf(kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2]);

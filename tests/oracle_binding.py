@@ -66,6 +66,7 @@ def lib():
         L.orc_rollover_weight.restype = C.c_float
         L.orc_density_mean.restype = C.c_float
         L.orc_prep_if_due.restype = C.c_int
+        L.orc_get_last_losses.restype = C.c_uint32
         _lib = L
     return _lib
 
@@ -221,6 +222,11 @@ class Oracle:
 
     def train_step(self):
         st = Stats(); self.L.orc_train_step(self.h, C.byref(st)); return st
+
+    def last_losses(self, cap=1 << 18):
+        ri = np.zeros(cap, np.uint32); lo = np.zeros(cap, np.float32); ek = np.zeros(cap, np.float32); ml = np.zeros(cap, np.float32)
+        k = int(self.L.orc_get_last_losses(self.h, cap, _p(ri, C.c_uint32), _p(lo, C.c_float), _p(ek, C.c_float), _p(ml, C.c_float)))
+        return ri[:k], lo[:k], ek[:k], ml[:k]
 
     def forward_f64(self, params, coords, valid_level):
         params = np.ascontiguousarray(params, np.float64); coords = np.ascontiguousarray(coords, np.float32); n = coords.shape[0]
