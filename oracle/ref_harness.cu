@@ -56,7 +56,7 @@ static void dump_host(const std::string& name, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
 	if (argc < 5) {
-		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K] [--time-only] [--pin-rays N]\n");
+		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--pin-rays N]\n");
 		return 1;
 	}
 	char buf[PATH_MAX]; ssize_t cnt = readlink("/proc/self/exe", buf, PATH_MAX);
@@ -65,13 +65,14 @@ int main(int argc, char** argv) {
 	g_out = argv[3];
 	const int n_steps = atoi(argv[4]);
 	bool no_albedo = false, supernormal = false, opti = false, l1 = false, rgbplus = true, time_only = false;
-	int dump_every = 1; uint32_t pin_rays = 0;
+	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps;
 	for (int i = 5; i < argc; ++i) {
 		std::string a = argv[i];
 		if (a == "--no-albedo") no_albedo = true; else if (a == "--supernormal") supernormal = true; else if (a == "--opti-lights") opti = true;
 		else if (a == "--l1") l1 = true; else if (a == "--no-rgbplus") rgbplus = false; else if (a == "--time-only") time_only = true;
 		else if (a == "--dump-every" && i + 1 < argc) dump_every = atoi(argv[++i]);
 		else if (a == "--pin-rays" && i + 1 < argc) pin_rays = (uint32_t)atoi(argv[++i]);
+		else if (a == "--dump-steps" && i + 1 < argc) { std::string l = argv[++i]; size_t p0 = 0; while (p0 < l.size()) { size_t q = l.find(',', p0); if (q == std::string::npos) q = l.size(); dump_steps.push_back(atoi(l.substr(p0, q - p0).c_str())); p0 = q + 1; } }
 	}
 
 	Testbed tb{ETestbedMode::Nerf};
@@ -126,11 +127,13 @@ int main(int argc, char** argv) {
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 	double total_ms = 0; uint64_t total_rays = 0;
 	for (int k = 0; k < n_steps; ++k) {
-		const bool dump = !time_only && (k % dump_every == 0 || k == n_steps - 1);
+		bool dump = !time_only && (k % dump_every == 0 || k == n_steps - 1);
+		if (!time_only && !dump_steps.empty()) { dump = false; for (int d : dump_steps) dump |= (d == k); }
 		const std::string tag = "step" + std::to_string(k);
 		// benchmark / parity knob: overwrite the batch-size controller's output (a public member) so that every step marches the
 		// same number of rays; with N <= 256 the compacted count can never exceed 2^18 and no arrival-order truncation occurs
-		if (pin_rays) tr.counters_rgb.rays_per_batch = pin_rays;
+		// (and the clamp of the sample budget to last step's count, whose victims also depend on arrival order: testbed_nerf.cu:3891-3896,1354-1357)
+		if (pin_rays) { tr.counters_rgb.rays_per_batch = pin_rays; if (!time_only) tr.counters_rgb.measured_batch_size_before_compaction = 0; }
 		if (dump) dump_state(tag + "_in");
 		const uint32_t R = tr.counters_rgb.rays_per_batch;
 		cudaEventRecord(e0, tb.m_training_stream);

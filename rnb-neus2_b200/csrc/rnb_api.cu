@@ -28,6 +28,9 @@ size_t backward_simt_scratch_halfs(const ModelDev&);
 bool mma_supported(const ModelDev&);
 size_t mma_pack_u32(const ModelDev&);
 void launch_mma(int, cudaStream_t, const ModelDev&, const __half*, uint32_t*, uint32_t, const float4*, const uint32_t*, uint32_t, const float*, __half*, const __half*, uint32_t, uint32_t, const uint32_t*, float*, int);
+bool tc_supported(const ModelDev&);
+size_t tc_blob_bytes(const ModelDev&);
+void launch_tc(int, cudaStream_t, const ModelDev&, const __half*, uint8_t*, uint32_t, const float4*, const uint32_t*, uint32_t, __half*, float*, float*, int);
 // rnb_loss.cu
 void launch_ray_dirw(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const float*, float*);
 void launch_compact_count(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const __half*, const float*, const __half*, uint32_t, float, uint32_t*);
@@ -78,6 +81,7 @@ struct rnb_ctx {
 	uint32_t training_step = 0, rays_per_batch = 4096, n_rays_total = 0, measured_before = 0, measured = 0;
 	uint32_t step_R = 0, step_nrt = 0; bool in_step = false;
 	bool use_mma = false; uint32_t* wpack = nullptr; int n_sm = 148;
+	bool use_tc = false; uint8_t* wtc = nullptr;      // tcgen05 / TMEM kernels (rnb_network_tc.cu) for pass A and the SDF probes
 	// instrumentation: kernel launch counter and optional per-stage CUDA-event timing (bench.py roofline)
 	uint64_t launches = 0;
 	bool prof = false;
@@ -213,6 +217,9 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 		const char* e = getenv("RNB_NETWORK");        // "simt" selects the CUDA-core kernels (cross-check path)
 		c->use_mma = mma_supported(M) && !(e && std::string(e) == "simt");
 		CU(cudaMalloc(&c->wpack, mma_pack_u32(M) * 4)); CU(cudaMemset(c->wpack, 0, mma_pack_u32(M) * 4));
+		// RNB_NETWORK=mma keeps the mma.sync tile kernels everywhere; default: tcgen05 kernels where they exist
+		c->use_tc = c->use_mma && tc_supported(M) && !(e && std::string(e) == "mma");
+		CU(cudaMalloc(&c->wtc, tc_blob_bytes(M))); CU(cudaMemset(c->wtc, 0, tc_blob_bytes(M)));
 	}
 	c->rays_per_batch = cfg->rays_per_batch;
 	int rc = ensure_ray_capacity(c, c->rays_per_batch); if (rc) return rc;
@@ -226,7 +233,7 @@ int rnb_destroy(rnb_ctx* c) {
 	if (!c) return RNB_OK;
 	void* ptrs[] = {c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps, c->density_grid, c->density_tmp, c->bitfield, c->mean_acc, c->mean, c->gpos, c->gidx, c->gdens,
 	                c->views_dev, c->ray_n, c->ray_indices, c->numsteps, c->counters, c->n_fwd, c->cbase, c->n_emit, c->ray_geom, c->ts, c->ray_dirw, c->loss_out, c->stats,
-	                c->pos4, c->cpos4, c->outA, c->out16, c->dout16, c->bw_scratch, c->bw_front, c->wpack};
+	                c->pos4, c->cpos4, c->outA, c->out16, c->dout16, c->bw_scratch, c->bw_front, c->wpack, c->wtc};
 	for (void* p : ptrs) cudaFree(p);
 	for (void* p : c->owned) cudaFree(p);
 	cudaFreeHost(c->counters_host); cudaFreeHost(c->stats_host);
@@ -395,7 +402,10 @@ int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t em
 }
 
 static void net_density(rnb_ctx* c, cudaStream_t st, uint32_t vl, uint32_t n) {
-	if (c->use_mma) {
+	if (c->use_tc) {
+		launch_tc(0, st, c->M, c->params, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm);
+		launch_tc(2, st, c->M, c->params, c->wtc, vl, c->gpos, nullptr, n, nullptr, nullptr, c->gdens, c->n_sm);
+	} else if (c->use_mma) {
 		launch_mma(0, st, c->M, c->params, c->wpack, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
 		launch_mma(4, st, c->M, c->params, c->wpack, vl, c->gpos, nullptr, n, nullptr, (__half*)c->gdens, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
 	} else launch_forward_simt(st, c->M, c->params, vl, 2, c->gpos, nullptr, n, nullptr, nullptr, nullptr, nullptr, c->gdens);
@@ -426,9 +436,13 @@ int rnb_prep(rnb_ctx* c, void* stream) {
 }
 
 // network stage dispatch: tensor-core tile kernels (default) or the CUDA-core kernels
-static void net_pack(rnb_ctx* c, cudaStream_t st, const __half* P) { if (c->use_mma) launch_mma(0, st, c->M, P, c->wpack, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, c->n_sm); }
+static void net_pack(rnb_ctx* c, cudaStream_t st, const __half* P) {
+	if (c->use_mma) launch_mma(0, st, c->M, P, c->wpack, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
+	if (c->use_tc) launch_tc(0, st, c->M, P, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm);
+}
 static void net_pass_a(rnb_ctx* c, cudaStream_t st, uint32_t vl, const float4* pos, const uint32_t* n_ptr, uint32_t n_max) {
-	if (c->use_mma) launch_mma(1, st, c->M, c->params, c->wpack, vl, pos, n_ptr, n_max, nullptr, c->outA, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
+	if (c->use_tc) launch_tc(1, st, c->M, c->params, c->wtc, vl, pos, n_ptr, n_max, c->outA, nullptr, nullptr, c->n_sm);
+	else if (c->use_mma) launch_mma(1, st, c->M, c->params, c->wpack, vl, pos, n_ptr, n_max, nullptr, c->outA, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
 	else launch_forward_simt(st, c->M, c->params, vl, 0, pos, n_ptr, n_max, c->ray_dirw, c->outA, nullptr, nullptr, nullptr);
 }
 static void net_pass_b(rnb_ctx* c, cudaStream_t st, const __half* P, uint32_t vl, const float4* pos, const uint32_t* n_ptr, uint32_t n_max, const float* dirw) {

@@ -47,7 +47,7 @@ __device__ __forceinline__ void corner_entries(bool hashed, uint32_t hsz, uint32
 // Returns the two features packed as half2; dy = {d f0/dx, d f0/dy, d f0/dz, d f1/dx, d f1/dy, d f1/dz}.
 __device__ __forceinline__ __half2 encode_level_packed(const ModelDev& M, const __half* __restrict__ P, uint32_t l, float x, float y, float z, float* __restrict__ dy) {
 	const uint32_t off = M.offsets[l];
-	const __half2* grid = reinterpret_cast<const __half2*>(P + M.off_grid) + off;
+	const __half2* grid = reinterpret_cast<const __half2*>(P + M.off_grid);      // 32-bit entry index + one wide multiply-add per corner
 	const uint32_t hsz = M.offsets[l + 1] - off, res = M.res[l];
 	const float scale = M.scale[l];
 	const LevelGeom g = level_geom(scale, x, y, z);
@@ -55,8 +55,59 @@ __device__ __forceinline__ __half2 encode_level_packed(const ModelDev& M, const 
 	corner_entries((M.hashed_mask >> l) & 1u, hsz, res, g, e);
 	float2 v[8];
 	#pragma unroll
-	for (int c = 0; c < 8; ++c) v[c] = __half22float2(__ldg(&grid[e[c]]));
+	for (int c = 0; c < 8; ++c) v[c] = __half22float2(__ldg(grid + (e[c] + off)));
 	const float wx[2] = {1.f - g.fx, g.fx}, wy[2] = {1.f - g.fy, g.fy}, wz[2] = {1.f - g.fz, g.fz};
+	const float wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
+	__half2 r = __floats2half2_rn(0.f, 0.f);
+	#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		const float w = wxy[c & 3] * wz[c >> 2];
+		r = __hadd2(r, __floats2half2_rn(w * v[c].x, w * v[c].y));
+	}
+	if (dy) {
+		const float sx[2] = {scale * wx[0], scale * wx[1]}, sy[2] = {scale * wy[0], scale * wy[1]};
+		#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			float a0 = 0.f, a1 = 0.f;
+			#pragma unroll
+			for (int idx = 0; idx < 4; ++idx) {
+				int c; float w;
+				if (d == 0) { c = (idx & 1) * 2 + (idx >> 1) * 4; w = sy[idx & 1] * wz[idx >> 1]; }
+				else if (d == 1) { c = (idx & 1) * 1 + (idx >> 1) * 4; w = sx[idx & 1] * wz[idx >> 1]; }
+				else { c = (idx & 1) * 1 + (idx >> 1) * 2; w = sx[idx & 1] * wy[idx >> 1]; }
+				const int cr = c | (1 << d);
+				a0 += w * (v[cr].x - v[c].x);
+				a1 += w * (v[cr].y - v[c].y);
+			}
+			dy[d] = a0; dy[3 + d] = a1;
+		}
+	}
+	return r;
+}
+
+// ---- batched gather -----------------------------------------------------------------------------------------------------
+// Memory-level parallelism for the thread-per-sample kernels: the corner loads of LB levels (8 * LB independent 4-byte loads)
+// are all issued before the first one is consumed, so one sample pays the L2 round trip once per batch instead of once
+// per level.  Arithmetic identical to encode_level_packed().
+struct LevelLoads { uint32_t raw[8]; float fx, fy, fz; };
+
+__device__ __forceinline__ void level_issue(const ModelDev& M, const __half* __restrict__ P, uint32_t l, float x, float y, float z, LevelLoads& Q) {
+	const uint32_t off = M.offsets[l];
+	const uint32_t* grid = reinterpret_cast<const uint32_t*>(P + M.off_grid);
+	const uint32_t hsz = M.offsets[l + 1] - off, res = M.res[l];
+	const LevelGeom g = level_geom(M.scale[l], x, y, z);
+	uint32_t e[8];
+	corner_entries((M.hashed_mask >> l) & 1u, hsz, res, g, e);
+	#pragma unroll
+	for (int c = 0; c < 8; ++c) Q.raw[c] = __ldg(grid + (e[c] + off));
+	Q.fx = g.fx; Q.fy = g.fy; Q.fz = g.fz;
+}
+
+__device__ __forceinline__ __half2 level_finish(float scale, const LevelLoads& Q, float* __restrict__ dy) {
+	float2 v[8];
+	#pragma unroll
+	for (int c = 0; c < 8; ++c) v[c] = __half22float2(*reinterpret_cast<const __half2*>(&Q.raw[c]));
+	const float wx[2] = {1.f - Q.fx, Q.fx}, wy[2] = {1.f - Q.fy, Q.fy}, wz[2] = {1.f - Q.fz, Q.fz};
 	const float wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
 	__half2 r = __floats2half2_rn(0.f, 0.f);
 	#pragma unroll
@@ -91,7 +142,7 @@ __device__ __forceinline__ __half2 encode_level_packed(const ModelDev& M, const 
 __device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restrict__ G, uint32_t l, float x, float y, float z,
                                               float d10, float d11, float ge0, float ge1, float gnx, float gny, float gnz) {
 	const uint32_t off = M.offsets[l];
-	float* gg = G + M.off_grid + (size_t)off * 2;
+	float2* gg = reinterpret_cast<float2*>(G + M.off_grid);
 	const uint32_t hsz = M.offsets[l + 1] - off, res = M.res[l];
 	const float scale = M.scale[l];
 	const LevelGeom g = level_geom(scale, x, y, z);
@@ -113,7 +164,7 @@ __device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restri
 		const float w1 = wx[bx] * wy[by] * wz[bz];
 		const float w2 = (bx ? ax[by + 2 * bz] : -ax[by + 2 * bz]) + (by ? ay[bx + 2 * bz] : -ay[bx + 2 * bz]) + (bz ? az[bx + 2 * by] : -az[bx + 2 * by]);
 		const float v0 = d10 * w1 + ge0 * w2, v1 = d11 * w1 + ge1 * w2;
-		if (v0 != 0.f || v1 != 0.f) atomicAdd(reinterpret_cast<float2*>(gg + 2 * e[c]), make_float2(v0, v1));
+		if (v0 != 0.f || v1 != 0.f) atomicAdd(gg + (e[c] + off), make_float2(v0, v1));
 	}
 }
 

@@ -1,0 +1,304 @@
+// rnb_network_tc.cu — fused hash-encode + SDF MLP + analytic normal on the 5th-generation tensor cores (tcgen05 / TMEM).
+//
+// Design (one CTA = 128 threads = one 128-sample tile at a time, several CTAs resident per SM):
+//   * thread t owns sample t of the tile.  It gathers the sample's L hash levels (8 corner loads each, all independent),
+//     packs the 32-wide MLP input row in registers and stores it with four 16-byte shared-memory stores;
+//   * activations live in shared memory in ONE "panel" layout: a [128 x C] binary16 tile is C/8 panels of 128 x 16 bytes
+//     (row r of panel j at j*2048 + r*16).  That layout is simultaneously
+//        - the K-major, no-swizzle operand of a forward layer            (tcgen05.mma A: rows = samples, K = features),
+//        - the MN-major operand of a weight-gradient product             (K = samples; used by the backward kernel),
+//     and a warp's row stores are 512 contiguous bytes (conflict free);
+//   * weights are staged once per CTA in the same layout ([out x in], K-major B operand of the forward layer and — read
+//     through an MN-major descriptor — the B operand of the transposed layer of the analytic-normal chain);
+//   * one elected thread issues tcgen05.mma (M = 128, N = 64 / 32, K = 16 per instruction), accumulators are in TMEM,
+//     completion is signalled with tcgen05.commit on an mbarrier, and every thread reads back ITS OWN row of the
+//     accumulator (TMEM lane == sample) with tcgen05.ld for ReLU / rounding / the normal;
+//   * dy/dx of the encoding (84 floats per sample, needed after the transposed chain) waits in shared memory, never in HBM.
+//
+// Replaces, for the samples before compaction and for the occupancy probes, NerfNetwork::forward_impl
+// (reference include/neural-graphics-primitives/nerf_network.h:97-253): kernel_grid (+dy_dx), FullyFusedMLP forward,
+// the one-hot FullyFusedMLP backward, kernel_grid_backward_input and ~15 glue kernels — 19 launches and ~10 global
+// temporaries in the reference; here one launch, 16 B in and 8 B out per sample.
+//
+// Numerics are those of rnb_network_mma.cu / the oracle: binary16 inputs and weights, fp32 accumulation, binary16
+// rounding at every layer output, dy/dx and the normal in fp32.
+#include "rnb_encode.cuh"
+
+namespace rnb {
+
+namespace tc {
+
+constexpr int TILE = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+	uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+	d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+	d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+	d |= (uint64_t)1 << 46;
+	return d;
+}
+// instruction descriptor, kind::f16: D fp32, A/B binary16 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+	return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+	asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	uint32_t done = 0;
+	while (!done) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"((uint32_t)COLS) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free(uint32_t base) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"((uint32_t)COLS) : "memory"); }
+
+// this thread's accumulator row: 32 consecutive fp32 columns starting at taddr (lane field = 32 * warp already set)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+	uint32_t r[32];
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+	               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+	             : "r"(taddr) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+	#pragma unroll
+	for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+
+// byte offset of element (row, col) of a panelised [rows x cols] binary16 tile
+__host__ __device__ constexpr uint32_t panel_off(uint32_t rows, uint32_t row, uint32_t col) { return (col >> 3) * rows * 16u + row * 16u + (col & 7u) * 2u; }
+
+// ---- weight blob for the tcgen05 kernels (bytes) -------------------------------------------------------------------
+// W1 : sdf layer 0 [SW x 32] in the kernels' input column order u' = [enc(2L) | x-0.5 (3) | 0 ...]   (panelised, rows = SW)
+// W2R: sdf layer 1 row 0 as SW floats                                                                (the SDF output and the one-hot chain)
+template <int SW>
+struct Blob {
+	static constexpr uint32_t W1 = 0;
+	static constexpr uint32_t W2R = W1 + SW * 32 * 2;
+	static constexpr uint32_t SDF_END = W2R + SW * 4;
+};
+
+template <int SW>
+__global__ void __launch_bounds__(256) k_pack_weights_tc(ModelDev M, const __half* __restrict__ P, uint8_t* __restrict__ out) {
+	using B = Blob<SW>;
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+	const __half* W1 = P + M.sdf_layers[0].off; const int cols = (int)M.sdf_layers[0].cols, ne = (int)M.n_enc;
+	for (int i = tid; i < SW * 32; i += nt) {
+		const int n = i / 32, k = i % 32;
+		const int kc = k < ne ? 3 + k : (k < ne + 3 ? k - ne : -1);        // u' column -> reference column (nerf_network.h:149-155)
+		const __half v = (kc >= 0 && kc < cols) ? W1[(size_t)n * cols + kc] : __float2half_rn(0.f);
+		*reinterpret_cast<__half*>(out + B::W1 + panel_off(SW, n, k)) = v;
+	}
+	const __half* W2 = P + M.sdf_layers[1].off;
+	for (int i = tid; i < SW; i += nt) reinterpret_cast<float*>(out + B::W2R)[i] = __half2float(W2[i]);
+}
+
+// ---- gather of one sample's MLP input row ---------------------------------------------------------------------------
+// u[j] = binary16 pair of columns 2j, 2j+1 of u'.  dyS (optional): dy/dx of the encoding, [6 * level + q][128 samples].
+template <bool WITH_DY, int LB>
+__device__ __forceinline__ void gather_row(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint32_t (&u)[16], float* __restrict__ dyS, int tid) {
+	const uint32_t L = M.n_levels;
+	#pragma unroll
+	for (uint32_t j = 0; j < 16; ++j) u[j] = 0u;
+	const uint32_t n_live = min(L, valid_level + 1u);          // levels > valid_level are zero (progressive training, grid.h:193-210)
+	#pragma unroll
+	for (uint32_t b = 0; b < 16; b += LB) {
+		if (b < n_live) {
+			LevelLoads Q[LB];
+			#pragma unroll
+			for (uint32_t i = 0; i < LB; ++i) if (b + i < 14 && b + i < n_live) level_issue(M, P, b + i, x, y, z, Q[i]);
+			#pragma unroll
+			for (uint32_t i = 0; i < LB; ++i) {
+				if (b + i < 14 && b + i < n_live) {
+					float dy[6];
+					const __half2 e = level_finish(M.scale[b + i], Q[i], WITH_DY ? dy : nullptr);
+					u[b + i] = *reinterpret_cast<const uint32_t*>(&e);
+					if (WITH_DY) {
+						#pragma unroll
+						for (int q = 0; q < 6; ++q) dyS[((b + i) * 6 + q) * TILE + tid] = dy[q];
+					}
+				}
+			}
+		}
+	}
+	const __half2 exy = __halves2half2(__hsub(__float2half_rn(x), __float2half_rn(0.5f)), __hsub(__float2half_rn(y), __float2half_rn(0.5f)));   // fill_positions_view_with_fixed_offset
+	const __half2 ez = __halves2half2(__hsub(__float2half_rn(z), __float2half_rn(0.5f)), __float2half_rn(0.f));
+	#pragma unroll
+	for (uint32_t j = 1; j < 15; ++j) {
+		if (j == L) { u[j] = *reinterpret_cast<const uint32_t*>(&exy); u[j + 1] = *reinterpret_cast<const uint32_t*>(&ez); }
+	}
+}
+
+// ---- pass A / SDF probe -----------------------------------------------------------------------------------------------
+// MODE 0: pass A  -> outA[row] = (sdf + bias, normal) as 4 x binary16
+// MODE 1: probe   -> sdf_out[row] (fp32, optional), dens_out[row] (fp32, optional): NerfNetwork::sdf / ::density, nerf_network.h:454-537
+template <int SW, int MODE>
+__global__ void __launch_bounds__(TILE, MODE == 0 ? 3 : 4) k_sdf_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
+                                                                   const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
+                                                                   __half* __restrict__ outA, float* __restrict__ sdf_out, float* __restrict__ dens_out) {
+	using B = Blob<SW>;
+	constexpr bool NORMAL = MODE == 0;
+	constexpr uint32_t XB = (B::SDF_END + 127u) & ~127u;                 // X tile  [128 x 32]
+	constexpr uint32_t GB = XB + TILE * 64;                             // G tile  [128 x SW]   (pass A only)
+	constexpr uint32_t DYB = GB + (NORMAL ? TILE * SW * 2 : 0);         // dy/dx   [84][128] fp32 (pass A only)
+	constexpr int TMEM_COLS = NORMAL ? 128 : 64;                        // D1: SW columns at 0, D2: 32 columns at 64
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ uint32_t tmem_slot;
+	__shared__ __align__(8) uint64_t bar;
+	const int tid = threadIdx.x, warp = tid >> 5;
+	for (uint32_t i = tid; i < B::SDF_END / 16; i += TILE) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
+	if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_slot);
+	if (tid == 0) mbar_init(&bar, 1);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = tmem_slot, trow = tmem + ((uint32_t)(warp * 32) << 16);
+	const float* w2r = reinterpret_cast<const float*>(smem + B::W2R);
+	float* dyS = reinterpret_cast<float*>(smem + DYB);
+	const uint32_t sW1 = smem_u32(smem + B::W1), sX = smem_u32(smem + XB), sG = smem_u32(smem + GB);
+	constexpr uint32_t ID1 = make_idesc(128, SW, 0, 0), ID2 = make_idesc(128, 32, 0, 1);
+	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
+	const uint32_t n_tiles = (n + TILE - 1) / TILE;
+	uint32_t phase = 0;
+	float dens_scale = 0.f; __half sc = __float2half_rn(0.f);
+	if (MODE == 1) { const __half var = __ldg(P + M.off_var); sc = __float2half_rn(__expf(__half2float(__hmul(var, __float2half_rn(10.0f))))); dens_scale = 1.f; }
+	(void)dens_scale;
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const uint32_t row = tile * TILE + tid;
+		const float4 p = pos4[min(row, n - 1)];
+		uint32_t u[16];
+		gather_row<NORMAL, NORMAL ? 5 : 7>(M, P, valid_level, p.x, p.y, p.z, u, dyS, tid);
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + XB + j * (TILE * 16) + tid * 16) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+		fence_async_smem();
+		tc_fence_before();
+		__syncthreads();
+		if (tid == 0) {
+			tc_fence_after();
+			#pragma unroll
+			for (int k = 0; k < 2; ++k)      // K = 32: two K-major steps of 2 panels each
+				umma(tmem, make_desc(sX + k * 2 * (TILE * 16), TILE * 16, 128), make_desc(sW1 + k * 2 * (SW * 16), SW * 16, 128), ID1, k);
+			umma_commit(&bar);
+		}
+		mbar_wait(&bar, phase); phase ^= 1;
+		tc_fence_after();
+		// hidden activation of this sample: ReLU, binary16 rounding; SDF output 0; one-hot chain input tm = relu'(h) .* W2[0,:]
+		float sdf = 0.f;
+		#pragma unroll
+		for (int c = 0; c < SW / 32; ++c) {
+			float h[32];
+			tmem_ld32(trow + c * 32, h);
+			uint32_t g[16];
+			#pragma unroll
+			for (int k = 0; k < 32; k += 2) {
+				const float h0 = hq(fmaxf(h[k], 0.f)), h1 = hq(fmaxf(h[k + 1], 0.f));
+				const float w0 = w2r[c * 32 + k], w1 = w2r[c * 32 + k + 1];
+				sdf = fmaf(h0, w0, sdf); sdf = fmaf(h1, w1, sdf);
+				if (NORMAL) g[k >> 1] = pack_h2(h0 > 0.f ? w0 : 0.f, h1 > 0.f ? w1 : 0.f);
+			}
+			if (NORMAL) {
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + GB + (c * 4 + j) * (TILE * 16) + tid * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+			}
+		}
+		const __half sdfb = __hadd(__float2half_rn(sdf), __float2half_rn(M.sdf_bias));
+		if (NORMAL) {
+			fence_async_smem();
+			tc_fence_before();
+			__syncthreads();
+			if (tid == 0) {
+				tc_fence_after();
+				#pragma unroll
+				for (int k = 0; k < SW / 16; ++k)      // d sdf / d u' = tm * W1 : A K-major (2 panels per step), B = W1 read MN-major (16 hidden rows per step)
+					umma(tmem + 64, make_desc(sG + k * 2 * (TILE * 16), TILE * 16, 128), make_desc(sW1 + k * 256, 128, SW * 16), ID2, k);
+				umma_commit(&bar);
+			}
+			mbar_wait(&bar, phase); phase ^= 1;
+			tc_fence_after();
+			float gin[32];
+			tmem_ld32(trow + 64, gin);
+			float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+			const uint32_t L = M.n_levels;
+			#pragma unroll
+			for (uint32_t l = 0; l < 16; ++l) {
+				const float g0 = hq(gin[2 * l]), g1 = hq(gin[2 * l + 1]);
+				if (l < L) {
+					if (l <= valid_level) {
+						const float* d = dyS + (l * 6) * TILE + tid;
+						n0 = fmaf(g0, d[0], n0); n1 = fmaf(g0, d[TILE], n1); n2 = fmaf(g0, d[2 * TILE], n2);
+						n0 = fmaf(g1, d[3 * TILE], n0); n1 = fmaf(g1, d[4 * TILE], n1); n2 = fmaf(g1, d[5 * TILE], n2);
+					}
+				} else if (l == L) { n0 += g0; n1 += g1; }
+				else if (l == L + 1) { n2 += g0; }
+			}
+			if (row < n) {
+				uint2 v; v.x = pack_h2(__half2float(sdfb), n0); v.y = pack_h2(n1, n2);
+				reinterpret_cast<uint2*>(outA)[row] = v;
+			}
+		} else if (row < n) {
+			if (sdf_out) sdf_out[row] = __half2float(sdfb);
+			if (dens_out) {   // sdf_to_density_variance_buffer, common_operation.cuh:310-328 (binary16 arithmetic)
+				const __half sg = __float2half_rn(1.0f / (1.0f + expf(-__half2float(__hmul(sdfb, sc)))));
+				dens_out[row] = __half2float(__hmul(__hmul(sc, sg), __hsub(__float2half_rn(1.0f), sg)));
+			}
+		}
+		// the next tile's MMA overwrites D1 / the X and G tiles: every thread must be past its TMEM loads and smem reads first.
+		// The __syncthreads before the next MMA issue provides that (tcgen05.wait::ld has completed in tmem_ld32).
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) tmem_free<TMEM_COLS>(tmem);
+}
+
+} // namespace tc
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+bool tc_supported(const ModelDev& M) { return M.sdf_in == 32 && M.n_sdf_layers == 2 && (M.sdf_width == 32 || M.sdf_width == 64); }
+size_t tc_blob_bytes(const ModelDev&) { return 65536; }
+
+template <int SW>
+static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __half* P, uint8_t* wtc, uint32_t vl, const float4* pos4, const uint32_t* n_ptr, uint32_t n_max,
+                         __half* outA, float* sdf_out, float* dens_out, int n_sm) {
+	using namespace tc;
+	using B = Blob<SW>;
+	if (what == 0) { k_pack_weights_tc<SW><<<4, 256, 0, st>>>(M, P, wtc); return; }
+	if (!n_max) return;
+	constexpr uint32_t XB = (B::SDF_END + 127u) & ~127u;
+	const uint32_t tiles = (n_max + TILE - 1) / TILE;
+	if (what == 1) {
+		const size_t smem = XB + TILE * 64 + TILE * SW * 2 + 84 * TILE * 4;
+		static bool attr = false;
+		if (!attr) { cudaFuncSetAttribute(k_sdf_tc<SW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+		k_sdf_tc<SW, 0><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 3), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr);
+	} else {
+		const size_t smem = XB + TILE * 64;
+		k_sdf_tc<SW, 1><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, nullptr, sdf_out, dens_out);
+	}
+}
+
+// what: 0 pack weights, 1 pass A (outA), 2 SDF probe (sdf_out / dens_out)
+void launch_tc(int what, cudaStream_t st, const ModelDev& M, const __half* P, uint8_t* wtc, uint32_t vl, const float4* pos4, const uint32_t* n_ptr, uint32_t n_max,
+               __half* outA, float* sdf_out, float* dens_out, int n_sm) {
+	if (M.sdf_width == 64) launch_tc_sw<64>(what, st, M, P, wtc, vl, pos4, n_ptr, n_max, outA, sdf_out, dens_out, n_sm);
+	else launch_tc_sw<32>(what, st, M, P, wtc, vl, pos4, n_ptr, n_max, outA, sdf_out, dens_out, n_sm);
+}
+
+} // namespace rnb

@@ -168,7 +168,7 @@ class Oracle:
         g = np.zeros(128 ** 3, np.float32); self.L.orc_get_density_grid(self.h, _p(g, C.c_float)); return g
 
     def set_density_grid(self, g, ema_step):
-        g = np.ascontiguousarray(g, np.float32); self.L.orc_set_density_grid(self.h, _p(g, C.c_float), ema_step)
+        g = np.ascontiguousarray(g, np.float32); assert g.size == 128 ** 3; self.L.orc_set_density_grid(self.h, _p(g, C.c_float), ema_step)
 
     def generate_samples(self, n_rays, n_rays_total, max_samples):
         ri = np.zeros(n_rays, np.uint32); rays = np.zeros((n_rays, 6), np.float32); ns = np.zeros((n_rays, 2), np.uint32)

@@ -53,7 +53,8 @@ def sorted_cmp(a, b):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="small")
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=34)
+    ap.add_argument("--dump-steps", default="0,1,2,3,32,33")
     ap.add_argument("--rays", type=int, default=256)
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--res", type=int, default=128)
@@ -75,7 +76,8 @@ def main():
         net_cfg = ref_scene.small_network_config(os.path.join(work, "small.json"))
     else:
         net_cfg = os.path.join(ROOT, "oracle", "_ref", "configs", "nerf", "base.json")
-    cmd = [HARNESS, scene_dir + "/", net_cfg, dump, str(args.steps), "--pin-rays", str(args.rays)]
+    dsteps = sorted(int(x) for x in args.dump_steps.split(",") if int(x) < args.steps)
+    cmd = [HARNESS, scene_dir + "/", net_cfg, dump, str(args.steps), "--pin-rays", str(args.rays), "--dump-steps", ",".join(map(str, dsteps))]
     if not args.albedo:
         cmd.append("--no-albedo")
     t0 = time.time()
@@ -83,6 +85,10 @@ def main():
     open(os.path.join(args.out, "ref_harness.log"), "w").write(log.stdout)
     if log.returncode != 0:
         print(log.stdout[-3000:]); raise SystemExit("ref_harness failed rc=%d" % log.returncode)
+    # second, identical run of the reference: its own run-to-run spread (atomicAdd order, fp16 atomics) is the noise floor
+    dump2 = dump + "2"; os.makedirs(dump2, exist_ok=True)
+    cmd2 = list(cmd); cmd2[3] = dump2
+    subprocess.run(cmd2, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     meta = ref_scene.read_meta(os.path.join(dump, "meta.txt"))
     views = ref_scene.load_dataset_dump(os.path.join(dump, "dataset.bin"))
     summary = {"config": args.config, "albedo": bool(args.albedo), "rays_per_step": args.rays, "ref_meta": meta, "ref_seconds": round(time.time() - t0, 1), "steps": []}
@@ -115,11 +121,11 @@ def main():
         summary["init_params"]["cuda_vs_ref_max_abs"] = float(np.abs(t.get_params() - p0).max())
 
     golden = {}
-    for k in range(args.steps):
+    for k in dsteps:
         tag = "step%d" % k
         pin = rd(tag + "_in_params_fp32.bin", np.float32)
         st = rd(tag + "_in_state.bin", np.uint64)
-        dg = rd(tag + "_in_density_grid.bin", np.float32)[:128 ** 3]
+        dg = np.zeros(128 ** 3, np.float32); d_in = rd(tag + "_in_density_grid.bin", np.float32); dg[:min(d_in.size, dg.size)] = d_in[:dg.size]   # empty before the first refresh
         bf = np.zeros(128 ** 3, np.uint8); b_in = rd(tag + "_in_bitfield.bin", np.uint8); bf[:min(b_in.size, bf.size)] = b_in[:bf.size]
         cnt = rd(tag + "_out_counters.bin", np.uint64)
         R, n_a, n_b, rays_next = int(cnt[0]), int(cnt[1]), int(cnt[2]), int(cnt[3])
@@ -128,12 +134,29 @@ def main():
         ref_p = rd(tag + "_out_params_fp32.bin", np.float32)
         ref_ema = h2f(rd(tag + "_out_params_ema_fp16.bin", np.uint16))
         row = {"step": k, "training_step": int(st[4]), "rays": R, "ref_samples": n_a, "ref_compacted": n_b, "ref_rays_next": rays_next}
+        try:
+            g2 = h2f(np.fromfile(os.path.join(dump2, tag + "_out_grads_fp16.bin"), np.uint16)); p2 = np.fromfile(os.path.join(dump2, tag + "_in_params_fp32.bin"), np.float32)
+            row["ref_run_to_run"] = {"grads": cmp_groups(o, g2, ref_g), "in_params": cmp_groups(o, p2, pin),
+                                     "loss_sorted": sorted_cmp(np.fromfile(os.path.join(dump2, tag + "_out_loss.bin"), np.float32), ref_loss)}
+        except Exception as e:
+            row["ref_run_to_run"] = {"error": str(e)}
+        if k == 0:
+            # Adam / EMA in isolation: the reference's own fp16 gradients through the oracle's optimizer from the same start (zero moments)
+            oa = Oracle(threads=1, **cfgd); oa.set_params(pin); oa.set_grads(ref_g); oa.optimizer_step()
+            pa, _, ea = oa.get_params()
+            row["adam_on_ref_grads"] = {"params_max_abs": float(np.abs(pa - ref_p).max()), "params_update_rel": cmp_groups(o, pa - pin, ref_p - pin), "ema_max_abs": float(np.abs(ea - ref_ema).max())}
+            if t is not None:
+                pkg2 = rnb_loader.load_package(); ta = pkg2.Testbed(product_config(pkg2, cfgd, rays_per_batch=args.rays, pin_rays_per_batch=1))
+                ta.set_params(pin); ta.stage_optimizer(ref_g); pc_ = ta.get_params()
+                row["adam_on_ref_grads"]["cuda_params_max_abs"] = float(np.abs(pc_ - ref_p).max())
+                row["adam_on_ref_grads"]["cuda_ema_max_abs"] = float(np.abs(h2f(ta.export_params_fp16(use_ema=True)) - ref_ema).max())
+                ta.close()
         impls = [("oracle", o)] + ([("cuda", t)] if t is not None else [])
         for name, impl in impls:
             impl.set_params(pin)
             if name == "oracle":
                 impl.set_density_grid(dg, int(st[8])); impl.set_bitfield(bf)
-                impl.set_train_state(training_step=int(st[4]), rays_per_batch=R, n_rays_total=int(st[6]), measured_before=int(st[7]), pin_rays=1)
+                impl.set_train_state(training_step=int(st[4]), rays_per_batch=R, n_rays_total=int(st[6]), measured_before=0, pin_rays=1)
                 impl.set_rng(int(st[0]), int(st[1]), int(st[2]), int(st[3]))
                 t1 = time.time(); s = impl.train_step(); dt = time.time() - t1
                 g = impl.get_grads(); ri, lo, ek, ml = impl.last_losses()
@@ -142,7 +165,7 @@ def main():
                 dens_after = impl.get_density_grid(); bits_after = impl.get_bitfield()
             else:
                 impl.import_density_grid(dg, int(st[8])); impl.set_bitfield(bf)
-                impl.set_train_state(int(st[4]), R, int(st[6]), int(st[7]))
+                impl.set_train_state(int(st[4]), R, int(st[6]), 0)
                 impl.set_rng([int(st[0]), int(st[1]), int(st[2]), int(st[3])])
                 ts = int(st[4]); skip = min(max(ts // 16, 1), 16)
                 if ts % skip == 0:
@@ -164,8 +187,8 @@ def main():
             res["params_after_vs_ref"] = cmp_groups(o, p_after - pin, ref_p - pin)       # relative error of the UPDATE
             res["params_after_max_abs"] = float(np.abs(p_after - ref_p).max())
             res["ema_after_max_abs"] = float(np.abs(np.asarray(ema_after) - ref_ema).max())
-            if k + 1 < args.steps:
-                dg_next = rd("step%d_in_density_grid.bin" % (k + 1), np.float32)[:128 ** 3]
+            if (k + 1) in dsteps:
+                dg_next = np.zeros(128 ** 3, np.float32); d_n = rd("step%d_in_density_grid.bin" % (k + 1), np.float32); dg_next[:min(d_n.size, dg_next.size)] = d_n[:dg_next.size]
                 b_next = rd("step%d_in_bitfield.bin" % (k + 1), np.uint8)
                 res["density_grid_rel"] = rel_err(np.maximum(dens_after, 0), np.maximum(dg_next, 0))
                 res["density_sign_mismatch"] = int(np.count_nonzero((dens_after < 0) != (dg_next < 0)))
@@ -173,10 +196,18 @@ def main():
                 res["bitfield_mip0_bits_differ"] = int(np.unpackbits(np.bitwise_xor(np.asarray(bits_after)[:nb], b_next[:nb])).sum())
                 res["bitfield_mip0_bits_set_ref"] = int(np.unpackbits(b_next[:nb]).sum())
             row[name] = res
-            if name == "oracle" and args.config == "small" and k in (0, args.steps - 1):
-                golden[tag] = dict(params_in=pin.astype(np.float16), state=st, density_grid=dg.astype(np.float16), bitfield=bf[:128 ** 3 // 8],
-                                   ref_counters=cnt, ref_loss_sorted=np.sort(ref_loss[:kk]), ref_ek_sorted=np.sort(ref_ek[:kk]), ref_mask_sorted=np.sort(ref_mask[:kk]),
-                                   ref_grads_fp16=rd(tag + "_out_grads_fp16.bin", np.uint16), ref_params_out=ref_p)
+            if name == "oracle" and args.config == "small" and k in (0, dsteps[-1]):
+                nm = o.off_grid
+                gd = dict(state=st, ref_counters=cnt, ref_loss_sorted=np.sort(ref_loss[:kk]), ref_ek_sorted=np.sort(ref_ek[:kk]), ref_mask_sorted=np.sort(ref_mask[:kk]),
+                          ref_grads_fp16=rd(tag + "_out_grads_fp16.bin", np.uint16), ref_params_out_mlp=ref_p[:nm].copy(), ref_params_out_var=ref_p[o.off_var:].copy(),
+                          ref_ema_out_mlp_fp16=rd(tag + "_out_params_ema_fp16.bin", np.uint16)[:nm].copy())
+                if k == 0:
+                    rs = np.random.RandomState(7); idx = np.sort(rs.choice(np.arange(o.off_grid, o.off_var), 4096, replace=False))
+                    gd.update(params_in_mlp=pin[:nm].copy(), params_in_grid_idx=idx.astype(np.uint32), params_in_grid_val=pin[idx].copy(),
+                              params_in_grid_sum=np.array([pin[o.off_grid:o.off_var].astype(np.float64).sum(), (pin[o.off_grid:o.off_var].astype(np.float64) ** 2).sum()]))
+                else:
+                    gd.update(params_in_fp16=pin.astype(np.float16), bitfield=bf.copy())
+                golden[tag] = gd
         print(json.dumps(row)); sys.stdout.flush()
         summary["steps"].append(row)
 
