@@ -178,6 +178,7 @@ int rnb_stat_buffer(rnb_ctx* ctx, float** stats_dev, uint64_t* n);
  * compute_loss_kernel_train_nerf (src/testbed_nerf.cu:1833-1841) */
 int rnb_get_grads_fp32(rnb_ctx* ctx, float* host, size_t n);
 int rnb_get_ray_losses(rnb_ctx* ctx, uint32_t cap, uint32_t* ray_idx_host, float* loss3_host, uint32_t* n_out);
+int rnb_get_ray_counts(rnb_ctx* ctx, uint32_t cap, uint32_t* marched_host, uint32_t* kept_host, uint32_t* n_out);
 
 /* instrumentation for bench.py: per-stage CUDA-event timing (events recorded on the caller's stream around each stage of
  * the step; resolved at the end of rnb_train_step_end) and a count of kernels launched by this ctx. */

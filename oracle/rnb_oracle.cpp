@@ -43,6 +43,10 @@ struct Oracle {
 	// scratch kept for inspection
 	std::vector<uint32_t> ray_indices, numsteps; std::vector<float> rays, coords;
 	std::vector<float> last_loss, last_ek, last_mask;   // per kept ray, in ray_indices order
+	// data-parallel restatement: rank r of `world` marches rays i == r (mod world); sums[] are all-reduced with the gradients
+	uint32_t world = 1, rank = 0; bool in_step = false; uint32_t step_R = 0;
+	double sums[4] = {0, 0, 0, 0};   // loss, ek, mask, compacted samples
+	uint32_t cnt_kept = 0, cnt_samples = 0, cnt_total = 0, cnt_trained = 0;
 };
 
 static void sync_half(Oracle* o) { for (size_t i = 0; i < o->m.n_params; ++i) o->pv[i] = hq(o->master[i]); }
@@ -145,6 +149,7 @@ void orc_set_flags(Oracle* o, const Flags* f) { o->flags = *f; }
 void orc_set_train_state(Oracle* o, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before, int pin_rays, uint32_t target_batch) {
 	o->training_step = training_step; o->rays_per_batch = rays_per_batch; o->n_rays_total = n_rays_total; o->measured_before = measured_before; o->pin_rays = pin_rays; o->target_batch = target_batch;
 }
+void orc_set_world(Oracle* o, uint32_t world, uint32_t rank) { o->world = world ? world : 1; o->rank = rank; }
 void orc_set_rng(Oracle* o, uint64_t state, uint64_t inc, uint64_t dstate, uint64_t dinc) { o->rng.state = state; o->rng.inc = inc; o->density_rng.state = dstate; o->density_rng.inc = dinc; }
 void orc_get_rng(Oracle* o, uint64_t* out) { out[0] = o->rng.state; out[1] = o->rng.inc; out[2] = o->density_rng.state; out[3] = o->density_rng.inc; }
 void orc_get_bitfield(Oracle* o, uint8_t* out) { std::memcpy(out, o->bitfield.data(), o->bitfield.size()); }
@@ -161,7 +166,10 @@ void orc_generate_samples(Oracle* o, uint32_t n_rays, uint32_t n_rays_total, uin
                           uint32_t* ray_indices, float* rays /*6 per ray: o, d_unnormalised*/, uint32_t* numsteps /*2 per ray*/, float* coords /*7 per sample*/, uint32_t* counters) {
 	std::vector<RayGen> rg(n_rays);
 	parallel_for(o->threads, n_rays, [&](int, size_t b, size_t e) {
-		for (size_t i = b; i < e; ++i) ray_setup((uint32_t)i, n_rays, n_rays_total, o->rng, o->views.data(), (uint32_t)o->views.size(), o->bitfield.data(), rg[i]);
+		for (size_t i = b; i < e; ++i) {
+			if (i % o->world != o->rank) { rg[i].valid = false; continue; }      // ray shard of this rank
+			ray_setup((uint32_t)i, n_rays, n_rays_total, o->rng, o->views.data(), (uint32_t)o->views.size(), o->bitfield.data(), rg[i]);
+		}
 	});
 	uint32_t n_kept = 0, counter = 0;
 	std::vector<uint32_t> slot(n_rays, 0xFFFFFFFFu);
@@ -268,7 +276,12 @@ float orc_rollover_weight(uint32_t s, uint32_t n_in, uint32_t n_batch) {
 }
 
 // Stage: network forward + backward (first and second order) on n compacted samples; accumulates into o->grads (overwrites).
+static void network_backward_impl(Oracle* o, const float* coords, const float* dout, uint64_t n, uint32_t n_in_for_rollover, uint32_t n_roll, uint32_t n_batch, uint32_t valid_level);
 void orc_network_backward(Oracle* o, const float* coords, const float* dout, uint64_t n, uint32_t n_in_for_rollover, uint32_t n_batch, uint32_t valid_level) {
+	network_backward_impl(o, coords, dout, n, n_in_for_rollover, n_batch, n_batch, valid_level);
+}
+// n_roll: size the compacted batch is padded to by roll-over (per rank: target / world); n_batch: global Eikonal divisor
+static void network_backward_impl(Oracle* o, const float* coords, const float* dout, uint64_t n, uint32_t n_in_for_rollover, uint32_t n_roll, uint32_t n_batch, uint32_t valid_level) {
 	const size_t n_mlp = o->m.off_grid;
 	std::fill(o->grads.begin(), o->grads.end(), 0.f);
 	const int T = o->threads;
@@ -281,7 +294,7 @@ void orc_network_backward(Oracle* o, const float* coords, const float* dout, uin
 		float gvar = 0.f;
 		for (size_t i = b; i < e; ++i) {
 			net.forward(coords + i * 7, c, true);
-			float w = orc_rollover_weight((uint32_t)i, n_in_for_rollover, n_batch);
+			float w = orc_rollover_weight((uint32_t)i, n_in_for_rollover, n_roll);
 			net.backward(c, dout + i * 16, w, n_batch, Gm, G, &gvar, T > 1);
 		}
 		atomic_add_f32(&G[o->m.off_var], gvar);
@@ -393,11 +406,13 @@ int orc_prep_if_due(Oracle* o) {
 }
 
 // One full training step: Testbed::train (prep cadence) + train_nerf + optimizer + controller.
-void orc_train_step(Oracle* o, OrcStats* st) {
+// [begin: everything up to and including backward] -> (data parallel: all-reduce o->grads and o->sums) -> [end: optimizer + controller]
+void orc_train_step_begin(Oracle* o) {
 	orc_prep_if_due(o);
 	const uint32_t vl = valid_level_for_step(o->m, (int)o->training_step);
 	const uint32_t R = o->rays_per_batch;
 	const uint32_t max_samples = o->target_batch * 16;
+	const uint32_t local_target = o->target_batch / o->world;
 	uint32_t max_inference;
 	if (o->measured_before == 0) { o->measured_before = max_inference = max_samples; }
 	else max_inference = next_multiple(std::min(o->measured_before, max_samples), 128u);
@@ -411,7 +426,7 @@ void orc_train_step(Oracle* o, OrcStats* st) {
 	std::vector<float> out_a((size_t)n_emitted_a * 16);
 	orc_network_forward(o, o->coords.data(), n_emitted_a, vl, 0, o->flags.no_albedo ? 0 : 1, out_a.data(), nullptr);
 	std::vector<uint32_t> n_fwd(K), cbase(K), n_emit(K);
-	uint32_t total = orc_compact(o, out_a.data(), o->numsteps.data(), K, o->target_batch, n_fwd.data(), cbase.data(), n_emit.data());
+	uint32_t total = orc_compact(o, out_a.data(), o->numsteps.data(), K, local_target, n_fwd.data(), cbase.data(), n_emit.data());
 	// gather compacted coords / outputs
 	std::vector<float> cc((size_t)total * 7), oc((size_t)total * 16), dout((size_t)total * 16, 0.f);
 	for (uint32_t k = 0; k < K; ++k) {
@@ -421,21 +436,33 @@ void orc_train_step(Oracle* o, OrcStats* st) {
 	std::vector<float> loss(K), ek(K), ml(K);
 	orc_loss(o, oc.data(), o->ray_indices.data(), n_fwd.data(), cbase.data(), n_emit.data(), K, R, nrt, o->training_step, dout.data(), loss.data(), ek.data(), ml.data());
 	o->last_loss = loss; o->last_ek = ek; o->last_mask = ml; o->ray_indices.resize(K);
-	const uint32_t n_in = std::min(total, o->target_batch);
-	orc_network_backward(o, cc.data(), dout.data(), n_in, n_in, o->target_batch, vl);
+	const uint32_t n_in = std::min(total, local_target);
+	network_backward_impl(o, cc.data(), dout.data(), n_in, n_in, local_target, o->target_batch, vl);
 	o->rng.advance();
+	double sl = 0, se = 0, sm = 0; for (uint32_t k = 0; k < K; ++k) { sl += loss[k]; se += ek[k]; sm += ml[k]; }
+	o->sums[0] = sl; o->sums[1] = se; o->sums[2] = sm; o->sums[3] = (double)total;
+	o->cnt_kept = K; o->cnt_samples = counters[1]; o->cnt_total = total; o->cnt_trained = n_in; o->step_R = R;
+	o->in_step = true;
+}
+
+void orc_train_step_end(Oracle* o, OrcStats* st) {
 	orc_optimizer_step(o);
 	++o->training_step;
-	o->measured_before = counters[1]; o->measured = total;
-	double sl = 0, se = 0, sm = 0; for (uint32_t k = 0; k < K; ++k) { sl += loss[k]; se += ek[k]; sm += ml[k]; }
-	const float f = (float)total / (float)o->target_batch;
-	if (st) { st->loss = (float)sl * f; st->ek_loss = (float)se * f; st->mask_loss = (float)sm * f; st->n_rays_kept = K; st->n_samples = counters[1]; st->n_compacted = total; st->n_emitted = n_in; }
+	o->in_step = false;
+	const uint32_t total = o->cnt_total, R = o->step_R;
+	o->measured_before = o->cnt_samples; o->measured = total;
+	const float f = (float)o->sums[3] / (float)o->target_batch;     // sums[3] is the global compacted count after the all-reduce
+	if (st) { st->loss = (float)o->sums[0] * f; st->ek_loss = (float)o->sums[1] * f; st->mask_loss = (float)o->sums[2] * f; st->n_rays_kept = o->cnt_kept; st->n_samples = o->cnt_samples; st->n_compacted = total; st->n_emitted = o->cnt_trained; }
 	if (!o->pin_rays && total > 0) {
 		uint32_t r = (uint32_t)((float)R * (float)o->target_batch / (float)total);
 		o->rays_per_batch = std::min(next_multiple(r, 128u), 1u << 18);
 	}
 	if (st) st->rays_per_batch_next = o->rays_per_batch;
 }
+
+void orc_train_step(Oracle* o, OrcStats* st) { orc_train_step_begin(o); orc_train_step_end(o, st); }
+void orc_get_sums(Oracle* o, double* out) { for (int i = 0; i < 4; ++i) out[i] = o->sums[i]; }
+void orc_set_sums(Oracle* o, const double* in) { for (int i = 0; i < 4; ++i) o->sums[i] = in[i]; }
 
 // per-ray loss terms of the last orc_train_step (compute_loss_kernel's loss_output / ek_loss_output / mask_loss_output)
 uint32_t orc_get_last_losses(Oracle* o, uint32_t cap, uint32_t* ray_idx, float* loss, float* ek, float* mask) {

@@ -53,7 +53,7 @@ EXPORTED_SYMBOLS = [
     "rnb_last_error", "rnb_abi_version", "rnb_create", "rnb_destroy", "rnb_default_config", "rnb_default_flags", "rnb_param_layout", "rnb_init_params",
     "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
     "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
-    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf",
+    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
 ]
 
@@ -263,6 +263,11 @@ class Testbed:
         ri = np.zeros(cap, np.uint32); l3 = np.zeros((cap, 3), np.float32); n = C.c_uint32(0)
         self._chk(self.L.rnb_get_ray_losses(self.h, C.c_uint32(cap), _p(ri, C.c_uint32), _p(l3, C.c_float), C.byref(n)))
         return ri[:n.value], l3[:n.value]
+
+    def ray_counts(self, cap=1 << 18):
+        a = np.zeros(cap, np.uint32); b = np.zeros(cap, np.uint32); n = C.c_uint32(0)
+        self._chk(self.L.rnb_get_ray_counts(self.h, C.c_uint32(cap), _p(a, C.c_uint32), _p(b, C.c_uint32), C.byref(n)))
+        return a[:n.value], b[:n.value]
 
     def stat_buffer(self):
         p = C.POINTER(C.c_float)(); n = C.c_uint64()

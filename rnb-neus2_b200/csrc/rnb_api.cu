@@ -591,6 +591,18 @@ int rnb_get_ray_losses(rnb_ctx* c, uint32_t cap, uint32_t* ray_idx, float* loss3
 	*n_out = K;
 	return RNB_OK;
 }
+// per kept ray of the last step: samples marched and samples kept by the transmittance cut (profiling / tests)
+int rnb_get_ray_counts(rnb_ctx* c, uint32_t cap, uint32_t* marched, uint32_t* kept, uint32_t* n_out) {
+	if (!c || !marched || !kept || !n_out) return fail(RNB_ERR_INVALID, "null argument");
+	uint32_t K = 0; CU(cudaMemcpy(&K, c->counters, 4, cudaMemcpyDeviceToHost));
+	K = std::min(K, std::min(cap, c->cap_rays));
+	std::vector<uint32_t> ns((size_t)K * 2);
+	CU(cudaMemcpy(ns.data(), c->numsteps, (size_t)K * 8, cudaMemcpyDeviceToHost));
+	for (uint32_t k = 0; k < K; ++k) marched[k] = ns[2 * k];
+	CU(cudaMemcpy(kept, c->n_fwd, (size_t)K * 4, cudaMemcpyDeviceToHost));
+	*n_out = K;
+	return RNB_OK;
+}
 int rnb_stat_buffer(rnb_ctx* c, float** s, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *s = c->stats; *n = 8; return RNB_OK; }
 
 int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream) {

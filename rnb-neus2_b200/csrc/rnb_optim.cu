@@ -17,25 +17,28 @@ struct AdamParams {
 	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf; float log2_beta1, log2_beta2;
 };
 
-// One thread owns 4 consecutive parameters (128-bit gradient load).  Fast path for the common case of an untouched
-// hash-grid quad whose EMA copy has already converged to the weight: nothing to write (the EMA update
-// (ema*d*old + w*(1-d))*new is a fixed point at ema == w because d*old + 1 - d == 1/new).
-__device__ __forceinline__ void adam_one(const AdamParams& A, uint32_t i, float g32, float* __restrict__ master, __half& wh, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
+// One thread owns 4 consecutive parameters: every array is moved with one 128-bit (fp32 / u32) or 64-bit (binary16) access.
+// Fast path for the common case of an untouched hash-grid quad whose EMA copy has already converged to the weight:
+// nothing to write (the EMA update (ema*d*old + w*(1-d))*new is a fixed point at ema == w because d*old + 1 - d == 1/new).
+struct AdamLane { float w, m1, m2; uint32_t step; };
+
+__device__ __forceinline__ bool adam_one(const AdamParams& A, uint32_t i, float g32, AdamLane& S, __half& wh) {
 	float gradient = hq(g32) / A.loss_scale;
 	const bool is_mat = i < A.n_matrix;
 	bool update = is_mat || gradient != 0.f;
 	if (A.only_sdf && i >= A.rgb_begin && i < A.rgb_end) update = false;
-	if (!update) return;
-	const float w = master[i];
+	if (!update) return false;
+	const float w = S.w;
 	if (is_mat) gradient += A.l2 * w;
-	const float fm = m1[i] = A.beta1 * m1[i] + (1 - A.beta1) * gradient;
-	const float sm = m2[i] = A.beta2 * m2[i] + (1 - A.beta2) * (gradient * gradient);
-	const uint32_t cs = ++steps[i];
+	const float fm = S.m1 = A.beta1 * S.m1 + (1 - A.beta1) * gradient;
+	const float sm = S.m2 = A.beta2 * S.m2 + (1 - A.beta2) * (gradient * gradient);
+	const uint32_t cs = ++S.step;
 	const float lr = A.base_lr * (sqrtf(1 - exp2f((float)cs * A.log2_beta2)) / (1 - exp2f((float)cs * A.log2_beta1)));
 	const float eff = fminf(fmaxf(lr / (sqrtf(sm) + A.eps), 0.f), 3.402823466e+38f);
 	const float nw = w - eff * fm;
-	master[i] = nw;
+	S.w = nw;
 	wh = __float2half_rn(nw);
+	return true;
 }
 
 __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restrict__ master, __half* __restrict__ params, __half* __restrict__ ema,
@@ -46,21 +49,35 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 		const float4 g = *reinterpret_cast<const float4*>(grads + i0);
 		uint2 pw = *reinterpret_cast<const uint2*>(params + i0), pe = *reinterpret_cast<const uint2*>(ema + i0);
 		const bool anyg = g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f;
-		if (!anyg && i0 >= A.n_matrix && pw.x == pe.x && pw.y == pe.y) return;
-		if (anyg) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);     // consumed: ready for the next step's atomics
+		const bool mat = i0 < A.n_matrix;
+		if (!anyg && !mat && pw.x == pe.x && pw.y == pe.y) return;
 		__half* wh = reinterpret_cast<__half*>(&pw); __half* eh = reinterpret_cast<__half*>(&pe);
-		const float gg[4] = {g.x, g.y, g.z, g.w};
-		#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			adam_one(A, i0 + q, gg[q], master, wh[q], m1, m2, steps);
-			eh[q] = __float2half_rn((__half2float(eh[q]) * A.ema_decay * A.ema_debias_old + __half2float(wh[q]) * (1 - A.ema_decay)) * A.ema_debias_new);
+		if (anyg || mat) {
+			if (anyg) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);     // consumed: ready for the next step's atomics
+			const float4 w4 = *reinterpret_cast<const float4*>(master + i0), a4 = *reinterpret_cast<const float4*>(m1 + i0), b4 = *reinterpret_cast<const float4*>(m2 + i0);
+			const uint4 s4 = *reinterpret_cast<const uint4*>(steps + i0);
+			AdamLane S[4] = {{w4.x, a4.x, b4.x, s4.x}, {w4.y, a4.y, b4.y, s4.y}, {w4.z, a4.z, b4.z, s4.z}, {w4.w, a4.w, b4.w, s4.w}};
+			const float gg[4] = {g.x, g.y, g.z, g.w};
+			bool any = false;
+			#pragma unroll
+			for (int q = 0; q < 4; ++q) any |= adam_one(A, i0 + q, gg[q], S[q], wh[q]);
+			if (any) {
+				*reinterpret_cast<float4*>(master + i0) = make_float4(S[0].w, S[1].w, S[2].w, S[3].w);
+				*reinterpret_cast<float4*>(m1 + i0) = make_float4(S[0].m1, S[1].m1, S[2].m1, S[3].m1);
+				*reinterpret_cast<float4*>(m2 + i0) = make_float4(S[0].m2, S[1].m2, S[2].m2, S[3].m2);
+				*reinterpret_cast<uint4*>(steps + i0) = make_uint4(S[0].step, S[1].step, S[2].step, S[3].step);
+			}
 		}
+		#pragma unroll
+		for (int q = 0; q < 4; ++q)
+			eh[q] = __float2half_rn((__half2float(eh[q]) * A.ema_decay * A.ema_debias_old + __half2float(wh[q]) * (1 - A.ema_decay)) * A.ema_debias_new);
 		*reinterpret_cast<uint2*>(params + i0) = pw; *reinterpret_cast<uint2*>(ema + i0) = pe;
 	} else {
 		for (uint32_t i = i0; i < A.n_params; ++i) {
 			const float g32 = grads[i]; grads[i] = 0.f;
 			__half wh = params[i];
-			adam_one(A, i, g32, master, wh, m1, m2, steps);
+			AdamLane S{master[i], m1[i], m2[i], steps[i]};
+			if (adam_one(A, i, g32, S, wh)) { master[i] = S.w; m1[i] = S.m1; m2[i] = S.m2; steps[i] = S.step; }
 			params[i] = wh;
 			ema[i] = __float2half_rn((__half2float(ema[i]) * A.ema_decay * A.ema_debias_old + __half2float(wh) * (1 - A.ema_decay)) * A.ema_debias_new);
 		}

@@ -220,6 +220,21 @@ class Oracle:
     def density_update(self, n_uniform, n_nonuniform, valid_level):
         self.L.orc_density_update(self.h, n_uniform, n_nonuniform, valid_level)
 
+    def set_world(self, world, rank):
+        self.L.orc_set_world(self.h, world, rank)
+
+    def train_step_begin(self):
+        self.L.orc_train_step_begin(self.h)
+
+    def train_step_end(self):
+        st = Stats(); self.L.orc_train_step_end(self.h, C.byref(st)); return st
+
+    def get_sums(self):
+        a = np.zeros(4, np.float64); self.L.orc_get_sums(self.h, _p(a, C.c_double)); return a
+
+    def set_sums(self, a):
+        a = np.ascontiguousarray(a, np.float64); self.L.orc_set_sums(self.h, _p(a, C.c_double))
+
     def train_step(self):
         st = Stats(); self.L.orc_train_step(self.h, C.byref(st)); return st
 

@@ -8,7 +8,7 @@ RNB_NETWORK=mma timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-bas
 import json,sys
 for n in ('tc','mma'):
     try:
-        d=json.load(open('%s/bench_%s.json'%(sys.argv[1] if len(sys.argv)>1 else 'gpurun_out/quick',n)))
+        d=json.load(open('%s/bench_%s.json'%(sys.argv[1] if len(sys.argv)>1 else 'gpurun_out/' + (sys.argv[1] if len(sys.argv) > 1 else 'quick') + '',n)))
         print(n, round(d['value']), 'rays/s', d['ms_per_step'], d['roofline']['stage_ms'])
     except Exception as e: print(n,'ERR',e)
 PY
