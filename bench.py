@@ -110,12 +110,57 @@ def cpu_baseline_from_state(t, views, flags_kw, threads, steps, rays):
     return rays * n / dt, dict(samples_per_step=int(st.n_samples), compacted_per_step=int(st.n_compacted), seconds=round(dt, 2))
 
 
+REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "bin", "ref_harness")
+
+
+def _has_gpu():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).returncode == 0
+    except Exception:
+        return False
+
+
+def run_reference_cuda(args):
+    """The UNMODIFIED reference (its own Testbed::train, tiny-cuda-nn kernels as sm_100 SASS, built by oracle/Makefile.ref into
+    oracle/_ref/) on one GPU of this box, on the same scene / config / pinned 4096 rays per step.  The reference has no CPU
+    implementation of this path (tiny-cuda-nn is CUDA only), so this — not a CPU port — is its own stock code path."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_scene
+    work = "/tmp/rnb_bench_ref"
+    scene_dir = os.path.join(work, "scene"); dump = os.path.join(work, "dump"); os.makedirs(dump, exist_ok=True)
+    t0 = time.time()
+    views, _ = build_views(args.views, args.width, args.height, False)
+    ref_scene.write_scene(scene_dir, views, workers=min(16, os.cpu_count() or 4))
+    scene_s = time.time() - t0
+    n = args.pretrain + args.warmup + args.steps
+    cmd = [REF_HARNESS, scene_dir + "/", os.path.join(ROOT, "oracle", "_ref", "configs", "nerf", "base.json"), dump, str(n), "--no-albedo", "--time-only",
+           "--pin-rays", str(RAYS_PER_STEP), "--time-from", str(args.pretrain + args.warmup)]
+    clocks = ClockSampler(0); clocks.start()
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    clk = clocks.stop()
+    if p.returncode != 0:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/ref_harness failed: " + p.stdout[-200:].replace("\n", " ")})); return
+    meta = ref_scene.read_meta(os.path.join(dump, "meta.txt"))
+    val = float(meta["rays_per_second"]); ms = float(meta["timed_ms"]) / max(int(meta["timed_steps"]), 1)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 1, "steps": int(meta["timed_steps"]), "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp16 accumulate)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pretrain_steps": args.pretrain, "scene_write_s": round(scene_s, 1),
+                       "note": "unmodified reference CUDA path (Testbed::train, tiny-cuda-nn; sm_100 SASS from oracle/Makefile.ref) on ONE B200 of this box, light draw pinned (oracle/ref_prelude.h), "
+                               "rays/step pinned by overwriting the controller output; per-step CUDA events around Testbed::train incl. its occupancy refreshes; the reference has no CPU or multi-GPU path"},
+            "clocks": clk,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "%s timed steps x %d rays on the GPU (the reference path is CUDA only; 1 host thread drives it)" % (meta["timed_steps"], RAYS_PER_STEP)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
 def run_reference(args):
-    """--impl reference: the reference has no CPU implementation of this path (tiny-cuda-nn is CUDA-only) and its CUDA
-    build needs cmake + a 14-minute compile, so this arm times the oracle port on all host cores."""
+    """--impl reference.  If the reference build (oracle/_ref, made by oracle/Makefile.ref) and a GPU are present: the reference's
+    own CUDA path (run_reference_cuda).  Otherwise the CPU restatement (oracle/) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if os.path.exists(REF_HARNESS) and _has_gpu() and not args.cpu_port:
+        return run_reference_cuda(args)
     from oracle_binding import Oracle, default_flags, build_oracle
     from common import FULL
     build_oracle()
@@ -124,16 +169,11 @@ def run_reference(args):
     views, gen_s = build_views(n_views, w, h, False)
     o = Oracle(threads=threads, **FULL)
     o.init_params(1337, None)
-    # built-in sphere start (the reference's utils/mlp_weights*.txt is not shipped to the GPU box): copy of the product's init is
-    # not allowed here (no product code on this arm), so the SDF MLP keeps its xavier init scaled to a sphere-like field
     o.set_views(views)
     o.set_flags(default_flags(no_albedo=1))
     rays = 512        # bounded sample of the 4096-ray step: every stage scales linearly in rays
     o.set_train_state(training_step=1, rays_per_batch=rays, pin_rays=1)
-    bf = bytearray(b"\xff" * (128 ** 3 // 8)) + bytearray(128 ** 3 - 128 ** 3 // 8)
-    import numpy as np
-    shell = _shell_bitfield()
-    o.set_bitfield(shell)
+    o.set_bitfield(_shell_bitfield())
     for _ in range(max(1, min(args.warmup, 2))):
         o.train_step()
     k = max(1, min(args.steps, 5))
@@ -184,6 +224,7 @@ def main():
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="--impl reference: time the CPU restatement instead of the reference CUDA build")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

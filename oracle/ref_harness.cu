@@ -56,7 +56,7 @@ static void dump_host(const std::string& name, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
 	if (argc < 5) {
-		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--pin-rays N]\n");
+		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--time-from K] [--pin-rays N]\n");
 		return 1;
 	}
 	char buf[PATH_MAX]; ssize_t cnt = readlink("/proc/self/exe", buf, PATH_MAX);
@@ -65,13 +65,14 @@ int main(int argc, char** argv) {
 	g_out = argv[3];
 	const int n_steps = atoi(argv[4]);
 	bool no_albedo = false, supernormal = false, opti = false, l1 = false, rgbplus = true, time_only = false;
-	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps;
+	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps; int time_from = -1;
 	for (int i = 5; i < argc; ++i) {
 		std::string a = argv[i];
 		if (a == "--no-albedo") no_albedo = true; else if (a == "--supernormal") supernormal = true; else if (a == "--opti-lights") opti = true;
 		else if (a == "--l1") l1 = true; else if (a == "--no-rgbplus") rgbplus = false; else if (a == "--time-only") time_only = true;
 		else if (a == "--dump-every" && i + 1 < argc) dump_every = atoi(argv[++i]);
 		else if (a == "--pin-rays" && i + 1 < argc) pin_rays = (uint32_t)atoi(argv[++i]);
+		else if (a == "--time-from" && i + 1 < argc) time_from = atoi(argv[++i]);
 		else if (a == "--dump-steps" && i + 1 < argc) { std::string l = argv[++i]; size_t p0 = 0; while (p0 < l.size()) { size_t q = l.find(',', p0); if (q == std::string::npos) q = l.size(); dump_steps.push_back(atoi(l.substr(p0, q - p0).c_str())); p0 = q + 1; } }
 	}
 
@@ -125,7 +126,7 @@ int main(int argc, char** argv) {
 	};
 
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-	double total_ms = 0; uint64_t total_rays = 0;
+	double total_ms = 0; uint64_t total_rays = 0; int timed_steps = 0;
 	for (int k = 0; k < n_steps; ++k) {
 		bool dump = !time_only && (k % dump_every == 0 || k == n_steps - 1);
 		if (!time_only && !dump_steps.empty()) { dump = false; for (int d : dump_steps) dump |= (d == k); }
@@ -141,7 +142,7 @@ int main(int argc, char** argv) {
 		cudaEventRecord(e1, tb.m_training_stream);
 		CUDA_CHECK_THROW(cudaDeviceSynchronize());
 		float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-		if (k >= n_steps / 2) { total_ms += ms; total_rays += R; }
+		if (k >= (time_from >= 0 ? time_from : n_steps / 2)) { total_ms += ms; total_rays += R; ++timed_steps; }
 		if (dump) {
 			dump_dev(tag + "_out_loss.bin", tr.counters_rgb.loss.data(), R);
 			dump_dev(tag + "_out_ek_loss.bin", tr.counters_rgb.ek_loss.data(), R);
@@ -160,7 +161,7 @@ int main(int argc, char** argv) {
 			printf("ref step %d rays %u samples %u compacted %u loss %g  %.3f ms\n", k, R, tr.counters_rgb.measured_batch_size_before_compaction, tr.counters_rgb.measured_batch_size, tb.m_loss_scalar.val(), ms);
 	}
 	if (!time_only) dump_state("final");
-	fprintf(meta, "timed_steps=%d\ntimed_ms=%.4f\ntimed_rays=%llu\nrays_per_second=%.1f\n", n_steps - n_steps / 2, total_ms, (unsigned long long)total_rays, total_ms > 0 ? total_rays / (total_ms * 1e-3) : 0.0);
+	fprintf(meta, "timed_steps=%d\ntimed_ms=%.4f\ntimed_rays=%llu\nrays_per_second=%.1f\n", timed_steps, total_ms, (unsigned long long)total_rays, total_ms > 0 ? total_rays / (total_ms * 1e-3) : 0.0);
 
 	// network probes on the final parameters: training weights (use_inference_params=false), positions on a fixed lattice
 	if (!time_only) {

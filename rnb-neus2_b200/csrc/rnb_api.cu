@@ -30,7 +30,7 @@ size_t mma_pack_u32(const ModelDev&);
 void launch_mma(int, cudaStream_t, const ModelDev&, const __half*, uint32_t*, uint32_t, const float4*, const uint32_t*, uint32_t, const float*, __half*, const __half*, uint32_t, uint32_t, const uint32_t*, float*, int);
 bool tc_supported(const ModelDev&);
 size_t tc_blob_bytes(const ModelDev&);
-void launch_tc(int, cudaStream_t, const ModelDev&, const __half*, uint8_t*, uint32_t, const float4*, const uint32_t*, uint32_t, __half*, float*, float*, int);
+void launch_tc(int, cudaStream_t, const ModelDev&, const __half*, uint8_t*, uint32_t, const float4*, const uint32_t*, uint32_t, __half*, float*, float*, int, const float* = nullptr);
 // rnb_loss.cu
 void launch_ray_dirw(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const float*, float*);
 void launch_compact_count(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const __half*, const float*, const __half*, uint32_t, float, uint32_t*);
@@ -446,7 +446,8 @@ static void net_pass_a(rnb_ctx* c, cudaStream_t st, uint32_t vl, const float4* p
 	else launch_forward_simt(st, c->M, c->params, vl, 0, pos, n_ptr, n_max, c->ray_dirw, c->outA, nullptr, nullptr, nullptr);
 }
 static void net_pass_b(rnb_ctx* c, cudaStream_t st, const __half* P, uint32_t vl, const float4* pos, const uint32_t* n_ptr, uint32_t n_max, const float* dirw) {
-	if (c->use_mma) launch_mma(2, st, c->M, P, c->wpack, vl, pos, n_ptr, n_max, dirw, c->out16, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
+	if (c->use_tc && P == c->params) launch_tc(3, st, c->M, P, c->wtc, vl, pos, n_ptr, n_max, c->out16, nullptr, nullptr, c->n_sm, dirw);
+	else if (c->use_mma) launch_mma(2, st, c->M, P, c->wpack, vl, pos, n_ptr, n_max, dirw, c->out16, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
 	else launch_forward_simt(st, c->M, P, vl, 1, pos, n_ptr, n_max, dirw, c->out16, nullptr, nullptr, nullptr);
 }
 static void net_backward(rnb_ctx* c, cudaStream_t st, uint32_t vl, const uint32_t* n_ptr, uint32_t n_max, uint32_t n_roll, const uint32_t* n_in_ptr) {

@@ -81,6 +81,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 	for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// store 16 / 32 packed words into this thread's TMEM lane (columns taddr .. taddr+15 / +31)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+	             ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem: lane = row, two binary16 per 32-bit column, 8 columns per K=16] . B[smem descriptor]
+__device__ __forceinline__ void umma_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+	asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
 
 // byte offset of element (row, col) of a panelised [rows x cols] binary16 tile
@@ -94,21 +105,50 @@ struct Blob {
 	static constexpr uint32_t W1 = 0;
 	static constexpr uint32_t W2R = W1 + SW * 32 * 2;
 	static constexpr uint32_t SDF_END = W2R + SW * 4;
+	// the rest is only staged by the full forward (pass B): all panelised [out x in]
+	static constexpr uint32_t W2 = SDF_END;                     // sdf layer 1      [16 x SW]
+	static constexpr uint32_t C1 = W2 + 16 * SW * 2;            // colour layer 0   [SW x 32] in the order r' = [sdf-MLP out (16) | x (3) | normal (3) | 0 (10)]
+	static constexpr uint32_t C2 = C1 + SW * 32 * 2;            // colour layer 1   [SW x SW] (3-matrix colour MLP only)
+	static constexpr uint32_t C3 = C2 + SW * SW * 2;            // colour output    [16 x SW]
+	static constexpr uint32_t END = C3 + 16 * SW * 2;
 };
 
 template <int SW>
 __global__ void __launch_bounds__(256) k_pack_weights_tc(ModelDev M, const __half* __restrict__ P, uint8_t* __restrict__ out) {
 	using B = Blob<SW>;
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+	const __half zero = __float2half_rn(0.f);
 	const __half* W1 = P + M.sdf_layers[0].off; const int cols = (int)M.sdf_layers[0].cols, ne = (int)M.n_enc;
 	for (int i = tid; i < SW * 32; i += nt) {
 		const int n = i / 32, k = i % 32;
 		const int kc = k < ne ? 3 + k : (k < ne + 3 ? k - ne : -1);        // u' column -> reference column (nerf_network.h:149-155)
-		const __half v = (kc >= 0 && kc < cols) ? W1[(size_t)n * cols + kc] : __float2half_rn(0.f);
-		*reinterpret_cast<__half*>(out + B::W1 + panel_off(SW, n, k)) = v;
+		*reinterpret_cast<__half*>(out + B::W1 + panel_off(SW, n, k)) = (kc >= 0 && kc < cols) ? W1[(size_t)n * cols + kc] : zero;
 	}
 	const __half* W2 = P + M.sdf_layers[1].off;
 	for (int i = tid; i < SW; i += nt) reinterpret_cast<float*>(out + B::W2R)[i] = __half2float(W2[i]);
+	for (int i = tid; i < 16 * SW; i += nt) { const int n = i / SW, k = i % SW; *reinterpret_cast<__half*>(out + B::W2 + panel_off(16, n, k)) = W2[(size_t)n * SW + k]; }
+	const __half* C1 = P + M.rgb_layers[0].off; const int c1cols = (int)M.rgb_layers[0].cols;
+	for (int i = tid; i < SW * 32; i += nt) {
+		const int n = i / 32, k = i % 32;
+		const int kc = k < 16 ? k : 16 + k;                                 // r' column -> reference column (16-31 = compiled-out direction encoding)
+		*reinterpret_cast<__half*>(out + B::C1 + panel_off(SW, n, k)) = kc < c1cols ? C1[(size_t)n * c1cols + kc] : zero;
+	}
+	if (M.n_rgb_layers == 3) {
+		const __half* C2 = P + M.rgb_layers[1].off;
+		for (int i = tid; i < SW * SW; i += nt) { const int n = i / SW, k = i % SW; *reinterpret_cast<__half*>(out + B::C2 + panel_off(SW, n, k)) = C2[(size_t)n * SW + k]; }
+	}
+	const __half* C3 = P + M.rgb_layers[M.n_rgb_layers - 1].off;
+	for (int i = tid; i < 16 * SW; i += nt) { const int n = i / SW, k = i % SW; *reinterpret_cast<__half*>(out + B::C3 + panel_off(16, n, k)) = C3[(size_t)n * SW + k]; }
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+	uint32_t r[16];
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+	             : "r"(taddr) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+	#pragma unroll
+	for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // ---- gather of one sample's MLP input row ---------------------------------------------------------------------------
@@ -150,21 +190,24 @@ __device__ __forceinline__ void gather_row(const ModelDev& M, const __half* __re
 // ---- pass A / SDF probe -----------------------------------------------------------------------------------------------
 // MODE 0: pass A  -> outA[row] = (sdf + bias, normal) as 4 x binary16
 // MODE 1: probe   -> sdf_out[row] (fp32, optional), dens_out[row] (fp32, optional): NerfNetwork::sdf / ::density, nerf_network.h:454-537
+// Activations are TMEM resident: every thread writes its input row / its tm row straight into its TMEM lane (tcgen05.st) and
+// the MMAs read the A operand from TMEM; shared memory only holds the weights and (pass A) the dy/dx scratch.
+// TMEM columns: [0,64) layer accumulator | [64,80) input row, then [64,96) tm row | [96,128) d sdf / d u'
 template <int SW, int MODE>
-__global__ void __launch_bounds__(TILE, MODE == 0 ? 3 : 4) k_sdf_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
-                                                                   const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
-                                                                   __half* __restrict__ outA, float* __restrict__ sdf_out, float* __restrict__ dens_out) {
+__global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
+                                                    const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
+                                                    __half* __restrict__ outA, float* __restrict__ sdf_out, float* __restrict__ dens_out) {
 	using B = Blob<SW>;
 	constexpr bool NORMAL = MODE == 0;
-	constexpr uint32_t XB = (B::SDF_END + 127u) & ~127u;                 // X tile  [128 x 32]
-	constexpr uint32_t GB = XB + TILE * 64;                             // G tile  [128 x SW]   (pass A only)
-	constexpr uint32_t DYB = GB + (NORMAL ? TILE * SW * 2 : 0);         // dy/dx   [84][128] fp32 (pass A only)
-	constexpr int TMEM_COLS = NORMAL ? 128 : 64;                        // D1: SW columns at 0, D2: 32 columns at 64
+	constexpr uint32_t DYB = (B::SDF_END + 127u) & ~127u;               // dy/dx [84][128] fp32 (pass A only)
+	constexpr int TMEM_COLS = 128;
+	constexpr uint32_t C_ACC = 0, C_IN = 64, C_TM = 64, C_GIN = 96;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint32_t tmem_slot;
 	__shared__ __align__(8) uint64_t bar;
 	const int tid = threadIdx.x, warp = tid >> 5;
 	for (uint32_t i = tid; i < B::SDF_END / 16; i += TILE) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
+	fence_async_smem();                                                  // weights: generic-proxy stores -> visible to the tensor core
 	if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_slot);
 	if (tid == 0) mbar_init(&bar, 1);
 	tc_fence_before();
@@ -173,29 +216,29 @@ __global__ void __launch_bounds__(TILE, MODE == 0 ? 3 : 4) k_sdf_tc(ModelDev M, 
 	const uint32_t tmem = tmem_slot, trow = tmem + ((uint32_t)(warp * 32) << 16);
 	const float* w2r = reinterpret_cast<const float*>(smem + B::W2R);
 	float* dyS = reinterpret_cast<float*>(smem + DYB);
-	const uint32_t sW1 = smem_u32(smem + B::W1), sX = smem_u32(smem + XB), sG = smem_u32(smem + GB);
+	const uint32_t sW1 = smem_u32(smem + B::W1);
 	constexpr uint32_t ID1 = make_idesc(128, SW, 0, 0), ID2 = make_idesc(128, 32, 0, 1);
 	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
 	const uint32_t n_tiles = (n + TILE - 1) / TILE;
 	uint32_t phase = 0;
-	float dens_scale = 0.f; __half sc = __float2half_rn(0.f);
-	if (MODE == 1) { const __half var = __ldg(P + M.off_var); sc = __float2half_rn(__expf(__half2float(__hmul(var, __float2half_rn(10.0f))))); dens_scale = 1.f; }
-	(void)dens_scale;
+	__half sc = __float2half_rn(0.f);
+	if (MODE == 1) { const __half var = __ldg(P + M.off_var); sc = __float2half_rn(__expf(__half2float(__hmul(var, __float2half_rn(10.0f))))); }
 	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 		const uint32_t row = tile * TILE + tid;
 		const float4 p = pos4[min(row, n - 1)];
-		uint32_t u[16];
-		gather_row<NORMAL, NORMAL ? 5 : 7>(M, P, valid_level, p.x, p.y, p.z, u, dyS, tid);
-		#pragma unroll
-		for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + XB + j * (TILE * 16) + tid * 16) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
-		fence_async_smem();
+		{
+			uint32_t u[16];
+			gather_row<NORMAL, NORMAL ? 5 : 7>(M, P, valid_level, p.x, p.y, p.z, u, dyS, tid);
+			tmem_st16(trow + C_IN, u);
+			tmem_st_wait();
+		}
 		tc_fence_before();
 		__syncthreads();
 		if (tid == 0) {
 			tc_fence_after();
 			#pragma unroll
-			for (int k = 0; k < 2; ++k)      // K = 32: two K-major steps of 2 panels each
-				umma(tmem, make_desc(sX + k * 2 * (TILE * 16), TILE * 16, 128), make_desc(sW1 + k * 2 * (SW * 16), SW * 16, 128), ID1, k);
+			for (int k = 0; k < 2; ++k)      // K = 32: A from TMEM (8 columns per step), B = W1 K-major (2 panels per step)
+				umma_ta(tmem + C_ACC, tmem + C_IN + k * 8, make_desc(sW1 + k * 2 * (SW * 16), SW * 16, 128), ID1, k);
 			umma_commit(&bar);
 		}
 		mbar_wait(&bar, phase); phase ^= 1;
@@ -205,7 +248,7 @@ __global__ void __launch_bounds__(TILE, MODE == 0 ? 3 : 4) k_sdf_tc(ModelDev M, 
 		#pragma unroll
 		for (int c = 0; c < SW / 32; ++c) {
 			float h[32];
-			tmem_ld32(trow + c * 32, h);
+			tmem_ld32(trow + C_ACC + c * 32, h);
 			uint32_t g[16];
 			#pragma unroll
 			for (int k = 0; k < 32; k += 2) {
@@ -214,27 +257,24 @@ __global__ void __launch_bounds__(TILE, MODE == 0 ? 3 : 4) k_sdf_tc(ModelDev M, 
 				sdf = fmaf(h0, w0, sdf); sdf = fmaf(h1, w1, sdf);
 				if (NORMAL) g[k >> 1] = pack_h2(h0 > 0.f ? w0 : 0.f, h1 > 0.f ? w1 : 0.f);
 			}
-			if (NORMAL) {
-				#pragma unroll
-				for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + GB + (c * 4 + j) * (TILE * 16) + tid * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-			}
+			if (NORMAL) tmem_st16(trow + C_TM + c * 16, g);
 		}
 		const __half sdfb = __hadd(__float2half_rn(sdf), __float2half_rn(M.sdf_bias));
 		if (NORMAL) {
-			fence_async_smem();
+			tmem_st_wait();
 			tc_fence_before();
 			__syncthreads();
 			if (tid == 0) {
 				tc_fence_after();
 				#pragma unroll
-				for (int k = 0; k < SW / 16; ++k)      // d sdf / d u' = tm * W1 : A K-major (2 panels per step), B = W1 read MN-major (16 hidden rows per step)
-					umma(tmem + 64, make_desc(sG + k * 2 * (TILE * 16), TILE * 16, 128), make_desc(sW1 + k * 256, 128, SW * 16), ID2, k);
+				for (int k = 0; k < SW / 16; ++k)      // d sdf / d u' = tm . W1 : A from TMEM, B = W1 read MN-major (16 hidden rows per step)
+					umma_ta(tmem + C_GIN, tmem + C_TM + k * 8, make_desc(sW1 + k * 256, 128, SW * 16), ID2, k);
 				umma_commit(&bar);
 			}
 			mbar_wait(&bar, phase); phase ^= 1;
 			tc_fence_after();
 			float gin[32];
-			tmem_ld32(trow + 64, gin);
+			tmem_ld32(trow + C_GIN, gin);
 			float n0 = 0.f, n1 = 0.f, n2 = 0.f;
 			const uint32_t L = M.n_levels;
 			#pragma unroll
@@ -260,8 +300,178 @@ __global__ void __launch_bounds__(TILE, MODE == 0 ? 3 : 4) k_sdf_tc(ModelDev M, 
 				dens_out[row] = __half2float(__hmul(__hmul(sc, sg), __hsub(__float2half_rn(1.0f), sg)));
 			}
 		}
-		// the next tile's MMA overwrites D1 / the X and G tiles: every thread must be past its TMEM loads and smem reads first.
-		// The __syncthreads before the next MMA issue provides that (tcgen05.wait::ld has completed in tmem_ld32).
+		// Reuse hazards: the next tile's tcgen05.st into [64,80) and its MMA into [0,64) come after this thread's TMEM loads
+		// (tcgen05.wait::ld inside tmem_ld32) and, for the other threads' lanes, after the __syncthreads that precedes the MMA issue.
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) tmem_free<TMEM_COLS>(tmem);
+}
+
+// ---- full forward (pass B): 16-wide output row for the compacted samples (nerf_network.h:221-250) --------------------------
+// Layer chain on tcgen05 with TMEM-resident activations:
+//   F1 X.W1^T -> [F2 H.W2^T | B1 tm.W1] -> F3 R.C1^T -> (F4 H1.C2^T) -> F5 H2.C3^T
+// TMEM columns: [0,64) accumulator of the layer in flight (F2 / B1 / F5 use [0,16) and [16,48)) | [64,128) A operands:
+//   X [64,80) -> H [64,96) + tm [96,128) -> R [64,80) -> H1 [64,96) -> H2 [64,96)
+template <int SW, bool RGB3>
+__global__ void __launch_bounds__(TILE, 3) k_full_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
+                                                     const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
+                                                     const float* __restrict__ ray_dirw, __half* __restrict__ out16) {
+	using B = Blob<SW>;
+	constexpr uint32_t DYB = (B::END + 127u) & ~127u;                   // dy/dx [84][128] fp32
+	constexpr int TMEM_COLS = 128;
+	constexpr uint32_t C_ACC = 0, C_Y = 0, C_GIN = 16, C_A = 64, C_TM = 96;
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ uint32_t tmem_slot;
+	__shared__ __align__(8) uint64_t bar;
+	const int tid = threadIdx.x, warp = tid >> 5;
+	for (uint32_t i = tid; i < B::END / 16; i += TILE) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
+	fence_async_smem();
+	if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_slot);
+	if (tid == 0) mbar_init(&bar, 1);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = tmem_slot, trow = tmem + ((uint32_t)(warp * 32) << 16);
+	const float* w2r = reinterpret_cast<const float*>(smem + B::W2R);
+	float* dyS = reinterpret_cast<float*>(smem + DYB);
+	const uint32_t sW1 = smem_u32(smem + B::W1), sW2 = smem_u32(smem + B::W2), sC1 = smem_u32(smem + B::C1), sC2 = smem_u32(smem + B::C2), sC3 = smem_u32(smem + B::C3);
+	constexpr uint32_t ID_W = make_idesc(128, SW, 0, 0), ID_16 = make_idesc(128, 16, 0, 0), ID_T32 = make_idesc(128, 32, 0, 1);
+	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
+	const uint32_t n_tiles = (n + TILE - 1) / TILE;
+	const __half var_h = __ldg(P + M.off_var);
+	uint32_t phase = 0;
+	auto issue_begin = [&]() { tmem_st_wait(); tc_fence_before(); __syncthreads(); };
+	auto issue_end = [&]() { mbar_wait(&bar, phase); phase ^= 1; tc_fence_after(); };
+	// relu + binary16 rounding of this thread's SW-wide accumulator row -> packed A operand at columns [C_A, C_A + SW/2)
+	auto relu_row_to_tmem = [&]() {
+		#pragma unroll
+		for (int c = 0; c < SW / 32; ++c) {
+			float h[32];
+			tmem_ld32(trow + C_ACC + c * 32, h);
+			uint32_t g[16];
+			#pragma unroll
+			for (int k = 0; k < 32; k += 2) g[k >> 1] = pack_h2(fmaxf(h[k], 0.f), fmaxf(h[k + 1], 0.f));
+			tmem_st16(trow + C_A + c * 16, g);
+		}
+	};
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const uint32_t row = tile * TILE + tid;
+		const float4 p = pos4[min(row, n - 1)];
+		const uint32_t slot = __float_as_uint(p.w);
+		{
+			uint32_t u[16];
+			gather_row<true, 5>(M, P, valid_level, p.x, p.y, p.z, u, dyS, tid);
+			tmem_st16(trow + C_A, u);
+		}
+		// F1: hidden = X . W1^T
+		issue_begin();
+		if (tid == 0) {
+			tc_fence_after();
+			#pragma unroll
+			for (int k = 0; k < 2; ++k) umma_ta(tmem + C_ACC, tmem + C_A + k * 8, make_desc(sW1 + k * 2 * (SW * 16), SW * 16, 128), ID_W, k);
+			umma_commit(&bar);
+		}
+		issue_end();
+		float sdf = 0.f;
+		#pragma unroll
+		for (int c = 0; c < SW / 32; ++c) {
+			float h[32];
+			tmem_ld32(trow + C_ACC + c * 32, h);
+			uint32_t hh[16], g[16];
+			#pragma unroll
+			for (int k = 0; k < 32; k += 2) {
+				const float h0 = hq(fmaxf(h[k], 0.f)), h1 = hq(fmaxf(h[k + 1], 0.f));
+				const float w0 = w2r[c * 32 + k], w1 = w2r[c * 32 + k + 1];
+				sdf = fmaf(h0, w0, sdf); sdf = fmaf(h1, w1, sdf);
+				hh[k >> 1] = pack_h2(h0, h1);
+				g[k >> 1] = pack_h2(h0 > 0.f ? w0 : 0.f, h1 > 0.f ? w1 : 0.f);
+			}
+			tmem_st16(trow + C_A + c * 16, hh);
+			tmem_st16(trow + C_TM + c * 16, g);
+		}
+		const __half sdfb = __hadd(__float2half_rn(sdf), __float2half_rn(M.sdf_bias));
+		// F2: y = H . W2^T (16 wide)   |   B1: d sdf / d u' = tm . W1
+		issue_begin();
+		if (tid == 0) {
+			tc_fence_after();
+			#pragma unroll
+			for (int k = 0; k < SW / 16; ++k) umma_ta(tmem + C_Y, tmem + C_A + k * 8, make_desc(sW2 + k * 2 * (16 * 16), 16 * 16, 128), ID_16, k);
+			#pragma unroll
+			for (int k = 0; k < SW / 16; ++k) umma_ta(tmem + C_GIN, tmem + C_TM + k * 8, make_desc(sW1 + k * 256, 128, SW * 16), ID_T32, k);
+			umma_commit(&bar);
+		}
+		issue_end();
+		float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+		{
+			float gin[32];
+			tmem_ld32(trow + C_GIN, gin);
+			const uint32_t L = M.n_levels;
+			#pragma unroll
+			for (uint32_t l = 0; l < 16; ++l) {
+				const float g0 = hq(gin[2 * l]), g1 = hq(gin[2 * l + 1]);
+				if (l < L) {
+					if (l <= valid_level) {
+						const float* d = dyS + (l * 6) * TILE + tid;
+						n0 = fmaf(g0, d[0], n0); n1 = fmaf(g0, d[TILE], n1); n2 = fmaf(g0, d[2 * TILE], n2);
+						n0 = fmaf(g1, d[3 * TILE], n0); n1 = fmaf(g1, d[4 * TILE], n1); n2 = fmaf(g1, d[5 * TILE], n2);
+					}
+				} else if (l == L) { n0 += g0; n1 += g1; }
+				else if (l == L + 1) { n2 += g0; }
+			}
+		}
+		{   // colour input r' (replaces H in TMEM): [y (16) | x y z n0 n1 n2 0 0 | 0 (8)]
+			float y[16];
+			tmem_ld16(trow + C_Y, y);
+			y[0] = sdf;                 // same accumulation as pass A (the transmittance cut was taken on it)
+			uint32_t r[16];
+			#pragma unroll
+			for (int k = 0; k < 16; k += 2) r[k >> 1] = pack_h2(y[k], y[k + 1]);
+			r[8] = pack_h2(p.x, p.y); r[9] = pack_h2(p.z, n0); r[10] = pack_h2(n1, n2); r[11] = 0u;
+			r[12] = r[13] = r[14] = r[15] = 0u;
+			tmem_st16(trow + C_A, r);
+		}
+		// F3: H1 = relu(R . C1^T)
+		issue_begin();
+		if (tid == 0) {
+			tc_fence_after();
+			#pragma unroll
+			for (int k = 0; k < 2; ++k) umma_ta(tmem + C_ACC, tmem + C_A + k * 8, make_desc(sC1 + k * 2 * (SW * 16), SW * 16, 128), ID_W, k);
+			umma_commit(&bar);
+		}
+		issue_end();
+		relu_row_to_tmem();
+		if constexpr (RGB3) {
+			// F4: H2 = relu(H1 . C2^T)
+			issue_begin();
+			if (tid == 0) {
+				tc_fence_after();
+				#pragma unroll
+				for (int k = 0; k < SW / 16; ++k) umma_ta(tmem + C_ACC, tmem + C_A + k * 8, make_desc(sC2 + k * 2 * (SW * 16), SW * 16, 128), ID_W, k);
+				umma_commit(&bar);
+			}
+			issue_end();
+			relu_row_to_tmem();
+		}
+		// F5: c = H_last . C3^T (16 wide)
+		issue_begin();
+		if (tid == 0) {
+			tc_fence_after();
+			#pragma unroll
+			for (int k = 0; k < SW / 16; ++k) umma_ta(tmem + C_Y, tmem + C_A + k * 8, make_desc(sC3 + k * 2 * (16 * 16), 16 * 16, 128), ID_16, k);
+			umma_commit(&bar);
+		}
+		issue_end();
+		float cc[16];
+		tmem_ld16(trow + C_Y, cc);
+		if (row < n) {
+			const float* dw = ray_dirw + 3 * (size_t)slot;
+			uint4 lo, hi;
+			lo.x = pack_h2(cc[0], cc[1]); lo.y = pack_h2(cc[2], __half2float(sdfb)); lo.z = pack_h2(n0, n1); lo.w = pack_h2(n2, __half2float(var_h));
+			hi.x = pack_h2(dw[0], dw[1]); hi.y = pack_h2(dw[2], cc[11]); hi.z = pack_h2(cc[12], cc[13]); hi.w = pack_h2(cc[14], cc[15]);
+			uint4* o = reinterpret_cast<uint4*>(out16 + (size_t)row * 16);
+			o[0] = lo; o[1] = hi;
+		}
 	}
 	tc_fence_before();
 	__syncthreads();
@@ -271,34 +481,48 @@ __global__ void __launch_bounds__(TILE, MODE == 0 ? 3 : 4) k_sdf_tc(ModelDev M, 
 } // namespace tc
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
-bool tc_supported(const ModelDev& M) { return M.sdf_in == 32 && M.n_sdf_layers == 2 && (M.sdf_width == 32 || M.sdf_width == 64); }
+bool tc_supported(const ModelDev& M) {
+	return M.sdf_in == 32 && M.rgb_in == 48 && M.n_sdf_layers == 2 && M.sdf_width == M.rgb_width && (M.sdf_width == 32 || M.sdf_width == 64) && (M.n_rgb_layers == 2 || M.n_rgb_layers == 3);
+}
 size_t tc_blob_bytes(const ModelDev&) { return 65536; }
 
 template <int SW>
 static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __half* P, uint8_t* wtc, uint32_t vl, const float4* pos4, const uint32_t* n_ptr, uint32_t n_max,
-                         __half* outA, float* sdf_out, float* dens_out, int n_sm) {
+                         __half* outA, float* sdf_out, float* dens_out, int n_sm, const float* ray_dirw) {
 	using namespace tc;
 	using B = Blob<SW>;
-	if (what == 0) { k_pack_weights_tc<SW><<<4, 256, 0, st>>>(M, P, wtc); return; }
+	if (what == 0) { k_pack_weights_tc<SW><<<8, 256, 0, st>>>(M, P, wtc); return; }
 	if (!n_max) return;
-	constexpr uint32_t XB = (B::SDF_END + 127u) & ~127u;
+	constexpr uint32_t DYB = (B::SDF_END + 127u) & ~127u;
 	const uint32_t tiles = (n_max + TILE - 1) / TILE;
 	if (what == 1) {
-		const size_t smem = XB + TILE * 64 + TILE * SW * 2 + 84 * TILE * 4;
+		const size_t smem = DYB + 84 * TILE * 4;
 		static bool attr = false;
 		if (!attr) { cudaFuncSetAttribute(k_sdf_tc<SW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-		k_sdf_tc<SW, 0><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 3), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr);
+		k_sdf_tc<SW, 0><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr);
+	} else if (what == 3) {
+		const size_t smem = ((B::END + 127u) & ~127u) + 84 * TILE * 4;
+		const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)n_sm * 3);
+		if (M.n_rgb_layers == 3) {
+			static bool attr = false;
+			if (!attr) { cudaFuncSetAttribute(k_full_tc<SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+			k_full_tc<SW, true><<<grid, TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, ray_dirw, outA);
+		} else {
+			static bool attr = false;
+			if (!attr) { cudaFuncSetAttribute(k_full_tc<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+			k_full_tc<SW, false><<<grid, TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, ray_dirw, outA);
+		}
 	} else {
-		const size_t smem = XB + TILE * 64;
+		const size_t smem = DYB;
 		k_sdf_tc<SW, 1><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, nullptr, sdf_out, dens_out);
 	}
 }
 
-// what: 0 pack weights, 1 pass A (outA), 2 SDF probe (sdf_out / dens_out)
+// what: 0 pack weights, 1 pass A (outA = 4 halfs per sample), 2 SDF probe (sdf_out / dens_out), 3 full forward (outA = 16 halfs per sample, needs ray_dirw)
 void launch_tc(int what, cudaStream_t st, const ModelDev& M, const __half* P, uint8_t* wtc, uint32_t vl, const float4* pos4, const uint32_t* n_ptr, uint32_t n_max,
-               __half* outA, float* sdf_out, float* dens_out, int n_sm) {
-	if (M.sdf_width == 64) launch_tc_sw<64>(what, st, M, P, wtc, vl, pos4, n_ptr, n_max, outA, sdf_out, dens_out, n_sm);
-	else launch_tc_sw<32>(what, st, M, P, wtc, vl, pos4, n_ptr, n_max, outA, sdf_out, dens_out, n_sm);
+               __half* outA, float* sdf_out, float* dens_out, int n_sm, const float* ray_dirw) {
+	if (M.sdf_width == 64) launch_tc_sw<64>(what, st, M, P, wtc, vl, pos4, n_ptr, n_max, outA, sdf_out, dens_out, n_sm, ray_dirw);
+	else launch_tc_sw<32>(what, st, M, P, wtc, vl, pos4, n_ptr, n_max, outA, sdf_out, dens_out, n_sm, ray_dirw);
 }
 
 } // namespace rnb
