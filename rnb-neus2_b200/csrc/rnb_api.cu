@@ -29,6 +29,7 @@ bool mma_supported(const ModelDev&);
 size_t mma_pack_u32(const ModelDev&);
 void launch_mma(int, cudaStream_t, const ModelDev&, const __half*, uint32_t*, uint32_t, const float4*, const uint32_t*, uint32_t, const float*, __half*, const __half*, uint32_t, uint32_t, const uint32_t*, float*, int);
 bool tc_supported(const ModelDev&);
+void set_bw_debug(int);
 size_t tc_blob_bytes(const ModelDev&);
 void launch_tc(int, cudaStream_t, const ModelDev&, const __half*, uint8_t*, uint32_t, const float4*, const uint32_t*, uint32_t, __half*, float*, float*, int, const float* = nullptr);
 // rnb_loss.cu
@@ -218,6 +219,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 		c->use_mma = mma_supported(M) && !(e && std::string(e) == "simt");
 		CU(cudaMalloc(&c->wpack, mma_pack_u32(M) * 4)); CU(cudaMemset(c->wpack, 0, mma_pack_u32(M) * 4));
 		// RNB_NETWORK=mma keeps the mma.sync tile kernels everywhere; default: tcgen05 kernels where they exist
+		if (const char* d = getenv("RNB_BW_DEBUG")) set_bw_debug(atoi(d));
 		c->use_tc = c->use_mma && tc_supported(M) && !(e && std::string(e) == "mma");
 		CU(cudaMalloc(&c->wtc, tc_blob_bytes(M))); CU(cudaMemset(c->wtc, 0, tc_blob_bytes(M)));
 	}

@@ -17,6 +17,10 @@
 
 namespace rnb {
 
+// profiling aid (RNB_BW_DEBUG): 1 = skip the hash scatter, 2 = skip the weight-gradient phase.  0 in production.
+__device__ int g_bw_debug = 0;
+void set_bw_debug(int v) { cudaMemcpyToSymbol(g_bw_debug, &v, sizeof(int)); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // packed weight blob (uint32 = half2 units)
 // ------------------------------------------------------------------------------------------------------------------
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(256, 1) k_backward_mma(ModelDev M, const __hal
 						const float* d = T.dy[s][r];
 						v0 = d[0] * gn[r][0] + d[1] * gn[r][1] + d[2] * gn[r][2];
 						v1 = d[3] * gn[r][0] + d[4] * gn[r][1] + d[5] * gn[r][2];
-						if (live[r]) scatter_level(M, G, l, T.px[r], T.py[r], T.pz[r], hq(dU[s][2 * r]), hq(dU[s][2 * r + 1]), T.G[s][2 * r], T.G[s][2 * r + 1], gn[r][0], gn[r][1], gn[r][2]);
+						if (live[r] && g_bw_debug != 1) scatter_level(M, G, l, T.px[r], T.py[r], T.pz[r], hq(dU[s][2 * r]), hq(dU[s][2 * r + 1]), T.G[s][2 * r], T.G[s][2 * r + 1], gn[r][0], gn[r][1], gn[r][2]);
 					}
 				} else {
 					const int d0 = c0 - ne;
@@ -636,6 +640,7 @@ __global__ void __launch_bounds__(256, 1) k_backward_mma(ModelDev M, const __hal
 		if constexpr (RGB3) { stage_afrag<RW / 16>(stg + ST::H2, ST::SRW, row0, lane, Q.H2); stage_afrag<RW / 16>(stg + ST::DH2, ST::SRW, row0, lane, dH2); }
 		stage_afrag<1>(stg + ST::DC, ST::S16, row0, lane, dC);
 		__syncthreads();
+		if (g_bw_debug == 2) { __syncthreads(); continue; }
 		// ---------------- phase 2: weight gradients, blocks distributed over the 8 warps ----------------
 		#pragma unroll
 		for (int i = 0; i < NW1; ++i) {             // dW1' [SW x 32]: blocks (mt, nb) ; first order dH^T U + second order tm^T V

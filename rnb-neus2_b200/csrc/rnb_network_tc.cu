@@ -153,24 +153,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // ---- gather of one sample's MLP input row ---------------------------------------------------------------------------
 // u[j] = binary16 pair of columns 2j, 2j+1 of u'.  dyS (optional): dy/dx of the encoding, [6 * level + q][128 samples].
-template <bool WITH_DY, int LB>
-__device__ __forceinline__ void gather_row(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint32_t (&u)[16], float* __restrict__ dyS, int tid) {
+// The row is produced four words (= four hash levels) at a time and stored straight into the thread's TMEM lane; the batch
+// loop is a real loop (one copy of the gather code in the instruction cache), only the four levels of a batch are unrolled so
+// that their 32 corner loads are in flight together.
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <bool WITH_DY>
+__device__ __forceinline__ void gather_row_to_tmem(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint32_t tcol, float* __restrict__ dyS, int tid) {
 	const uint32_t L = M.n_levels;
-	#pragma unroll
-	for (uint32_t j = 0; j < 16; ++j) u[j] = 0u;
 	const uint32_t n_live = min(L, valid_level + 1u);          // levels > valid_level are zero (progressive training, grid.h:193-210)
-	#pragma unroll
-	for (uint32_t b = 0; b < 16; b += LB) {
+	const __half2 exy = __halves2half2(__hsub(__float2half_rn(x), __float2half_rn(0.5f)), __hsub(__float2half_rn(y), __float2half_rn(0.5f)));   // fill_positions_view_with_fixed_offset
+	const __half2 ez = __halves2half2(__hsub(__float2half_rn(z), __float2half_rn(0.5f)), __float2half_rn(0.f));
+	#pragma unroll 1
+	for (uint32_t b = 0; b < 16; b += 4) {
+		uint32_t w[4] = {0u, 0u, 0u, 0u};
 		if (b < n_live) {
-			LevelLoads Q[LB];
+			LevelLoads Q[4];
 			#pragma unroll
-			for (uint32_t i = 0; i < LB; ++i) if (b + i < 14 && b + i < n_live) level_issue(M, P, b + i, x, y, z, Q[i]);
+			for (uint32_t i = 0; i < 4; ++i) if (b + i < n_live) level_issue(M, P, b + i, x, y, z, Q[i]);
 			#pragma unroll
-			for (uint32_t i = 0; i < LB; ++i) {
-				if (b + i < 14 && b + i < n_live) {
+			for (uint32_t i = 0; i < 4; ++i) {
+				if (b + i < n_live) {
 					float dy[6];
 					const __half2 e = level_finish(M.scale[b + i], Q[i], WITH_DY ? dy : nullptr);
-					u[b + i] = *reinterpret_cast<const uint32_t*>(&e);
+					w[i] = *reinterpret_cast<const uint32_t*>(&e);
 					if (WITH_DY) {
 						#pragma unroll
 						for (int q = 0; q < 6; ++q) dyS[((b + i) * 6 + q) * TILE + tid] = dy[q];
@@ -178,12 +186,12 @@ __device__ __forceinline__ void gather_row(const ModelDev& M, const __half* __re
 				}
 			}
 		}
-	}
-	const __half2 exy = __halves2half2(__hsub(__float2half_rn(x), __float2half_rn(0.5f)), __hsub(__float2half_rn(y), __float2half_rn(0.5f)));   // fill_positions_view_with_fixed_offset
-	const __half2 ez = __halves2half2(__hsub(__float2half_rn(z), __float2half_rn(0.5f)), __float2half_rn(0.f));
-	#pragma unroll
-	for (uint32_t j = 1; j < 15; ++j) {
-		if (j == L) { u[j] = *reinterpret_cast<const uint32_t*>(&exy); u[j + 1] = *reinterpret_cast<const uint32_t*>(&ez); }
+		#pragma unroll
+		for (uint32_t i = 0; i < 4; ++i) {
+			if (b + i == L) w[i] = *reinterpret_cast<const uint32_t*>(&exy);
+			else if (b + i == L + 1) w[i] = *reinterpret_cast<const uint32_t*>(&ez);
+		}
+		tmem_st4(tcol + b, w[0], w[1], w[2], w[3]);
 	}
 }
 
@@ -226,12 +234,8 @@ __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __
 	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 		const uint32_t row = tile * TILE + tid;
 		const float4 p = pos4[min(row, n - 1)];
-		{
-			uint32_t u[16];
-			gather_row<NORMAL, NORMAL ? 5 : 7>(M, P, valid_level, p.x, p.y, p.z, u, dyS, tid);
-			tmem_st16(trow + C_IN, u);
-			tmem_st_wait();
-		}
+		gather_row_to_tmem<NORMAL>(M, P, valid_level, p.x, p.y, p.z, trow + C_IN, dyS, tid);
+		tmem_st_wait();
 		tc_fence_before();
 		__syncthreads();
 		if (tid == 0) {
@@ -359,11 +363,7 @@ __global__ void __launch_bounds__(TILE, 3) k_full_tc(ModelDev M, const __half* _
 		const uint32_t row = tile * TILE + tid;
 		const float4 p = pos4[min(row, n - 1)];
 		const uint32_t slot = __float_as_uint(p.w);
-		{
-			uint32_t u[16];
-			gather_row<true, 5>(M, P, valid_level, p.x, p.y, p.z, u, dyS, tid);
-			tmem_st16(trow + C_A, u);
-		}
+		gather_row_to_tmem<true>(M, P, valid_level, p.x, p.y, p.z, trow + C_A, dyS, tid);
 		// F1: hidden = X . W1^T
 		issue_begin();
 		if (tid == 0) {
