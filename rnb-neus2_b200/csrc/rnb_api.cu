@@ -30,6 +30,7 @@ size_t mma_pack_u32(const ModelDev&);
 void launch_mma(int, cudaStream_t, const ModelDev&, const __half*, uint32_t*, uint32_t, const float4*, const uint32_t*, uint32_t, const float*, __half*, const __half*, uint32_t, uint32_t, const uint32_t*, float*, int);
 bool tc_supported(const ModelDev&);
 void set_bw_debug(int);
+void launch_tc_backward(cudaStream_t, const ModelDev&, const __half*, const uint8_t*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, float*, int);
 size_t tc_blob_bytes(const ModelDev&);
 void launch_tc(int, cudaStream_t, const ModelDev&, const __half*, uint8_t*, uint32_t, const float4*, const uint32_t*, uint32_t, __half*, float*, float*, int, const float* = nullptr);
 // rnb_loss.cu
@@ -82,7 +83,7 @@ struct rnb_ctx {
 	uint32_t training_step = 0, rays_per_batch = 4096, n_rays_total = 0, measured_before = 0, measured = 0;
 	uint32_t step_R = 0, step_nrt = 0; bool in_step = false;
 	bool use_mma = false; uint32_t* wpack = nullptr; int n_sm = 148;
-	bool use_tc = false; uint8_t* wtc = nullptr;      // tcgen05 / TMEM kernels (rnb_network_tc.cu) for pass A and the SDF probes
+	bool use_tc = false, use_tc_bwd = false; uint8_t* wtc = nullptr;      // tcgen05 / TMEM kernels (rnb_network_tc.cu) for pass A and the SDF probes
 	// instrumentation: kernel launch counter and optional per-stage CUDA-event timing (bench.py roofline)
 	uint64_t launches = 0;
 	bool prof = false;
@@ -221,6 +222,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 		// RNB_NETWORK=mma keeps the mma.sync tile kernels everywhere; default: tcgen05 kernels where they exist
 		if (const char* d = getenv("RNB_BW_DEBUG")) set_bw_debug(atoi(d));
 		c->use_tc = c->use_mma && tc_supported(M) && !(e && std::string(e) == "mma");
+		c->use_tc_bwd = c->use_tc && !(getenv("RNB_BACKWARD") && std::string(getenv("RNB_BACKWARD")) == "mma");     // RNB_BACKWARD=mma: mma.sync backward
 		CU(cudaMalloc(&c->wtc, tc_blob_bytes(M))); CU(cudaMemset(c->wtc, 0, tc_blob_bytes(M)));
 	}
 	c->rays_per_batch = cfg->rays_per_batch;
@@ -453,7 +455,8 @@ static void net_pass_b(rnb_ctx* c, cudaStream_t st, const __half* P, uint32_t vl
 	else launch_forward_simt(st, c->M, P, vl, 1, pos, n_ptr, n_max, dirw, c->out16, nullptr, nullptr, nullptr);
 }
 static void net_backward(rnb_ctx* c, cudaStream_t st, uint32_t vl, const uint32_t* n_ptr, uint32_t n_max, uint32_t n_roll, const uint32_t* n_in_ptr) {
-	if (c->use_mma) launch_mma(3, st, c->M, c->params, c->wpack, vl, c->cpos4, n_ptr, n_max, nullptr, nullptr, c->dout16, n_roll, c->cfg.target_batch_size, n_in_ptr, c->grads, c->n_sm);
+	if (c->use_tc_bwd) launch_tc_backward(st, c->M, c->params, c->wtc, vl, c->cpos4, c->dout16, n_ptr, n_max, n_roll, c->cfg.target_batch_size, n_in_ptr, c->grads, c->n_sm);
+	else if (c->use_mma) launch_mma(3, st, c->M, c->params, c->wpack, vl, c->cpos4, n_ptr, n_max, nullptr, nullptr, c->dout16, n_roll, c->cfg.target_batch_size, n_in_ptr, c->grads, c->n_sm);
 	else launch_backward_simt(st, c->M, c->params, vl, c->cpos4, c->dout16, n_ptr, n_max, n_roll, c->cfg.target_batch_size, n_in_ptr, nullptr, c->grads, c->bw_scratch, c->bw_front);
 }
 

@@ -478,6 +478,412 @@ __global__ void __launch_bounds__(TILE, 3) k_full_tc(ModelDev M, const __half* _
 	if (warp == 0) tmem_free<TMEM_COLS>(tmem);
 }
 
+// ---- backward (k_backward_tc) -------------------------------------------------------------------------------------------
+// One CTA = 128 threads = one 128-sample tile at a time, persistent over tiles, one CTA per SM (it owns the whole TMEM).
+// Replaces NerfNetwork::backward_impl (nerf_network.h:257-452): colour/SDF MLP backward incl. weight gradients
+// (fully_fused_mlp.cu:913-1031), the one-hot chain and its double backward (:1036-1142), kernel_grid_backward and
+// kernel_grid_backward_input_backward_grid (grid.h:366-495,556-683) — ~30 launches + 10 CUTLASS GEMMs in the reference.
+//   * forward recompute and the data-gradient chain run as tcgen05 layers on panelised shared-memory tiles (A operand K-major);
+//   * every tile that is an operand of a weight-gradient product stays in shared memory and is consumed a second time through
+//     MN-major descriptors (K = samples): dW (+)= dY^T X is issued as soon as both tiles exist and runs on the tensor pipe while
+//     the threads do the next epilogue;
+//   * the five weight-gradient accumulators live in TMEM for the whole kernel (160 columns, M = 64) and are flushed with one
+//     atomicAdd per element per CTA; dy/dx of the encoding (84 floats per sample) also waits in TMEM, not in shared memory;
+//   * the merged first+second-order hash scatter reads d(enc) and dsdf/d(enc) back from TMEM one level at a time.
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
+	uint32_t r0, r1;
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+	a = __uint_as_float(r0); b = __uint_as_float(r1);
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ void tmem_st4f(uint32_t taddr, float a, float b, float c, float d) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+	uint32_t r[4];
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// gather for the backward: the MLP input row goes to the X tile in shared memory (it is a weight-gradient operand), dy/dx to TMEM
+__device__ __forceinline__ void gather_row_bwd(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint8_t* __restrict__ xtile, uint32_t tcol_dy, int tid) {
+	const uint32_t L = M.n_levels;
+	const uint32_t n_live = min(L, valid_level + 1u);
+	const __half2 exy = __halves2half2(__hsub(__float2half_rn(x), __float2half_rn(0.5f)), __hsub(__float2half_rn(y), __float2half_rn(0.5f)));
+	const __half2 ez = __halves2half2(__hsub(__float2half_rn(z), __float2half_rn(0.5f)), __float2half_rn(0.f));
+	#pragma unroll 1
+	for (uint32_t b = 0; b < 16; b += 4) {
+		uint32_t w[4] = {0u, 0u, 0u, 0u};
+		if (b < n_live) {
+			LevelLoads Q[4];
+			#pragma unroll
+			for (uint32_t i = 0; i < 4; ++i) if (b + i < n_live) level_issue(M, P, b + i, x, y, z, Q[i]);
+			#pragma unroll
+			for (uint32_t i = 0; i < 4; ++i) {
+				if (b + i < n_live) {
+					float dy[6];
+					const __half2 e = level_finish(M.scale[b + i], Q[i], dy);
+					w[i] = *reinterpret_cast<const uint32_t*>(&e);
+					tmem_st4f(tcol_dy + (b + i) * 8, dy[0], dy[1], dy[2], dy[3]);      // 8 columns per level: aligned x4 / x2 accesses
+					tmem_st2(tcol_dy + (b + i) * 8 + 4, dy[4], dy[5]);
+				}
+			}
+		}
+		#pragma unroll
+		for (uint32_t i = 0; i < 4; ++i) {
+			if (b + i == L) w[i] = *reinterpret_cast<const uint32_t*>(&exy);
+			else if (b + i == L + 1) w[i] = *reinterpret_cast<const uint32_t*>(&ez);
+		}
+		*reinterpret_cast<uint4*>(xtile + (b >> 2) * (TILE * 16) + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+	}
+}
+
+template <int SW, bool RGB3>
+__global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
+                                                         const float4* __restrict__ pos4, const __half* __restrict__ dout16, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
+                                                         uint32_t n_roll, uint32_t n_batch, const uint32_t* __restrict__ n_in_ptr, float* __restrict__ G) {
+	using B = Blob<SW>;
+	constexpr uint32_t T32 = TILE * 64, TW = TILE * SW * 2, T16 = TILE * 32;        // tile bytes: 32-, SW-, 16-wide
+	constexpr uint32_t XB = (B::END + 127u) & ~127u, VB = XB + T32, RB = VB + T32, HB = RB + T32, TMB = HB + TW, DHB = TMB + TW, F1B = DHB + TW,
+	                   H1B = F1B + TW, DH1B = H1B + TW, H2B = DH1B + TW, DH2B = H2B + TW, DYB = DH2B + TW, DCB = DYB + T16, E0B = DCB + T16, SM_END = E0B + T16;
+	// TMEM columns
+	constexpr uint32_t C_D = 0, C_D2 = 64, C_16 = 128, C_GIN = 144, C_32 = 176, C_DY = 208;            // chain accumulators, gin (kept for the scatter), dR / dU, dy/dx (14 levels x 8 columns, 6 used)
+	constexpr uint32_t A_W1 = 320, A_W2T = 352, A_C1 = 368, A_C2 = 400, A_C3T = 464;                   // weight-gradient accumulators (M = 64)
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ uint32_t tmem_slot;
+	__shared__ __align__(8) uint64_t bar, bar_dw;
+	const int tid = threadIdx.x, warp = tid >> 5;
+	for (uint32_t i = tid; i < B::END / 16; i += TILE) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
+	for (uint32_t i = tid; i < (SM_END - XB) / 16; i += TILE) reinterpret_cast<uint4*>(smem + XB)[i] = make_uint4(0u, 0u, 0u, 0u);
+	__syncthreads();
+	{   // E0: column 0 = 1 (column sums through the tensor core)
+		const __half2 one = __halves2half2(__float2half_rn(1.f), __float2half_rn(0.f));
+		*reinterpret_cast<uint4*>(smem + E0B + tid * 16) = make_uint4(*reinterpret_cast<const uint32_t*>(&one), 0u, 0u, 0u);
+	}
+	fence_async_smem();
+	if (warp == 0) tmem_alloc<512>(&tmem_slot);
+	if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar_dw, 1); }
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = tmem_slot, trow = tmem + ((uint32_t)(warp * 32) << 16);
+	const float* w2r = reinterpret_cast<const float*>(smem + B::W2R);
+	const uint32_t sW1 = smem_u32(smem + B::W1), sW2 = smem_u32(smem + B::W2), sC1 = smem_u32(smem + B::C1), sC2 = smem_u32(smem + B::C2), sC3 = smem_u32(smem + B::C3);
+	const uint32_t sX = smem_u32(smem + XB), sV = smem_u32(smem + VB), sR = smem_u32(smem + RB), sH = smem_u32(smem + HB), sTM = smem_u32(smem + TMB), sDH = smem_u32(smem + DHB),
+	               sF1 = smem_u32(smem + F1B), sH1 = smem_u32(smem + H1B), sDH1 = smem_u32(smem + DH1B), sH2 = smem_u32(smem + H2B), sDH2 = smem_u32(smem + DH2B),
+	               sDY = smem_u32(smem + DYB), sDC = smem_u32(smem + DCB), sE0 = smem_u32(smem + E0B);
+	constexpr uint32_t PS = TILE * 16;                                   // panel stride of every 128-row tile
+	constexpr uint32_t ID_W = make_idesc(128, SW, 0, 0), ID_16 = make_idesc(128, 16, 0, 0), ID_T32 = make_idesc(128, 32, 0, 1), ID_TW = make_idesc(128, SW, 0, 1);
+	constexpr uint32_t IDG_16 = make_idesc(64, 16, 1, 1), IDG_32 = make_idesc(64, 32, 1, 1), IDG_W = make_idesc(64, SW, 1, 1);
+	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
+	const uint32_t n_in = n_in_ptr ? *n_in_ptr : n;
+	const uint32_t n_tiles = (n + TILE - 1) / TILE;
+	const float inv_nb = 1.0f / (float)n_batch;
+	const uint32_t L = M.n_levels, n_live = min(L, valid_level + 1u);
+	uint32_t phase = 0, phase_dw = 0;
+	float var_acc = 0.f;
+	bool first = true;
+	auto issue_begin = [&]() { tmem_st_wait(); fence_async_smem(); tc_fence_before(); __syncthreads(); };
+	auto issue_end = [&]() { mbar_wait(&bar, phase); phase ^= 1; tc_fence_after(); };
+	// chain layer: D[128 x N] = A(smem tile, K-major, K = 16 * ksteps) . B
+	auto chain = [&](uint32_t d_col, uint32_t sA, int ksteps, uint32_t sB, uint32_t b_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc) {
+		for (int k = 0; k < ksteps; ++k) umma(tmem + d_col, make_desc(sA + k * 2 * PS, PS, 128), make_desc(sB + k * b_kstep, b_lbo, b_sbo), idesc, k);
+	};
+	// weight-gradient product: ACC[64 x N] (+)= A^T(smem tile [128 x 64], MN-major) . B(smem tile [128 x N], MN-major), K = 128 samples
+	auto wgrad = [&](uint32_t acc_col, uint32_t sA, uint32_t sB, uint32_t idesc, bool accumulate) {
+		for (int k = 0; k < 8; ++k) umma(tmem + acc_col, make_desc(sA + k * 256, 128, PS), make_desc(sB + k * 256, 128, PS), idesc, (accumulate || k > 0) ? 1u : 0u);
+	};
+	// this thread's row of a 64-/32-wide result -> relu'(mask) .* binary16 -> panelised tile
+	auto row64_masked_to_tile = [&](uint32_t col, uint64_t mask, uint32_t dst) {
+		#pragma unroll
+		for (int c = 0; c < SW / 32; ++c) {
+			float v[32];
+			tmem_ld32(trow + col + c * 32, v);
+			uint32_t g[16];
+			#pragma unroll
+			for (int k = 0; k < 32; k += 2) g[k >> 1] = pack_h2(((mask >> (c * 32 + k)) & 1ull) ? v[k] : 0.f, ((mask >> (c * 32 + k + 1)) & 1ull) ? v[k + 1] : 0.f);
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + dst + (c * 4 + j) * PS + tid * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+		}
+	};
+	auto row64_relu_to_tile = [&](uint32_t col, uint32_t dst) -> uint64_t {
+		uint64_t mask = 0ull;
+		#pragma unroll
+		for (int c = 0; c < SW / 32; ++c) {
+			float v[32];
+			tmem_ld32(trow + col + c * 32, v);
+			uint32_t g[16];
+			#pragma unroll
+			for (int k = 0; k < 32; k += 2) {
+				const float a = hq(fmaxf(v[k], 0.f)), b = hq(fmaxf(v[k + 1], 0.f));
+				if (a > 0.f) mask |= 1ull << (c * 32 + k);
+				if (b > 0.f) mask |= 1ull << (c * 32 + k + 1);
+				g[k >> 1] = pack_h2(a, b);
+			}
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + dst + (c * 4 + j) * PS + tid * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+		}
+		return mask;
+	};
+
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const uint32_t row = tile * TILE + tid;
+		const bool live = row < n;
+		const float4 p = pos4[min(row, n - 1)];
+		// incoming gradient row, scaled by the roll-over multiplicity, binary16 (fill_rollover_and_rescale, common_device.h:525-535)
+		float d[11];
+		{
+			const uint4* dp = reinterpret_cast<const uint4*>(dout16 + (size_t)min(row, n - 1) * 16);
+			const uint4 lo = __ldg(dp), hi = __ldg(dp + 1);
+			const float w = live ? rollover_weight(row, min(n_in, n_roll), n_roll) : 0.f;
+			const uint32_t u[6] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y};
+			#pragma unroll
+			for (int i = 0; i < 11; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i >> 1])); d[i] = hq(((i & 1) ? f.y : f.x) * w); }
+		}
+		var_acc += d[7];
+		// the previous tile's weight-gradient products read X, TM, V, DH ... : they must have completed before those tiles are rewritten
+		if (!first) { mbar_wait(&bar_dw, phase_dw); phase_dw ^= 1; tc_fence_after(); }
+		gather_row_bwd(M, P, valid_level, p.x, p.y, p.z, smem + XB, trow + C_DY, tid);
+		*reinterpret_cast<uint4*>(smem + DCB + tid * 16) = make_uint4(pack_h2(d[0], d[1]), pack_h2(d[2], 0.f), 0u, 0u);      // dL/dc: only the albedo logits carry gradient
+		// ---- F1: hidden = X . W1^T
+		issue_begin();
+		if (tid == 0) { tc_fence_after(); chain(C_D, sX, 2, sW1, 2 * (SW * 16), SW * 16, 128, ID_W); umma_commit(&bar); }
+		issue_end();
+		uint64_t m0 = 0ull;
+		float sdf = 0.f;
+		#pragma unroll
+		for (int c = 0; c < SW / 32; ++c) {
+			float h[32];
+			tmem_ld32(trow + C_D + c * 32, h);
+			uint32_t hh[16], g[16];
+			#pragma unroll
+			for (int k = 0; k < 32; k += 2) {
+				const float h0 = hq(fmaxf(h[k], 0.f)), h1 = hq(fmaxf(h[k + 1], 0.f));
+				const float w0 = w2r[c * 32 + k], w1 = w2r[c * 32 + k + 1];
+				sdf = fmaf(h0, w0, sdf); sdf = fmaf(h1, w1, sdf);
+				if (h0 > 0.f) m0 |= 1ull << (c * 32 + k);
+				if (h1 > 0.f) m0 |= 1ull << (c * 32 + k + 1);
+				hh[k >> 1] = pack_h2(h0, h1);
+				g[k >> 1] = pack_h2(h0 > 0.f ? w0 : 0.f, h1 > 0.f ? w1 : 0.f);
+			}
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				*reinterpret_cast<uint4*>(smem + HB + (c * 4 + j) * PS + tid * 16) = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+				*reinterpret_cast<uint4*>(smem + TMB + (c * 4 + j) * PS + tid * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+			}
+		}
+		// ---- F2: y = H . W2^T | B1: gin = tm . W1
+		issue_begin();
+		if (tid == 0) {
+			tc_fence_after();
+			chain(C_16, sH, SW / 16, sW2, 2 * (16 * 16), 16 * 16, 128, ID_16);
+			chain(C_GIN, sTM, SW / 16, sW1, 256, 128, SW * 16, ID_T32);
+			umma_commit(&bar);
+		}
+		issue_end();
+		float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+		{
+			float gin[32];
+			tmem_ld32(trow + C_GIN, gin);
+			#pragma unroll
+			for (uint32_t l = 0; l < 16; ++l) {
+				const float g0 = hq(gin[2 * l]), g1 = hq(gin[2 * l + 1]);
+				if (l < L) {
+					if (l < n_live) {
+						float a[4], b2[2];
+						tmem_ld4(trow + C_DY + l * 8, a); tmem_ld2(trow + C_DY + l * 8 + 4, b2[0], b2[1]);
+						n0 = fmaf(g0, a[0], n0); n1 = fmaf(g0, a[1], n1); n2 = fmaf(g0, a[2], n2);
+						n0 = fmaf(g1, a[3], n0); n1 = fmaf(g1, b2[0], n1); n2 = fmaf(g1, b2[1], n2);
+					}
+				} else if (l == L) { n0 += g0; n1 += g1; }
+				else if (l == L + 1) { n2 += g0; }
+			}
+		}
+		{   // colour input r' tile: [y (16) | x y z n0 n1 n2 0 0 | 0 (8)]
+			float y[16];
+			tmem_ld16(trow + C_16, y);
+			y[0] = sdf;
+			uint32_t r[8];
+			#pragma unroll
+			for (int k = 0; k < 16; k += 2) r[k >> 1] = pack_h2(y[k], y[k + 1]);
+			*reinterpret_cast<uint4*>(smem + RB + 0 * PS + tid * 16) = make_uint4(r[0], r[1], r[2], r[3]);
+			*reinterpret_cast<uint4*>(smem + RB + 1 * PS + tid * 16) = make_uint4(r[4], r[5], r[6], r[7]);
+			*reinterpret_cast<uint4*>(smem + RB + 2 * PS + tid * 16) = make_uint4(pack_h2(p.x, p.y), pack_h2(p.z, n0), pack_h2(n1, n2), 0u);
+		}
+		// ---- F3: H1 = relu(R . C1^T)
+		issue_begin();
+		if (tid == 0) { tc_fence_after(); chain(C_D, sR, 2, sC1, 2 * (SW * 16), SW * 16, 128, ID_W); umma_commit(&bar); }
+		issue_end();
+		const uint64_t m1 = row64_relu_to_tile(C_D, H1B);
+		uint64_t m2 = 0ull;
+		if constexpr (RGB3) {
+			// ---- F4: H2 = relu(H1 . C2^T) | B2: dH2 = relu'(H2) .* (dC . C3)
+			issue_begin();
+			if (tid == 0) {
+				tc_fence_after();
+				chain(C_D, sH1, SW / 16, sC2, 2 * (SW * 16), SW * 16, 128, ID_W);
+				chain(C_D2, sDC, 1, sC3, 0, 128, 16 * 16, ID_TW);
+				umma_commit(&bar);
+			}
+			issue_end();
+			m2 = row64_relu_to_tile(C_D, H2B);
+			row64_masked_to_tile(C_D2, m2, DH2B);
+			// ---- B3: dH1 = relu'(H1) .* (dH2 . C2);   dC3^T += H2^T . dC
+			issue_begin();
+			if (tid == 0) {
+				tc_fence_after();
+				chain(C_D, sDH2, SW / 16, sC2, 256, 128, SW * 16, ID_TW);
+				umma_commit(&bar);
+				wgrad(A_C3T, sH2, sDC, IDG_16, !first);
+			}
+			issue_end();
+			row64_masked_to_tile(C_D, m1, DH1B);
+		} else {
+			// two-matrix colour MLP: dH1 = relu'(H1) .* (dC . C3)
+			issue_begin();
+			if (tid == 0) { tc_fence_after(); chain(C_D, sDC, 1, sC3, 0, 128, 16 * 16, ID_TW); umma_commit(&bar); }
+			issue_end();
+			row64_masked_to_tile(C_D, m1, DH1B);
+		}
+		// ---- B4: dR = dH1 . C1 (32 wide);   dC2 += dH2^T . H1  /  dC3^T += H1^T . dC
+		issue_begin();
+		if (tid == 0) {
+			tc_fence_after();
+			chain(C_32, sDH1, SW / 16, sC1, 256, 128, SW * 16, ID_T32);
+			umma_commit(&bar);
+			if (RGB3) wgrad(A_C2, sDH2, sH1, IDG_W, !first); else wgrad(A_C3T, sH1, sDC, IDG_16, !first);
+		}
+		issue_end();
+		float gn[3];
+		{
+			float dr[32];
+			tmem_ld32(trow + C_32, dr);
+			// dL/dy = dL/dr'[0:16] (+ dout[3] on the sdf, binary16 add);  g_n = dL/dr'[normal] + dout[4:7]/N + dout[8:11]   (nerf_network.h:343-373)
+			uint32_t r[8];
+			const float y0 = __half2float(__hadd(__float2half_rn(dr[0]), __float2half_rn(d[3])));
+			r[0] = pack_h2(y0, hq(dr[1]));
+			#pragma unroll
+			for (int k = 2; k < 16; k += 2) r[k >> 1] = pack_h2(dr[k], dr[k + 1]);
+			*reinterpret_cast<uint4*>(smem + DYB + 0 * PS + tid * 16) = make_uint4(r[0], r[1], r[2], r[3]);
+			*reinterpret_cast<uint4*>(smem + DYB + 1 * PS + tid * 16) = make_uint4(r[4], r[5], r[6], r[7]);
+			gn[0] = hq(dr[19]) + d[4] * inv_nb + d[8]; gn[1] = hq(dr[20]) + d[5] * inv_nb + d[9]; gn[2] = hq(dr[21]) + d[6] * inv_nb + d[10];
+		}
+		{   // second-order input V = (dy/dx) g_n per encoding column, g_n on the position columns (fully_fused_mlp.cu:1036-1142 front[0])
+			#pragma unroll 1
+			for (uint32_t b = 0; b < 16; b += 4) {
+				uint32_t w[4] = {0u, 0u, 0u, 0u};
+				#pragma unroll
+				for (uint32_t i = 0; i < 4; ++i) {
+					const uint32_t l = b + i;
+					if (l < n_live) {
+						float a[4], b2[2];
+						tmem_ld4(trow + C_DY + l * 8, a); tmem_ld2(trow + C_DY + l * 8 + 4, b2[0], b2[1]);
+						w[i] = pack_h2(a[0] * gn[0] + a[1] * gn[1] + a[2] * gn[2], a[3] * gn[0] + b2[0] * gn[1] + b2[1] * gn[2]);
+					} else if (l == L) w[i] = pack_h2(gn[0], gn[1]);
+					else if (l == L + 1) w[i] = pack_h2(gn[2], 0.f);
+				}
+				*reinterpret_cast<uint4*>(smem + VB + (b >> 2) * PS + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+			}
+		}
+		// ---- B5: dH = relu'(H) .* (dY . W2) | S1: front1 = relu'(H) .* (V . W1^T);   dC1 += dH1^T . R
+		issue_begin();
+		if (tid == 0) {
+			tc_fence_after();
+			chain(C_D, sDY, 1, sW2, 0, 128, 16 * 16, ID_TW);
+			chain(C_D2, sV, 2, sW1, 2 * (SW * 16), SW * 16, 128, ID_W);
+			umma_commit(&bar);
+			wgrad(A_C1, sDH1, sR, IDG_32, !first);
+		}
+		issue_end();
+		row64_masked_to_tile(C_D, m0, DHB);
+		row64_masked_to_tile(C_D2, m0, F1B);
+		// ---- B6: dU = dH . W1 (32 wide);   dW2^T += H^T . dY + front1^T . e0;   dW1 += dH^T . X + tm^T . V
+		issue_begin();
+		if (tid == 0) {
+			tc_fence_after();
+			chain(C_32, sDH, SW / 16, sW1, 256, 128, SW * 16, ID_T32);
+			umma_commit(&bar);
+			wgrad(A_W2T, sH, sDY, IDG_16, !first);
+			wgrad(A_W2T, sF1, sE0, IDG_16, true);
+			wgrad(A_W1, sDH, sX, IDG_32, !first);
+			wgrad(A_W1, sTM, sV, IDG_32, true);
+			umma_commit(&bar_dw);
+		}
+		issue_end();
+		// ---- merged first + second order hash scatter, one level at a time (values re-read from TMEM)
+		#pragma unroll 1
+		for (uint32_t l = 0; l < n_live; ++l) {
+			float du0, du1, g0, g1;
+			tmem_ld2(trow + C_32 + 2 * l, du0, du1);          // tcgen05.ld is warp-collective: executed by every lane, live or not
+			tmem_ld2(trow + C_GIN + 2 * l, g0, g1);
+			if (live) scatter_level(M, G, l, p.x, p.y, p.z, hq(du0), hq(du1), hq(g0), hq(g1), gn[0], gn[1], gn[2]);
+		}
+		first = false;
+	}
+	// ---- flush: TMEM accumulators -> global gradient buffer (un-permuting the input columns); one atomicAdd per element per CTA
+	if (!first) { mbar_wait(&bar_dw, phase_dw); tc_fence_after(); }
+	if (!first) {
+		// M = 64 accumulator: row r lives in lane (r / 16) * 32 + r % 16.  The TMEM loads are warp-collective (all lanes), only the
+		// lanes that hold a row issue atomics.
+		const int r = (tid >> 5) * 16 + (tid & 15);
+		const bool own = (tid & 31) < 16 && r < SW;
+		const int ne = (int)M.n_enc;
+		{   // dW1 [SW x 32] in u' order
+			float v[32]; tmem_ld32(trow + A_W1, v);
+			const LayerDesc& Ld = M.sdf_layers[0];
+			if (own) {
+				#pragma unroll
+				for (int k = 0; k < 32; ++k) { const int kc = k < ne ? 3 + k : (k < ne + 3 ? k - ne : -1); if (kc >= 0 && kc < (int)Ld.cols && v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + kc], v[k]); }
+			}
+		}
+		{   // dW2^T [SW x 16]
+			float v[16]; tmem_ld16(trow + A_W2T, v);
+			const LayerDesc& Ld = M.sdf_layers[1];
+			if (own) {
+				#pragma unroll
+				for (int o = 0; o < 16; ++o) if (v[o] != 0.f) atomicAdd(&G[Ld.off + (size_t)o * Ld.cols + r], v[o]);
+			}
+		}
+		{   // dC1 [SW x 32] in r' order
+			float v[32]; tmem_ld32(trow + A_C1, v);
+			const LayerDesc& Ld = M.rgb_layers[0];
+			if (own) {
+				#pragma unroll
+				for (int k = 0; k < 32; ++k) { const int kc = k < 16 ? k : 16 + k; if (kc < (int)Ld.cols && v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + kc], v[k]); }
+			}
+		}
+		if constexpr (RGB3) {
+			const LayerDesc& Ld = M.rgb_layers[1];
+			#pragma unroll
+			for (int c = 0; c < SW / 32; ++c) {
+				float v[32]; tmem_ld32(trow + A_C2 + c * 32, v);
+				if (own) {
+					#pragma unroll
+					for (int k = 0; k < 32; ++k) if (v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + c * 32 + k], v[k]);
+				}
+			}
+		}
+		{   // dC3^T [SW x 16]
+			float v[16]; tmem_ld16(trow + A_C3T, v);
+			const LayerDesc& Ld = M.rgb_layers[M.n_rgb_layers - 1];
+			if (own) {
+				#pragma unroll
+				for (int o = 0; o < 16; ++o) if (v[o] != 0.f) atomicAdd(&G[Ld.off + (size_t)o * Ld.cols + r], v[o]);
+			}
+		}
+	}
+	for (int o = 16; o; o >>= 1) var_acc += __shfl_xor_sync(0xffffffffu, var_acc, o);
+	if ((tid & 31) == 0 && var_acc != 0.f) atomicAdd(&G[M.off_var], var_acc);
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) tmem_free<512>(tmem);
+}
+
 } // namespace tc
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -512,10 +918,36 @@ static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __h
 			if (!attr) { cudaFuncSetAttribute(k_full_tc<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
 			k_full_tc<SW, false><<<grid, TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, ray_dirw, outA);
 		}
+	} else if (what == 4) {
+		return;      // backward: see launch_tc_backward
 	} else {
 		const size_t smem = DYB;
 		k_sdf_tc<SW, 1><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, nullptr, sdf_out, dens_out);
 	}
+}
+
+template <int SW>
+static void launch_tc_backward_sw(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
+                                  uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
+	using namespace tc;
+	using B = Blob<SW>;
+	if (!n_max) return;
+	const size_t smem = ((B::END + 127u) & ~127u) + 3 * (TILE * 64) + 8 * (TILE * SW * 2) + 3 * (TILE * 32) + 8192 /* M = 64 products of a 32-wide tile read 4 panels past it */;
+	const uint32_t grid = std::min<uint32_t>((n_max + TILE - 1) / TILE, (uint32_t)n_sm);
+	if (M.n_rgb_layers == 3) {
+		static bool attr = false;
+		if (!attr) { cudaFuncSetAttribute(k_backward_tc<SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+		k_backward_tc<SW, true><<<grid, TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+	} else {
+		static bool attr = false;
+		if (!attr) { cudaFuncSetAttribute(k_backward_tc<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+		k_backward_tc<SW, false><<<grid, TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+	}
+}
+void launch_tc_backward(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
+                        uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
+	if (M.sdf_width == 64) launch_tc_backward_sw<64>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
+	else launch_tc_backward_sw<32>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
 }
 
 // what: 0 pack weights, 1 pass A (outA = 4 halfs per sample), 2 SDF probe (sdf_out / dens_out), 3 full forward (outA = 16 halfs per sample, needs ray_dirw)
