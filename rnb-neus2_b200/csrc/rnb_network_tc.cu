@@ -248,9 +248,10 @@ __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __
 		mbar_wait(&bar, phase); phase ^= 1;
 		tc_fence_after();
 		// hidden activation of this sample: ReLU, binary16 rounding; SDF output 0; one-hot chain input tm = relu'(h) .* W2[0,:]
-		float sdf = 0.f;
+		float sdf = 0.f;          // = part(columns 0-31) + part(columns 32-63): the same order in pass A, pass B and the backward recompute
 		#pragma unroll
 		for (int c = 0; c < SW / 32; ++c) {
+			float part = 0.f;
 			float h[32];
 			tmem_ld32(trow + C_ACC + c * 32, h);
 			uint32_t g[16];
@@ -258,10 +259,11 @@ __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __
 			for (int k = 0; k < 32; k += 2) {
 				const float h0 = hq(fmaxf(h[k], 0.f)), h1 = hq(fmaxf(h[k + 1], 0.f));
 				const float w0 = w2r[c * 32 + k], w1 = w2r[c * 32 + k + 1];
-				sdf = fmaf(h0, w0, sdf); sdf = fmaf(h1, w1, sdf);
+				part = fmaf(h0, w0, part); part = fmaf(h1, w1, part);
 				if (NORMAL) g[k >> 1] = pack_h2(h0 > 0.f ? w0 : 0.f, h1 > 0.f ? w1 : 0.f);
 			}
 			if (NORMAL) tmem_st16(trow + C_TM + c * 16, g);
+			sdf += part;
 		}
 		const __half sdfb = __hadd(__float2half_rn(sdf), __float2half_rn(M.sdf_bias));
 		if (NORMAL) {
@@ -281,18 +283,21 @@ __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __
 			tmem_ld32(trow + C_GIN, gin);
 			float n0 = 0.f, n1 = 0.f, n2 = 0.f;
 			const uint32_t L = M.n_levels;
+			float q0 = 0.f, q1 = 0.f, q2 = 0.f;       // levels 8-15 are summed apart (the backward kernel splits a sample over two threads the same way)
 			#pragma unroll
 			for (uint32_t l = 0; l < 16; ++l) {
 				const float g0 = hq(gin[2 * l]), g1 = hq(gin[2 * l + 1]);
+				float& a0 = l < 8 ? n0 : q0; float& a1 = l < 8 ? n1 : q1; float& a2 = l < 8 ? n2 : q2;
 				if (l < L) {
 					if (l <= valid_level) {
 						const float* d = dyS + (l * 6) * TILE + tid;
-						n0 = fmaf(g0, d[0], n0); n1 = fmaf(g0, d[TILE], n1); n2 = fmaf(g0, d[2 * TILE], n2);
-						n0 = fmaf(g1, d[3 * TILE], n0); n1 = fmaf(g1, d[4 * TILE], n1); n2 = fmaf(g1, d[5 * TILE], n2);
+						a0 = fmaf(g0, d[0], a0); a1 = fmaf(g0, d[TILE], a1); a2 = fmaf(g0, d[2 * TILE], a2);
+						a0 = fmaf(g1, d[3 * TILE], a0); a1 = fmaf(g1, d[4 * TILE], a1); a2 = fmaf(g1, d[5 * TILE], a2);
 					}
-				} else if (l == L) { n0 += g0; n1 += g1; }
-				else if (l == L + 1) { n2 += g0; }
+				} else if (l == L) { a0 += g0; a1 += g1; }
+				else if (l == L + 1) { a2 += g0; }
 			}
+			n0 += q0; n1 += q1; n2 += q2;
 			if (row < n) {
 				uint2 v; v.x = pack_h2(__half2float(sdfb), n0); v.y = pack_h2(n1, n2);
 				reinterpret_cast<uint2*>(outA)[row] = v;
@@ -373,9 +378,10 @@ __global__ void __launch_bounds__(TILE, 3) k_full_tc(ModelDev M, const __half* _
 			umma_commit(&bar);
 		}
 		issue_end();
-		float sdf = 0.f;
+		float sdf = 0.f;          // = part(columns 0-31) + part(columns 32-63): the same order in pass A, pass B and the backward recompute
 		#pragma unroll
 		for (int c = 0; c < SW / 32; ++c) {
+			float part = 0.f;
 			float h[32];
 			tmem_ld32(trow + C_ACC + c * 32, h);
 			uint32_t hh[16], g[16];
@@ -383,12 +389,13 @@ __global__ void __launch_bounds__(TILE, 3) k_full_tc(ModelDev M, const __half* _
 			for (int k = 0; k < 32; k += 2) {
 				const float h0 = hq(fmaxf(h[k], 0.f)), h1 = hq(fmaxf(h[k + 1], 0.f));
 				const float w0 = w2r[c * 32 + k], w1 = w2r[c * 32 + k + 1];
-				sdf = fmaf(h0, w0, sdf); sdf = fmaf(h1, w1, sdf);
+				part = fmaf(h0, w0, part); part = fmaf(h1, w1, part);
 				hh[k >> 1] = pack_h2(h0, h1);
 				g[k >> 1] = pack_h2(h0 > 0.f ? w0 : 0.f, h1 > 0.f ? w1 : 0.f);
 			}
 			tmem_st16(trow + C_A + c * 16, hh);
 			tmem_st16(trow + C_TM + c * 16, g);
+			sdf += part;
 		}
 		const __half sdfb = __hadd(__float2half_rn(sdf), __float2half_rn(M.sdf_bias));
 		// F2: y = H . W2^T (16 wide)   |   B1: d sdf / d u' = tm . W1
@@ -407,18 +414,21 @@ __global__ void __launch_bounds__(TILE, 3) k_full_tc(ModelDev M, const __half* _
 			float gin[32];
 			tmem_ld32(trow + C_GIN, gin);
 			const uint32_t L = M.n_levels;
+			float q0 = 0.f, q1 = 0.f, q2 = 0.f;       // levels 8-15 are summed apart (the backward kernel splits a sample over two threads the same way)
 			#pragma unroll
 			for (uint32_t l = 0; l < 16; ++l) {
 				const float g0 = hq(gin[2 * l]), g1 = hq(gin[2 * l + 1]);
+				float& a0 = l < 8 ? n0 : q0; float& a1 = l < 8 ? n1 : q1; float& a2 = l < 8 ? n2 : q2;
 				if (l < L) {
 					if (l <= valid_level) {
 						const float* d = dyS + (l * 6) * TILE + tid;
-						n0 = fmaf(g0, d[0], n0); n1 = fmaf(g0, d[TILE], n1); n2 = fmaf(g0, d[2 * TILE], n2);
-						n0 = fmaf(g1, d[3 * TILE], n0); n1 = fmaf(g1, d[4 * TILE], n1); n2 = fmaf(g1, d[5 * TILE], n2);
+						a0 = fmaf(g0, d[0], a0); a1 = fmaf(g0, d[TILE], a1); a2 = fmaf(g0, d[2 * TILE], a2);
+						a0 = fmaf(g1, d[3 * TILE], a0); a1 = fmaf(g1, d[4 * TILE], a1); a2 = fmaf(g1, d[5 * TILE], a2);
 					}
-				} else if (l == L) { n0 += g0; n1 += g1; }
-				else if (l == L + 1) { n2 += g0; }
+				} else if (l == L) { a0 += g0; a1 += g1; }
+				else if (l == L + 1) { a2 += g0; }
 			}
+			n0 += q0; n1 += q1; n2 += q2;
 		}
 		{   // colour input r' (replaces H in TMEM): [y (16) | x y z n0 n1 n2 0 0 | 0 (8)]
 			float y[16];
@@ -510,14 +520,16 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
 	for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// gather for the backward: the MLP input row goes to the X tile in shared memory (it is a weight-gradient operand), dy/dx to TMEM
-__device__ __forceinline__ void gather_row_bwd(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint8_t* __restrict__ xtile, uint32_t tcol_dy, int tid) {
+// gather for the backward: the MLP input row goes to the X tile in shared memory (it is a weight-gradient operand), dy/dx to TMEM.
+// Two threads share one sample: `half` 0 gathers levels 0-7 (X chunks 0,1), `half` 1 levels 8-15 (chunks 2,3).
+__device__ __forceinline__ void gather_row_bwd(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint8_t* __restrict__ xtile, uint32_t tcol_dy, int row, int half) {
 	const uint32_t L = M.n_levels;
 	const uint32_t n_live = min(L, valid_level + 1u);
 	const __half2 exy = __halves2half2(__hsub(__float2half_rn(x), __float2half_rn(0.5f)), __hsub(__float2half_rn(y), __float2half_rn(0.5f)));
 	const __half2 ez = __halves2half2(__hsub(__float2half_rn(z), __float2half_rn(0.5f)), __float2half_rn(0.f));
 	#pragma unroll 1
-	for (uint32_t b = 0; b < 16; b += 4) {
+	for (uint32_t bb = 0; bb < 8; bb += 4) {
+		const uint32_t b = bb + 8u * (uint32_t)half;
 		uint32_t w[4] = {0u, 0u, 0u, 0u};
 		if (b < n_live) {
 			LevelLoads Q[4];
@@ -539,31 +551,35 @@ __device__ __forceinline__ void gather_row_bwd(const ModelDev& M, const __half* 
 			if (b + i == L) w[i] = *reinterpret_cast<const uint32_t*>(&exy);
 			else if (b + i == L + 1) w[i] = *reinterpret_cast<const uint32_t*>(&ez);
 		}
-		*reinterpret_cast<uint4*>(xtile + (b >> 2) * (TILE * 16) + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+		*reinterpret_cast<uint4*>(xtile + (b >> 2) * (TILE * 16) + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 	}
 }
 
+// 256 threads: thread pair (t, t + 128) shares sample row t of the 128-sample tile (and TMEM lane t: a warp reaches the lane
+// quarter warp % 4).  The pair splits the gather / V / scatter by hash levels and every 64-wide epilogue by column halves, which
+// doubles the warps per SM of this one-CTA-per-SM kernel.
 template <int SW, bool RGB3>
-__global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
-                                                         const float4* __restrict__ pos4, const __half* __restrict__ dout16, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
-                                                         uint32_t n_roll, uint32_t n_batch, const uint32_t* __restrict__ n_in_ptr, float* __restrict__ G) {
+__global__ void __launch_bounds__(2 * TILE, 1) k_backward_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
+                                                             const float4* __restrict__ pos4, const __half* __restrict__ dout16, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
+                                                             uint32_t n_roll, uint32_t n_batch, const uint32_t* __restrict__ n_in_ptr, float* __restrict__ G) {
 	using B = Blob<SW>;
 	constexpr uint32_t T32 = TILE * 64, TW = TILE * SW * 2, T16 = TILE * 32;        // tile bytes: 32-, SW-, 16-wide
 	constexpr uint32_t XB = (B::END + 127u) & ~127u, VB = XB + T32, RB = VB + T32, HB = RB + T32, TMB = HB + TW, DHB = TMB + TW, F1B = DHB + TW,
-	                   H1B = F1B + TW, DH1B = H1B + TW, H2B = DH1B + TW, DH2B = H2B + TW, DYB = DH2B + TW, DCB = DYB + T16, E0B = DCB + T16, SM_END = E0B + T16;
+	                   H1B = F1B + TW, DH1B = H1B + TW, H2B = DH1B + TW, DH2B = H2B + TW, DYB = DH2B + TW, DCB = DYB + T16, E0B = DCB + T16, EXB = E0B + T16, SM_END = EXB + TILE * 32;
 	// TMEM columns
 	constexpr uint32_t C_D = 0, C_D2 = 64, C_16 = 128, C_GIN = 144, C_32 = 176, C_DY = 208;            // chain accumulators, gin (kept for the scatter), dR / dU, dy/dx (14 levels x 8 columns, 6 used)
 	constexpr uint32_t A_W1 = 320, A_W2T = 352, A_C1 = 368, A_C2 = 400, A_C3T = 464;                   // weight-gradient accumulators (M = 64)
+	constexpr int NH = SW / 32;                                         // column halves of a hidden row that carry data (SW = 32: only half 0)
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint32_t tmem_slot;
 	__shared__ __align__(8) uint64_t bar, bar_dw;
-	const int tid = threadIdx.x, warp = tid >> 5;
-	for (uint32_t i = tid; i < B::END / 16; i += TILE) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
-	for (uint32_t i = tid; i < (SM_END - XB) / 16; i += TILE) reinterpret_cast<uint4*>(smem + XB)[i] = make_uint4(0u, 0u, 0u, 0u);
+	const int tid = threadIdx.x, warp = tid >> 5, half = tid >> 7, row_t = tid & (TILE - 1);
+	for (uint32_t i = tid; i < B::END / 16; i += 2 * TILE) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
+	for (uint32_t i = tid; i < (SM_END - XB) / 16; i += 2 * TILE) reinterpret_cast<uint4*>(smem + XB)[i] = make_uint4(0u, 0u, 0u, 0u);
 	__syncthreads();
-	{   // E0: column 0 = 1 (column sums through the tensor core)
+	if (half == 0) {   // E0: column 0 = 1 (column sums through the tensor core)
 		const __half2 one = __halves2half2(__float2half_rn(1.f), __float2half_rn(0.f));
-		*reinterpret_cast<uint4*>(smem + E0B + tid * 16) = make_uint4(*reinterpret_cast<const uint32_t*>(&one), 0u, 0u, 0u);
+		*reinterpret_cast<uint4*>(smem + E0B + row_t * 16) = make_uint4(*reinterpret_cast<const uint32_t*>(&one), 0u, 0u, 0u);
 	}
 	fence_async_smem();
 	if (warp == 0) tmem_alloc<512>(&tmem_slot);
@@ -571,8 +587,9 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
-	const uint32_t tmem = tmem_slot, trow = tmem + ((uint32_t)(warp * 32) << 16);
+	const uint32_t tmem = tmem_slot, trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 	const float* w2r = reinterpret_cast<const float*>(smem + B::W2R);
+	float* ex = reinterpret_cast<float*>(smem + EXB);                   // pair exchange: [0,128) sdf part of half 0, [128,256) half 1, [256 + 3 * (128 h + row)] normal parts
 	const uint32_t sW1 = smem_u32(smem + B::W1), sW2 = smem_u32(smem + B::W2), sC1 = smem_u32(smem + B::C1), sC2 = smem_u32(smem + B::C2), sC3 = smem_u32(smem + B::C3);
 	const uint32_t sX = smem_u32(smem + XB), sV = smem_u32(smem + VB), sR = smem_u32(smem + RB), sH = smem_u32(smem + HB), sTM = smem_u32(smem + TMB), sDH = smem_u32(smem + DHB),
 	               sF1 = smem_u32(smem + F1B), sH1 = smem_u32(smem + H1B), sDH1 = smem_u32(smem + DH1B), sH2 = smem_u32(smem + H2B), sDH2 = smem_u32(smem + DH2B),
@@ -585,6 +602,7 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 	const uint32_t n_tiles = (n + TILE - 1) / TILE;
 	const float inv_nb = 1.0f / (float)n_batch;
 	const uint32_t L = M.n_levels, n_live = min(L, valid_level + 1u);
+	const uint32_t l_begin = 8u * (uint32_t)half, l_end = l_begin + 8u;      // this thread's hash levels (and u' words)
 	uint32_t phase = 0, phase_dw = 0;
 	float var_acc = 0.f;
 	bool first = true;
@@ -598,41 +616,39 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 	auto wgrad = [&](uint32_t acc_col, uint32_t sA, uint32_t sB, uint32_t idesc, bool accumulate) {
 		for (int k = 0; k < 8; ++k) umma(tmem + acc_col, make_desc(sA + k * 256, 128, PS), make_desc(sB + k * 256, 128, PS), idesc, (accumulate || k > 0) ? 1u : 0u);
 	};
-	// this thread's row of a 64-/32-wide result -> relu'(mask) .* binary16 -> panelised tile
-	auto row64_masked_to_tile = [&](uint32_t col, uint64_t mask, uint32_t dst) {
-		#pragma unroll
-		for (int c = 0; c < SW / 32; ++c) {
+	// this thread's 32 columns (col .. col+31 of its half) of a hidden-wide result: relu'(mask) .* binary16 -> 4 chunks of the panelised tile
+	auto half_masked_to_tile = [&](uint32_t col, uint32_t mask, uint32_t dst) {
+		if (half < NH) {
 			float v[32];
-			tmem_ld32(trow + col + c * 32, v);
+			tmem_ld32(trow + col + half * 32, v);
 			uint32_t g[16];
 			#pragma unroll
-			for (int k = 0; k < 32; k += 2) g[k >> 1] = pack_h2(((mask >> (c * 32 + k)) & 1ull) ? v[k] : 0.f, ((mask >> (c * 32 + k + 1)) & 1ull) ? v[k + 1] : 0.f);
+			for (int k = 0; k < 32; k += 2) g[k >> 1] = pack_h2(((mask >> k) & 1u) ? v[k] : 0.f, ((mask >> (k + 1)) & 1u) ? v[k + 1] : 0.f);
 			#pragma unroll
-			for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + dst + (c * 4 + j) * PS + tid * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+			for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + dst + (half * 4 + j) * PS + row_t * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
 		}
 	};
-	auto row64_relu_to_tile = [&](uint32_t col, uint32_t dst) -> uint64_t {
-		uint64_t mask = 0ull;
-		#pragma unroll
-		for (int c = 0; c < SW / 32; ++c) {
+	auto half_relu_to_tile = [&](uint32_t col, uint32_t dst) -> uint32_t {
+		uint32_t mask = 0u;
+		if (half < NH) {
 			float v[32];
-			tmem_ld32(trow + col + c * 32, v);
+			tmem_ld32(trow + col + half * 32, v);
 			uint32_t g[16];
 			#pragma unroll
 			for (int k = 0; k < 32; k += 2) {
 				const float a = hq(fmaxf(v[k], 0.f)), b = hq(fmaxf(v[k + 1], 0.f));
-				if (a > 0.f) mask |= 1ull << (c * 32 + k);
-				if (b > 0.f) mask |= 1ull << (c * 32 + k + 1);
+				if (a > 0.f) mask |= 1u << k;
+				if (b > 0.f) mask |= 1u << (k + 1);
 				g[k >> 1] = pack_h2(a, b);
 			}
 			#pragma unroll
-			for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + dst + (c * 4 + j) * PS + tid * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+			for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(smem + dst + (half * 4 + j) * PS + row_t * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
 		}
 		return mask;
 	};
 
 	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		const uint32_t row = tile * TILE + tid;
+		const uint32_t row = tile * TILE + row_t;
 		const bool live = row < n;
 		const float4 p = pos4[min(row, n - 1)];
 		// incoming gradient row, scaled by the roll-over multiplicity, binary16 (fill_rollover_and_rescale, common_device.h:525-535)
@@ -645,37 +661,39 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 			#pragma unroll
 			for (int i = 0; i < 11; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i >> 1])); d[i] = hq(((i & 1) ? f.y : f.x) * w); }
 		}
-		var_acc += d[7];
+		if (half == 0) var_acc += d[7];
 		// the previous tile's weight-gradient products read X, TM, V, DH ... : they must have completed before those tiles are rewritten
 		if (!first) { mbar_wait(&bar_dw, phase_dw); phase_dw ^= 1; tc_fence_after(); }
-		gather_row_bwd(M, P, valid_level, p.x, p.y, p.z, smem + XB, trow + C_DY, tid);
-		*reinterpret_cast<uint4*>(smem + DCB + tid * 16) = make_uint4(pack_h2(d[0], d[1]), pack_h2(d[2], 0.f), 0u, 0u);      // dL/dc: only the albedo logits carry gradient
+		gather_row_bwd(M, P, valid_level, p.x, p.y, p.z, smem + XB, trow + C_DY, row_t, half);
+		if (half == 0) *reinterpret_cast<uint4*>(smem + DCB + row_t * 16) = make_uint4(pack_h2(d[0], d[1]), pack_h2(d[2], 0.f), 0u, 0u);      // dL/dc: only the albedo logits carry gradient
 		// ---- F1: hidden = X . W1^T
 		issue_begin();
 		if (tid == 0) { tc_fence_after(); chain(C_D, sX, 2, sW1, 2 * (SW * 16), SW * 16, 128, ID_W); umma_commit(&bar); }
 		issue_end();
-		uint64_t m0 = 0ull;
-		float sdf = 0.f;
-		#pragma unroll
-		for (int c = 0; c < SW / 32; ++c) {
-			float h[32];
-			tmem_ld32(trow + C_D + c * 32, h);
-			uint32_t hh[16], g[16];
-			#pragma unroll
-			for (int k = 0; k < 32; k += 2) {
-				const float h0 = hq(fmaxf(h[k], 0.f)), h1 = hq(fmaxf(h[k + 1], 0.f));
-				const float w0 = w2r[c * 32 + k], w1 = w2r[c * 32 + k + 1];
-				sdf = fmaf(h0, w0, sdf); sdf = fmaf(h1, w1, sdf);
-				if (h0 > 0.f) m0 |= 1ull << (c * 32 + k);
-				if (h1 > 0.f) m0 |= 1ull << (c * 32 + k + 1);
-				hh[k >> 1] = pack_h2(h0, h1);
-				g[k >> 1] = pack_h2(h0 > 0.f ? w0 : 0.f, h1 > 0.f ? w1 : 0.f);
+		uint32_t m0 = 0u;
+		{
+			float part = 0.f;
+			if (half < NH) {
+				float h[32];
+				tmem_ld32(trow + C_D + half * 32, h);
+				uint32_t hh[16], g[16];
+				#pragma unroll
+				for (int k = 0; k < 32; k += 2) {
+					const float h0 = hq(fmaxf(h[k], 0.f)), h1 = hq(fmaxf(h[k + 1], 0.f));
+					const float w0 = w2r[half * 32 + k], w1 = w2r[half * 32 + k + 1];
+					part = fmaf(h0, w0, part); part = fmaf(h1, w1, part);
+					if (h0 > 0.f) m0 |= 1u << k;
+					if (h1 > 0.f) m0 |= 1u << (k + 1);
+					hh[k >> 1] = pack_h2(h0, h1);
+					g[k >> 1] = pack_h2(h0 > 0.f ? w0 : 0.f, h1 > 0.f ? w1 : 0.f);
+				}
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					*reinterpret_cast<uint4*>(smem + HB + (half * 4 + j) * PS + row_t * 16) = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+					*reinterpret_cast<uint4*>(smem + TMB + (half * 4 + j) * PS + row_t * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+				}
 			}
-			#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				*reinterpret_cast<uint4*>(smem + HB + (c * 4 + j) * PS + tid * 16) = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
-				*reinterpret_cast<uint4*>(smem + TMB + (c * 4 + j) * PS + tid * 16) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-			}
+			ex[half * TILE + row_t] = part;                    // sdf = part(columns 0-31) + part(columns 32-63): same order in every kernel
 		}
 		// ---- F2: y = H . W2^T | B1: gin = tm . W1
 		issue_begin();
@@ -686,41 +704,48 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 			umma_commit(&bar);
 		}
 		issue_end();
-		float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-		{
-			float gin[32];
-			tmem_ld32(trow + C_GIN, gin);
+		{   // normal: each thread sums its levels (half 1 also the position columns); the pair's parts are added in a fixed order
+			float np0 = 0.f, np1 = 0.f, np2 = 0.f;
+			float gin[16];
+			tmem_ld16(trow + C_GIN + half * 16, gin);
 			#pragma unroll
-			for (uint32_t l = 0; l < 16; ++l) {
-				const float g0 = hq(gin[2 * l]), g1 = hq(gin[2 * l + 1]);
+			for (uint32_t i = 0; i < 8; ++i) {
+				const uint32_t l = l_begin + i;
+				const float g0 = hq(gin[2 * i]), g1 = hq(gin[2 * i + 1]);
 				if (l < L) {
 					if (l < n_live) {
 						float a[4], b2[2];
 						tmem_ld4(trow + C_DY + l * 8, a); tmem_ld2(trow + C_DY + l * 8 + 4, b2[0], b2[1]);
-						n0 = fmaf(g0, a[0], n0); n1 = fmaf(g0, a[1], n1); n2 = fmaf(g0, a[2], n2);
-						n0 = fmaf(g1, a[3], n0); n1 = fmaf(g1, b2[0], n1); n2 = fmaf(g1, b2[1], n2);
+						np0 = fmaf(g0, a[0], np0); np1 = fmaf(g0, a[1], np1); np2 = fmaf(g0, a[2], np2);
+						np0 = fmaf(g1, a[3], np0); np1 = fmaf(g1, b2[0], np1); np2 = fmaf(g1, b2[1], np2);
 					}
-				} else if (l == L) { n0 += g0; n1 += g1; }
-				else if (l == L + 1) { n2 += g0; }
+				} else if (l == L) { np0 += g0; np1 += g1; }
+				else if (l == L + 1) { np2 += g0; }
+			}
+			float* q = ex + 2 * TILE + 3 * (half * TILE + row_t);
+			q[0] = np0; q[1] = np1; q[2] = np2;
+			if (half == 1) {   // colour input r' chunks 0,1: y (16)
+				float y[16];
+				tmem_ld16(trow + C_16, y);
+				y[0] = ex[row_t] + ex[TILE + row_t];
+				uint32_t r[8];
+				#pragma unroll
+				for (int k = 0; k < 16; k += 2) r[k >> 1] = pack_h2(y[k], y[k + 1]);
+				*reinterpret_cast<uint4*>(smem + RB + 0 * PS + row_t * 16) = make_uint4(r[0], r[1], r[2], r[3]);
+				*reinterpret_cast<uint4*>(smem + RB + 1 * PS + row_t * 16) = make_uint4(r[4], r[5], r[6], r[7]);
 			}
 		}
-		{   // colour input r' tile: [y (16) | x y z n0 n1 n2 0 0 | 0 (8)]
-			float y[16];
-			tmem_ld16(trow + C_16, y);
-			y[0] = sdf;
-			uint32_t r[8];
-			#pragma unroll
-			for (int k = 0; k < 16; k += 2) r[k >> 1] = pack_h2(y[k], y[k + 1]);
-			*reinterpret_cast<uint4*>(smem + RB + 0 * PS + tid * 16) = make_uint4(r[0], r[1], r[2], r[3]);
-			*reinterpret_cast<uint4*>(smem + RB + 1 * PS + tid * 16) = make_uint4(r[4], r[5], r[6], r[7]);
-			*reinterpret_cast<uint4*>(smem + RB + 2 * PS + tid * 16) = make_uint4(pack_h2(p.x, p.y), pack_h2(p.z, n0), pack_h2(n1, n2), 0u);
+		__syncthreads();
+		if (half == 0) {   // r' chunk 2: x y z n0 n1 n2 0 0
+			const float* qa = ex + 2 * TILE + 3 * row_t; const float* qb = ex + 2 * TILE + 3 * (TILE + row_t);
+			const float n0 = qa[0] + qb[0], n1 = qa[1] + qb[1], n2 = qa[2] + qb[2];
+			*reinterpret_cast<uint4*>(smem + RB + 2 * PS + row_t * 16) = make_uint4(pack_h2(p.x, p.y), pack_h2(p.z, n0), pack_h2(n1, n2), 0u);
 		}
 		// ---- F3: H1 = relu(R . C1^T)
 		issue_begin();
 		if (tid == 0) { tc_fence_after(); chain(C_D, sR, 2, sC1, 2 * (SW * 16), SW * 16, 128, ID_W); umma_commit(&bar); }
 		issue_end();
-		const uint64_t m1 = row64_relu_to_tile(C_D, H1B);
-		uint64_t m2 = 0ull;
+		const uint32_t m1 = half_relu_to_tile(C_D, H1B);
 		if constexpr (RGB3) {
 			// ---- F4: H2 = relu(H1 . C2^T) | B2: dH2 = relu'(H2) .* (dC . C3)
 			issue_begin();
@@ -731,8 +756,8 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 				umma_commit(&bar);
 			}
 			issue_end();
-			m2 = row64_relu_to_tile(C_D, H2B);
-			row64_masked_to_tile(C_D2, m2, DH2B);
+			const uint32_t m2 = half_relu_to_tile(C_D, H2B);
+			half_masked_to_tile(C_D2, m2, DH2B);
 			// ---- B3: dH1 = relu'(H1) .* (dH2 . C2);   dC3^T += H2^T . dC
 			issue_begin();
 			if (tid == 0) {
@@ -742,13 +767,13 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 				wgrad(A_C3T, sH2, sDC, IDG_16, !first);
 			}
 			issue_end();
-			row64_masked_to_tile(C_D, m1, DH1B);
+			half_masked_to_tile(C_D, m1, DH1B);
 		} else {
 			// two-matrix colour MLP: dH1 = relu'(H1) .* (dC . C3)
 			issue_begin();
 			if (tid == 0) { tc_fence_after(); chain(C_D, sDC, 1, sC3, 0, 128, 16 * 16, ID_TW); umma_commit(&bar); }
 			issue_end();
-			row64_masked_to_tile(C_D, m1, DH1B);
+			half_masked_to_tile(C_D, m1, DH1B);
 		}
 		// ---- B4: dR = dH1 . C1 (32 wide);   dC2 += dH2^T . H1  /  dC3^T += H1^T . dC
 		issue_begin();
@@ -761,21 +786,27 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 		issue_end();
 		float gn[3];
 		{
-			float dr[32];
-			tmem_ld32(trow + C_32, dr);
-			// dL/dy = dL/dr'[0:16] (+ dout[3] on the sdf, binary16 add);  g_n = dL/dr'[normal] + dout[4:7]/N + dout[8:11]   (nerf_network.h:343-373)
-			uint32_t r[8];
-			const float y0 = __half2float(__hadd(__float2half_rn(dr[0]), __float2half_rn(d[3])));
-			r[0] = pack_h2(y0, hq(dr[1]));
-			#pragma unroll
-			for (int k = 2; k < 16; k += 2) r[k >> 1] = pack_h2(dr[k], dr[k + 1]);
-			*reinterpret_cast<uint4*>(smem + DYB + 0 * PS + tid * 16) = make_uint4(r[0], r[1], r[2], r[3]);
-			*reinterpret_cast<uint4*>(smem + DYB + 1 * PS + tid * 16) = make_uint4(r[4], r[5], r[6], r[7]);
-			gn[0] = hq(dr[19]) + d[4] * inv_nb + d[8]; gn[1] = hq(dr[20]) + d[5] * inv_nb + d[9]; gn[2] = hq(dr[21]) + d[6] * inv_nb + d[10];
+			// g_n = dL/dr'[normal] + dout[4:7]/N + dout[8:11]   (nerf_network.h:343-373): both threads of the pair need it
+			float t4[4];
+			tmem_ld4(trow + C_32 + 16, t4);        // columns 16..19: x y z n0
+			float t20, t21;
+			tmem_ld2(trow + C_32 + 20, t20, t21);
+			gn[0] = hq(t4[3]) + d[4] * inv_nb + d[8]; gn[1] = hq(t20) + d[5] * inv_nb + d[9]; gn[2] = hq(t21) + d[6] * inv_nb + d[10];
+			if (half == 0) {   // dL/dy = dL/dr'[0:16] (+ dout[3] on the sdf, binary16 add)
+				float dr[16];
+				tmem_ld16(trow + C_32, dr);
+				uint32_t r[8];
+				const float y0 = __half2float(__hadd(__float2half_rn(dr[0]), __float2half_rn(d[3])));
+				r[0] = pack_h2(y0, hq(dr[1]));
+				#pragma unroll
+				for (int k = 2; k < 16; k += 2) r[k >> 1] = pack_h2(dr[k], dr[k + 1]);
+				*reinterpret_cast<uint4*>(smem + DYB + 0 * PS + row_t * 16) = make_uint4(r[0], r[1], r[2], r[3]);
+				*reinterpret_cast<uint4*>(smem + DYB + 1 * PS + row_t * 16) = make_uint4(r[4], r[5], r[6], r[7]);
+			}
 		}
 		{   // second-order input V = (dy/dx) g_n per encoding column, g_n on the position columns (fully_fused_mlp.cu:1036-1142 front[0])
 			#pragma unroll 1
-			for (uint32_t b = 0; b < 16; b += 4) {
+			for (uint32_t b = l_begin; b < l_end; b += 4) {
 				uint32_t w[4] = {0u, 0u, 0u, 0u};
 				#pragma unroll
 				for (uint32_t i = 0; i < 4; ++i) {
@@ -787,7 +818,7 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 					} else if (l == L) w[i] = pack_h2(gn[0], gn[1]);
 					else if (l == L + 1) w[i] = pack_h2(gn[2], 0.f);
 				}
-				*reinterpret_cast<uint4*>(smem + VB + (b >> 2) * PS + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+				*reinterpret_cast<uint4*>(smem + VB + (b >> 2) * PS + row_t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 			}
 		}
 		// ---- B5: dH = relu'(H) .* (dY . W2) | S1: front1 = relu'(H) .* (V . W1^T);   dC1 += dH1^T . R
@@ -800,8 +831,8 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 			wgrad(A_C1, sDH1, sR, IDG_32, !first);
 		}
 		issue_end();
-		row64_masked_to_tile(C_D, m0, DHB);
-		row64_masked_to_tile(C_D2, m0, F1B);
+		half_masked_to_tile(C_D, m0, DHB);
+		half_masked_to_tile(C_D2, m0, F1B);
 		// ---- B6: dU = dH . W1 (32 wide);   dW2^T += H^T . dY + front1^T . e0;   dW1 += dH^T . X + tm^T . V
 		issue_begin();
 		if (tid == 0) {
@@ -815,9 +846,9 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 			umma_commit(&bar_dw);
 		}
 		issue_end();
-		// ---- merged first + second order hash scatter, one level at a time (values re-read from TMEM)
+		// ---- merged first + second order hash scatter, this thread's levels, one at a time (values re-read from TMEM)
 		#pragma unroll 1
-		for (uint32_t l = 0; l < n_live; ++l) {
+		for (uint32_t l = l_begin; l < min(l_end, n_live); ++l) {
 			float du0, du1, g0, g1;
 			tmem_ld2(trow + C_32 + 2 * l, du0, du1);          // tcgen05.ld is warp-collective: executed by every lane, live or not
 			tmem_ld2(trow + C_GIN + 2 * l, g0, g1);
@@ -829,51 +860,54 @@ __global__ void __launch_bounds__(TILE, 1) k_backward_tc(ModelDev M, const __hal
 	if (!first) { mbar_wait(&bar_dw, phase_dw); tc_fence_after(); }
 	if (!first) {
 		// M = 64 accumulator: row r lives in lane (r / 16) * 32 + r % 16.  The TMEM loads are warp-collective (all lanes), only the
-		// lanes that hold a row issue atomics.
-		const int r = (tid >> 5) * 16 + (tid & 15);
+		// lanes that hold a row issue atomics.  The two halves of the CTA split the accumulators.
+		const int r = (warp & 3) * 16 + (tid & 15);
 		const bool own = (tid & 31) < 16 && r < SW;
 		const int ne = (int)M.n_enc;
-		{   // dW1 [SW x 32] in u' order
-			float v[32]; tmem_ld32(trow + A_W1, v);
-			const LayerDesc& Ld = M.sdf_layers[0];
-			if (own) {
-				#pragma unroll
-				for (int k = 0; k < 32; ++k) { const int kc = k < ne ? 3 + k : (k < ne + 3 ? k - ne : -1); if (kc >= 0 && kc < (int)Ld.cols && v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + kc], v[k]); }
-			}
-		}
-		{   // dW2^T [SW x 16]
-			float v[16]; tmem_ld16(trow + A_W2T, v);
-			const LayerDesc& Ld = M.sdf_layers[1];
-			if (own) {
-				#pragma unroll
-				for (int o = 0; o < 16; ++o) if (v[o] != 0.f) atomicAdd(&G[Ld.off + (size_t)o * Ld.cols + r], v[o]);
-			}
-		}
-		{   // dC1 [SW x 32] in r' order
-			float v[32]; tmem_ld32(trow + A_C1, v);
-			const LayerDesc& Ld = M.rgb_layers[0];
-			if (own) {
-				#pragma unroll
-				for (int k = 0; k < 32; ++k) { const int kc = k < 16 ? k : 16 + k; if (kc < (int)Ld.cols && v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + kc], v[k]); }
-			}
-		}
-		if constexpr (RGB3) {
-			const LayerDesc& Ld = M.rgb_layers[1];
-			#pragma unroll
-			for (int c = 0; c < SW / 32; ++c) {
-				float v[32]; tmem_ld32(trow + A_C2 + c * 32, v);
+		if (half == 0) {
+			{   // dW1 [SW x 32] in u' order
+				float v[32]; tmem_ld32(trow + A_W1, v);
+				const LayerDesc& Ld = M.sdf_layers[0];
 				if (own) {
 					#pragma unroll
-					for (int k = 0; k < 32; ++k) if (v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + c * 32 + k], v[k]);
+					for (int k = 0; k < 32; ++k) { const int kc = k < ne ? 3 + k : (k < ne + 3 ? k - ne : -1); if (kc >= 0 && kc < (int)Ld.cols && v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + kc], v[k]); }
 				}
 			}
-		}
-		{   // dC3^T [SW x 16]
-			float v[16]; tmem_ld16(trow + A_C3T, v);
-			const LayerDesc& Ld = M.rgb_layers[M.n_rgb_layers - 1];
-			if (own) {
+			{   // dW2^T [SW x 16]
+				float v[16]; tmem_ld16(trow + A_W2T, v);
+				const LayerDesc& Ld = M.sdf_layers[1];
+				if (own) {
+					#pragma unroll
+					for (int o = 0; o < 16; ++o) if (v[o] != 0.f) atomicAdd(&G[Ld.off + (size_t)o * Ld.cols + r], v[o]);
+				}
+			}
+			{   // dC1 [SW x 32] in r' order
+				float v[32]; tmem_ld32(trow + A_C1, v);
+				const LayerDesc& Ld = M.rgb_layers[0];
+				if (own) {
+					#pragma unroll
+					for (int k = 0; k < 32; ++k) { const int kc = k < 16 ? k : 16 + k; if (kc < (int)Ld.cols && v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + kc], v[k]); }
+				}
+			}
+		} else {
+			if constexpr (RGB3) {
+				const LayerDesc& Ld = M.rgb_layers[1];
 				#pragma unroll
-				for (int o = 0; o < 16; ++o) if (v[o] != 0.f) atomicAdd(&G[Ld.off + (size_t)o * Ld.cols + r], v[o]);
+				for (int c = 0; c < SW / 32; ++c) {
+					float v[32]; tmem_ld32(trow + A_C2 + c * 32, v);
+					if (own) {
+						#pragma unroll
+						for (int k = 0; k < 32; ++k) if (v[k] != 0.f) atomicAdd(&G[Ld.off + (size_t)r * Ld.cols + c * 32 + k], v[k]);
+					}
+				}
+			}
+			{   // dC3^T [SW x 16]
+				float v[16]; tmem_ld16(trow + A_C3T, v);
+				const LayerDesc& Ld = M.rgb_layers[M.n_rgb_layers - 1];
+				if (own) {
+					#pragma unroll
+					for (int o = 0; o < 16; ++o) if (v[o] != 0.f) atomicAdd(&G[Ld.off + (size_t)o * Ld.cols + r], v[o]);
+				}
 			}
 		}
 	}
@@ -932,16 +966,16 @@ static void launch_tc_backward_sw(cudaStream_t st, const ModelDev& M, const __ha
 	using namespace tc;
 	using B = Blob<SW>;
 	if (!n_max) return;
-	const size_t smem = ((B::END + 127u) & ~127u) + 3 * (TILE * 64) + 8 * (TILE * SW * 2) + 3 * (TILE * 32) + 8192 /* M = 64 products of a 32-wide tile read 4 panels past it */;
+	const size_t smem = ((B::END + 127u) & ~127u) + 3 * (TILE * 64) + 8 * (TILE * SW * 2) + 3 * (TILE * 32) + TILE * 32 /* pair exchange */ + 8192 /* M = 64 products of a 32-wide tile read 4 panels past it */;
 	const uint32_t grid = std::min<uint32_t>((n_max + TILE - 1) / TILE, (uint32_t)n_sm);
 	if (M.n_rgb_layers == 3) {
 		static bool attr = false;
 		if (!attr) { cudaFuncSetAttribute(k_backward_tc<SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-		k_backward_tc<SW, true><<<grid, TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+		k_backward_tc<SW, true><<<grid, 2 * TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
 	} else {
 		static bool attr = false;
 		if (!attr) { cudaFuncSetAttribute(k_backward_tc<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-		k_backward_tc<SW, false><<<grid, TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+		k_backward_tc<SW, false><<<grid, 2 * TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
 	}
 }
 void launch_tc_backward(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
