@@ -85,9 +85,23 @@ __global__ void __launch_bounds__(256) k_march(uint32_t n_rays, uint32_t world, 
 	uint32_t nsamp = 0;
 	bool done = false;
 	for (int chunk = 0; chunk < 80 && !done; ++chunk) {
-		float tl = t0, tc = t0;
-		#pragma unroll
-		for (int j = 0; j < 32; ++j) { if (j == (int)lane) tl = tc; tc += DT; }
+		// Lattice t_{k+1} = fl(t_k + dt) (the reference adds dt step by step, testbed_nerf.cu:311-323,1337-1347).  Inside one binade
+		// every t is a multiple of the same ulp, so the rounded sum advances the BIT PATTERN by a constant D = rn(dt / ulp) (a tie
+		// would need ulp = 2^-32, excluded below): lane j takes bits(t0) + j D.  A chunk that leaves the binade (t crossing 0.5, 1, 2)
+		// or starts below 2^-7 falls back to the sequential adds.
+		float tl, tc;
+		{
+			const uint32_t b0 = __float_as_uint(t0), ebits = b0 & 0x7F800000u;
+			const uint32_t D = __float_as_uint(__uint_as_float(ebits) + DT) - ebits;
+			const uint32_t last = b0 + 32u * D;
+			if (ebits >= 0x3C000000u && ebits < 0x7F000000u && (last & 0x7F800000u) == ebits && (int)b0 > 0) {
+				tl = __uint_as_float(b0 + lane * D); tc = __uint_as_float(last);
+			} else {
+				tl = t0; tc = t0;
+				#pragma unroll
+				for (int j = 0; j < 32; ++j) { if (j == (int)lane) tl = tc; tc += DT; }
+			}
+		}
 		t0 = tc;
 		const float px = fmaf(tl, r.dx, r.ox), py = fmaf(tl, r.dy, r.oy), pz = fmaf(tl, r.dz, r.oz);
 		const bool inside = px >= 0.f && px <= 1.f && py >= 0.f && py <= 1.f && pz >= 0.f && pz <= 1.f;
