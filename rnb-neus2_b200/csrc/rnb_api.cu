@@ -82,6 +82,11 @@ struct rnb_ctx {
 	Pcg32 rng, density_rng;
 	uint32_t training_step = 0, rays_per_batch = 4096, n_rays_total = 0, measured_before = 0, measured = 0;
 	uint32_t step_R = 0, step_nrt = 0; bool in_step = false;
+	// software pipelining of the ray march (it reads only the bitfield, the dataset and the rng, never the parameters): with a
+	// pinned batch size the march of step N+1 is launched on a side stream when the backward of step N has finished, so that it
+	// shares the SMs with the (HBM-bound) optimizer / the gradient all-reduce instead of running alone
+	cudaStream_t side = nullptr; cudaEvent_t ev_bwd = nullptr, ev_march = nullptr;
+	bool prelaunch = true; bool pre_valid = false; uint32_t pre_R = 0, pre_nrt = 0; uint64_t pre_rng_state = 0, pre_rng_inc = 0;
 	bool use_mma = false; uint32_t* wpack = nullptr; int n_sm = 148;
 	bool use_tc = false, use_tc_bwd = false; uint8_t* wtc = nullptr;      // tcgen05 / TMEM kernels (rnb_network_tc.cu) for pass A and the SDF probes
 	// instrumentation: kernel launch counter and optional per-stage CUDA-event timing (bench.py roofline)
@@ -113,6 +118,9 @@ static void prof_resolve(rnb_ctx* c) {      // call after the stream has been sy
 #define KT(name, nk, call) do { prof_begin(c, st, name); call; prof_end(c, st); c->launches += (nk); } while (0)
 
 static uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
+
+// a pre-launched march is only usable if nothing it depends on changed: drop it (after it has drained) otherwise
+static void drop_prelaunch(rnb_ctx* c) { if (c->pre_valid) { cudaStreamSynchronize(c->side); c->pre_valid = false; } }
 
 static uint32_t valid_level_for_step(const rnb_ctx* c, int step) {   // grid.h:1430-1437
 	if (step <= 0) return c->cfg.n_levels;
@@ -214,6 +222,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 	CU(cudaMalloc(&c->counters, 16 * 4)); CU(cudaMemset(c->counters, 0, 16 * 4));
 	CU(cudaMalloc(&c->stats, 8 * 4)); CU(cudaMemset(c->stats, 0, 8 * 4));
 	CU(cudaMallocHost(&c->counters_host, 16 * 4)); CU(cudaMallocHost(&c->stats_host, 8 * 4));
+	CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_march, cudaEventDisableTiming));
 	{
 		cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev)); c->n_sm = prop.multiProcessorCount;
 		const char* e = getenv("RNB_NETWORK");        // "simt" selects the CUDA-core kernels (cross-check path)
@@ -221,6 +230,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 		CU(cudaMalloc(&c->wpack, mma_pack_u32(M) * 4)); CU(cudaMemset(c->wpack, 0, mma_pack_u32(M) * 4));
 		// RNB_NETWORK=mma keeps the mma.sync tile kernels everywhere; default: tcgen05 kernels where they exist
 		if (const char* d = getenv("RNB_BW_DEBUG")) set_bw_debug(atoi(d));
+		if (const char* d = getenv("RNB_PRELAUNCH")) c->prelaunch = atoi(d) != 0;
 		c->use_tc = c->use_mma && tc_supported(M) && !(e && std::string(e) == "mma");
 		c->use_tc_bwd = c->use_tc && !(getenv("RNB_BACKWARD") && std::string(getenv("RNB_BACKWARD")) == "mma");     // RNB_BACKWARD=mma: mma.sync backward
 		CU(cudaMalloc(&c->wtc, tc_blob_bytes(M))); CU(cudaMemset(c->wtc, 0, tc_blob_bytes(M)));
@@ -241,6 +251,9 @@ int rnb_destroy(rnb_ctx* c) {
 	for (void* p : ptrs) cudaFree(p);
 	for (void* p : c->owned) cudaFree(p);
 	cudaFreeHost(c->counters_host); cudaFreeHost(c->stats_host);
+	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+	if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
+	if (c->ev_march) cudaEventDestroy(c->ev_march);
 	delete c;
 	return RNB_OK;
 }
@@ -344,6 +357,7 @@ int rnb_get_bitfield(rnb_ctx* c, uint8_t* host, size_t n) {
 }
 int rnb_set_bitfield(rnb_ctx* c, const uint8_t* host, size_t n) {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "bitfield is 128^3 bytes");
+	drop_prelaunch(c);
 	CU(cudaMemcpy(c->bitfield, host, n, cudaMemcpyHostToDevice));
 	return RNB_OK;
 }
@@ -353,6 +367,7 @@ int rnb_get_train_state(rnb_ctx* c, uint32_t out[4]) {
 	return RNB_OK;
 }
 int rnb_set_train_state(rnb_ctx* c, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) {
+	if (c) drop_prelaunch(c);
 	if (!c || rays_per_batch == 0 || rays_per_batch > (1u << 18)) return fail(RNB_ERR_INVALID, "bad train state");
 	c->training_step = training_step; c->rays_per_batch = rays_per_batch; c->n_rays_total = n_rays_total; c->measured_before = measured_before;
 	return ensure_ray_capacity(c, rays_per_batch);
@@ -363,11 +378,13 @@ int rnb_get_rng(rnb_ctx* c, uint64_t out[4]) {
 }
 int rnb_set_rng(rnb_ctx* c, const uint64_t in[4]) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	drop_prelaunch(c);
 	c->rng.state = in[0]; c->rng.inc = in[1]; c->density_rng.state = in[2]; c->density_rng.inc = in[3]; return RNB_OK;
 }
 
 static int set_views(rnb_ctx* c, const rnb_view* views, uint32_t n, bool upload) {
 	if (!c || !views || n == 0) return fail(RNB_ERR_INVALID, "no views");
+	drop_prelaunch(c);
 	for (void* p : c->owned) cudaFree(p);
 	c->owned.clear();
 	std::vector<ViewDev> vd(n);
@@ -396,6 +413,7 @@ int rnb_set_flags(rnb_ctx* c, const rnb_flags* f) { if (!c || !f) return fail(RN
 
 int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t ema_step) {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "density grid is 128^3 floats");
+	drop_prelaunch(c);
 	CU(cudaMemcpy(c->density_grid, host, n * 4, cudaMemcpyHostToDevice));
 	c->density_ema_step = ema_step;
 	// update_density_grid_mean_and_bitfield (testbed_nerf.cu:3497-3517): bitfield follows the imported grid
@@ -435,6 +453,7 @@ static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint3
 }
 int rnb_prep(rnb_ctx* c, void* stream) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	drop_prelaunch(c);
 	if (c->training_step < 256) return density_update(c, (cudaStream_t)stream, GRID_CELLS, 0);
 	return density_update(c, (cudaStream_t)stream, GRID_CELLS / 4, GRID_CELLS / 4);
 }
@@ -467,7 +486,13 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt, uin
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
 	const ModelDev& M = c->M;
 	const uint32_t G = c->cfg.world_size, local_target = c->cfg.target_batch_size / G;
-	KT("march", 1, launch_march(st, R, G, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts));
+	if (c->pre_valid && c->pre_R == R && c->pre_nrt == nrt && c->pre_rng_state == c->rng.state && c->pre_rng_inc == c->rng.inc) {
+		CU(cudaStreamWaitEvent(st, c->ev_march, 0));            // this step's march already ran in the shadow of the previous optimizer step
+		c->pre_valid = false;
+	} else {
+		drop_prelaunch(c);
+		KT("march", 1, launch_march(st, R, G, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts));
+	}
 	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->ray_n, c->ray_indices, c->numsteps, c->counters),
 	                   launch_emit(st, R, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4),
 	                   launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw)));
@@ -515,6 +540,19 @@ int rnb_train_step_begin(rnb_ctx* c, void* stream) {
 	rc = step_front(c, st, R, nrt, max_inference); if (rc) return rc;
 	c->rng.advance();                                               // :4118
 	c->in_step = true;
+	// pre-launch the NEXT step's march behind this step's backward (pinned batch size only: the adaptive controller fixes the next
+	// batch size after this step's counters are read; not on steps that refresh the occupancy grid first; not while profiling stages)
+	{
+		const uint32_t ts_next = c->training_step + 1, skip = std::min(std::max(ts_next / 16u, 1u), 16u);
+		if (c->cfg.pin_rays_per_batch && !c->prof && c->prelaunch && ts_next % skip != 0 && R <= c->cap_rays) {
+			CU(cudaEventRecord(c->ev_bwd, st));
+			CU(cudaStreamWaitEvent(c->side, c->ev_bwd, 0));
+			launch_march(c->side, R, c->cfg.world_size, c->cfg.rank, c->n_rays_total, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts);
+			CU(cudaEventRecord(c->ev_march, c->side));
+			c->launches += 1;
+			c->pre_valid = true; c->pre_R = R; c->pre_nrt = c->n_rays_total; c->pre_rng_state = c->rng.state; c->pre_rng_inc = c->rng.inc;
+		}
+	}
 	return RNB_OK;
 }
 
@@ -632,6 +670,7 @@ int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, flo
 int rnb_stage_generate(rnb_ctx* c, uint32_t n_rays, uint32_t n_rays_total, uint32_t max_samples, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t counters[2]) {
 	if (!c || !c->views_dev) return fail(RNB_ERR_STATE, "no dataset");
 	if (max_samples > c->max_samples) return fail(RNB_ERR_INVALID, "max_samples exceeds capacity");
+	drop_prelaunch(c);
 	int rc = ensure_ray_capacity(c, n_rays); if (rc) return rc;
 	launch_march(0, n_rays, c->cfg.world_size, c->cfg.rank, n_rays_total, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts);
 	launch_scan_rays(0, n_rays, max_samples, c->ray_n, c->ray_indices, c->numsteps, c->counters);
