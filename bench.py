@@ -240,6 +240,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("RNB_NCCL_DEBUG", "WARN")      # keep stdout to the single JSON line (NCCL prints its version banner there otherwise)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
