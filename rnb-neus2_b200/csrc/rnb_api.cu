@@ -655,11 +655,15 @@ int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, flo
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
 	float4* tmp = nullptr;
 	const size_t CH = 1u << 20;
+	const __half* P = use_ema ? c->ema : c->params;
+	if (c->use_tc && !normal_dev) launch_tc(0, st, c->M, P, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm);     // weight blob of the requested parameter set (re-packed by the next training step)
 	CU(cudaMallocAsync(&tmp, CH * 16, st));
 	for (size_t o = 0; o < n; o += CH) {
 		const size_t m = std::min(CH, n - o);
 		CU(cudaMemcpy2DAsync(tmp, 16, xyz_dev + o * 3, 12, 12, m, cudaMemcpyDeviceToDevice, st));
-		launch_forward_simt(st, c->M, use_ema ? c->ema : c->params, vl, 2, tmp, nullptr, (uint32_t)m, nullptr, nullptr, sdf_dev ? sdf_dev + o : nullptr, normal_dev ? normal_dev + o * 3 : nullptr, density_dev ? density_dev + o : nullptr);
+		// sdf / density only (marching-cubes sweep): the tcgen05 probe kernel; with normals: the CUDA-core kernel
+		if (c->use_tc && !normal_dev) launch_tc(2, st, c->M, P, c->wtc, vl, tmp, nullptr, (uint32_t)m, nullptr, sdf_dev ? sdf_dev + o : nullptr, density_dev ? density_dev + o : nullptr, c->n_sm);
+		else launch_forward_simt(st, c->M, P, vl, 2, tmp, nullptr, (uint32_t)m, nullptr, nullptr, sdf_dev ? sdf_dev + o : nullptr, normal_dev ? normal_dev + o * 3 : nullptr, density_dev ? density_dev + o : nullptr);
 	}
 	CU(cudaFreeAsync(tmp, st));
 	CU(cudaGetLastError());

@@ -209,3 +209,30 @@ def test_full_training_steps_track_the_oracle(pkg, small_scene):
     # three Adam steps move every touched weight by ~3e-3; trajectories agree to a fraction of that
     assert np.abs(p[:o.off_grid] - m_ref[:o.off_grid]).max() < 2e-3
     assert rel_err(p[:o.off_grid], m_ref[:o.off_grid]) < 5e-3
+
+
+@pytest.mark.parametrize("use_ema", [False, True])
+def test_eval_sdf_matches_oracle(pkg, use_ema):
+    """rnb_eval_sdf (NerfNetwork::sdf / ::density, nerf_network.h:454-537) on device buffers: the tcgen05 probe path (sdf, density)
+    and the CUDA-core path (with normals) against the oracle."""
+    import torch
+    o, t = make_pair(pkg, MID, seed_params=11)
+    if use_ema:                               # snapshot hand-off: EMA weights := training weights (trainer.h:263-275)
+        h = t.export_params_fp16(use_ema=False); t.import_params_fp16(h)
+        m = np.asarray(h).view(np.float16).astype(np.float32); o.set_params(m)
+    rs = np.random.RandomState(3)
+    xyz = rs.uniform(0.05, 0.95, (40000, 3)).astype(np.float32)
+    vl = o.valid_level(0)
+    s_ref, d_ref = o.eval_sdf(xyz, vl, use_ema=False)
+    x = torch.from_numpy(xyz).cuda()
+    sdf = torch.empty(xyz.shape[0], device="cuda"); dens = torch.empty_like(sdf); nrm = torch.empty(xyz.shape[0], 3, device="cuda")
+    t.eval_sdf_device(x.data_ptr(), xyz.shape[0], sdf.data_ptr(), None, dens.data_ptr(), use_ema=use_ema)
+    torch.cuda.synchronize()
+    assert rel_err(sdf.cpu().numpy(), s_ref) < TOL
+    assert rel_err(dens.cpu().numpy(), d_ref) < 5e-3          # binary16 arithmetic of sdf_to_density_variance_buffer
+    sdf2 = torch.empty_like(sdf)
+    t.eval_sdf_device(x.data_ptr(), xyz.shape[0], sdf2.data_ptr(), nrm.data_ptr(), None, use_ema=use_ema)
+    torch.cuda.synchronize()
+    assert rel_err(sdf2.cpu().numpy(), s_ref) < TOL
+    assert np.isfinite(nrm.cpu().numpy()).all()
+    assert half_close(sdf2.cpu().numpy(), sdf.cpu().numpy(), ulps=2.0).mean() > 0.999      # the two kernels agree to binary16 rounding
