@@ -293,14 +293,19 @@ def main():
             tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
         return ms, t.launch_count() - l0, last
 
+    # value, e2e and the per-stage pass are all taken on the SAME training steps: the state after warm-up is checkpointed on the device
+    # and restored between the passes (the cost of a step changes with the training step: live hash levels, samples per ray)
+    t.checkpoint_save()
     clocks = ClockSampler(local_rank); clocks.start()
     ms, launches, _ = timed(args.steps, False)
     clk = clocks.stop()
     # end to end through the public call with the per-step read-back of the loss scalars / counters
+    t.checkpoint_restore()
     ms_e2e, _, last = timed(args.steps, True)
     # per-stage device timing for the roofline (events on the launching stream; separate pass so that `value` is undisturbed)
+    t.checkpoint_restore()
     t.profile_enable(True)
-    timed(min(args.steps, 100), True)
+    timed(args.steps, True)
     prof = t.profile_read(); t.profile_enable(False)
 
     value = R * args.steps / (ms * 1e-3)

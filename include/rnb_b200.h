@@ -180,6 +180,12 @@ int rnb_get_grads_fp32(rnb_ctx* ctx, float* host, size_t n);
 int rnb_get_ray_losses(rnb_ctx* ctx, uint32_t cap, uint32_t* ray_idx_host, float* loss3_host, uint32_t* n_out);
 int rnb_get_ray_counts(rnb_ctx* ctx, uint32_t cap, uint32_t* marched_host, uint32_t* kept_host, uint32_t* n_out);
 
+/* in-memory checkpoint / resume of the complete training state (one device-side slot): parameters (fp32 master, fp16, EMA), Adam
+ * moments and per-parameter step counters (tcnn adam.h), density grid + bitfield, both pcg32 streams, controller counters.
+ * The reference's file snapshot (src/testbed.cu:3280-3390) is served by rnb_export_* / rnb_import_* instead. */
+int rnb_checkpoint_save(rnb_ctx* ctx);
+int rnb_checkpoint_restore(rnb_ctx* ctx);
+
 /* instrumentation for bench.py: per-stage CUDA-event timing (events recorded on the caller's stream around each stage of
  * the step; resolved at the end of rnb_train_step_end) and a count of kernels launched by this ctx. */
 int rnb_profile_enable(rnb_ctx* ctx, int on);

@@ -53,7 +53,7 @@ EXPORTED_SYMBOLS = [
     "rnb_last_error", "rnb_abi_version", "rnb_create", "rnb_destroy", "rnb_default_config", "rnb_default_flags", "rnb_param_layout", "rnb_init_params",
     "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
     "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
-    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf",
+    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
 ]
 
@@ -273,6 +273,12 @@ class Testbed:
         p = C.POINTER(C.c_float)(); n = C.c_uint64()
         self._chk(self.L.rnb_stat_buffer(self.h, C.byref(p), C.byref(n)))
         return C.cast(p, C.c_void_p).value, int(n.value)
+
+    def checkpoint_save(self):
+        self._chk(self.L.rnb_checkpoint_save(self.h))
+
+    def checkpoint_restore(self):
+        self._chk(self.L.rnb_checkpoint_restore(self.h))
 
     def profile_enable(self, on=True):
         self._chk(self.L.rnb_profile_enable(self.h, int(on)))

@@ -86,6 +86,8 @@ struct rnb_ctx {
 	// pinned batch size the march of step N+1 is launched on a side stream when the backward of step N has finished, so that it
 	// shares the SMs with the (HBM-bound) optimizer / the gradient all-reduce instead of running alone
 	cudaStream_t side = nullptr; cudaEvent_t ev_bwd = nullptr, ev_march = nullptr;
+	// in-memory checkpoint (rnb_checkpoint_save / _restore): one device-side slot of everything a step reads and writes
+	struct Ckpt { void* buf = nullptr; size_t bytes = 0; bool valid = false; uint32_t opt_step, density_ema_step, training_step, rays_per_batch, n_rays_total, measured_before, measured; float lr_factor; Pcg32 rng, density_rng; } ck;
 	bool prelaunch = true; bool pre_valid = false; uint32_t pre_R = 0, pre_nrt = 0; uint64_t pre_rng_state = 0, pre_rng_inc = 0;
 	bool use_mma = false; uint32_t* wpack = nullptr; int n_sm = 148;
 	bool use_tc = false, use_tc_bwd = false; uint8_t* wtc = nullptr;      // tcgen05 / TMEM kernels (rnb_network_tc.cu) for pass A and the SDF probes
@@ -251,6 +253,7 @@ int rnb_destroy(rnb_ctx* c) {
 	for (void* p : ptrs) cudaFree(p);
 	for (void* p : c->owned) cudaFree(p);
 	cudaFreeHost(c->counters_host); cudaFreeHost(c->stats_host);
+	cudaFree(c->ck.buf);
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
 	if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
 	if (c->ev_march) cudaEventDestroy(c->ev_march);
@@ -599,6 +602,56 @@ int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
 	int rc = rnb_train_step(c, stream, stats);
 	if (!rc && stats) stats->density_grid_updated = updated;
 	return rc;
+}
+
+// ---- in-memory checkpoint / resume (one slot, device side) -------------------------------------------------------------
+// Everything Testbed::train reads and writes between steps: fp32 master / fp16 / EMA parameters, Adam moments and per-parameter
+// step counters, density grid + bitfield, both pcg32 streams, the controller counters.  (The gradient buffer is zero between
+// steps.)  Used by bench.py to time `value` and `e2e` on the SAME training steps; the file-level snapshot of the reference
+// (src/testbed.cu:3280-3390) keeps only the EMA fp16 weights and the density grid and goes through rnb_export_* / rnb_import_*.
+int rnb_checkpoint_save(rnb_ctx* c) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (c->in_step) return fail(RNB_ERR_STATE, "checkpoint inside a step");
+	drop_prelaunch(c);
+	const size_t np = c->M.n_params, need = np * 20 + (size_t)GRID_CELLS * 4 + GRID_CELLS;
+	if (c->ck.bytes < need) { cudaFree(c->ck.buf); c->ck.buf = nullptr; CU(cudaMalloc(&c->ck.buf, need)); c->ck.bytes = need; }
+	CU(cudaDeviceSynchronize());
+	uint8_t* b = (uint8_t*)c->ck.buf;
+	CU(cudaMemcpy(b, c->master, np * 4, cudaMemcpyDeviceToDevice)); b += np * 4;
+	CU(cudaMemcpy(b, c->m1, np * 4, cudaMemcpyDeviceToDevice)); b += np * 4;
+	CU(cudaMemcpy(b, c->m2, np * 4, cudaMemcpyDeviceToDevice)); b += np * 4;
+	CU(cudaMemcpy(b, c->steps, np * 4, cudaMemcpyDeviceToDevice)); b += np * 4;
+	CU(cudaMemcpy(b, c->params, np * 2, cudaMemcpyDeviceToDevice)); b += np * 2;
+	CU(cudaMemcpy(b, c->ema, np * 2, cudaMemcpyDeviceToDevice)); b += np * 2;
+	CU(cudaMemcpy(b, c->density_grid, (size_t)GRID_CELLS * 4, cudaMemcpyDeviceToDevice)); b += (size_t)GRID_CELLS * 4;
+	CU(cudaMemcpy(b, c->bitfield, GRID_CELLS, cudaMemcpyDeviceToDevice));
+	auto& k = c->ck;
+	k.opt_step = c->opt_step; k.lr_factor = c->lr_factor; k.density_ema_step = c->density_ema_step; k.training_step = c->training_step; k.rays_per_batch = c->rays_per_batch;
+	k.n_rays_total = c->n_rays_total; k.measured_before = c->measured_before; k.measured = c->measured; k.rng = c->rng; k.density_rng = c->density_rng;
+	k.valid = true;
+	return RNB_OK;
+}
+int rnb_checkpoint_restore(rnb_ctx* c) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (!c->ck.valid) return fail(RNB_ERR_STATE, "no checkpoint");
+	if (c->in_step) return fail(RNB_ERR_STATE, "restore inside a step");
+	drop_prelaunch(c);
+	CU(cudaDeviceSynchronize());
+	const size_t np = c->M.n_params;
+	const uint8_t* b = (const uint8_t*)c->ck.buf;
+	CU(cudaMemcpy(c->master, b, np * 4, cudaMemcpyDeviceToDevice)); b += np * 4;
+	CU(cudaMemcpy(c->m1, b, np * 4, cudaMemcpyDeviceToDevice)); b += np * 4;
+	CU(cudaMemcpy(c->m2, b, np * 4, cudaMemcpyDeviceToDevice)); b += np * 4;
+	CU(cudaMemcpy(c->steps, b, np * 4, cudaMemcpyDeviceToDevice)); b += np * 4;
+	CU(cudaMemcpy(c->params, b, np * 2, cudaMemcpyDeviceToDevice)); b += np * 2;
+	CU(cudaMemcpy(c->ema, b, np * 2, cudaMemcpyDeviceToDevice)); b += np * 2;
+	CU(cudaMemcpy(c->density_grid, b, (size_t)GRID_CELLS * 4, cudaMemcpyDeviceToDevice)); b += (size_t)GRID_CELLS * 4;
+	CU(cudaMemcpy(c->bitfield, b, GRID_CELLS, cudaMemcpyDeviceToDevice));
+	CU(cudaMemset(c->grads, 0, np * 4));
+	const auto& k = c->ck;
+	c->opt_step = k.opt_step; c->lr_factor = k.lr_factor; c->density_ema_step = k.density_ema_step; c->training_step = k.training_step; c->rays_per_batch = k.rays_per_batch;
+	c->n_rays_total = k.n_rays_total; c->measured_before = k.measured_before; c->measured = k.measured; c->rng = k.rng; c->density_rng = k.density_rng;
+	return RNB_OK;
 }
 
 int rnb_profile_enable(rnb_ctx* c, int on) {

@@ -236,3 +236,26 @@ def test_eval_sdf_matches_oracle(pkg, use_ema):
     assert rel_err(sdf2.cpu().numpy(), s_ref) < TOL
     assert np.isfinite(nrm.cpu().numpy()).all()
     assert half_close(sdf2.cpu().numpy(), sdf.cpu().numpy(), ulps=2.0).mean() > 0.999      # the two kernels agree to binary16 rounding
+
+
+def test_checkpoint_restore_replays_the_same_steps(pkg, small_scene):
+    """rnb_checkpoint_save / _restore: the complete training state (parameters, Adam moments and step counters, EMA, density grid,
+    bitfield, rng streams, counters).  Replayed steps see the same rays and samples; parameters agree up to the summation order of the
+    floating-point atomics."""
+    f = orc_flags(no_albedo=0, light_mode=-2)
+    o, t = make_pair(pkg, SMALL, views=small_scene, flags=f, rays_per_batch=512)
+    t.set_train_state(0, 512)
+    for _ in range(20):
+        t.train(want_stats=False)
+    t.checkpoint_save()
+    a = [t.train() for _ in range(4)]
+    pa = t.get_params().copy(); st_a = t.get_train_state(); rng_a = t.get_rng()
+    t.checkpoint_restore()
+    b = [t.train() for _ in range(4)]
+    pb = t.get_params(); st_b = t.get_train_state(); rng_b = t.get_rng()
+    assert st_a == st_b and rng_a == rng_b
+    for x, y in zip(a, b):
+        assert x.n_samples == y.n_samples and x.n_rays_kept == y.n_rays_kept and x.training_step == y.training_step
+        assert abs(x.n_samples_compacted - y.n_samples_compacted) <= 2
+        assert abs(x.loss - y.loss) <= 1e-3 * abs(x.loss) + 1e-7
+    assert rel_err(pb, pa) < 1e-4
