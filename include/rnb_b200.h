@@ -195,6 +195,9 @@ int rnb_launch_count(rnb_ctx* ctx, uint64_t* out);
 /* replaces NerfNetwork::sdf / density (nerf_network.h:454-537) used by marching cubes (src/testbed_nerf.cu:4252)
  * and the grid refresh.  xyz_dev: n x 3 floats in [0,1]^3; outputs may be NULL. */
 int rnb_eval_sdf(rnb_ctx* ctx, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream);
+/* replaces Testbed::get_density_on_grid (src/testbed_nerf.cu:4218-4269), the marching-cubes sweep: SDF (incl. bias, fp32) at the lattice
+ * points idx / res * (aabb_max - aabb_min) + aabb_min, out_dev[x + y*res[0] + z*res[0]*res[1]]; positions are generated in the kernel */
+int rnb_sdf_on_grid(rnb_ctx* ctx, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float* out_dev, int use_ema, void* stream);
 
 /* ---- stage-level entry points (host buffers; parity tests and micro-benchmarks) --------------------------------
  * Each mirrors one reference kernel / call; see DESIGN.md for the mapping. */

@@ -53,7 +53,7 @@ EXPORTED_SYMBOLS = [
     "rnb_last_error", "rnb_abi_version", "rnb_create", "rnb_destroy", "rnb_default_config", "rnb_default_flags", "rnb_param_layout", "rnb_init_params",
     "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
     "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
-    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf",
+    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf", "rnb_sdf_on_grid",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
 ]
 
@@ -294,6 +294,10 @@ class Testbed:
 
     def eval_sdf_device(self, xyz_dev_ptr, n, sdf_ptr=None, normal_ptr=None, density_ptr=None, use_ema=True, stream=None):
         self._chk(self.L.rnb_eval_sdf(self.h, C.c_void_p(xyz_dev_ptr), C.c_size_t(n), C.c_void_p(sdf_ptr), C.c_void_p(normal_ptr), C.c_void_p(density_ptr), int(use_ema), C.c_void_p(stream)))
+
+    def sdf_on_grid_device(self, res, aabb_min, aabb_max, out_ptr, use_ema=True, stream=None):
+        r = (C.c_uint32 * 3)(*[int(x) for x in res]); a = (C.c_float * 3)(*[float(x) for x in aabb_min]); b = (C.c_float * 3)(*[float(x) for x in aabb_max])
+        self._chk(self.L.rnb_sdf_on_grid(self.h, r, a, b, C.c_void_p(out_ptr), int(use_ema), C.c_void_p(stream)))
 
     # --- stage-level calls (host buffers) ---
     def stage_generate(self, n_rays, n_rays_total, max_samples):

@@ -30,6 +30,7 @@ size_t mma_pack_u32(const ModelDev&);
 void launch_mma(int, cudaStream_t, const ModelDev&, const __half*, uint32_t*, uint32_t, const float4*, const uint32_t*, uint32_t, const float*, __half*, const __half*, uint32_t, uint32_t, const uint32_t*, float*, int);
 bool tc_supported(const ModelDev&);
 void set_bw_debug(int);
+void launch_tc_sdf_grid(cudaStream_t, const ModelDev&, const __half*, const uint8_t*, uint32_t, const uint32_t[3], const float[3], const float[3], float*, int);
 void launch_tc_backward(cudaStream_t, const ModelDev&, const __half*, const uint8_t*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, float*, int);
 size_t tc_blob_bytes(const ModelDev&);
 void launch_tc(int, cudaStream_t, const ModelDev&, const __half*, uint8_t*, uint32_t, const float4*, const uint32_t*, uint32_t, __half*, float*, float*, int, const float* = nullptr);
@@ -719,6 +720,22 @@ int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, flo
 		else launch_forward_simt(st, c->M, P, vl, 2, tmp, nullptr, (uint32_t)m, nullptr, nullptr, sdf_dev ? sdf_dev + o : nullptr, normal_dev ? normal_dev + o * 3 : nullptr, density_dev ? density_dev + o : nullptr);
 	}
 	CU(cudaFreeAsync(tmp, st));
+	CU(cudaGetLastError());
+	return RNB_OK;
+}
+
+// SDF on a lattice — Testbed::get_density_on_grid (src/testbed_nerf.cu:4218-4269: generate_grid_samples_nerf_uniform + NerfNetwork::sdf in
+// 1 M-point batches + grid_samples_half_to_float) in one launch: the lattice positions are generated inside the tcgen05 probe kernel
+// (the reference materialises 12 B per point first: 12.9 GB at 1024^3).  out_dev[x + y rx + z rx ry] = sdf (incl. bias), fp32.
+int rnb_sdf_on_grid(rnb_ctx* c, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float* out_dev, int use_ema, void* stream) {
+	if (!c || !res || !aabb_min || !aabb_max || !out_dev) return fail(RNB_ERR_INVALID, "null argument");
+	if ((uint64_t)res[0] * res[1] * res[2] > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice larger than 2^32 points");
+	if (!c->use_tc) return fail(RNB_ERR_STATE, "rnb_sdf_on_grid needs the tcgen05 network path");
+	cudaStream_t st = (cudaStream_t)stream;
+	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
+	const __half* P = use_ema ? c->ema : c->params;
+	launch_tc(0, st, c->M, P, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm);
+	launch_tc_sdf_grid(st, c->M, P, c->wtc, vl, res, aabb_min, aabb_max, out_dev, c->n_sm);
 	CU(cudaGetLastError());
 	return RNB_OK;
 }

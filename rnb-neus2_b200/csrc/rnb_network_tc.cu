@@ -195,7 +195,13 @@ __device__ __forceinline__ void gather_row_to_tmem(const ModelDev& M, const __ha
 	}
 }
 
+// lattice of Testbed::get_density_on_grid (generate_grid_samples_nerf_uniform, testbed_nerf.cu:541-553): point (x, y, z) of a
+// res^3 lattice sits at idx / res * (aabb.max - aabb.min) + aabb.min (no half-cell offset); the last multiply-add is fused as nvcc
+// contracts it in the reference build
+struct GridSpec { uint32_t rx, ry, rz; float inv[3], ext[3], mn[3]; };
+
 // ---- pass A / SDF probe -----------------------------------------------------------------------------------------------
+// MODE 2: SDF on a lattice -> sdf_out[x + y rx + z rx ry] (marching-cubes sweep; positions are generated in the kernel, no position buffer)
 // MODE 0: pass A  -> outA[row] = (sdf + bias, normal) as 4 x binary16
 // MODE 1: probe   -> sdf_out[row] (fp32, optional), dens_out[row] (fp32, optional): NerfNetwork::sdf / ::density, nerf_network.h:454-537
 // Activations are TMEM resident: every thread writes its input row / its tm row straight into its TMEM lane (tcgen05.st) and
@@ -204,7 +210,7 @@ __device__ __forceinline__ void gather_row_to_tmem(const ModelDev& M, const __ha
 template <int SW, int MODE>
 __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
                                                     const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
-                                                    __half* __restrict__ outA, float* __restrict__ sdf_out, float* __restrict__ dens_out) {
+                                                    __half* __restrict__ outA, float* __restrict__ sdf_out, float* __restrict__ dens_out, GridSpec gs) {
 	using B = Blob<SW>;
 	constexpr bool NORMAL = MODE == 0;
 	constexpr uint32_t DYB = (B::SDF_END + 127u) & ~127u;               // dy/dx [84][128] fp32 (pass A only)
@@ -230,10 +236,15 @@ __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __
 	const uint32_t n_tiles = (n + TILE - 1) / TILE;
 	uint32_t phase = 0;
 	__half sc = __float2half_rn(0.f);
-	if (MODE == 1) { const __half var = __ldg(P + M.off_var); sc = __float2half_rn(__expf(__half2float(__hmul(var, __float2half_rn(10.0f))))); }
+	if (MODE != 0) { const __half var = __ldg(P + M.off_var); sc = __float2half_rn(__expf(__half2float(__hmul(var, __float2half_rn(10.0f))))); }
 	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 		const uint32_t row = tile * TILE + tid;
-		const float4 p = pos4[min(row, n - 1)];
+		float4 p;
+		if (MODE == 2) {
+			const uint32_t r = min(row, n - 1), ix = r % gs.rx, iy = (r / gs.rx) % gs.ry, iz = r / (gs.rx * gs.ry);
+			p = make_float4(__fmaf_rn(__fmul_rn((float)ix, gs.inv[0]), gs.ext[0], gs.mn[0]), __fmaf_rn(__fmul_rn((float)iy, gs.inv[1]), gs.ext[1], gs.mn[1]),
+			                __fmaf_rn(__fmul_rn((float)iz, gs.inv[2]), gs.ext[2], gs.mn[2]), 0.f);
+		} else p = pos4[min(row, n - 1)];
 		gather_row_to_tmem<NORMAL>(M, P, valid_level, p.x, p.y, p.z, trow + C_IN, dyS, tid);
 		tmem_st_wait();
 		tc_fence_before();
@@ -939,7 +950,7 @@ static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __h
 		const size_t smem = DYB + 84 * TILE * 4;
 		static bool attr = false;
 		if (!attr) { cudaFuncSetAttribute(k_sdf_tc<SW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-		k_sdf_tc<SW, 0><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr);
+		k_sdf_tc<SW, 0><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr, GridSpec{});
 	} else if (what == 3) {
 		const size_t smem = ((B::END + 127u) & ~127u) + 84 * TILE * 4;
 		const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)n_sm * 3);
@@ -956,7 +967,7 @@ static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __h
 		return;      // backward: see launch_tc_backward
 	} else {
 		const size_t smem = DYB;
-		k_sdf_tc<SW, 1><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, nullptr, sdf_out, dens_out);
+		k_sdf_tc<SW, 1><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, nullptr, sdf_out, dens_out, GridSpec{});
 	}
 }
 
@@ -982,6 +993,18 @@ void launch_tc_backward(cudaStream_t st, const ModelDev& M, const __half* P, con
                         uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
 	if (M.sdf_width == 64) launch_tc_backward_sw<64>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
 	else launch_tc_backward_sw<32>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
+}
+
+// SDF on a res[0] x res[1] x res[2] lattice (Testbed::get_density_on_grid, testbed_nerf.cu:4218-4269); the weight blob must be packed
+void launch_tc_sdf_grid(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const uint32_t res[3], const float mn[3], const float mx[3], float* sdf_out, int n_sm) {
+	using namespace tc;
+	GridSpec gs; gs.rx = res[0]; gs.ry = res[1]; gs.rz = res[2];
+	for (int d = 0; d < 3; ++d) { gs.inv[d] = 1.f / (float)res[d]; gs.ext[d] = mx[d] - mn[d]; gs.mn[d] = mn[d]; }
+	const uint64_t n64 = (uint64_t)res[0] * res[1] * res[2];
+	if (!n64) return;
+	const uint32_t n = (uint32_t)n64, tiles = (n + TILE - 1) / TILE, grid = std::min<uint32_t>(tiles, (uint32_t)n_sm * 4);
+	if (M.sdf_width == 64) k_sdf_tc<64, 2><<<grid, TILE, (Blob<64>::SDF_END + 127u) & ~127u, st>>>(M, P, wtc, vl, nullptr, nullptr, n, nullptr, sdf_out, nullptr, gs);
+	else k_sdf_tc<32, 2><<<grid, TILE, (Blob<32>::SDF_END + 127u) & ~127u, st>>>(M, P, wtc, vl, nullptr, nullptr, n, nullptr, sdf_out, nullptr, gs);
 }
 
 // what: 0 pack weights, 1 pass A (outA = 4 halfs per sample), 2 SDF probe (sdf_out / dens_out), 3 full forward (outA = 16 halfs per sample, needs ray_dirw)

@@ -259,3 +259,25 @@ def test_checkpoint_restore_replays_the_same_steps(pkg, small_scene):
         assert abs(x.n_samples_compacted - y.n_samples_compacted) <= 2
         assert abs(x.loss - y.loss) <= 1e-3 * abs(x.loss) + 1e-7
     assert rel_err(pb, pa) < 1e-4
+
+
+def test_sdf_on_grid_matches_oracle(pkg):
+    """rnb_sdf_on_grid (Testbed::get_density_on_grid, testbed_nerf.cu:4218-4269): lattice positions generated inside the tcgen05 probe
+    kernel; against the oracle at the same lattice points and against rnb_eval_sdf on explicit positions."""
+    import torch
+    o, t = make_pair(pkg, MID, seed_params=7)
+    res = (40, 36, 33); mn = np.array([0.1, 0.05, 0.2], np.float32); mx = np.array([0.9, 0.95, 0.85], np.float32)
+    out = torch.empty(res[0] * res[1] * res[2], device="cuda")
+    t.sdf_on_grid_device(res, mn, mx, out.data_ptr(), use_ema=False)
+    torch.cuda.synchronize()
+    iz, iy, ix = np.meshgrid(np.arange(res[2]), np.arange(res[1]), np.arange(res[0]), indexing="ij")       # x fastest
+    idx = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], 1).astype(np.float32)
+    inv = (np.float32(1.0) / np.array(res, np.float32)).astype(np.float32)
+    pos = ((idx * inv) * (mx - mn) + mn).astype(np.float32)
+    s_ref, _ = o.eval_sdf(pos, o.valid_level(0))
+    got = out.cpu().numpy()
+    assert rel_err(got, s_ref) < TOL
+    x = torch.from_numpy(pos).cuda(); s2 = torch.empty(pos.shape[0], device="cuda")
+    t.eval_sdf_device(x.data_ptr(), pos.shape[0], s2.data_ptr(), None, None, use_ema=False)
+    torch.cuda.synchronize()
+    assert half_close(got, s2.cpu().numpy(), ulps=1.0).mean() > 0.999
