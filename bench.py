@@ -230,6 +230,9 @@ def main():
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
+    # stdout carries exactly one JSON line: everything libraries print (NCCL banner, torch warnings) goes to stderr until then
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1); os.dup2(2, 1)
     import numpy as np
     import torch
     import rnb_loader
@@ -240,7 +243,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("RNB_NCCL_DEBUG", "WARN")      # keep stdout to the single JSON line (NCCL prints its version banner there otherwise)
+        os.environ["NCCL_DEBUG"] = os.environ.get("RNB_NCCL_DEBUG", "NONE")      # keep stdout to the single JSON line (NCCL prints its version banner there otherwise)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
@@ -351,9 +354,11 @@ def main():
         threads = os.cpu_count() or 1
         v, info = cpu_baseline_from_state(t, views, flags_kw, threads, 3, 512)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": "3 steps x 512 rays from the same training state (%s)" % json.dumps(info)}
+    sys.stdout.flush(); os.dup2(_saved_stdout, 1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line)); sys.stdout.flush()
     if dist:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
