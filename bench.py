@@ -249,7 +249,9 @@ def main():
     n_gpus = world
     R = RAYS_PER_STEP * n_gpus                      # weak scaling: 4096 rays per GPU per step, global batch R
     views, gen_s = build_views(args.views, args.width, args.height, False)
-    cfg = pkg.default_config(rays_per_batch=R, pin_rays_per_batch=1, world_size=world, rank=rank)
+    # weak scaling with the per-GPU work fixed: 4096 rays AND a 2^18-sample training batch per GPU (the reference's target_batch_size is a
+    # global cap; leaving it at 2^18 for N GPUs would shrink every rank's network passes by N and read as super-linear scaling)
+    cfg = pkg.default_config(rays_per_batch=R, pin_rays_per_batch=1, world_size=world, rank=rank, target_batch_size=(1 << 18) * n_gpus)
     flags_kw = dict(no_albedo=1)
     t = pkg.Testbed(cfg, pkg.default_flags(**flags_kw))
     t.init_params()
@@ -342,7 +344,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_global": R, "pretrain_steps": args.pretrain, "samples_per_step": int(ns), "compacted_samples_per_step": int(nc), "live_hash_levels": L,
                        "cache": "working set (hash table 21 MB + gradients 42 MB + optimizer state 170 MB + 1.5 GB images) exceeds L2; no flush needed",
-                       "parallelism": "dp%d ray-sharded, fp32 gradient all-reduce" % n_gpus if n_gpus > 1 else "single GPU", "network_path": os.environ.get("RNB_NETWORK", "tcgen05 forward + mma.sync backward"),
+                       "parallelism": "dp%d ray-sharded (4096 rays + 2^18-sample batch per GPU), fp32 gradient all-reduce" % n_gpus if n_gpus > 1 else "single GPU", "network_path": os.environ.get("RNB_NETWORK", "tcgen05 forward + mma.sync backward"),
                        "dataset_upload_s": round(upload_s, 3), "dataset_bytes": dataset_bytes, "scene_render_s": round(gen_s, 1)},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,
