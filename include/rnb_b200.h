@@ -199,6 +199,37 @@ int rnb_eval_sdf(rnb_ctx* ctx, const float* xyz_dev, size_t n, float* sdf_dev, f
  * points idx / res * (aabb_max - aabb_min) + aabb_min, out_dev[x + y*res[0] + z*res[0]*res[1]]; positions are generated in the kernel */
 int rnb_sdf_on_grid(rnb_ctx* ctx, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float* out_dev, int use_ema, void* stream);
 
+/* ---- mesh extraction and export ----------------------------------------------------------------
+ * The mesh lives in device memory owned by the context (MeshState verts / vert_normals / vert_colors / indices,
+ * include/neural-graphics-primitives/testbed.h:418-447).  Vertices are numbered in lattice order (point x + y rx + z rx ry, its
+ * +x, +y, +z edge), triangles in cell order: the reference's mesh up to the permutation its atomicAdd slot hand-out picks. */
+typedef struct rnb_mesh_info {
+	uint32_t n_verts;          /* vertices on the iso-surface */
+	uint32_t n_verts_padded;   /* array length: rounded up to 128, padding zero (src/marching_cubes.cu:810-812); this is what gets saved */
+	uint32_t n_indices;        /* 3 x triangles */
+	uint32_t res[3];           /* lattice actually used */
+	float stage_ms[4];         /* device time of the last extraction (CUDA events): SDF sweep, count + scan, vertices + normals + faces, colours */
+} rnb_mesh_info;
+/* replaces Testbed::marching_cubes (src/testbed_nerf.cu:4297-4348): res rounded up to multiples of 16, SDF sweep over the aabb,
+ * marching_cubes_gpu, area-weighted vertex normals (compute_mesh_1ring), vertex colours (compute_mesh_vertex_colors).
+ * Synchronises the stream (the vertex count sizes the arrays, as in the reference). */
+int rnb_marching_cubes(rnb_ctx* ctx, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh, int use_ema, void* stream, rnb_mesh_info* info);
+/* replaces marching_cubes_gpu (src/marching_cubes.cu:794-822) + compute_mesh_1ring (:722-728) on a caller-provided lattice of values
+ * density_dev[x + y res[0] + z res[0] res[1]] (res[0] a multiple of 4); with_colors != 0 also runs the colour network at the vertices */
+int rnb_marching_cubes_from_density(rnb_ctx* ctx, const float* density_dev, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh,
+                                    int with_colors, int use_ema, void* stream, rnb_mesh_info* info);
+/* device pointers of the current mesh (valid until the next extraction or rnb_destroy); any out pointer may be NULL */
+int rnb_mesh_buffers(rnb_ctx* ctx, float** verts_dev, float** normals_dev, float** colors_dev, uint32_t** indices_dev, rnb_mesh_info* info);
+/* replaces the copies of Testbed::compute_marching_cubes_mesh (src/python_api.cu:99-130): host arrays of n_verts_padded x 3 floats and
+ * n_indices uint32; any pointer may be NULL */
+int rnb_mesh_download(rnb_ctx* ctx, float* verts_host, float* normals_host, float* colors_host, uint32_t* indices_host);
+/* replaces save_mesh (src/marching_cubes.cu:824-982) for device arrays: Wavefront OBJ ("v x y z r g b", "vn", "f a//a b//b c//c"; the
+ * unwrap/texture variant is not provided) or ASCII PLY when the path ends in "ply".  Byte-identical to the reference's fprintf output
+ * for the same arrays: p = n2w_s * ((v - nerf_offset) / nerf_scale) + n2w_t, "%0.5f" / "%0.3f", normals normalised, triangles reversed
+ * unless invert_normals.  The text is formatted on the GPU. */
+int rnb_save_mesh(const float* verts_dev, const float* normals_dev, const float* colors_dev, const uint32_t* indices_dev, uint32_t n_verts, uint32_t n_indices,
+                  const char* path, float nerf_scale, const float nerf_offset[3], float n2w_s, const float n2w_t[3], int invert_normals, void* stream, uint64_t* bytes_written);
+
 /* ---- stage-level entry points (host buffers; parity tests and micro-benchmarks) --------------------------------
  * Each mirrors one reference kernel / call; see DESIGN.md for the mapping. */
 /* generate_training_samples_nerf (src/testbed_nerf.cu:1216-1387) */

@@ -20,7 +20,9 @@
 #include <tiny-cuda-nn/common.h>
 #include <tiny-cuda-nn/trainer.h>
 #include <tiny-cuda-nn/network.h>
+#include <neural-graphics-primitives/marching_cubes.h>
 #include <filesystem/path.h>
+#include <chrono>
 
 #include <cstdio>
 #include <cstdlib>
@@ -56,7 +58,7 @@ static void dump_host(const std::string& name, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
 	if (argc < 5) {
-		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--time-from K] [--pin-rays N]\n");
+		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--time-from K] [--pin-rays N] [--mesh RES]\n");
 		return 1;
 	}
 	char buf[PATH_MAX]; ssize_t cnt = readlink("/proc/self/exe", buf, PATH_MAX);
@@ -65,7 +67,7 @@ int main(int argc, char** argv) {
 	g_out = argv[3];
 	const int n_steps = atoi(argv[4]);
 	bool no_albedo = false, supernormal = false, opti = false, l1 = false, rgbplus = true, time_only = false;
-	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps; int time_from = -1;
+	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps; int time_from = -1; int mesh_res = 0;
 	for (int i = 5; i < argc; ++i) {
 		std::string a = argv[i];
 		if (a == "--no-albedo") no_albedo = true; else if (a == "--supernormal") supernormal = true; else if (a == "--opti-lights") opti = true;
@@ -73,6 +75,7 @@ int main(int argc, char** argv) {
 		else if (a == "--dump-every" && i + 1 < argc) dump_every = atoi(argv[++i]);
 		else if (a == "--pin-rays" && i + 1 < argc) pin_rays = (uint32_t)atoi(argv[++i]);
 		else if (a == "--time-from" && i + 1 < argc) time_from = atoi(argv[++i]);
+		else if (a == "--mesh" && i + 1 < argc) mesh_res = atoi(argv[++i]);
 		else if (a == "--dump-steps" && i + 1 < argc) { std::string l = argv[++i]; size_t p0 = 0; while (p0 < l.size()) { size_t q = l.find(',', p0); if (q == std::string::npos) q = l.size(); dump_steps.push_back(atoi(l.substr(p0, q - p0).c_str())); p0 = q + 1; } }
 	}
 
@@ -180,6 +183,33 @@ int main(int argc, char** argv) {
 		CUDA_CHECK_THROW(cudaDeviceSynchronize());
 		dump_host("probe_coords.bin", coords.data(), coords.size() * 4);
 		dump_dev("probe_out_fp16.bin", (const uint16_t*)out.data(), (size_t)n * 16);
+	}
+	// mesh path: the SDF lattice of get_density_on_grid, then compute_and_save_marching_cubes_mesh exactly as
+	// src/main.cu:460 calls it (empty aabb -> m_render_aabb, threshold 0, no unwrap), and the mesh arrays it leaves in m_mesh
+	if (mesh_res > 0) {
+		const BoundingBox aabb = tb.m_render_aabb;
+		const uint32_t r16 = next_multiple((uint32_t)mesh_res, 16u);
+		GPUMemory<float> dens = tb.get_density_on_grid(Eigen::Vector3i::Constant((int)r16), aabb);
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
+		dump_dev("mesh_density.bin", dens.data(), dens.size());
+		dump_dev("mesh_params_inference_fp16.bin", (const uint16_t*)tb.m_trainer->params_inference(), n_params);
+		const std::string obj = g_out + "/ref_mesh.obj", ply = g_out + "/ref_mesh.ply";
+		cudaEvent_t m0, m1; cudaEventCreate(&m0); cudaEventCreate(&m1);
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
+		const auto w0 = std::chrono::steady_clock::now();
+		tb.compute_and_save_marching_cubes_mesh(obj.c_str(), Eigen::Vector3i::Constant(mesh_res), {}, 0.0f, false);
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
+		const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+		dump_dev("mesh_verts.bin", (const float*)tb.m_mesh.verts.data(), tb.m_mesh.verts.size() * 3);
+		dump_dev("mesh_normals.bin", (const float*)tb.m_mesh.vert_normals.data(), tb.m_mesh.vert_normals.size() * 3);
+		dump_dev("mesh_colors.bin", (const float*)tb.m_mesh.vert_colors.data(), tb.m_mesh.vert_colors.size() * 3);
+		dump_dev("mesh_indices.bin", tb.m_mesh.indices.data(), tb.m_mesh.indices.size());
+		const auto& ds = tr.dataset;
+		save_mesh(tb.m_mesh.verts, tb.m_mesh.vert_normals, tb.m_mesh.vert_colors, tb.m_mesh.indices, ply.c_str(), false, ds.scale, ds.offset, ds.n2w_s, ds.n2w_t, ds.from_na);
+		fprintf(meta, "mesh_res=%u\nmesh_aabb_min=%g %g %g\nmesh_aabb_max=%g %g %g\nmesh_verts=%zu\nmesh_indices=%zu\nmesh_seconds=%.4f\n", r16, aabb.min.x(), aabb.min.y(), aabb.min.z(),
+		        aabb.max.x(), aabb.max.y(), aabb.max.z(), tb.m_mesh.verts.size(), tb.m_mesh.indices.size(), wall);
+		fprintf(meta, "dataset_scale=%.9g\ndataset_offset=%.9g %.9g %.9g\nn2w_s=%.9g\nn2w_t=%.9g %.9g %.9g\nfrom_na=%d\nmesh_training_step=%u\n", ds.scale, ds.offset.x(), ds.offset.y(), ds.offset.z(),
+		        ds.n2w_s, ds.n2w_t.x(), ds.n2w_t.y(), ds.n2w_t.z(), (int)ds.from_na, (unsigned)tb.m_training_step);
 	}
 	fclose(meta);
 	printf("ref_harness done\n");

@@ -7,6 +7,7 @@
 #include "orc_common.h"
 #include "orc_network.h"
 #include "orc_render.h"
+#include "orc_mesh.h"
 #include <random>
 #include <limits>
 #include <cstdio>
@@ -491,4 +492,21 @@ void orc_backward_f64(Oracle* o, const double* params, const float* coords, cons
 extern "C" void orc_pcg32_seq(uint64_t seed, uint64_t seq, int64_t advance, uint32_t n, uint32_t* out_u) {
 	orc::Pcg32 r(seed, seq); r.advance(advance);
 	for (uint32_t i = 0; i < n; ++i) out_u[i] = r.next_uint();
+}
+
+// ---- mesh path (orc_mesh.h) ---------------------------------------------------------------------------------------------
+struct OrcMesh { orc_mesh::Mesh m; };
+extern "C" OrcMesh* orc_marching_cubes(const float* density, const uint32_t res[3], const float mn[3], const float mx[3], float thresh, uint32_t counts[3]) {
+	OrcMesh* h = new OrcMesh{orc_mesh::marching_cubes(density, res, mn, mx, thresh)};
+	counts[0] = h->m.n_verts; counts[1] = (uint32_t)(h->m.verts.size() / 3); counts[2] = (uint32_t)h->m.indices.size();
+	return h;
+}
+extern "C" void orc_mesh_get(OrcMesh* h, float* verts, float* normals, uint32_t* indices) {
+	memcpy(verts, h->m.verts.data(), h->m.verts.size() * 4); memcpy(normals, h->m.normals.data(), h->m.normals.size() * 4);
+	memcpy(indices, h->m.indices.data(), h->m.indices.size() * 4);
+}
+extern "C" void orc_mesh_free(OrcMesh* h) { delete h; }
+extern "C" int orc_save_mesh(const float* verts, const float* normals, const float* colors, const uint32_t* indices, uint32_t n_verts, uint32_t n_indices, const char* path,
+                             float nerf_scale, const float off[3], float n2w_s, const float n2w_t[3], int invert_normals) {
+	return orc_mesh::save_mesh(verts, normals, colors, indices, n_verts, n_indices, path, nerf_scale, off, n2w_s, n2w_t, invert_normals);
 }

@@ -54,8 +54,25 @@ EXPORTED_SYMBOLS = [
     "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
     "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
     "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf", "rnb_sdf_on_grid",
+    "rnb_marching_cubes", "rnb_marching_cubes_from_density", "rnb_mesh_buffers", "rnb_mesh_download", "rnb_save_mesh",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
 ]
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [("n_verts", C.c_uint32), ("n_verts_padded", C.c_uint32), ("n_indices", C.c_uint32), ("res", C.c_uint32 * 3), ("stage_ms", C.c_float * 4)]
+
+
+def save_mesh_device(path, verts_ptr, normals_ptr, colors_ptr, indices_ptr, n_verts, n_indices, nerf_scale=1.0, nerf_offset=(0.0, 0.0, 0.0), n2w_s=1.0, n2w_t=(0.0, 0.0, 0.0),
+                     invert_normals=False, stream=None):
+    """rnb_save_mesh on device arrays (OBJ, or ASCII PLY for a path ending in "ply"); returns the bytes written."""
+    nb = C.c_uint64(0)
+    rc = lib().rnb_save_mesh(C.c_void_p(verts_ptr), C.c_void_p(normals_ptr), C.c_void_p(colors_ptr), C.c_void_p(indices_ptr), C.c_uint32(n_verts), C.c_uint32(n_indices), str(path).encode(),
+                             C.c_float(nerf_scale), (C.c_float * 3)(*[float(x) for x in nerf_offset]), C.c_float(n2w_s), (C.c_float * 3)(*[float(x) for x in n2w_t]), int(invert_normals),
+                             C.c_void_p(stream), C.byref(nb))
+    if rc != 0:
+        raise RnbError(lib().rnb_last_error().decode())
+    return int(nb.value)
 
 
 def build(verbose=False):
@@ -298,6 +315,60 @@ class Testbed:
     def sdf_on_grid_device(self, res, aabb_min, aabb_max, out_ptr, use_ema=True, stream=None):
         r = (C.c_uint32 * 3)(*[int(x) for x in res]); a = (C.c_float * 3)(*[float(x) for x in aabb_min]); b = (C.c_float * 3)(*[float(x) for x in aabb_max])
         self._chk(self.L.rnb_sdf_on_grid(self.h, r, a, b, C.c_void_p(out_ptr), int(use_ema), C.c_void_p(stream)))
+
+    # --- mesh extraction and export ---
+    def _mesh_info(self, info):
+        return dict(n_verts=int(info.n_verts), n_verts_padded=int(info.n_verts_padded), n_indices=int(info.n_indices), res=tuple(int(x) for x in info.res),
+                    stage_ms=dict(zip(("sdf_sweep", "count_scan", "vertices_normals_faces", "colors"), (round(float(x), 4) for x in info.stage_ms))))
+
+    def marching_cubes(self, res, aabb_min=(0.0, 0.0, 0.0), aabb_max=(1.0, 1.0, 1.0), thresh=0.0, use_ema=True, stream=None):
+        """Testbed::marching_cubes (src/testbed_nerf.cu:4297-4348): the mesh stays on the device; returns its sizes."""
+        if np.isscalar(res):
+            res = (res, res, res)
+        r = (C.c_uint32 * 3)(*[int(x) for x in res]); a = (C.c_float * 3)(*[float(x) for x in aabb_min]); b = (C.c_float * 3)(*[float(x) for x in aabb_max])
+        info = MeshInfo()
+        self._chk(self.L.rnb_marching_cubes(self.h, r, a, b, C.c_float(thresh), int(use_ema), C.c_void_p(stream), C.byref(info)))
+        return self._mesh_info(info)
+
+    def marching_cubes_from_density(self, density_dev_ptr, res, aabb_min=(0.0, 0.0, 0.0), aabb_max=(1.0, 1.0, 1.0), thresh=0.0, with_colors=True, use_ema=True, stream=None):
+        """marching_cubes_gpu (src/marching_cubes.cu:794-822) + normals (+ colours) on a device lattice density[x + y rx + z rx ry]."""
+        r = (C.c_uint32 * 3)(*[int(x) for x in res]); a = (C.c_float * 3)(*[float(x) for x in aabb_min]); b = (C.c_float * 3)(*[float(x) for x in aabb_max])
+        info = MeshInfo()
+        self._chk(self.L.rnb_marching_cubes_from_density(self.h, C.c_void_p(density_dev_ptr), r, a, b, C.c_float(thresh), int(with_colors), int(use_ema), C.c_void_p(stream), C.byref(info)))
+        return self._mesh_info(info)
+
+    def mesh_buffers(self):
+        v = C.c_void_p(); n = C.c_void_p(); c = C.c_void_p(); i = C.c_void_p(); info = MeshInfo()
+        self._chk(self.L.rnb_mesh_buffers(self.h, C.byref(v), C.byref(n), C.byref(c), C.byref(i), C.byref(info)))
+        return dict(verts=v.value, normals=n.value, colors=c.value, indices=i.value, **self._mesh_info(info))
+
+    def mesh_download(self):
+        """Host copies: V [n_verts_padded, 3], N (unnormalised area-weighted sums), C, F [n_tris, 3]."""
+        m = self.mesh_buffers()
+        nv, ni = m["n_verts_padded"], m["n_indices"]
+        V = np.zeros((nv, 3), np.float32); N = np.zeros((nv, 3), np.float32); Cc = np.zeros((nv, 3), np.float32); F = np.zeros(ni, np.uint32)
+        self._chk(self.L.rnb_mesh_download(self.h, _p(V, C.c_float), _p(N, C.c_float), _p(Cc, C.c_float), _p(F, C.c_uint32)))
+        return dict(V=V, N=N, C=Cc, F=F.reshape(-1, 3), n_verts=m["n_verts"])
+
+    def compute_marching_cubes_mesh(self, res, aabb_min=(0.0, 0.0, 0.0), aabb_max=(1.0, 1.0, 1.0), thresh=0.0, use_ema=True):
+        """Testbed::compute_marching_cubes_mesh (src/python_api.cu:99-122): dict V, N (normalised), C, F."""
+        self.marching_cubes(res, aabb_min, aabb_max, thresh, use_ema)
+        m = self.mesh_download()
+        z = (m["N"] * m["N"]).sum(1, keepdims=True)
+        m["N"] = np.where(z > 0, m["N"] / np.sqrt(np.maximum(z, 1e-45)), m["N"]).astype(np.float32)
+        return m
+
+    def save_mesh(self, path, nerf_scale=1.0, nerf_offset=(0.0, 0.0, 0.0), n2w_s=1.0, n2w_t=(0.0, 0.0, 0.0), invert_normals=False, stream=None):
+        """save_mesh (src/marching_cubes.cu:824-982) of the current mesh; returns the bytes written."""
+        m = self.mesh_buffers()
+        return save_mesh_device(path, m["verts"], m["normals"], m["colors"], m["indices"], m["n_verts_padded"], m["n_indices"], nerf_scale, nerf_offset, n2w_s, n2w_t, invert_normals, stream)
+
+    def compute_and_save_marching_cubes_mesh(self, path, res, aabb_min=(0.0, 0.0, 0.0), aabb_max=(1.0, 1.0, 1.0), thresh=0.0, use_ema=True,
+                                             nerf_scale=1.0, nerf_offset=(0.0, 0.0, 0.0), n2w_s=1.0, n2w_t=(0.0, 0.0, 0.0), from_na=False):
+        """Testbed::compute_and_save_marching_cubes_mesh (src/testbed.cu:369-381); the dataset's scale / offset / n2w come from the caller."""
+        info = self.marching_cubes(res, aabb_min, aabb_max, thresh, use_ema)
+        self.save_mesh(path, nerf_scale, nerf_offset, n2w_s, n2w_t, invert_normals=from_na)
+        return info
 
     # --- stage-level calls (host buffers) ---
     def stage_generate(self, n_rays, n_rays_total, max_samples):

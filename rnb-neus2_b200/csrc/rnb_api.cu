@@ -52,6 +52,11 @@ void launch_widen_params(cudaStream_t, uint32_t, const __half*, float*);
 void launch_init_grid(cudaStream_t, Pcg32, uint64_t, float*);
 void launch_grid_samples(cudaStream_t, uint32_t, Pcg32, uint32_t, const float*, float4*, uint32_t*, float);
 void launch_grid_finish(cudaStream_t, uint32_t, const uint32_t*, const float*, float, float*, float*, double*, float*, uint8_t*);
+// rnb_mesh.cu
+std::string mesh_extract(cudaStream_t, const float*, const uint32_t[3], const float[3], const float[3], float, void**, size_t*, float**, float**, uint32_t**, uint32_t*, uint32_t*, uint32_t*, float[2], uint64_t*);
+void launch_mesh_color_inputs(cudaStream_t, uint32_t, const float*, float4*, float*);
+void launch_mesh_colors(cudaStream_t, uint32_t, const __half*, float*);
+std::string mesh_write(cudaStream_t, const float*, const float*, const float*, const uint32_t*, uint32_t, uint32_t, const char*, float, const float[3], float, const float[3], int, uint64_t*, uint64_t*);
 }
 
 using namespace rnb;
@@ -90,6 +95,9 @@ struct rnb_ctx {
 	// in-memory checkpoint (rnb_checkpoint_save / _restore): one device-side slot of everything a step reads and writes
 	struct Ckpt { void* buf = nullptr; size_t bytes = 0; bool valid = false; uint32_t opt_step, density_ema_step, training_step, rays_per_batch, n_rays_total, measured_before, measured; float lr_factor; Pcg32 rng, density_rng; } ck;
 	bool prelaunch = true; bool pre_valid = false; uint32_t pre_R = 0, pre_nrt = 0; uint64_t pre_rng_state = 0, pre_rng_inc = 0;
+	// last extracted mesh (rnb_marching_cubes*): MeshState verts / vert_normals / vert_colors / indices (testbed.h:418-447), device memory
+	struct Mesh { float *verts = nullptr, *normals = nullptr, *colors = nullptr; uint32_t* indices = nullptr; uint32_t n_verts = 0, n_verts_padded = 0, n_indices = 0; float ms[4] = {0, 0, 0, 0}; } mesh;
+	void* mesh_ws = nullptr; size_t mesh_ws_bytes = 0; float* mesh_density = nullptr; size_t mesh_density_bytes = 0;    // grow-only scratch of the mesh path
 	bool use_mma = false; uint32_t* wpack = nullptr; int n_sm = 148;
 	bool use_tc = false, use_tc_bwd = false; uint8_t* wtc = nullptr;      // tcgen05 / TMEM kernels (rnb_network_tc.cu) for pass A and the SDF probes
 	// instrumentation: kernel launch counter and optional per-stage CUDA-event timing (bench.py roofline)
@@ -255,6 +263,7 @@ int rnb_destroy(rnb_ctx* c) {
 	for (void* p : c->owned) cudaFree(p);
 	cudaFreeHost(c->counters_host); cudaFreeHost(c->stats_host);
 	cudaFree(c->ck.buf);
+	cudaFree(c->mesh.verts); cudaFree(c->mesh.normals); cudaFree(c->mesh.colors); cudaFree(c->mesh.indices); cudaFree(c->mesh_ws); cudaFree(c->mesh_density);
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
 	if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
 	if (c->ev_march) cudaEventDestroy(c->ev_march);
@@ -737,6 +746,117 @@ int rnb_sdf_on_grid(rnb_ctx* c, const uint32_t res[3], const float aabb_min[3], 
 	launch_tc(0, st, c->M, P, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm);
 	launch_tc_sdf_grid(st, c->M, P, c->wtc, vl, res, aabb_min, aabb_max, out_dev, c->n_sm);
 	CU(cudaGetLastError());
+	return RNB_OK;
+}
+
+// ---- mesh extraction ----------------------------------------------------------------------------------------
+static void mesh_free(rnb_ctx* c) {
+	cudaFree(c->mesh.verts); cudaFree(c->mesh.normals); cudaFree(c->mesh.colors); cudaFree(c->mesh.indices);
+	c->mesh = rnb_ctx::Mesh();
+}
+
+// marching_cubes_gpu + compute_mesh_1ring + compute_mesh_vertex_colors on a caller-provided lattice of SDF values
+// (src/marching_cubes.cu:794-822, :722-728, src/testbed_nerf.cu:4193-4216).  with_colors == 0 skips the network pass (colours zero).
+int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh,
+                                    int with_colors, int use_ema, void* stream, rnb_mesh_info* info) {
+	if (!c || !density_dev || !res || !aabb_min || !aabb_max) return fail(RNB_ERR_INVALID, "null argument");
+	if (res[0] == 0 || res[1] == 0 || res[2] == 0 || res[0] % 4 != 0) return fail(RNB_ERR_INVALID, "lattice x resolution must be a positive multiple of 4");
+	if ((uint64_t)res[0] * res[1] * res[2] > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice larger than 2^32 points");
+	if ((uintptr_t)density_dev & 15u) return fail(RNB_ERR_INVALID, "density lattice must be 16-byte aligned");
+	if (c->in_step) return fail(RNB_ERR_STATE, "training step in flight");
+	cudaStream_t st = (cudaStream_t)stream;
+	mesh_free(c);
+	rnb_ctx::Mesh& m = c->mesh;
+	const std::string e = mesh_extract(st, density_dev, res, aabb_min, aabb_max, thresh, &c->mesh_ws, &c->mesh_ws_bytes, &m.verts, &m.normals, &m.indices, &m.n_verts, &m.n_verts_padded, &m.n_indices, m.ms + 1, &c->launches);
+	m.ms[0] = 0.f;
+	if (!e.empty()) { mesh_free(c); return fail(RNB_ERR_CUDA, e); }
+	const size_t nvp = std::max<uint32_t>(m.n_verts_padded, 1);
+	CU(cudaMalloc(&m.colors, nvp * 12));
+	CU(cudaMemsetAsync(m.colors, 0, nvp * 12, st));
+	cudaEvent_t ec[2];
+	CU(cudaEventCreate(&ec[0])); CU(cudaEventCreate(&ec[1]));
+	CU(cudaEventRecord(ec[0], st));
+	if (with_colors && m.n_verts_padded) {
+		// the padding vertices (zeros) go through the network as well, as in the reference
+		const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
+		const __half* P = use_ema ? c->ema : c->params;
+		const uint32_t CH = c->cap_compact;
+		float* dirw = nullptr;
+		CU(cudaMallocAsync(&dirw, (size_t)std::min(CH, m.n_verts_padded) * 12, st));
+		net_pack(c, st, P);
+		for (uint32_t o = 0; o < m.n_verts_padded; o += CH) {
+			const uint32_t k = std::min(CH, m.n_verts_padded - o);
+			launch_mesh_color_inputs(st, k, m.verts + (size_t)o * 3, c->cpos4, dirw);
+			net_pass_b(c, st, P, vl, c->cpos4, nullptr, k, dirw);
+			launch_mesh_colors(st, k, c->out16, m.colors + (size_t)o * 3);
+			c->launches += 3;
+		}
+		CU(cudaFreeAsync(dirw, st));
+		if (P != c->params) net_pack(c, st, c->params);
+	}
+	CU(cudaEventRecord(ec[1], st));
+	CU(cudaStreamSynchronize(st));
+	CU(cudaGetLastError());
+	cudaEventElapsedTime(&m.ms[3], ec[0], ec[1]);
+	cudaEventDestroy(ec[0]); cudaEventDestroy(ec[1]);
+	if (info) {
+		info->n_verts = m.n_verts; info->n_verts_padded = m.n_verts_padded; info->n_indices = m.n_indices; info->res[0] = res[0]; info->res[1] = res[1]; info->res[2] = res[2];
+		for (int k = 0; k < 4; ++k) info->stage_ms[k] = m.ms[k];
+	}
+	return RNB_OK;
+}
+
+// Testbed::marching_cubes (src/testbed_nerf.cu:4297-4348): resolution rounded up to multiples of 16, SDF sweep, extraction, normals, colours.
+int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_min[3], const float aabb_max[3], float thresh, int use_ema, void* stream, rnb_mesh_info* info) {
+	if (!c || !res_in || !aabb_min || !aabb_max) return fail(RNB_ERR_INVALID, "null argument");
+	const uint32_t res[3] = {next_multiple(res_in[0], 16u), next_multiple(res_in[1], 16u), next_multiple(res_in[2], 16u)};
+	const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
+	if (n == 0 || n > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice empty or larger than 2^32 points");
+	if (c->mesh_density_bytes < n * 4) { cudaFree(c->mesh_density); c->mesh_density = nullptr; c->mesh_density_bytes = 0; CU(cudaMalloc(&c->mesh_density, n * 4)); c->mesh_density_bytes = n * 4; }
+	cudaEvent_t es[2];
+	CU(cudaEventCreate(&es[0])); CU(cudaEventCreate(&es[1]));
+	CU(cudaEventRecord(es[0], (cudaStream_t)stream));
+	int rc = rnb_sdf_on_grid(c, res, aabb_min, aabb_max, c->mesh_density, use_ema, stream);
+	CU(cudaEventRecord(es[1], (cudaStream_t)stream));
+	c->launches += 2;
+	if (rc == RNB_OK) rc = rnb_marching_cubes_from_density(c, c->mesh_density, res, aabb_min, aabb_max, thresh, 1, use_ema, stream, info);
+	if (rc == RNB_OK) { cudaEventElapsedTime(&c->mesh.ms[0], es[0], es[1]); if (info) info->stage_ms[0] = c->mesh.ms[0]; }
+	cudaEventDestroy(es[0]); cudaEventDestroy(es[1]);
+	return rc;
+}
+
+int rnb_mesh_buffers(rnb_ctx* c, float** verts, float** normals, float** colors, uint32_t** indices, rnb_mesh_info* info) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (!c->mesh.verts) return fail(RNB_ERR_STATE, "no mesh: call rnb_marching_cubes first");
+	if (verts) *verts = c->mesh.verts;
+	if (normals) *normals = c->mesh.normals;
+	if (colors) *colors = c->mesh.colors;
+	if (indices) *indices = c->mesh.indices;
+	if (info) { info->n_verts = c->mesh.n_verts; info->n_verts_padded = c->mesh.n_verts_padded; info->n_indices = c->mesh.n_indices; info->res[0] = info->res[1] = info->res[2] = 0; for (int k = 0; k < 4; ++k) info->stage_ms[k] = c->mesh.ms[k]; }
+	return RNB_OK;
+}
+
+// host copies of the mesh (Testbed::compute_marching_cubes_mesh, src/python_api.cu:99-130); each pointer may be null
+int rnb_mesh_download(rnb_ctx* c, float* verts, float* normals, float* colors, uint32_t* indices) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (!c->mesh.verts) return fail(RNB_ERR_STATE, "no mesh: call rnb_marching_cubes first");
+	const size_t vb = (size_t)c->mesh.n_verts_padded * 12;
+	if (verts) CU(cudaMemcpy(verts, c->mesh.verts, vb, cudaMemcpyDeviceToHost));
+	if (normals) CU(cudaMemcpy(normals, c->mesh.normals, vb, cudaMemcpyDeviceToHost));
+	if (colors) CU(cudaMemcpy(colors, c->mesh.colors, vb, cudaMemcpyDeviceToHost));
+	if (indices) CU(cudaMemcpy(indices, c->mesh.indices, (size_t)c->mesh.n_indices * 4, cudaMemcpyDeviceToHost));
+	return RNB_OK;
+}
+
+// save_mesh (src/marching_cubes.cu:824-982) on device arrays; no context needed
+int rnb_save_mesh(const float* verts_dev, const float* normals_dev, const float* colors_dev, const uint32_t* indices_dev, uint32_t n_verts, uint32_t n_indices, const char* path,
+                  float nerf_scale, const float nerf_offset[3], float n2w_s, const float n2w_t[3], int invert_normals, void* stream, uint64_t* bytes_written) {
+	if (!path || !nerf_offset || !n2w_t) return fail(RNB_ERR_INVALID, "null argument");
+	if ((n_verts && (!verts_dev || !normals_dev || !colors_dev)) || (n_indices && !indices_dev)) return fail(RNB_ERR_INVALID, "null mesh array");
+	if (n_indices % 3) return fail(RNB_ERR_INVALID, "index count is not a multiple of 3");
+	uint64_t launches = 0;
+	const std::string e = mesh_write((cudaStream_t)stream, verts_dev, normals_dev, colors_dev, indices_dev, n_verts, n_indices, path, nerf_scale, nerf_offset, n2w_s, n2w_t, invert_normals, bytes_written, &launches);
+	if (!e.empty()) return fail(RNB_ERR_CUDA, e);
 	return RNB_OK;
 }
 

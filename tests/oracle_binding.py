@@ -12,7 +12,7 @@ _SO = os.path.join(_ROOT, "oracle", "librnb_oracle.so")
 
 
 def build_oracle(force=False):
-    src = [os.path.join(_ROOT, "oracle", f) for f in ("rnb_oracle.cpp", "orc_common.h", "orc_network.h", "orc_render.h")]
+    src = [os.path.join(_ROOT, "oracle", f) for f in ("rnb_oracle.cpp", "orc_common.h", "orc_network.h", "orc_render.h", "orc_mesh.h", "orc_mc_tables.h")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle")], stdout=subprocess.DEVNULL)
     return _SO
@@ -67,6 +67,8 @@ def lib():
         L.orc_density_mean.restype = C.c_float
         L.orc_prep_if_due.restype = C.c_int
         L.orc_get_last_losses.restype = C.c_uint32
+        L.orc_marching_cubes.restype = C.c_void_p
+        L.orc_save_mesh.restype = C.c_int
         _lib = L
     return _lib
 
@@ -257,3 +259,25 @@ class Oracle:
 def pcg32(seed, advance, n):
     u = np.zeros(n, np.uint32); f = np.zeros(n, np.float32)
     lib().orc_pcg32(C.c_uint64(seed), C.c_int64(advance), n, _p(u, C.c_uint32), _p(f, C.c_float)); return u, f
+
+
+# ---- mesh path (oracle/orc_mesh.h) ----
+def marching_cubes(density, aabb_min=(0, 0, 0), aabb_max=(1, 1, 1), thresh=0.0):
+    """density[z, y, x] float32 -> (verts [Vp,3] incl. zero padding to a multiple of 128, normals [Vp,3], indices [T*3], n_verts)."""
+    d = np.ascontiguousarray(density, np.float32)
+    res = (C.c_uint32 * 3)(d.shape[2], d.shape[1], d.shape[0])
+    mn = (C.c_float * 3)(*aabb_min); mx = (C.c_float * 3)(*aabb_max); cnt = (C.c_uint32 * 3)()
+    L = lib()
+    h = C.c_void_p(L.orc_marching_cubes(_p(d, C.c_float), res, mn, mx, C.c_float(thresh), cnt))
+    verts = np.zeros((cnt[1], 3), np.float32); normals = np.zeros((cnt[1], 3), np.float32); idx = np.zeros(cnt[2], np.uint32)
+    L.orc_mesh_get(h, _p(verts, C.c_float), _p(normals, C.c_float), _p(idx, C.c_uint32))
+    L.orc_mesh_free(h)
+    return verts, normals, idx, int(cnt[0])
+
+
+def save_mesh(path, verts, normals, colors, indices, nerf_scale=1.0, nerf_offset=(0, 0, 0), n2w_s=1.0, n2w_t=(0, 0, 0), invert_normals=False):
+    v = np.ascontiguousarray(verts, np.float32); n = np.ascontiguousarray(normals, np.float32); c = np.ascontiguousarray(colors, np.float32)
+    i = np.ascontiguousarray(indices, np.uint32)
+    rc = lib().orc_save_mesh(_p(v, C.c_float), _p(n, C.c_float), _p(c, C.c_float), _p(i, C.c_uint32), C.c_uint32(v.shape[0]), C.c_uint32(i.size), str(path).encode(),
+                             C.c_float(nerf_scale), (C.c_float * 3)(*nerf_offset), C.c_float(n2w_s), (C.c_float * 3)(*n2w_t), int(invert_normals))
+    assert rc == 0, "oracle save_mesh failed"

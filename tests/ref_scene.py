@@ -32,7 +32,7 @@ def _png_job(a):
     _png16_rgba(*a)
 
 
-def write_scene(out_dir, views, workers=1):
+def write_scene(out_dir, views, workers=1, n2w=None):
     os.makedirs(os.path.join(out_dir, "normals"), exist_ok=True)
     os.makedirs(os.path.join(out_dir, "albedos"), exist_ok=True)
     os.makedirs(os.path.join(out_dir, "output"), exist_ok=True)
@@ -57,7 +57,7 @@ def write_scene(out_dir, views, workers=1):
     else:
         for j in jobs:
             _png_job(j)
-    tj = {"w": w, "h": h, "aabb_scale": 1.0, "scale": 0.5, "offset": [0.5, 0.5, 0.5], "from_na": True, "n2w": np.eye(4).tolist(), "frames": frames}
+    tj = {"w": w, "h": h, "aabb_scale": 1.0, "scale": 0.5, "offset": [0.5, 0.5, 0.5], "from_na": True, "n2w": (np.eye(4) if n2w is None else np.asarray(n2w)).tolist(), "frames": frames}
     with open(os.path.join(out_dir, "transform.json"), "w") as f:
         json.dump(tj, f)
 
