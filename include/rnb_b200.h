@@ -208,14 +208,14 @@ typedef struct rnb_mesh_info {
 	uint32_t n_verts_padded;   /* array length: rounded up to 128, padding zero (src/marching_cubes.cu:810-812); this is what gets saved */
 	uint32_t n_indices;        /* 3 x triangles */
 	uint32_t res[3];           /* lattice actually used */
-	float stage_ms[4];         /* device time of the last extraction (CUDA events): SDF sweep, count + scan, vertices + normals + faces, colours */
+	float stage_ms[4];         /* device time of the last extraction (CUDA events): SDF sweep, sign bits + count + scan, vertices + normals + faces, colours */
 } rnb_mesh_info;
 /* replaces Testbed::marching_cubes (src/testbed_nerf.cu:4297-4348): res rounded up to multiples of 16, SDF sweep over the aabb,
  * marching_cubes_gpu, area-weighted vertex normals (compute_mesh_1ring), vertex colours (compute_mesh_vertex_colors).
  * Synchronises the stream (the vertex count sizes the arrays, as in the reference). */
 int rnb_marching_cubes(rnb_ctx* ctx, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh, int use_ema, void* stream, rnb_mesh_info* info);
 /* replaces marching_cubes_gpu (src/marching_cubes.cu:794-822) + compute_mesh_1ring (:722-728) on a caller-provided lattice of values
- * density_dev[x + y res[0] + z res[0] res[1]] (res[0] a multiple of 4); with_colors != 0 also runs the colour network at the vertices */
+ * density_dev[x + y res[0] + z res[0] res[1]] (res[0] a multiple of 16, as every lattice the reference builds); with_colors != 0 also runs the colour network at the vertices */
 int rnb_marching_cubes_from_density(rnb_ctx* ctx, const float* density_dev, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh,
                                     int with_colors, int use_ema, void* stream, rnb_mesh_info* info);
 /* device pointers of the current mesh (valid until the next extraction or rnb_destroy); any out pointer may be NULL */

@@ -58,7 +58,7 @@ static void dump_host(const std::string& name, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
 	if (argc < 5) {
-		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--time-from K] [--pin-rays N] [--mesh RES]\n");
+		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--time-from K] [--pin-rays N] [--mesh RES] [--save-snapshot FILE] [--load-snapshot FILE]\n");
 		return 1;
 	}
 	char buf[PATH_MAX]; ssize_t cnt = readlink("/proc/self/exe", buf, PATH_MAX);
@@ -67,7 +67,7 @@ int main(int argc, char** argv) {
 	g_out = argv[3];
 	const int n_steps = atoi(argv[4]);
 	bool no_albedo = false, supernormal = false, opti = false, l1 = false, rgbplus = true, time_only = false;
-	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps; int time_from = -1; int mesh_res = 0;
+	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps; int time_from = -1; int mesh_res = 0; std::string save_snapshot, load_snapshot;
 	for (int i = 5; i < argc; ++i) {
 		std::string a = argv[i];
 		if (a == "--no-albedo") no_albedo = true; else if (a == "--supernormal") supernormal = true; else if (a == "--opti-lights") opti = true;
@@ -76,6 +76,8 @@ int main(int argc, char** argv) {
 		else if (a == "--pin-rays" && i + 1 < argc) pin_rays = (uint32_t)atoi(argv[++i]);
 		else if (a == "--time-from" && i + 1 < argc) time_from = atoi(argv[++i]);
 		else if (a == "--mesh" && i + 1 < argc) mesh_res = atoi(argv[++i]);
+		else if (a == "--save-snapshot" && i + 1 < argc) save_snapshot = argv[++i];
+		else if (a == "--load-snapshot" && i + 1 < argc) load_snapshot = argv[++i];
 		else if (a == "--dump-steps" && i + 1 < argc) { std::string l = argv[++i]; size_t p0 = 0; while (p0 < l.size()) { size_t q = l.find(',', p0); if (q == std::string::npos) q = l.size(); dump_steps.push_back(atoi(l.substr(p0, q - p0).c_str())); p0 = q + 1; } }
 	}
 
@@ -90,6 +92,8 @@ int main(int argc, char** argv) {
 	if (rgbplus) tb.apply_rgbplus();
 	if (opti) tb.apply_light_opti();
 	if (no_albedo) tb.apply_no_albedo(true);
+	// snapshot hand-off: Testbed::load_snapshot exactly as src/main.cu:312 calls it, after the dataset and the network config
+	if (!load_snapshot.empty()) tb.load_snapshot(load_snapshot);
 
 	auto& tr = tb.m_nerf.training;
 	const size_t n_params = tb.m_network->n_params();
@@ -183,6 +187,11 @@ int main(int argc, char** argv) {
 		CUDA_CHECK_THROW(cudaDeviceSynchronize());
 		dump_host("probe_coords.bin", coords.data(), coords.size() * 4);
 		dump_dev("probe_out_fp16.bin", (const uint16_t*)out.data(), (size_t)n * 16);
+	}
+	if (!save_snapshot.empty()) {          // src/main.cu:465-468
+		tb.save_snapshot(save_snapshot, false);
+		dump_dev("snapshot_params_inference_fp16.bin", (const uint16_t*)tb.m_trainer->params_inference(), n_params);
+		dump_dev("snapshot_density_grid.bin", tb.m_nerf.density_grid.data(), tb.m_nerf.density_grid.size());
 	}
 	// mesh path: the SDF lattice of get_density_on_grid, then compute_and_save_marching_cubes_mesh exactly as
 	// src/main.cu:460 calls it (empty aabb -> m_render_aabb, threshold 0, no unwrap), and the mesh arrays it leaves in m_mesh

@@ -137,6 +137,7 @@ class Testbed:
         self._chk(self.L.rnb_param_layout(self.h, lay))
         self.off_sdf, self.off_rgb, self.off_grid, self.off_var, self.n_params = [int(x) for x in lay]
         self._keep = []
+        self.last_measured_batch_size = 0; self.last_loss = 0.0       # of the last step whose statistics were read (snapshot fields)
         if flags is not None:
             self.set_flags(flags)
 
@@ -256,6 +257,8 @@ class Testbed:
     def train(self, stream=None, want_stats=True):
         st = StepStats()
         self._chk(self.L.rnb_train(self.h, C.c_void_p(stream), C.byref(st) if want_stats else None))
+        if want_stats:
+            self.last_measured_batch_size = int(st.n_samples_compacted); self.last_loss = float(st.loss)
         return st
 
     def train_step_begin(self, stream=None):
@@ -264,6 +267,7 @@ class Testbed:
     def train_step_end(self, stream=None):
         st = StepStats()
         self._chk(self.L.rnb_train_step_end(self.h, C.c_void_p(stream), C.byref(st)))
+        self.last_measured_batch_size = int(st.n_samples_compacted); self.last_loss = float(st.loss)
         return st
 
     def grad_buffer(self):
@@ -316,10 +320,39 @@ class Testbed:
         r = (C.c_uint32 * 3)(*[int(x) for x in res]); a = (C.c_float * 3)(*[float(x) for x in aabb_min]); b = (C.c_float * 3)(*[float(x) for x in aabb_max])
         self._chk(self.L.rnb_sdf_on_grid(self.h, r, a, b, C.c_void_p(out_ptr), int(use_ema), C.c_void_p(stream)))
 
+    # --- snapshot hand-off ---
+    def save_snapshot(self, path, network_config, loss=None, aabb_scale=1, dataset=None):
+        """Testbed::save_snapshot(path, include_optimizer_state=false) (src/testbed.cu:3280-3314): the inference (EMA) parameters as
+        binary16, the occupancy grid as binary16, the batch-size controller and the training step, inside `network_config`."""
+        from . import snapshot as snap
+        ts, rays, _, measured_before = self.get_train_state()
+        grid, _ = self.export_density_grid()
+        if ts == 0:
+            grid = np.zeros(0, np.float32)              # never populated: the reference's grid is still empty
+        cfg = snap.build_snapshot(network_config, self.export_params_fp16(use_ema=True), grid, ts, self.last_loss if loss is None else loss, rays, self.last_measured_batch_size, measured_before,
+                                  aabb_scale=aabb_scale, dataset=dataset)
+        snap.write_snapshot(path, cfg)
+        return cfg
+
+    def load_snapshot(self, path):
+        """Testbed::load_snapshot (src/testbed.cu:3333-3390): parameters (training, inference and fp32 master all take the stored
+        binary16 values, Adam restarts: trainer.h:263-275), occupancy grid + bitfield, controller state, training step."""
+        from . import snapshot as snap
+        cfg = snap.read_snapshot(path)
+        d = snap.parse_snapshot(cfg)
+        if d["params_fp16"].size != self.n_params:
+            raise RnbError("Can't set params because CPU buffer has the wrong size.")
+        self.import_params_fp16(d["params_fp16"])
+        if d["density_grid"].size:
+            self.import_density_grid(d["density_grid"], 0)
+        self.set_train_state(d["training_step"], d["rays_per_batch"], 0, d["measured_batch_size_before_compaction"])
+        self.last_measured_batch_size = d["measured_batch_size"]
+        return cfg
+
     # --- mesh extraction and export (SURVEY N2) ---
     def _mesh_info(self, info):
         return dict(n_verts=int(info.n_verts), n_verts_padded=int(info.n_verts_padded), n_indices=int(info.n_indices), res=tuple(int(x) for x in info.res),
-                    stage_ms=dict(zip(("sdf_sweep", "count_scan", "vertices_normals_faces", "colors"), (round(float(x), 4) for x in info.stage_ms))))
+                    stage_ms=dict(zip(("sdf_sweep", "bits_count_scan", "vertices_normals_faces", "colors"), (round(float(x), 4) for x in info.stage_ms))))
 
     def marching_cubes(self, res, aabb_min=(0.0, 0.0, 0.0), aabb_max=(1.0, 1.0, 1.0), thresh=0.0, use_ema=True, stream=None):
         """Testbed::marching_cubes (src/testbed_nerf.cu:4297-4348): the mesh stays on the device; returns its sizes."""

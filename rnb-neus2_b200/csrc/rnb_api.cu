@@ -760,9 +760,9 @@ static void mesh_free(rnb_ctx* c) {
 int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh,
                                     int with_colors, int use_ema, void* stream, rnb_mesh_info* info) {
 	if (!c || !density_dev || !res || !aabb_min || !aabb_max) return fail(RNB_ERR_INVALID, "null argument");
-	if (res[0] == 0 || res[1] == 0 || res[2] == 0 || res[0] % 4 != 0) return fail(RNB_ERR_INVALID, "lattice x resolution must be a positive multiple of 4");
+	if (res[0] == 0 || res[1] == 0 || res[2] == 0 || res[0] % 16 != 0) return fail(RNB_ERR_INVALID, "lattice x resolution must be a positive multiple of 16");
 	if ((uint64_t)res[0] * res[1] * res[2] > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice larger than 2^32 points");
-	if ((uintptr_t)density_dev & 15u) return fail(RNB_ERR_INVALID, "density lattice must be 16-byte aligned");
+	if ((uintptr_t)density_dev & 3u) return fail(RNB_ERR_INVALID, "density lattice must be 4-byte aligned");
 	if (c->in_step) return fail(RNB_ERR_STATE, "training step in flight");
 	cudaStream_t st = (cudaStream_t)stream;
 	mesh_free(c);
@@ -782,7 +782,7 @@ int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const 
 		const __half* P = use_ema ? c->ema : c->params;
 		const uint32_t CH = c->cap_compact;
 		float* dirw = nullptr;
-		CU(cudaMallocAsync(&dirw, (size_t)std::min(CH, m.n_verts_padded) * 12, st));
+		CU(cudaMalloc(&dirw, (size_t)std::min(CH, m.n_verts_padded) * 12));
 		net_pack(c, st, P);
 		for (uint32_t o = 0; o < m.n_verts_padded; o += CH) {
 			const uint32_t k = std::min(CH, m.n_verts_padded - o);
@@ -791,8 +791,9 @@ int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const 
 			launch_mesh_colors(st, k, c->out16, m.colors + (size_t)o * 3);
 			c->launches += 3;
 		}
-		CU(cudaFreeAsync(dirw, st));
 		if (P != c->params) net_pack(c, st, c->params);
+		CU(cudaStreamSynchronize(st));
+		CU(cudaFree(dirw));
 	}
 	CU(cudaEventRecord(ec[1], st));
 	CU(cudaStreamSynchronize(st));

@@ -7,8 +7,11 @@
 //    lexicographic one (lattice point x + y rx + z rx ry; its +x, +y, +z edge in that order; triangles in table order), the
 //    same on every run.  The reference's numbering is whatever order its atomics retire in, so its output is this mesh up
 //    to a permutation of the vertices and of the triangles;
-//  * one 32-bit word per lattice point (first vertex id << 2 | x-edge crossed | y-edge crossed << 1) replaces the reference's
-//    three ints per point (12.9 GB at 1024^3 -> 4.3 GB);
+//  * the lattice is read once, into one sign bit per point; counting, numbering and case lookup run bit-parallel on 16 points per
+//    thread, and the fp32 values are touched again only at the crossing edges (the reference reads the lattice in four passes
+//    of 4-7 loads per point);
+//  * one 32-bit word per vertex-owning lattice point (first vertex id << 2 | x-edge crossed | y-edge crossed << 1) replaces the
+//    reference's three ints per point (12.9 GB at 1024^3 written and cleared -> 4.3 GB reserved, only the surface touched);
 //  * vertex normals are gathered per vertex from the (at most four) cells around its edge in a fixed order instead of
 //    being scattered with float atomics: same addends, deterministic sum;
 //  * the OBJ text is formatted on the GPU (exact "%0.5f" / "%0.3f" / "%u" of glibc in integer arithmetic, ordered scan of the
@@ -32,8 +35,6 @@ struct McGrid {
 	float thresh;
 };
 
-constexpr int MC_THREADS = 256, MC_PER_THREAD = 4, MC_BLOCK = MC_THREADS * MC_PER_THREAD;
-
 // exclusive prefix over the block (in thread order) + block total; red: >= blockDim/32 words of shared memory
 __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* red, uint32_t& total) {
 	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -49,76 +50,90 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* red, u
 	return base + inc - v;
 }
 
-// The four lattice points a thread owns (consecutive in x; rx % 4 == 0 keeps them in one row) with everything the three
-// passes derive from the density: per point the crossing flags of its +x/+y/+z edges and the case mask of the cell it is
-// the origin of.  in-bits: bit i of b[dz][dy] = density(x0 + i, y + dy, z + dz) > thresh, i = 0..4.
-struct Quad {
-	uint32_t x0, y, z, idx0;
-	float f00[5], f10[4], f01[4];
-	uint32_t b00, b10, b01, b11;
-	bool has_x4, has_y, has_z;
-};
-
-__device__ __forceinline__ uint32_t above_bits(const float4 v, float nxt, float th) {
-	return (uint32_t)(v.x > th) | ((uint32_t)(v.y > th) << 1) | ((uint32_t)(v.z > th) << 2) | ((uint32_t)(v.w > th) << 3) | ((uint32_t)(nxt > th) << 4);
+// Sign bits.  Everything marching cubes decides (which edges carry a vertex, which case a cell is) depends on the lattice
+// only through density > thresh, so pass 0 reads the lattice ONCE, perfectly coalesced, and leaves one bit per point
+// (bit idx & 31 of word idx >> 5; 134 MB at 1024^3, L2-resident); the counting, vertex and face passes work on 16 points per
+// thread in bit-parallel form and touch the fp32 lattice again only at the (sparse) crossing edges.
+__global__ void __launch_bounds__(256) k_mc_bits(uint32_t n, float thresh, const float* __restrict__ D, uint32_t* __restrict__ bits) {
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint64_t base = warp * 128;                     // 128 points (four words) per warp
+	if (base >= n) return;
+	uint32_t mine = 0;
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const uint64_t i = base + k * 32 + lane;
+		const bool above = i < n && __ldg(D + i) > thresh;
+		const uint32_t b = __ballot_sync(0xFFFFFFFFu, above);
+		if (lane == (uint32_t)k) mine = b;
+	}
+	if (lane < 4 && base + lane * 32 < n) bits[(base >> 5) + lane] = mine;
 }
 
-__device__ __forceinline__ bool load_quad(const McGrid& g, const float* __restrict__ D, uint32_t q, Quad& Q) {
+constexpr int MC_THREADS = 256, MC_PER_THREAD = 16, MC_BLOCK = MC_THREADS * MC_PER_THREAD;
+
+// The 16 lattice points a thread owns (consecutive in x; rx % 16 == 0 keeps them in one row).  b[dz][dy]: bit i = sign bit of
+// point (x0 + i, y + dy, z + dz), i = 0..16 (bit 16 = first point of the next group, 0 past the end of the row).
+struct Group {
+	uint32_t x0, y, z, idx0;
+	uint32_t b00, b10, b01, b11;
+	uint32_t edge_x;        // points that have a +x neighbour
+	bool has_y, has_z;
+};
+__device__ __forceinline__ uint32_t bits17(const uint32_t* __restrict__ bits, uint32_t idx, bool more) {
+	const uint32_t w = __ldg(bits + (idx >> 5));
+	if ((idx & 31u) == 0) return more ? (w & 0x1FFFFu) : (w & 0xFFFFu);
+	uint32_t r = w >> 16;
+	if (more) r |= (__ldg(bits + (idx >> 5) + 1) & 1u) << 16;
+	return r;
+}
+__device__ __forceinline__ bool load_group(const McGrid& g, const uint32_t* __restrict__ bits, uint32_t q, Group& G) {
 	const uint64_t i0 = (uint64_t)q * MC_PER_THREAD;
 	if (i0 >= g.n) return false;
 	const uint32_t idx = (uint32_t)i0, rxy = g.rx * g.ry;
-	Q.idx0 = idx; Q.z = idx / rxy; const uint32_t r = idx - Q.z * rxy; Q.y = r / g.rx; Q.x0 = r - Q.y * g.rx;
-	Q.has_x4 = Q.x0 + 4 < g.rx; Q.has_y = Q.y + 1 < g.ry; Q.has_z = Q.z + 1 < g.rz;
-	const float4 a = __ldg(reinterpret_cast<const float4*>(D + idx));
-	const float an = Q.has_x4 ? __ldg(D + idx + 4) : 0.f;
-	Q.f00[0] = a.x; Q.f00[1] = a.y; Q.f00[2] = a.z; Q.f00[3] = a.w; Q.f00[4] = an;
-	Q.b00 = above_bits(a, an, g.thresh);
-	Q.b10 = Q.b01 = Q.b11 = 0;
-	if (Q.has_y) {
-		const float4 b = __ldg(reinterpret_cast<const float4*>(D + idx + g.rx));
-		const float bn = Q.has_x4 ? __ldg(D + idx + g.rx + 4) : 0.f;
-		Q.f10[0] = b.x; Q.f10[1] = b.y; Q.f10[2] = b.z; Q.f10[3] = b.w;
-		Q.b10 = above_bits(b, bn, g.thresh);
-	}
-	if (Q.has_z) {
-		const float4 c = __ldg(reinterpret_cast<const float4*>(D + idx + rxy));
-		const float cn = Q.has_x4 ? __ldg(D + idx + rxy + 4) : 0.f;
-		Q.f01[0] = c.x; Q.f01[1] = c.y; Q.f01[2] = c.z; Q.f01[3] = c.w;
-		Q.b01 = above_bits(c, cn, g.thresh);
-		if (Q.has_y) {
-			const float4 d = __ldg(reinterpret_cast<const float4*>(D + idx + rxy + g.rx));
-			const float dn = Q.has_x4 ? __ldg(D + idx + rxy + g.rx + 4) : 0.f;
-			Q.b11 = above_bits(d, dn, g.thresh);
-		}
-	}
+	G.idx0 = idx; G.z = idx / rxy; const uint32_t r = idx - G.z * rxy; G.y = r / g.rx; G.x0 = r - G.y * g.rx;
+	const bool more = G.x0 + 16 < g.rx;
+	G.has_y = G.y + 1 < g.ry; G.has_z = G.z + 1 < g.rz;
+	G.edge_x = more ? 0xFFFFu : 0x7FFFu;
+	G.b00 = bits17(bits, idx, more);
+	G.b10 = G.has_y ? bits17(bits, idx + g.rx, more) : 0u;
+	G.b01 = G.has_z ? bits17(bits, idx + rxy, more) : 0u;
+	G.b11 = (G.has_y && G.has_z) ? bits17(bits, idx + rxy + g.rx, more) : 0u;
 	return true;
 }
-// edge crossings of point i of the quad (gen_vertices, :289-327): bit 0 = +x, bit 1 = +y, bit 2 = +z
-__device__ __forceinline__ uint32_t quad_cross(const McGrid& g, const Quad& Q, int i) {
-	const uint32_t in = (Q.b00 >> i) & 1u;
-	const uint32_t cx = (Q.x0 + i + 1 < g.rx) ? (in ^ ((Q.b00 >> (i + 1)) & 1u)) : 0u;
-	const uint32_t cy = Q.has_y ? (in ^ ((Q.b10 >> i) & 1u)) : 0u;
-	const uint32_t cz = Q.has_z ? (in ^ ((Q.b01 >> i) & 1u)) : 0u;
-	return cx | (cy << 1) | (cz << 2);
+// crossed +x / +y / +z edges per point (gen_vertices, :289-327), one bit per point
+__device__ __forceinline__ void group_cross(const Group& G, uint32_t& cx, uint32_t& cy, uint32_t& cz) {
+	cx = (G.b00 ^ (G.b00 >> 1)) & G.edge_x;
+	cy = G.has_y ? ((G.b00 ^ G.b10) & 0xFFFFu) : 0u;
+	cz = G.has_z ? ((G.b00 ^ G.b01) & 0xFFFFu) : 0u;
 }
-// case mask of the cell with origin at point i (gen_faces, :668-679), 0 for points that are not a cell origin
-__device__ __forceinline__ uint32_t quad_mask(const McGrid& g, const Quad& Q, int i) {
-	if (!(Q.x0 + i + 1 < g.rx) || !Q.has_y || !Q.has_z) return 0u;
+// cells (by origin point) that are neither all-below nor all-above
+__device__ __forceinline__ uint32_t group_active_cells(const Group& G) {
+	if (!G.has_y || !G.has_z) return 0u;
+	const uint32_t s00 = G.b00 >> 1, s10 = G.b10 >> 1, s01 = G.b01 >> 1, s11 = G.b11 >> 1;
+	const uint32_t any = G.b00 | s00 | G.b10 | s10 | G.b01 | s01 | G.b11 | s11, all = G.b00 & s00 & G.b10 & s10 & G.b01 & s01 & G.b11 & s11;
+	return (any & ~all) & G.edge_x;
+}
+// case mask of the cell with origin at point i (gen_faces, :668-679)
+__device__ __forceinline__ uint32_t group_mask(const Group& G, int i) {
 	const int j = i + 1;
-	return ((Q.b00 >> i) & 1u) | (((Q.b00 >> j) & 1u) << 1) | (((Q.b10 >> j) & 1u) << 2) | (((Q.b10 >> i) & 1u) << 3) |
-	       (((Q.b01 >> i) & 1u) << 4) | (((Q.b01 >> j) & 1u) << 5) | (((Q.b11 >> j) & 1u) << 6) | (((Q.b11 >> i) & 1u) << 7);
+	return ((G.b00 >> i) & 1u) | (((G.b00 >> j) & 1u) << 1) | (((G.b10 >> j) & 1u) << 2) | (((G.b10 >> i) & 1u) << 3) |
+	       (((G.b01 >> i) & 1u) << 4) | (((G.b01 >> j) & 1u) << 5) | (((G.b11 >> j) & 1u) << 6) | (((G.b11 >> i) & 1u) << 7);
+}
+__device__ __forceinline__ uint32_t group_index_count(const Group& G, uint32_t active) {
+	uint32_t ni = 0;
+	while (active) { const int i = __ffs(active) - 1; active &= active - 1; ni += mc_index_count(MC_TRIANGLES[group_mask(G, i)]); }
+	return ni;
 }
 
 // pass 1: vertices and triangle indices per block of MC_BLOCK lattice points
-__global__ void __launch_bounds__(MC_THREADS) k_mc_count(McGrid g, const float* __restrict__ D, uint32_t* __restrict__ blockV, uint32_t* __restrict__ blockI) {
+__global__ void __launch_bounds__(MC_THREADS) k_mc_count(McGrid g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ blockV, uint32_t* __restrict__ blockI) {
 	__shared__ uint32_t red[MC_THREADS / 32];
-	Quad Q; uint32_t nv = 0, ni = 0;
-	if (load_quad(g, D, blockIdx.x * MC_THREADS + threadIdx.x, Q)) {
-		#pragma unroll
-		for (int i = 0; i < MC_PER_THREAD; ++i) {
-			nv += __popc(quad_cross(g, Q, i));
-			ni += mc_index_count(MC_TRIANGLES[quad_mask(g, Q, i)]);
-		}
+	Group G; uint32_t nv = 0, ni = 0;
+	if (load_group(g, bits, blockIdx.x * MC_THREADS + threadIdx.x, G)) {
+		uint32_t cx, cy, cz; group_cross(G, cx, cy, cz);
+		nv = __popc(cx) + __popc(cy) + __popc(cz);
+		ni = group_index_count(G, group_active_cells(G));
 	}
 	uint32_t tv, ti;
 	block_exclusive(nv, red, tv);
@@ -170,26 +185,23 @@ constexpr uint64_t MC_EDGE_OWNER = (0ull) | (9ull << 5) | (2ull << 10) | (8ull <
 __device__ __forceinline__ uint32_t edge_owner(uint32_t e) { return (uint32_t)(MC_EDGE_OWNER >> (5 * e)) & 31u; }
 
 // pass 3: triangle indices (gen_faces, :680-719)
-__global__ void __launch_bounds__(MC_THREADS) k_mc_faces(McGrid g, const float* __restrict__ D, const uint32_t* __restrict__ blockI,
+__global__ void __launch_bounds__(MC_THREADS) k_mc_faces(McGrid g, const uint32_t* __restrict__ bits, const uint32_t* __restrict__ blockI,
                                                           const uint32_t* __restrict__ point_word, uint32_t* __restrict__ indices) {
 	__shared__ uint32_t red[MC_THREADS / 32];
-	Quad Q; uint32_t mask[MC_PER_THREAD] = {0, 0, 0, 0}, ni = 0;
-	const bool live = load_quad(g, D, blockIdx.x * MC_THREADS + threadIdx.x, Q);
-	if (live) {
-		#pragma unroll
-		for (int i = 0; i < MC_PER_THREAD; ++i) { mask[i] = quad_mask(g, Q, i); ni += mc_index_count(MC_TRIANGLES[mask[i]]); }
-	}
+	Group G; uint32_t active = 0, ni = 0;
+	const bool live = load_group(g, bits, blockIdx.x * MC_THREADS + threadIdx.x, G);
+	if (live) { active = group_active_cells(G); ni = group_index_count(G, active); }
 	uint32_t tot;
 	uint32_t t = blockI[blockIdx.x] + block_exclusive(ni, red, tot);
-	if (!live || !ni) return;
+	if (!ni) return;
 	const uint32_t rxy = g.rx * g.ry;
-	#pragma unroll
-	for (int i = 0; i < MC_PER_THREAD; ++i) {
-		uint64_t row = MC_TRIANGLES[mask[i]];
+	while (active) {
+		const int i = __ffs(active) - 1; active &= active - 1;
+		uint64_t row = MC_TRIANGLES[group_mask(G, i)];
 		const uint32_t cnt = mc_index_count(row);
 		for (uint32_t k = 0; k < cnt; ++k, row >>= 4) {
 			const uint32_t o = edge_owner((uint32_t)row & 15u);
-			const uint32_t w = __ldg(point_word + (Q.idx0 + i + (o & 1u) + ((o >> 1) & 1u) * g.rx + ((o >> 2) & 1u) * rxy));
+			const uint32_t w = __ldg(point_word + (G.idx0 + i + (o & 1u) + ((o >> 1) & 1u) * g.rx + ((o >> 2) & 1u) * rxy));
 			const uint32_t axis = o >> 3;
 			indices[t++] = (w >> 2) + (axis == 0 ? 0u : axis == 1 ? (w & 1u) : (w & 1u) + ((w >> 1) & 1u));
 		}
@@ -248,43 +260,55 @@ __device__ void vertex_normal(const McGrid& g, const float* __restrict__ D, uint
 		}
 	}
 }
-// pass 2: vertex positions, vertex normals and the per-point word (first vertex id << 2 | +x crossed | +y crossed << 1)
-__global__ void __launch_bounds__(MC_THREADS) k_mc_vertices(McGrid g, const float* __restrict__ D, const uint32_t* __restrict__ blockV,
+// pass 2: vertex positions and, for every point that owns a vertex, its word (first vertex id << 2 | +x crossed | +y crossed << 1);
+// points without crossings are never looked up by the face pass.  The slot of the vertex normal receives the edge the vertex
+// sits on (owner point, axis) for k_mc_normals, which runs one thread per vertex: the surface is sparse in the lattice, and
+// a thread per lattice group would leave 31 lanes of a warp waiting for the one that found vertices.
+__global__ void __launch_bounds__(MC_THREADS) k_mc_vertices(McGrid g, const float* __restrict__ D, const uint32_t* __restrict__ bits, const uint32_t* __restrict__ blockV,
                                                              uint32_t* __restrict__ point_word, float* __restrict__ verts, float* __restrict__ normals) {
 	__shared__ uint32_t red[MC_THREADS / 32];
-	Quad Q; uint32_t cr[MC_PER_THREAD] = {0, 0, 0, 0}, nv = 0;
-	const bool live = load_quad(g, D, blockIdx.x * MC_THREADS + threadIdx.x, Q);
-	if (live) {
-		#pragma unroll
-		for (int i = 0; i < MC_PER_THREAD; ++i) { cr[i] = quad_cross(g, Q, i); nv += __popc(cr[i]); }
-	}
+	Group G; uint32_t cx = 0, cy = 0, cz = 0, nv = 0;
+	const bool live = load_group(g, bits, blockIdx.x * MC_THREADS + threadIdx.x, G);
+	if (live) { group_cross(G, cx, cy, cz); nv = __popc(cx) + __popc(cy) + __popc(cz); }
 	uint32_t tot;
 	uint32_t v = blockV[blockIdx.x] + block_exclusive(nv, red, tot);
-	if (!live) return;
-	uint32_t word[MC_PER_THREAD];
-	const uint32_t v0 = v;
-	const float fy = (float)Q.y, fz = (float)Q.z;
-	#pragma unroll
-	for (int i = 0; i < MC_PER_THREAD; ++i) {
-		word[i] = (v << 2) | (cr[i] & 3u);
-		if (!cr[i]) continue;
-		const float fx = (float)(Q.x0 + i), f0 = Q.f00[i];
+	if (!nv) return;
+	const uint32_t rxy = g.rx * g.ry;
+	const float fy = (float)G.y, fz = (float)G.z;
+	uint32_t any = cx | cy | cz;
+	while (any) {
+		const int i = __ffs(any) - 1; any &= any - 1;
+		const uint32_t p = G.idx0 + i, bx = (cx >> i) & 1u, by = (cy >> i) & 1u, bz = (cz >> i) & 1u;
+		point_word[p] = (v << 2) | bx | (by << 1);
+		const float fx = (float)(G.x0 + i), f0 = __ldg(D + p);
 		// dt = (thresh - f0) / (f1 - f0); vertex = (lattice + dt e_axis) * scale + offset   (:296-300)
-		if (cr[i] & 1u) { const float dt = (g.thresh - f0) / (Q.f00[i + 1] - f0); float* o = verts + (size_t)v * 3; o[0] = fmaf(fx + dt, g.sx, g.ox); o[1] = fmaf(fy, g.sy, g.oy); o[2] = fmaf(fz, g.sz, g.oz); ++v; }
-		if (cr[i] & 2u) { const float dt = (g.thresh - f0) / (Q.f10[i] - f0); float* o = verts + (size_t)v * 3; o[0] = fmaf(fx, g.sx, g.ox); o[1] = fmaf(fy + dt, g.sy, g.oy); o[2] = fmaf(fz, g.sz, g.oz); ++v; }
-		if (cr[i] & 4u) { const float dt = (g.thresh - f0) / (Q.f01[i] - f0); float* o = verts + (size_t)v * 3; o[0] = fmaf(fx, g.sx, g.ox); o[1] = fmaf(fy, g.sy, g.oy); o[2] = fmaf(fz + dt, g.sz, g.oz); ++v; }
+		if (bx) {
+			const float dt = (g.thresh - f0) / (__ldg(D + p + 1) - f0); float* o = verts + (size_t)v * 3; float* nn = normals + (size_t)v * 3;
+			o[0] = fmaf(fx + dt, g.sx, g.ox); o[1] = fmaf(fy, g.sy, g.oy); o[2] = fmaf(fz, g.sz, g.oz);
+			nn[0] = __uint_as_float(p); nn[1] = __uint_as_float(0u); ++v;
+		}
+		if (by) {
+			const float dt = (g.thresh - f0) / (__ldg(D + p + g.rx) - f0); float* o = verts + (size_t)v * 3; float* nn = normals + (size_t)v * 3;
+			o[0] = fmaf(fx, g.sx, g.ox); o[1] = fmaf(fy + dt, g.sy, g.oy); o[2] = fmaf(fz, g.sz, g.oz);
+			nn[0] = __uint_as_float(p); nn[1] = __uint_as_float(1u); ++v;
+		}
+		if (bz) {
+			const float dt = (g.thresh - f0) / (__ldg(D + p + rxy) - f0); float* o = verts + (size_t)v * 3; float* nn = normals + (size_t)v * 3;
+			o[0] = fmaf(fx, g.sx, g.ox); o[1] = fmaf(fy, g.sy, g.oy); o[2] = fmaf(fz + dt, g.sz, g.oz);
+			nn[0] = __uint_as_float(p); nn[1] = __uint_as_float(2u); ++v;
+		}
 	}
-	*reinterpret_cast<uint4*>(point_word + Q.idx0) = make_uint4(word[0], word[1], word[2], word[3]);
-	if (v == v0) return;
-	v = v0;
-	for (int i = 0; i < MC_PER_THREAD; ++i)
-		for (uint32_t axis = 0; axis < 3; ++axis)
-			if (cr[i] & (1u << axis)) {
-				float n[3];
-				vertex_normal(g, D, Q.x0 + i, Q.y, Q.z, axis, n);
-				float* o = normals + (size_t)v * 3; o[0] = n[0]; o[1] = n[1]; o[2] = n[2];
-				++v;
-			}
+}
+
+__global__ void __launch_bounds__(256) k_mc_normals(McGrid g, const float* __restrict__ D, uint32_t n_verts, float* __restrict__ normals) {
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n_verts) return;
+	float* nn = normals + (size_t)v * 3;
+	const uint32_t p = __float_as_uint(nn[0]), axis = __float_as_uint(nn[1]), rxy = g.rx * g.ry;
+	const uint32_t z = p / rxy, r = p - z * rxy, y = r / g.rx, x = r - y * g.rx;
+	float nl[3];
+	vertex_normal(g, D, x, y, z, axis, nl);
+	nn[0] = nl[0]; nn[1] = nl[1]; nn[2] = nl[2];
 }
 
 // ---- vertex colours: network inputs (generate_nerf_network_inputs_from_positions, src/testbed_nerf.cu:793-799) and output
@@ -442,39 +466,42 @@ McGrid make_mc_grid(const uint32_t res[3], const float mn[3], const float mx[3],
 
 // marching_cubes_gpu (:794-822) + compute_mesh_1ring normals.  Allocates *verts / *normals (n_verts rounded up to 128, the
 // padding zeroed, :810-812) and *indices with cudaMalloc; the caller frees them.  ws / ws_bytes: grow-only scratch kept by the
-// caller between calls (one word per lattice point + the block counters).  ms[0] = count + scan, ms[1] = vertices + normals +
-// faces (CUDA events).  Returns "" or an error message.  launches += kernels run.
+// caller between calls (one word and one bit per lattice point + the block counters).  ms[0] = sign bits + count + scan, ms[1] = vertices +
+// normals + faces (CUDA events).  Returns "" or an error message.  launches += kernels run.
 std::string mesh_extract(cudaStream_t st, const float* density, const uint32_t res[3], const float mn[3], const float mx[3], float thresh, void** ws, size_t* ws_bytes,
                          float** verts_out, float** normals_out, uint32_t** indices_out, uint32_t* n_verts, uint32_t* n_verts_padded, uint32_t* n_indices, float ms[2], uint64_t* launches) {
 	std::string err;
 	const McGrid g = make_mc_grid(res, mn, mx, thresh);
 	const uint32_t nb = (uint32_t)(((uint64_t)g.n + MC_BLOCK - 1) / MC_BLOCK);
 	const size_t nb_pad = ((size_t)nb + 63) & ~(size_t)63;
-	const size_t need = (size_t)g.n * 4 + nb_pad * 8 + 256;
-	uint32_t *blockV = nullptr, *blockI = nullptr, *totals = nullptr, *words = nullptr, *indices = nullptr;
+	const size_t n_bitwords = (((size_t)g.n + 31) / 32 + 64) & ~(size_t)63;
+	const size_t need = (size_t)g.n * 4 + n_bitwords * 4 + nb_pad * 8 + 256;
+	uint32_t *blockV = nullptr, *blockI = nullptr, *totals = nullptr, *words = nullptr, *bits = nullptr, *indices = nullptr;
 	float *verts = nullptr, *normals = nullptr;
 	uint32_t tot[2] = {0, 0}, nvp = 0;
 	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 	ms[0] = ms[1] = 0.f;
 	if (*ws_bytes < need) { cudaFree(*ws); *ws = nullptr; *ws_bytes = 0; MCU(cudaMalloc(ws, need)); *ws_bytes = need; }
-	words = (uint32_t*)*ws; blockV = words + g.n; blockI = blockV + nb_pad; totals = blockI + nb_pad;
+	words = (uint32_t*)*ws; bits = words + g.n; blockV = bits + n_bitwords; blockI = blockV + nb_pad; totals = blockI + nb_pad;
 	for (auto& e : ev) MCU(cudaEventCreate(&e));
 	MCU(cudaEventRecord(ev[0], st));
-	k_mc_count<<<nb, MC_THREADS, 0, st>>>(g, density, blockV, blockI);
+	k_mc_bits<<<(uint32_t)((((uint64_t)g.n + 127) / 128 * 32 + 255) / 256), 256, 0, st>>>(g.n, thresh, density, bits);
+	k_mc_count<<<nb, MC_THREADS, 0, st>>>(g, bits, blockV, blockI);
 	k_scan_counts<uint32_t><<<2, 1024, 0, st>>>(blockV, blockV, nb, nb_pad, totals);
 	MCU(cudaEventRecord(ev[1], st));
 	MCU(cudaMemcpyAsync(tot, totals, 8, cudaMemcpyDeviceToHost, st));
 	MCU(cudaStreamSynchronize(st));
-	*launches += 2;
+	*launches += 3;
 	if (tot[0] >= (1u << 30)) { err = "more than 2^30 vertices"; goto done; }
 	nvp = (tot[0] + 127u) & ~127u;
 	MCU(cudaMalloc(&verts, std::max<size_t>(nvp, 1) * 12)); MCU(cudaMalloc(&normals, std::max<size_t>(nvp, 1) * 12));
 	MCU(cudaMalloc(&indices, std::max<size_t>(tot[1], 1) * 4));
 	MCU(cudaMemsetAsync(verts, 0, std::max<size_t>(nvp, 1) * 12, st)); MCU(cudaMemsetAsync(normals, 0, std::max<size_t>(nvp, 1) * 12, st));
 	if (tot[0]) {
-		k_mc_vertices<<<nb, MC_THREADS, 0, st>>>(g, density, blockV, words, verts, normals);
-		k_mc_faces<<<nb, MC_THREADS, 0, st>>>(g, density, blockI, words, indices);
-		*launches += 2;
+		k_mc_vertices<<<nb, MC_THREADS, 0, st>>>(g, density, bits, blockV, words, verts, normals);
+		k_mc_faces<<<nb, MC_THREADS, 0, st>>>(g, bits, blockI, words, indices);
+		k_mc_normals<<<(tot[0] + 255) / 256, 256, 0, st>>>(g, density, tot[0], normals);
+		*launches += 3;
 	}
 	MCU(cudaEventRecord(ev[2], st));
 	MCU(cudaGetLastError());

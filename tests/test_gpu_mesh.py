@@ -27,7 +27,7 @@ def tb(pkg):
     return t
 
 
-@pytest.mark.parametrize("case", ["sphere", "bumpy", "noise", "empty", "thin"])
+@pytest.mark.parametrize("case", ["sphere", "bumpy", "noise", "noise48", "empty", "thin"])
 def test_extraction_matches_oracle_bit_for_bit(tb, case):
     mn, mx, th = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), 0.0
     if case == "sphere":
@@ -38,10 +38,13 @@ def test_extraction_matches_oracle_bit_for_bit(tb, case):
     elif case == "noise":                      # all 256 cube cases, surface through the lattice boundary
         th = 0.05
         d = np.random.RandomState(1).uniform(-1, 1, (24, 20, 32)).astype(np.float32)
+    elif case == "noise48":                    # rows of 48: the 16-point groups straddle the 32-bit words of the sign-bit array
+        th = -0.1
+        d = np.random.RandomState(2).uniform(-1, 1, (7, 9, 48)).astype(np.float32)
     elif case == "empty":
         d = np.full((8, 8, 16), 1.0, np.float32)
     else:                                      # smallest lattice the API takes, one crossing plane
-        d = np.zeros((2, 3, 4), np.float32) - 1.0; d[:, :, 2:] = 1.0
+        d = np.zeros((2, 3, 16), np.float32) - 1.0; d[:, :, 9:] = 1.0
     info, m = _extract(tb, d, mn, mx, th)
     V, N, I, nv = ob.marching_cubes(d, mn, mx, th)
     assert info["n_verts"] == nv and info["n_verts_padded"] == V.shape[0] and info["n_indices"] == I.size

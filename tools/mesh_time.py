@@ -24,7 +24,7 @@ for res in (256, 512, 1024):
     w0 = time.time(); info = t.marching_cubes_from_density(sd.data_ptr(), (res,) * 3, with_colors=False); torch.cuda.synchronize(); t_mc = time.time() - w0
     w0 = time.time(); info = t.marching_cubes_from_density(sd.data_ptr(), (res,) * 3, with_colors=True); torch.cuda.synchronize(); t_mcc = time.time() - w0
     row = {"res": res, "sdf_sweep_ms": round(ev[0].elapsed_time(ev[1]), 3), "extract_normals_ms": round(t_mc * 1e3, 3), "extract_normals_colors_ms": round(t_mcc * 1e3, 3), **info}
-    row["roofline"] = {"alg_bytes_per_point": 16, "GBps": round(16 * n / ((info["stage_ms"]["count_scan"] + info["stage_ms"]["vertices_normals_faces"]) * 1e-3) / 1e9, 1)}
+    row["roofline"] = {"alg_bytes_per_point": 4, "GBps": round(4 * n / ((info["stage_ms"]["bits_count_scan"] + info["stage_ms"]["vertices_normals_faces"]) * 1e-3) / 1e9, 1)}
     if res <= 512:
         path = "/tmp/mesh_%d.obj" % res
         w0 = time.time(); nb = t.save_mesh(path, 0.5, (0.5, 0.5, 0.5), 1.0, (0, 0, 0), True); row["obj_write_ms"] = round((time.time() - w0) * 1e3, 3); row["obj_bytes"] = nb
