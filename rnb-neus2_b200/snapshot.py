@@ -197,10 +197,12 @@ def _half_blob(values):
 
 
 def movement_defaults():
-    """Initial values of the movement buffers of a static scene (nerf_network.h:852-905: rotation = 6D identity in 12 slots,
-    transition = 4 zeros; the local (per-frame delta) buffers have the same shapes, transform_network.h)."""
+    """Initial values of the movement buffers of a static scene, as the reference build writes them (checked against its own
+    snapshot, tests/golden/ref_snapshot_small.npz): accumulated rotation = 3x3 identity in 12 binary16 slots and transition = 4
+    zeros (nerf_network.h:76-80, 852-905); the per-frame delta network keeps a 6D rotation (1,0,0,0,1,0 in 8 slots) and 4 zeros."""
     rot = np.zeros(12, np.float16); rot[[0, 4, 8]] = 1.0
-    return {"rotation": rot.tobytes(), "transition": _half_blob(np.zeros(4)), "local_rotation": rot.tobytes(), "local_transition": _half_blob(np.zeros(4))}
+    lrot = np.zeros(8, np.float16); lrot[[0, 4]] = 1.0
+    return {"rotation": rot.tobytes(), "transition": _half_blob(np.zeros(4)), "local_rotation": lrot.tobytes(), "local_transition": _half_blob(np.zeros(4))}
 
 
 def build_snapshot(network_config, params_fp16, density_grid, training_step, loss, rays_per_batch, measured_batch_size, measured_batch_size_before_compaction,

@@ -126,6 +126,10 @@ def main():
     pc = np.fromfile(os.path.join(dumpB, "probe_coords.bin"), np.float32).reshape(-1, 7)
     pout = h2f(np.fromfile(os.path.join(dumpB, "probe_out_fp16.bin"), np.uint16)).reshape(-1, 16)
     co, _ = t3.stage_forward(pc)
+    # the reference has not run Testbed::train since the load, so its encoding still has every level enabled (the progressive
+    # mask is set per training step, src/testbed.cu:2787-2793); the like-for-like probe on our side is training step 0
+    t3.set_train_state(0, ours["rays_per_batch"], 0, 0)
+    co_all, _ = t3.stage_forward(pc)
     summary["B"] = {"file_bytes": os.path.getsize(our_file),
                     "ref_params_equal": bool(np.array_equal(pf, ours["params_fp16"].astype(np.float32))),
                     "ref_grid_equal": bool(np.array_equal(gB, ours["density_grid"])),
@@ -134,7 +138,8 @@ def main():
                     "ref_measured_before": int(stB[7]), "our_measured_before": ours["measured_batch_size_before_compaction"],
                     "ref_measured": int(stB[9]), "our_measured": ours["measured_batch_size"],
                     "bitfield_mip0_bits_differ": int(np.unpackbits(np.bitwise_xor(np.asarray(b3)[:nb], bB[:nb])).sum()), "bitfield_mip0_bits_set": int(np.unpackbits(bB[:nb]).sum()),
-                    "probe_cuda_vs_ref": {"albedo_raw": rel_err(co[:, 0:3], pout[:, 0:3]), "sdf": rel_err(co[:, 3], pout[:, 3]), "normal": rel_err(co[:, 4:7], pout[:, 4:7])}}
+                    "probe_cuda_vs_ref": {"albedo_raw": rel_err(co[:, 0:3], pout[:, 0:3]), "sdf": rel_err(co[:, 3], pout[:, 3]), "normal": rel_err(co[:, 4:7], pout[:, 4:7])},
+                    "probe_cuda_all_levels_vs_ref": {"albedo_raw": rel_err(co_all[:, 0:3], pout[:, 0:3]), "sdf": rel_err(co_all[:, 3], pout[:, 3]), "normal": rel_err(co_all[:, 4:7], pout[:, 4:7])}}
     print(json.dumps(summary)[:6000])
     json.dump(summary, open(os.path.join(args.out, "summary_snapshot.json"), "w"), indent=1)
     # fixture for the CPU suite: the reference's file with the two big blobs cut to their first 4 KiB (+ their hashes in the summary)

@@ -62,3 +62,26 @@ def test_snapshot_object_layout_and_errors(tmp_path):
         snap.parse_snapshot(bad)
     empty = snap.build_snapshot({}, p, np.zeros(0, np.float32), 0, 0.0, 1, 1, 1)            # untrained model: empty grid is valid
     assert snap.parse_snapshot(empty)["density_grid"].size == 0
+
+
+def test_reference_snapshot_fixture():
+    """tests/golden/ref_snapshot_small.npz: the file Testbed::save_snapshot of the reference build wrote on the B200 box
+    (tests/ref_pin_snapshot.py), its two large blobs cut to 4 KiB.  Our codec must decode it and re-encode it byte for byte, the
+    object must parse, and the movement blobs must be the static-scene defaults this repo writes."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_snapshot_small.npz"))
+    raw = g["truncated"].tobytes()
+    cfg = snap.unpackb(raw)
+    assert snap.packb(cfg) == raw
+    assert msgpack.unpackb(raw, raw=False, strict_map_key=False) == cfg
+    s = cfg["snapshot"]
+    assert sorted(s) == ["density_grid_binary", "density_grid_size", "local_rotation", "local_transition", "loss", "n_params", "nerf", "params_binary", "rotation",
+                         "training_step", "transition"]
+    assert sorted(s["nerf"]) == ["aabb_scale", "dataset", "rgb"] and sorted(s["nerf"]["rgb"]) == ["measured_batch_size", "measured_batch_size_before_compaction", "rays_per_batch"]
+    assert s["density_grid_size"] == 128 and s["n_params"] == 241156 and s["training_step"] == 40
+    assert np.array_equal(np.frombuffer(s["params_binary"], np.uint16), g["params_head"])
+    assert np.array_equal(np.frombuffer(s["density_grid_binary"], np.float16), g["grid_head"].astype(np.float16))
+    for k, v in snap.movement_defaults().items():
+        assert s[k] == v, k
+    for k in ("encoding", "network", "rgb_network", "optimizer", "loss", "dir_encoding"):
+        assert k in cfg
