@@ -322,7 +322,10 @@ int rnb_init_params(rnb_ctx* c, const float* sdf_init, size_t n_sdf_init) {
 	const float var[4] = {0.3f, 0.3f, 0.3f, 0.3f};
 	CU(cudaMemcpy(c->master + M.off_var, var, 16, cudaMemcpyHostToDevice));
 	launch_cast_params(0, M.n_params, c->master, c->params);
-	CU(cudaMemset(c->ema, 0, (size_t)M.n_params * 2)); CU(cudaMemset(c->m1, 0, (size_t)M.n_params * 4)); CU(cudaMemset(c->m2, 0, (size_t)M.n_params * 4));
+	// before the first optimizer step the inference parameters are the training parameters (trainer.h:100-109); the EMA recurrence
+	// ignores this content at its first step (debias factor 1 - decay^0 = 0, ema.h:121-122)
+	CU(cudaMemcpy(c->ema, c->params, (size_t)M.n_params * 2, cudaMemcpyDeviceToDevice));
+	CU(cudaMemset(c->m1, 0, (size_t)M.n_params * 4)); CU(cudaMemset(c->m2, 0, (size_t)M.n_params * 4));
 	CU(cudaMemset(c->steps, 0, (size_t)M.n_params * 4)); CU(cudaMemset(c->grads, 0, (size_t)M.n_params * 4));
 	c->opt_step = 0; c->lr_factor = 1.f;
 	CU(cudaDeviceSynchronize());

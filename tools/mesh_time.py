@@ -28,7 +28,8 @@ for res in (256, 512, 1024):
     if res <= 512:
         path = "/tmp/mesh_%d.obj" % res
         w0 = time.time(); nb = t.save_mesh(path, 0.5, (0.5, 0.5, 0.5), 1.0, (0, 0, 0), True); row["obj_write_ms"] = round((time.time() - w0) * 1e3, 3); row["obj_bytes"] = nb
-        w0 = time.time(); t.compute_and_save_marching_cubes_mesh(path, res, nerf_scale=0.5, nerf_offset=(0.5, 0.5, 0.5), from_na=True); row["pipeline_ms"] = round((time.time() - w0) * 1e3, 3)
+        for key in ("pipeline_first_ms", "pipeline_ms"):        # first call at a resolution grows the scratch buffers
+            w0 = time.time(); t.compute_and_save_marching_cubes_mesh(path, res, nerf_scale=0.5, nerf_offset=(0.5, 0.5, 0.5), from_na=True); row[key] = round((time.time() - w0) * 1e3, 3)
         os.remove(path)
     del sd
     rows.append(row); print(json.dumps(row)); sys.stdout.flush()
