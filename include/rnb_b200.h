@@ -156,6 +156,15 @@ int rnb_set_rng(rnb_ctx* ctx, const uint64_t in[4]);
  * rnb_upload_dataset: pixel pointers are host pointers, copied into device memory owned by ctx. */
 int rnb_set_dataset(rnb_ctx* ctx, const rnb_view* views_host, uint32_t n_views);
 int rnb_upload_dataset(rnb_ctx* ctx, const rnb_view* views_host, uint32_t n_views);
+/* ---- dataset ingest: the image half of load_nerf (src/nerf_loader.cu:556-760) ----
+ * rnb_load_png_rgba16 replaces stbi_load_16(path, &w, &h, &comp, 4) (:612, :653): any non-interlaced PNG (grey / RGB / palette / +alpha,
+ * 8 or 16 bit, tRNS keys) as 16-bit RGBA in host memory (8-bit samples widened to v * 257, missing alpha 65535); free with rnb_free_host.
+ * rnb_load_dataset_images decodes all normal / albedo maps on `threads` host threads (0 = all cores) into pinned staging, uploads them
+ * as they finish and installs the views (meta[i]: intrinsics + camera matrix as for rnb_upload_dataset; pixel pointers ignored). */
+int  rnb_load_png_rgba16(const char* path, uint32_t* w, uint32_t* h, uint16_t** pixels_host);
+void rnb_free_host(void* p);
+int  rnb_load_dataset_images(rnb_ctx* ctx, const rnb_view* meta, uint32_t n_views, const char* const* normal_paths, const char* const* albedo_paths /* NULL or entries NULL: no albedo */,
+                             uint32_t threads, void* stream);
 int rnb_set_flags(rnb_ctx* ctx, const rnb_flags* flags);
 
 /* replaces Testbed::training_prep_nerf (src/testbed_nerf.cu:4125-4138): one occupancy-grid refresh. */

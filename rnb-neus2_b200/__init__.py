@@ -54,7 +54,7 @@ EXPORTED_SYMBOLS = [
     "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
     "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
     "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf", "rnb_sdf_on_grid",
-    "rnb_marching_cubes", "rnb_marching_cubes_from_density", "rnb_mesh_buffers", "rnb_mesh_download", "rnb_save_mesh",
+    "rnb_load_png_rgba16", "rnb_free_host", "rnb_load_dataset_images", "rnb_marching_cubes", "rnb_marching_cubes_from_density", "rnb_mesh_buffers", "rnb_mesh_download", "rnb_save_mesh",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
 ]
 
@@ -75,6 +75,18 @@ def save_mesh_device(path, verts_ptr, normals_ptr, colors_ptr, indices_ptr, n_ve
     return int(nb.value)
 
 
+def load_png_rgba16(path):
+    """rnb_load_png_rgba16: a PNG as stbi_load_16(..., 4) returns it — uint16 [h, w, 4].  Host code (works without a GPU)."""
+    w = C.c_uint32(); h = C.c_uint32(); px = C.POINTER(C.c_uint16)()
+    L = lib()
+    if L.rnb_load_png_rgba16(str(path).encode(), C.byref(w), C.byref(h), C.byref(px)) != 0:
+        raise RnbError(L.rnb_last_error().decode())
+    try:
+        return np.ctypeslib.as_array(px, shape=(h.value, w.value, 4)).copy()
+    finally:
+        L.rnb_free_host(px)
+
+
 def build(verbose=False):
     """Compile csrc/*.cu for sm_100a into librnb_b200.so (in-tree)."""
     out = None if verbose else subprocess.DEVNULL
@@ -93,6 +105,7 @@ def lib():
             raise RnbError("librnb_b200.so is missing: run __graft_entry__.build() (no CPU fallback exists)")
         L = C.CDLL(_SO)
         L.rnb_last_error.restype = C.c_char_p
+        L.rnb_free_host.restype = None
         L.rnb_abi_version.restype = C.c_uint32
         _lib = L
     return _lib
@@ -319,6 +332,26 @@ class Testbed:
     def sdf_on_grid_device(self, res, aabb_min, aabb_max, out_ptr, use_ema=True, stream=None):
         r = (C.c_uint32 * 3)(*[int(x) for x in res]); a = (C.c_float * 3)(*[float(x) for x in aabb_min]); b = (C.c_float * 3)(*[float(x) for x in aabb_max])
         self._chk(self.L.rnb_sdf_on_grid(self.h, r, a, b, C.c_void_p(out_ptr), int(use_ema), C.c_void_p(stream)))
+
+    # --- dataset ingest ---
+    def load_training_data_dir(self, path, threads=0, stream=None):
+        """Testbed::load_training_data on a scene directory / transform.json (src/testbed.cu load_nerf -> src/nerf_loader.cu): the JSON is read
+        on the host (dataset.py), the PNGs are decoded by the library's host threads and uploaded.  Returns the dataset description
+        (scale, offset, n2w, from_na, ... — what save_mesh needs later)."""
+        from . import dataset as ds
+        meta = ds.load_transforms(path)
+        n = len(meta["views"])
+        arr = (View * n)()
+        for i, v in enumerate(meta["views"]):
+            arr[i].normal_px = None; arr[i].albedo_px = None; arr[i].w = v["w"]; arr[i].h = v["h"]
+            arr[i].fx = float(v["fx"]); arr[i].fy = float(v["fy"]); arr[i].cx = float(v["cx"]); arr[i].cy = float(v["cy"])
+            for k in range(12):
+                arr[i].xform[k] = float(v["xform"][k])
+        normals = (C.c_char_p * n)(*[v["normal_path"].encode() for v in meta["views"]])
+        albedos = (C.c_char_p * n)(*[(v["albedo_path"].encode() if v["albedo_path"] else None) for v in meta["views"]])
+        self._chk(self.L.rnb_load_dataset_images(self.h, arr, n, normals, albedos, int(threads), C.c_void_p(stream)))
+        self.dataset = meta
+        return meta
 
     # --- snapshot hand-off (SURVEY N3) ---
     def save_snapshot(self, path, network_config, loss=None, aabb_scale=1, dataset=None):

@@ -52,6 +52,9 @@ void launch_widen_params(cudaStream_t, uint32_t, const __half*, float*);
 void launch_init_grid(cudaStream_t, Pcg32, uint64_t, float*);
 void launch_grid_samples(cudaStream_t, uint32_t, Pcg32, uint32_t, const float*, float4*, uint32_t*, float);
 void launch_grid_finish(cudaStream_t, uint32_t, const uint32_t*, const float*, float, float*, float*, double*, float*, uint8_t*);
+// rnb_dataset.cu
+std::string load_png_rgba16_host(const char*, uint32_t*, uint32_t*, uint16_t**);
+std::string load_images_to_device(cudaStream_t, uint32_t, const char* const*, uint32_t, void**, uint32_t*, double*);
 // rnb_mesh.cu
 std::string mesh_extract(cudaStream_t, const float*, const uint32_t[3], const float[3], const float[3], float, void**, size_t*, float**, float**, uint32_t**, uint32_t*, uint32_t*, uint32_t*, float[2], uint64_t*);
 void launch_mesh_color_inputs(cudaStream_t, uint32_t, const float*, float4*, float*);
@@ -425,6 +428,43 @@ static int set_views(rnb_ctx* c, const rnb_view* views, uint32_t n, bool upload)
 }
 int rnb_set_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { return set_views(c, v, n, false); }
 int rnb_upload_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { return set_views(c, v, n, true); }
+
+// ---- dataset ingest -----------------------------------------------------------------------------------------
+// stbi_load_16(path, &w, &h, &comp, 4) as load_nerf uses it (src/nerf_loader.cu:612,653): any PNG -> 16-bit RGBA in host memory
+int rnb_load_png_rgba16(const char* path, uint32_t* w, uint32_t* h, uint16_t** pixels_host) {
+	if (!path || !w || !h || !pixels_host) return fail(RNB_ERR_INVALID, "null argument");
+	const std::string e = load_png_rgba16_host(path, w, h, pixels_host);
+	if (!e.empty()) return fail(RNB_ERR_INVALID, e);
+	return RNB_OK;
+}
+void rnb_free_host(void* p) { free(p); }
+
+// the image half of load_nerf (src/nerf_loader.cu:556-760): decode every normal / albedo map on host threads into pinned staging
+// and upload; meta[i] carries intrinsics and the camera matrix (pixel pointers ignored; w/h checked against the files when non-zero)
+int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const char* const* normal_paths, const char* const* albedo_paths, uint32_t threads, void* stream) {
+	if (!c || !meta || !normal_paths || n == 0) return fail(RNB_ERR_INVALID, "no views");
+	std::vector<const char*> paths(2 * (size_t)n, nullptr);
+	for (uint32_t i = 0; i < n; ++i) {
+		if (!normal_paths[i]) return fail(RNB_ERR_INVALID, "view without normal map");
+		paths[i] = normal_paths[i]; paths[n + i] = albedo_paths ? albedo_paths[i] : nullptr;
+	}
+	std::vector<void*> dev(2 * (size_t)n, nullptr); std::vector<uint32_t> wh(4 * (size_t)n, 0);
+	const std::string e = load_images_to_device((cudaStream_t)stream, 2 * n, paths.data(), threads, dev.data(), wh.data(), nullptr);
+	if (!e.empty()) return fail(RNB_ERR_INVALID, e);
+	std::vector<rnb_view> v(meta, meta + n);
+	std::string bad;
+	for (uint32_t i = 0; i < n && bad.empty(); ++i) {
+		const uint32_t w = wh[2 * i], h = wh[2 * i + 1];
+		if (dev[n + i] && (wh[2 * (n + i)] != w || wh[2 * (n + i) + 1] != h)) bad = std::string("normal and albedo map differ in size: ") + normal_paths[i];
+		if ((v[i].w > 0 && (uint32_t)v[i].w != w) || (v[i].h > 0 && (uint32_t)v[i].h != h)) bad = std::string("image size does not match the metadata: ") + normal_paths[i];
+		v[i].normal_px = dev[i]; v[i].albedo_px = dev[n + i]; v[i].w = (int32_t)w; v[i].h = (int32_t)h;
+	}
+	int rc = bad.empty() ? set_views(c, v.data(), n, false) : fail(RNB_ERR_INVALID, bad);
+	if (rc != RNB_OK) { for (void* d : dev) cudaFree(d); return rc; }
+	for (void* d : dev) if (d) c->owned.push_back(d);          // the context owns the uploaded pixels (freed by the next dataset call / rnb_destroy)
+	return RNB_OK;
+}
+
 int rnb_set_flags(rnb_ctx* c, const rnb_flags* f) { if (!c || !f) return fail(RNB_ERR_INVALID, "null argument"); c->flags = *f; return RNB_OK; }
 
 int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t ema_step) {
