@@ -83,7 +83,10 @@ int main(int argc, char** argv) {
 
 	Testbed tb{ETestbedMode::Nerf};
 	tb.set_max_iter((uint32_t)n_steps + 1000000u);
+	const auto load_t0 = std::chrono::steady_clock::now();
 	tb.load_training_data(scene);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	const double load_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - load_t0).count();      // Testbed::load_training_data = load_nerf: JSON + image decode + upload
 	tb.reload_network_from_file(config);
 	tb.m_train = true;
 	// same order as src/main.cu:369-398
@@ -99,6 +102,7 @@ int main(int argc, char** argv) {
 	const size_t n_params = tb.m_network->n_params();
 	FILE* meta = fopen((g_out + "/meta.txt").c_str(), "w");
 	fprintf(meta, "n_params=%zu\nn_images=%zu\nn_steps=%d\nno_albedo=%d\nsupernormal=%d\nopti_lights=%d\nl1=%d\nrgbplus=%d\n", n_params, tr.dataset.n_images, n_steps, no_albedo, supernormal, opti, l1, rgbplus);
+	fprintf(meta, "load_seconds=%.4f\n", load_seconds);
 	fprintf(meta, "mask_loss_weight=%g\nek_loss_weight=%g\naabb_min=%g %g %g\naabb_max=%g %g %g\n", tb.m_mask_loss_weight, tb.m_ek_loss_weight,
 	        tb.m_aabb.min.x(), tb.m_aabb.min.y(), tb.m_aabb.min.z(), tb.m_aabb.max.x(), tb.m_aabb.max.y(), tb.m_aabb.max.z());
 
