@@ -54,7 +54,7 @@ void launch_grid_samples(cudaStream_t, uint32_t, Pcg32, uint32_t, const float*, 
 void launch_grid_finish(cudaStream_t, uint32_t, const uint32_t*, const float*, float, float*, float*, double*, float*, uint8_t*);
 // rnb_dataset.cu
 std::string load_png_rgba16_host(const char*, uint32_t*, uint32_t*, uint16_t**);
-std::string load_images_to_device(cudaStream_t, uint32_t, const char* const*, uint32_t, void**, uint32_t*, double*);
+std::string load_images_to_device(cudaStream_t, uint32_t, const char* const*, uint32_t, void**, void**, uint32_t*, void**, size_t*);
 // rnb_mesh.cu
 std::string mesh_extract(cudaStream_t, const float*, const uint32_t[3], const float[3], const float[3], float, void**, size_t*, float**, float**, uint32_t**, uint32_t*, uint32_t*, uint32_t*, float[2], uint64_t*);
 void launch_mesh_color_inputs(cudaStream_t, uint32_t, const float*, float4*, float*);
@@ -100,6 +100,7 @@ struct rnb_ctx {
 	bool prelaunch = true; bool pre_valid = false; uint32_t pre_R = 0, pre_nrt = 0; uint64_t pre_rng_state = 0, pre_rng_inc = 0;
 	// last extracted mesh (rnb_marching_cubes*): MeshState verts / vert_normals / vert_colors / indices (testbed.h:418-447), device memory
 	struct Mesh { float *verts = nullptr, *normals = nullptr, *colors = nullptr; uint32_t* indices = nullptr; uint32_t n_verts = 0, n_verts_padded = 0, n_indices = 0; float ms[4] = {0, 0, 0, 0}; } mesh;
+	void* pin_stage = nullptr; size_t pin_stage_bytes = 0;      // pinned staging of the dataset loader (grow-only)
 	void* mesh_ws = nullptr; size_t mesh_ws_bytes = 0; float* mesh_density = nullptr; size_t mesh_density_bytes = 0;    // grow-only scratch of the mesh path
 	bool use_mma = false; uint32_t* wpack = nullptr; int n_sm = 148;
 	bool use_tc = false, use_tc_bwd = false; uint8_t* wtc = nullptr;      // tcgen05 / TMEM kernels (rnb_network_tc.cu) for pass A and the SDF probes
@@ -266,7 +267,7 @@ int rnb_destroy(rnb_ctx* c) {
 	for (void* p : c->owned) cudaFree(p);
 	cudaFreeHost(c->counters_host); cudaFreeHost(c->stats_host);
 	cudaFree(c->ck.buf);
-	cudaFree(c->mesh.verts); cudaFree(c->mesh.normals); cudaFree(c->mesh.colors); cudaFree(c->mesh.indices); cudaFree(c->mesh_ws); cudaFree(c->mesh_density);
+	cudaFree(c->mesh.verts); cudaFree(c->mesh.normals); cudaFree(c->mesh.colors); cudaFree(c->mesh.indices); cudaFree(c->mesh_ws); cudaFree(c->mesh_density); cudaFreeHost(c->pin_stage);
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
 	if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
 	if (c->ev_march) cudaEventDestroy(c->ev_march);
@@ -449,7 +450,8 @@ int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const 
 		paths[i] = normal_paths[i]; paths[n + i] = albedo_paths ? albedo_paths[i] : nullptr;
 	}
 	std::vector<void*> dev(2 * (size_t)n, nullptr); std::vector<uint32_t> wh(4 * (size_t)n, 0);
-	const std::string e = load_images_to_device((cudaStream_t)stream, 2 * n, paths.data(), threads, dev.data(), wh.data(), nullptr);
+	void* arena = nullptr;
+	const std::string e = load_images_to_device((cudaStream_t)stream, 2 * n, paths.data(), threads, &arena, dev.data(), wh.data(), &c->pin_stage, &c->pin_stage_bytes);
 	if (!e.empty()) return fail(RNB_ERR_INVALID, e);
 	std::vector<rnb_view> v(meta, meta + n);
 	std::string bad;
@@ -460,8 +462,8 @@ int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const 
 		v[i].normal_px = dev[i]; v[i].albedo_px = dev[n + i]; v[i].w = (int32_t)w; v[i].h = (int32_t)h;
 	}
 	int rc = bad.empty() ? set_views(c, v.data(), n, false) : fail(RNB_ERR_INVALID, bad);
-	if (rc != RNB_OK) { for (void* d : dev) cudaFree(d); return rc; }
-	for (void* d : dev) if (d) c->owned.push_back(d);          // the context owns the uploaded pixels (freed by the next dataset call / rnb_destroy)
+	if (rc != RNB_OK) { cudaFree(arena); return rc; }
+	c->owned.push_back(arena);                                  // the context owns the uploaded pixels (freed by the next dataset call / rnb_destroy)
 	return RNB_OK;
 }
 

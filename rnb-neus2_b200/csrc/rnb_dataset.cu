@@ -16,6 +16,8 @@
 #include <thread>
 #include <atomic>
 #include <mutex>
+#include <chrono>
+#include <algorithm>
 
 namespace rnb {
 
@@ -131,51 +133,90 @@ std::string load_png_rgba16_host(const char* path, uint32_t* w, uint32_t* h, uin
 	return "";
 }
 
-// n images (paths[i] may be null: slot skipped) -> device buffers dev[i] (cudaMalloc, caller owns), sizes wh[2i], wh[2i+1].
-// `threads` host threads inflate; each finished image is copied from its pinned staging slot on `st` right away.
-std::string load_images_to_device(cudaStream_t st, uint32_t n, const char* const* paths, uint32_t threads, void** dev, uint32_t* wh, double* seconds_decode) {
+// width / height from the IHDR chunk (the first 33 bytes of a PNG)
+static std::string png_size(const char* path, uint32_t* w, uint32_t* h) {
+	FILE* f = fopen(path, "rb");
+	if (!f) return std::string("image not found: ") + path;
+	uint8_t hd[33]; const size_t got = fread(hd, 1, sizeof(hd), f); fclose(f);
+	static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+	if (got != sizeof(hd) || memcmp(hd, sig, 8) != 0 || memcmp(hd + 12, "IHDR", 4) != 0) return std::string("not a PNG file: ") + path;
+	*w = be32(hd + 16); *h = be32(hd + 20);
+	if (*w == 0 || *h == 0) return std::string("PNG without IHDR: ") + path;
+	return "";
+}
+
+// n images (paths[i] may be null: slot skipped) -> ONE device allocation *arena (cudaMalloc, caller owns) with image i at dev[i]
+// (256-byte aligned), sizes wh[2i], wh[2i+1].  The headers are read first, so that device memory and the pinned staging (one slot
+// per thread in *stage, grow-only, kept by the caller between calls) are allocated once; then `threads` host threads inflate, each
+// into its own slot, and hand the image to the copy engine at once (cudaMemcpyAsync + an event guarding the slot's reuse).
+std::string load_images_to_device(cudaStream_t st, uint32_t n, const char* const* paths, uint32_t threads, void** arena, void** dev, uint32_t* wh, void** stage, size_t* stage_bytes) {
 	if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
 	threads = std::min<uint32_t>(threads, std::max<uint32_t>(n, 1));
+	const bool debug = getenv("RNB_DATASET_DEBUG") != nullptr;
+	auto now_us = []() { return (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const long long wall0 = now_us();
+	*arena = nullptr;
+	std::vector<size_t> off(n, 0); size_t total = 0, max_bytes = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		dev[i] = nullptr; wh[2 * i] = wh[2 * i + 1] = 0;
+		if (!paths[i]) continue;
+		const std::string e = png_size(paths[i], &wh[2 * i], &wh[2 * i + 1]);
+		if (!e.empty()) return e;
+		const size_t bytes = (size_t)wh[2 * i] * wh[2 * i + 1] * 8;
+		off[i] = total; total += (bytes + 255) & ~(size_t)255; max_bytes = std::max(max_bytes, bytes);
+	}
+	if (total == 0) return "";
+	if (cudaMalloc(arena, total) != cudaSuccess) { *arena = nullptr; return std::string("cudaMalloc of the dataset failed: ") + cudaGetErrorString(cudaGetLastError()); }
+	const size_t slot = (max_bytes + 4095) & ~(size_t)4095, need = slot * threads;
+	if (*stage_bytes < need) {
+		if (*stage) cudaFreeHost(*stage);
+		*stage = nullptr; *stage_bytes = 0;
+		if (cudaMallocHost(stage, need) != cudaSuccess) { cudaFree(*arena); *arena = nullptr; return std::string("pinned staging allocation failed: ") + cudaGetErrorString(cudaGetLastError()); }
+		*stage_bytes = need;
+	}
+	const long long setup_us = now_us() - wall0;
 	std::atomic<uint32_t> next{0};
+	std::atomic<bool> failed{false};
 	std::mutex mu; std::string err;
+	std::atomic<long long> us_wait{0}, us_decode{0}, us_enqueue{0};
 	std::vector<std::thread> pool;
-	for (uint32_t i = 0; i < n; ++i) dev[i] = nullptr;
 	int device = 0; cudaGetDevice(&device);
-	for (uint32_t t = 0; t < threads; ++t) pool.emplace_back([&, device]() {
+	for (uint32_t t = 0; t < threads; ++t) pool.emplace_back([&, device, t]() {
 		cudaSetDevice(device);
-		uint16_t* pinned = nullptr; size_t cap = 0;
+		uint16_t* pinned = (uint16_t*)((char*)*stage + slot * t);
 		cudaEvent_t done; cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
 		bool in_flight = false;
 		for (;;) {
 			const uint32_t i = next.fetch_add(1);
-			if (i >= n) break;
-			{ std::lock_guard<std::mutex> l(mu); if (!err.empty()) break; }
+			if (i >= n || failed.load()) break;
 			if (!paths[i]) continue;
-			uint32_t w = 0, h = 0; std::string e;
-			e = decode_png_rgba16(paths[i], &w, &h, [&](uint32_t ww, uint32_t hh) -> uint16_t* {
-				const size_t need = (size_t)ww * hh * 8;
-				if (in_flight) { cudaEventSynchronize(done); in_flight = false; }       // the previous image of this thread has left the staging slot
-				if (need > cap) { if (pinned) cudaFreeHost(pinned); pinned = nullptr; cap = 0; if (cudaMallocHost(&pinned, need) != cudaSuccess) return nullptr; cap = need; }
+			uint32_t w = 0, h = 0; long long wait_us = 0; const long long t0 = now_us();
+			std::string e = decode_png_rgba16(paths[i], &w, &h, [&](uint32_t ww, uint32_t hh) -> uint16_t* {
+				if (ww != wh[2 * i] || hh != wh[2 * i + 1]) return nullptr;
+				const long long p0 = now_us();
+				if (in_flight) { cudaEventSynchronize(done); in_flight = false; }       // the previous image of this thread has left the slot
+				wait_us = now_us() - p0;
 				return pinned;
 			});
+			const long long t1 = now_us();
+			us_wait += wait_us; us_decode += t1 - t0 - wait_us;
 			if (e.empty()) {
 				const size_t bytes = (size_t)w * h * 8;
-				void* d = nullptr;
-				std::lock_guard<std::mutex> l(mu);                                       // one stream: enqueue in a critical section
-				if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemcpyAsync(d, pinned, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaEventRecord(done, st) != cudaSuccess) {
-					if (err.empty()) err = std::string("upload failed: ") + cudaGetErrorString(cudaGetLastError());
-					cudaFree(d);
-				} else { dev[i] = d; wh[2 * i] = w; wh[2 * i + 1] = h; in_flight = true; }
-			} else { std::lock_guard<std::mutex> l(mu); if (err.empty()) err = e; }
+				dev[i] = (char*)*arena + off[i];
+				if (cudaMemcpyAsync(dev[i], pinned, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaEventRecord(done, st) != cudaSuccess) e = std::string("upload failed: ") + cudaGetErrorString(cudaGetLastError());
+				else in_flight = true;
+				us_enqueue += now_us() - t1;
+			}
+			if (!e.empty()) { std::lock_guard<std::mutex> l(mu); if (err.empty()) err = e; failed = true; }
 		}
 		if (in_flight) cudaEventSynchronize(done);
-		if (pinned) cudaFreeHost(pinned);
 		cudaEventDestroy(done);
 	});
 	for (auto& th : pool) th.join();
 	cudaStreamSynchronize(st);
-	(void)seconds_decode;
-	if (!err.empty()) { for (uint32_t i = 0; i < n; ++i) { cudaFree(dev[i]); dev[i] = nullptr; } }
+	if (debug) fprintf(stderr, "[rnb dataset] %u images, %u threads: wall %.1f ms (headers + allocations %.1f ms); summed over threads: decode %.1f ms, waiting for the slot %.1f ms, enqueue %.1f ms\n",
+	                   n, threads, (now_us() - wall0) * 1e-3, setup_us * 1e-3, us_decode.load() * 1e-3, us_wait.load() * 1e-3, us_enqueue.load() * 1e-3);
+	if (!err.empty()) { cudaFree(*arena); *arena = nullptr; for (uint32_t i = 0; i < n; ++i) dev[i] = nullptr; }
 	return err;
 }
 

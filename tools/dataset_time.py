@@ -4,6 +4,7 @@ import json, os, subprocess, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ["RNB_DATASET_DEBUG"] = "1"
 import rnb_loader, ref_scene
 from common import FULL, product_config
 
