@@ -219,6 +219,10 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 	c->off_rgb = off;
 	add(M.rgb_layers, M.n_rgb_layers, M.rgb_in, M.rgb_width, cfg->rgb_n_hidden_layers);
 	M.off_grid = off; off += offset * 2; M.off_var = off; off += 4; M.n_params = off;
+	// paired 16-byte gradient atomics need every level's first entry on a 16-byte boundary of the fp32 gradient buffer
+	M.scatter_pair = (M.off_grid % 4 == 0) ? 1u : 0u;
+	for (uint32_t i = 0; i < M.n_levels; ++i) if (M.offsets[i] % 2) M.scatter_pair = 0;
+	if (const char* e = getenv("RNB_SCATTER_PAIR")) M.scatter_pair = M.scatter_pair && atoi(e) != 0;
 	const size_t np = M.n_params;
 	CU(cudaMalloc(&c->master, np * 4)); CU(cudaMalloc(&c->params, np * 2)); CU(cudaMalloc(&c->ema, np * 2)); CU(cudaMalloc(&c->grads, np * 4));
 	CU(cudaMalloc(&c->m1, np * 4)); CU(cudaMalloc(&c->m2, np * 4)); CU(cudaMalloc(&c->steps, np * 4));

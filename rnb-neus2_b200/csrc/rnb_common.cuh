@@ -30,6 +30,7 @@ struct ModelDev {
 	float scale[MAX_LEVELS];
 	uint32_t off_grid, off_var, n_params;
 	uint32_t hashed_mask;                       // bit l: level l is hashed (res^3 > entries), else dense
+	uint32_t scatter_pair;                      // 1: x-neighbour corners whose entries are adjacent are reduced with one 16-byte atomic (needs 16-byte aligned level bases)
 	float sdf_bias;
 };
 

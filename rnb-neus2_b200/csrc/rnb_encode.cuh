@@ -158,13 +158,29 @@ __device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restri
 		ay[i] = sgy * (wx[i & 1] * wz[i >> 1]);
 		az[i] = sgz * (wx[i & 1] * wy[i >> 1]);
 	}
+	float2 v[8];
 	#pragma unroll
 	for (int c = 0; c < 8; ++c) {
 		const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
 		const float w1 = wx[bx] * wy[by] * wz[bz];
 		const float w2 = (bx ? ax[by + 2 * bz] : -ax[by + 2 * bz]) + (by ? ay[bx + 2 * bz] : -ay[bx + 2 * bz]) + (bz ? az[bx + 2 * by] : -az[bx + 2 * by]);
-		const float v0 = d10 * w1 + ge0 * w2, v1 = d11 * w1 + ge1 * w2;
-		if (v0 != 0.f || v1 != 0.f) atomicAdd(gg + (e[c] + off), make_float2(v0, v1));
+		v[c] = make_float2(d10 * w1 + ge0 * w2, d11 * w1 + ge1 * w2);
+	}
+	// The two corners of an x-edge are neighbours in memory whenever their entry indices differ only in bit 0: always in a dense
+	// level with an even base index, and in a hashed level whenever the cell's x is even (the x prime is 1, so x ^ (x + 1) == 1).
+	// Those pairs go out as ONE 16-byte reduction instead of two 8-byte ones: the backward is bound by the number of atomics.
+	#pragma unroll
+	for (int c = 0; c < 8; c += 2) {
+		const bool z0 = v[c].x == 0.f && v[c].y == 0.f, z1 = v[c + 1].x == 0.f && v[c + 1].y == 0.f;
+		if (z0 && z1) continue;
+		if (M.scatter_pair && ((e[c] ^ e[c + 1]) == 1u)) {
+			const bool lo = e[c] < e[c + 1];
+			const float2 a = lo ? v[c] : v[c + 1], b = lo ? v[c + 1] : v[c];
+			atomicAdd(reinterpret_cast<float4*>(gg + (min(e[c], e[c + 1]) + off)), make_float4(a.x, a.y, b.x, b.y));
+		} else {
+			if (!z0) atomicAdd(gg + (e[c] + off), v[c]);
+			if (!z1) atomicAdd(gg + (e[c + 1] + off), v[c + 1]);
+		}
 	}
 }
 
