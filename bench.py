@@ -213,6 +213,16 @@ def _shell_bitfield():
     return out
 
 
+def _network_path():
+    # mirrors the selection in csrc/rnb_api.cu (RNB_NETWORK=simt|mma, RNB_BACKWARD=mma are cross-check paths)
+    net = os.environ.get("RNB_NETWORK", "")
+    if net in ("simt", "mma"):
+        return {"simt": "CUDA-core kernels (cross-check path)", "mma": "mma.sync tile kernels (cross-check path)"}[net]
+    if os.environ.get("RNB_BACKWARD", "") == "mma":
+        return "tcgen05 forward + mma.sync backward"
+    return "tcgen05 forward + tcgen05 backward"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -344,7 +354,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_global": R, "pretrain_steps": args.pretrain, "samples_per_step": int(ns), "compacted_samples_per_step": int(nc), "live_hash_levels": L,
                        "cache": "working set (hash table 21 MB + gradients 42 MB + optimizer state 170 MB + 1.5 GB images) exceeds L2; no flush needed",
-                       "parallelism": "dp%d ray-sharded (4096 rays + 2^18-sample batch per GPU), fp32 gradient all-reduce" % n_gpus if n_gpus > 1 else "single GPU", "network_path": os.environ.get("RNB_NETWORK", "tcgen05 forward + mma.sync backward"),
+                       "parallelism": "dp%d ray-sharded (4096 rays + 2^18-sample batch per GPU), fp32 gradient all-reduce" % n_gpus if n_gpus > 1 else "single GPU", "network_path": _network_path(),
                        "dataset_upload_s": round(upload_s, 3), "dataset_bytes": dataset_bytes, "scene_render_s": round(gen_s, 1)},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,

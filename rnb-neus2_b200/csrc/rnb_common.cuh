@@ -31,6 +31,7 @@ struct ModelDev {
 	uint32_t off_grid, off_var, n_params;
 	uint32_t hashed_mask;                       // bit l: level l is hashed (res^3 > entries), else dense
 	uint32_t scatter_pair;                      // 1: x-neighbour corners whose entries are adjacent are reduced with one 16-byte atomic (needs 16-byte aligned level bases)
+	uint32_t scatter_agg;                       // levels [0, scatter_agg) use the warp-aggregated scatter in the tcgen05 backward (rnb_encode.cuh: scatter_level_agg)
 	float sdf_bias;
 };
 

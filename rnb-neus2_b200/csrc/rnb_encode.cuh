@@ -139,15 +139,15 @@ __device__ __forceinline__ __half2 level_finish(float scale, const LevelLoads& Q
 // Merged first- and second-order gradient scatter for one (sample, level):
 //   dgrid[corner] += dL/denc * w_c  +  dsdf/denc * scale * sum_dim gn[dim] * (+-1) * w_c^(dim)
 // (kernel_grid_backward grid.h:366-495 and kernel_grid_backward_input_backward_grid grid.h:556-683 hit the same 8 corners).
-__device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restrict__ G, uint32_t l, float x, float y, float z,
-                                              float d10, float d11, float ge0, float ge1, float gnx, float gny, float gnz) {
+// scatter_values(): the 8 corner entries and the 8 (2-feature) contributions; `cell` identifies the lattice cell within the level.
+__device__ __forceinline__ void scatter_values(const ModelDev& M, uint32_t l, float x, float y, float z, float d10, float d11, float ge0, float ge1,
+                                               float gnx, float gny, float gnz, uint32_t (&e)[8], float2 (&v)[8], uint32_t& cell) {
 	const uint32_t off = M.offsets[l];
-	float2* gg = reinterpret_cast<float2*>(G + M.off_grid);
 	const uint32_t hsz = M.offsets[l + 1] - off, res = M.res[l];
 	const float scale = M.scale[l];
 	const LevelGeom g = level_geom(scale, x, y, z);
-	uint32_t e[8];
 	corner_entries((M.hashed_mask >> l) & 1u, hsz, res, g, e);
+	cell = g.gx | (g.gy << 10) | (g.gz << 20);            // unique for res <= 1024 (the host enables aggregation only there)
 	const float wx[2] = {1.f - g.fx, g.fx}, wy[2] = {1.f - g.fy, g.fy}, wz[2] = {1.f - g.fz, g.fz};
 	const float sgx = scale * gnx, sgy = scale * gny, sgz = scale * gnz;
 	// w1 = wx wy wz ; w2 = (+-sgx) wy wz + (+-sgy) wx wz + (+-sgz) wx wy   (sign = + on the upper corner of that axis)
@@ -158,7 +158,6 @@ __device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restri
 		ay[i] = sgy * (wx[i & 1] * wz[i >> 1]);
 		az[i] = sgz * (wx[i & 1] * wy[i >> 1]);
 	}
-	float2 v[8];
 	#pragma unroll
 	for (int c = 0; c < 8; ++c) {
 		const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
@@ -166,6 +165,12 @@ __device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restri
 		const float w2 = (bx ? ax[by + 2 * bz] : -ax[by + 2 * bz]) + (by ? ay[bx + 2 * bz] : -ay[bx + 2 * bz]) + (bz ? az[bx + 2 * by] : -az[bx + 2 * by]);
 		v[c] = make_float2(d10 * w1 + ge0 * w2, d11 * w1 + ge1 * w2);
 	}
+}
+
+// scatter_emit(): the reductions into the fp32 gradient buffer.
+__device__ __forceinline__ void scatter_emit(const ModelDev& M, float* __restrict__ G, uint32_t l, const uint32_t (&e)[8], const float2 (&v)[8]) {
+	const uint32_t off = M.offsets[l];
+	float2* gg = reinterpret_cast<float2*>(G + M.off_grid);
 	// The two corners of an x-edge are neighbours in memory whenever their entry indices differ only in bit 0: always in a dense
 	// level with an even base index, and in a hashed level whenever the cell's x is even (the x prime is 1, so x ^ (x + 1) == 1).
 	// Those pairs go out as ONE 16-byte reduction instead of two 8-byte ones: the backward is bound by the number of atomics.
@@ -181,6 +186,50 @@ __device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restri
 			if (!z0) atomicAdd(gg + (e[c] + off), v[c]);
 			if (!z1) atomicAdd(gg + (e[c + 1] + off), v[c + 1]);
 		}
+	}
+}
+
+__device__ __forceinline__ void scatter_level(const ModelDev& M, float* __restrict__ G, uint32_t l, float x, float y, float z,
+                                              float d10, float d11, float ge0, float ge1, float gnx, float gny, float gnz) {
+	uint32_t e[8], cell; float2 v[8];
+	scatter_values(M, l, x, y, z, d10, d11, ge0, ge1, gnx, gny, gnz, e, v, cell);
+	scatter_emit(M, G, l, e, v);
+}
+
+// Warp-aggregated scatter.  Consecutive compacted samples are consecutive lattice points of one ray (step sqrt(3)/1024), so in a
+// coarse level a run of adjacent lanes falls into the same cell (26 lanes at res 16, 5 at res 72, 2-3 at res 151) and would send
+// its 8 reductions to the same 8 addresses.  A run of adjacent lanes with an identical cell is a segment: the contributions
+// are summed with a segmented shuffle reduction (log2(longest run) steps, warp-uniform) and only the segment's first lane issues
+// the reductions.  Must be called by all 32 lanes; lanes that are not `live` contribute nothing.
+__device__ __forceinline__ void scatter_level_agg(const ModelDev& M, float* __restrict__ G, uint32_t l, bool live, float x, float y, float z,
+                                                  float d10, float d11, float ge0, float ge1, float gnx, float gny, float gnz) {
+	constexpr uint32_t FULL = 0xffffffffu;
+	uint32_t e[8], cell; float2 v[8];
+	scatter_values(M, l, x, y, z, d10, d11, ge0, ge1, gnx, gny, gnz, e, v, cell);
+	if (!live) {
+		cell = 0xffffffffu;
+		#pragma unroll
+		for (int c = 0; c < 8; ++c) v[c] = make_float2(0.f, 0.f);
+	}
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t prev = __shfl_up_sync(FULL, cell, 1);
+	const bool head = lane == 0u || prev != cell;
+	const uint32_t heads = __ballot_sync(FULL, head);
+	if (32 - __popc(heads) >= 4) {                       // warp-uniform: worth it once a few lanes' reductions are saved
+		const uint32_t above = lane == 31u ? 0u : (heads >> (lane + 1u));
+		const uint32_t seg_last = above ? lane + (uint32_t)__ffs(above) - 1u : 31u;
+		const uint32_t run = __reduce_max_sync(FULL, seg_last - lane);        // longest segment - 1
+		for (uint32_t d = 1; d <= run; d <<= 1) {        // before the step lane i holds the sum over [i, min(i + d - 1, seg_last)]
+			const bool take = lane + d <= seg_last;
+			#pragma unroll
+			for (int c = 0; c < 8; ++c) {
+				const float ox = __shfl_down_sync(FULL, v[c].x, d), oy = __shfl_down_sync(FULL, v[c].y, d);
+				if (take) { v[c].x += ox; v[c].y += oy; }
+			}
+		}
+		if (head) scatter_emit(M, G, l, e, v);
+	} else {
+		scatter_emit(M, G, l, e, v);
 	}
 }
 

@@ -863,7 +863,8 @@ __global__ void __launch_bounds__(2 * TILE, 1) k_backward_tc(ModelDev M, const _
 			float du0, du1, g0, g1;
 			tmem_ld2(trow + C_32 + 2 * l, du0, du1);          // tcgen05.ld is warp-collective: executed by every lane, live or not
 			tmem_ld2(trow + C_GIN + 2 * l, g0, g1);
-			if (live) scatter_level(M, G, l, p.x, p.y, p.z, hq(du0), hq(du1), hq(g0), hq(g1), gn[0], gn[1], gn[2]);
+			if (l < M.scatter_agg) scatter_level_agg(M, G, l, live, p.x, p.y, p.z, hq(du0), hq(du1), hq(g0), hq(g1), gn[0], gn[1], gn[2]);      // warp-uniform branch
+			else if (live) scatter_level(M, G, l, p.x, p.y, p.z, hq(du0), hq(du1), hq(g0), hq(g1), gn[0], gn[1], gn[2]);
 		}
 		first = false;
 	}
