@@ -239,6 +239,23 @@ int rnb_mesh_download(rnb_ctx* ctx, float* verts_host, float* normals_host, floa
 int rnb_save_mesh(const float* verts_dev, const float* normals_dev, const float* colors_dev, const uint32_t* indices_dev, uint32_t n_verts, uint32_t n_indices,
                   const char* path, float nerf_scale, const float nerf_offset[3], float n2w_s, const float n2w_t[3], int invert_normals, void* stream, uint64_t* bytes_written);
 
+/* ---- ray / mesh queries of the albedo-scaling stage --------------------------------------------------
+ * Replace the two trimesh calls of compute_albedo_scale_ratios (rnb_neus2/albedo_scaling.py:285-289 and :316-329): a triangle mesh
+ * (host arrays, e.g. the stage-1 mesh read back from its OBJ or from rnb_mesh_download) is binned into a uniform cell grid once;
+ * rays are traced on the GPU in binary64.  There is no CPU path: rnb_raymesh_create fails with RNB_ERR_CUDA without a device. */
+typedef struct rnb_raymesh rnb_raymesh;
+/* grid_res: cells along the longest axis of the mesh box, 0 = chosen from the triangle count */
+int rnb_raymesh_create(const float* verts_host /* n_verts x 3 */, uint32_t n_verts, const uint32_t* indices_host /* n_tris x 3 */, uint32_t n_tris, uint32_t grid_res, rnb_raymesh** out);
+int rnb_raymesh_destroy(rnb_raymesh* rm);
+int rnb_raymesh_info(rnb_raymesh* rm, uint32_t res_out[3], uint64_t* n_cell_refs);
+/* t_max_host == NULL: closest intersection with t > 0 (mesh.ray.intersects_location(..., multiple_hits=False)):
+ *     t_out[i] = ray parameter (distance when the direction has unit length) or +inf, tri_out[i] = triangle or 0xffffffff.
+ * t_max_host != NULL: occlusion test, is there ANY intersection with 0 < t < t_max[i] (what :321-329 derives from the multiple_hits=True
+ *     list): tri_out[i] = a blocking triangle or 0xffffffff, t_out[i] = its parameter or +inf.
+ * origins / dirs: n x 3 binary64, host memory; results are complete when the call returns. */
+int rnb_raymesh_intersect(rnb_raymesh* rm, const double* origins_host, const double* dirs_host, const double* t_max_host, uint32_t n,
+                          double* t_out_host, uint32_t* tri_out_host, void* stream);
+
 /* ---- stage-level entry points (host buffers; parity tests and micro-benchmarks) --------------------------------
  * Each mirrors one reference kernel / call; see DESIGN.md for the mapping. */
 /* generate_training_samples_nerf (src/testbed_nerf.cu:1216-1387) */

@@ -56,6 +56,7 @@ EXPORTED_SYMBOLS = [
     "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf", "rnb_sdf_on_grid",
     "rnb_load_png_rgba16", "rnb_free_host", "rnb_load_dataset_images", "rnb_marching_cubes", "rnb_marching_cubes_from_density", "rnb_mesh_buffers", "rnb_mesh_download", "rnb_save_mesh",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
+    "rnb_raymesh_create", "rnb_raymesh_destroy", "rnb_raymesh_info", "rnb_raymesh_intersect",
 ]
 
 
@@ -73,6 +74,60 @@ def save_mesh_device(path, verts_ptr, normals_ptr, colors_ptr, indices_ptr, n_ve
     if rc != 0:
         raise RnbError(lib().rnb_last_error().decode())
     return int(nb.value)
+
+
+class RayMesh:
+    """Ray queries against a triangle mesh on the GPU (rnb_raymesh_*, csrc/rnb_raymesh.cu) — what the reference's albedo-scaling stage
+    asks of trimesh (`mesh.ray.intersects_location`, rnb_neus2/albedo_scaling.py:285-289,316-329).  No CPU path."""
+    NO_TRI = 0xFFFFFFFF
+
+    def __init__(self, verts, tris, grid_res=0):
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+        self.tris = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
+        self.h = C.c_void_p()
+        L = lib()
+        rc = L.rnb_raymesh_create(_p(self.verts, C.c_float), C.c_uint32(self.verts.shape[0]), _p(self.tris, C.c_uint32), C.c_uint32(self.tris.shape[0]), C.c_uint32(grid_res), C.byref(self.h))
+        if rc != 0:
+            raise RnbError(L.rnb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            lib().rnb_raymesh_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        res = (C.c_uint32 * 3)(); refs = C.c_uint64(0)
+        if lib().rnb_raymesh_info(self.h, res, C.byref(refs)) != 0:
+            raise RnbError(lib().rnb_last_error().decode())
+        return dict(res=tuple(int(x) for x in res), n_cell_refs=int(refs.value))
+
+    def _run(self, origins, dirs, t_max):
+        o = np.ascontiguousarray(origins, np.float64).reshape(-1, 3); d = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+        if o.shape != d.shape:
+            raise ValueError("origins and directions differ in shape")
+        n = o.shape[0]
+        tm = np.ascontiguousarray(t_max, np.float64).reshape(-1) if t_max is not None else None
+        if tm is not None and tm.shape[0] != n:
+            raise ValueError("t_max needs one entry per ray")
+        t = np.full(n, np.inf, np.float64); tri = np.full(n, self.NO_TRI, np.uint32)
+        rc = lib().rnb_raymesh_intersect(self.h, _p(o, C.c_double), _p(d, C.c_double), _p(tm, C.c_double), C.c_uint32(n), _p(t, C.c_double), _p(tri, C.c_uint32), C.c_void_p(None))
+        if rc != 0:
+            raise RnbError(lib().rnb_last_error().decode())
+        return t, tri
+
+    def first_hit(self, origins, dirs):
+        """closest intersection with t > 0 per ray: (t, triangle); t = inf and triangle = NO_TRI for a miss"""
+        return self._run(origins, dirs, None)
+
+    def any_hit(self, origins, dirs, t_max):
+        """bool per ray: some intersection with 0 < t < t_max"""
+        return self._run(origins, dirs, t_max)[1] != self.NO_TRI
 
 
 def load_png_rgba16(path):

@@ -177,6 +177,7 @@ static int ensure_ray_capacity(rnb_ctx* c, uint32_t R) {
 extern "C" {
 
 const char* rnb_last_error(void) { return g_err.c_str(); }
+int rnb_set_error_(int code, const char* msg) { return fail(code, msg ? msg : ""); }      // for the other translation units of the library (rnb_raymesh.cu)
 uint32_t rnb_abi_version(void) { return RNB_ABI_VERSION; }
 
 void rnb_default_config(rnb_config* c) {

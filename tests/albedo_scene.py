@@ -1,0 +1,72 @@
+"""Synthetic scene for the albedo-scaling tests: a sphere mesh, a ring of pinhole cameras looking at it, and albedo images that show one
+view-independent texture multiplied by a per-view, per-channel gain.  The stage under test must recover the gains."""
+import numpy as np
+
+
+def icosphere(subdiv=3, radius=1.0, center=(0.0, 0.0, 0.0)):
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdiv):
+        cache = {}; nf = []
+
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = v[a] + v[b]; v.append(m / np.linalg.norm(m)); cache[k] = len(v) - 1
+            return cache[k]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return (np.array(v) * radius + np.array(center)).astype(np.float32), np.array(f, dtype=np.uint32)
+
+
+def texture(p):
+    """smooth, strictly positive RGB texture of the surface point (n, 3) -> (n, 3)"""
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    return np.stack([0.45 + 0.25 * np.sin(2.1 * x + 0.3) * np.cos(1.7 * y), 0.5 + 0.2 * np.sin(1.3 * y - 0.8 * z), 0.4 + 0.25 * np.cos(1.9 * z + 0.6 * x)], axis=1)
+
+
+def ring_cameras(n_views, w, h, dist=3.2, focal=None, elev=0.25):
+    """K (float32), R_c2w (float32, columns right/down/forward), centres (float32 3x1)"""
+    focal = focal or 1.25 * w
+    Ks, Rs, Cs = [], [], []
+    for i in range(n_views):
+        a = 2 * np.pi * i / n_views
+        C = np.array([dist * np.cos(a), dist * np.sin(a), dist * elev * np.sin(2 * a + 0.4)])
+        fwd = -C / np.linalg.norm(C)
+        right = np.cross(fwd, np.array([0.0, 0.0, 1.0])); right /= np.linalg.norm(right)
+        down = np.cross(fwd, right)
+        Ks.append(np.array([[focal, 0, w / 2], [0, focal, h / 2], [0, 0, 1]], dtype=np.float32))
+        Rs.append(np.stack([right, down, fwd], axis=1).astype(np.float32)); Cs.append(C.reshape(3, 1).astype(np.float32))
+    return np.array(Ks), np.array(Rs), np.array(Cs)
+
+
+def render_views(Ks, Rs, Cs, w, h, gains, radius=1.0):
+    """albedos [V, h, w, 3] float32 = gain_v * texture(first hit on the analytic sphere), masks [V, h, w]"""
+    V = len(Ks)
+    alb = np.zeros((V, h, w, 3), np.float32); msk = np.zeros((V, h, w), np.float32)
+    uu, vv = np.meshgrid(np.arange(w), np.arange(h))
+    px = np.stack([uu.ravel(), vv.ravel(), np.ones(w * h)], axis=0).astype(np.float64)
+    for i in range(V):
+        d = (Rs[i].astype(np.float64) @ (np.linalg.inv(Ks[i].astype(np.float64)) @ px)).T
+        d /= np.linalg.norm(d, axis=1)[:, None]
+        o = Cs[i].astype(np.float64).reshape(1, 3)
+        b = (d * o).sum(1); c = (o * o).sum() - radius * radius
+        disc = b * b - c
+        hit = disc > 0
+        t = -b - np.sqrt(np.where(hit, disc, 0.0))
+        p = o + d * t[:, None]
+        col = texture(p) * gains[i][None, :]
+        alb[i] = np.where(hit[:, None], col, 0.0).reshape(h, w, 3).astype(np.float32)
+        msk[i] = hit.reshape(h, w).astype(np.float32)
+    return alb, msk
+
+
+def expected_factors(gains):
+    inv = 1.0 / np.asarray(gains, dtype=np.float64)
+    inv = inv / inv[0]
+    return inv / inv.mean(axis=0)

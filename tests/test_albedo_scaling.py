@@ -1,0 +1,142 @@
+"""Albedo-scaling stage on the CPU: the oracle restatement against a known-answer scene, and the product's host logic
+(rnb-neus2_b200/albedo_scaling.py) against the oracle with the ray queries served by the host build of the kernel's traversal."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import orc_albedo  # noqa: E402
+from albedo_scene import expected_factors, icosphere, render_views, ring_cameras  # noqa: E402
+from test_raymesh_host import _trace, host_lib  # noqa: E402,F401
+
+V, W, H, NS = 8, 96, 80, 400
+GAINS = np.array([[1.0, 1.0, 1.0], [0.8, 0.9, 1.1], [1.2, 0.7, 0.95], [0.9, 1.1, 1.3], [1.05, 0.85, 0.75], [0.7, 1.2, 1.0], [1.3, 1.0, 0.9], [0.95, 0.95, 1.15]])
+
+
+def scene():
+    verts, tris = icosphere(3)
+    K, R, Cc = ring_cameras(V, W, H)
+    alb, msk = render_views(K, R, Cc, W, H, GAINS)
+    return verts, tris, K, R, Cc, alb, msk
+
+
+def seeded_choose(seed):
+    rng = np.random.RandomState(seed)
+    return lambda n, k: rng.choice(n, k, replace=False)
+
+
+class HostRayMesh:
+    """test double with the RayMesh interface, backed by the host compilation of the kernel's traversal code"""
+    NO_TRI = 0xFFFFFFFF
+
+    def __init__(self, L, verts, tris):
+        self.L, self.verts, self.tris = L, np.ascontiguousarray(verts, np.float32), np.ascontiguousarray(tris, np.uint32)
+
+    def first_hit(self, o, d):
+        t, tri, _ = _trace(self.L, self.verts, self.tris, o, d)
+        return t, tri
+
+    def any_hit(self, o, d, t_max):
+        return _trace(self.L, self.verts, self.tris, o, d, t_max)[1] != self.NO_TRI
+
+
+def test_oracle_recovers_known_gains():
+    verts, tris, K, R, Cc, alb, msk = scene()
+    got = orc_albedo.albedo_scale_ratios(alb, msk, K, R, Cc, verts, tris, NS, seeded_choose(0))
+    want = expected_factors(GAINS)
+    assert got.shape == (V, 3)
+    assert np.max(np.abs(got / want - 1)) < 0.03          # chained medians of 8 views; polyhedral sphere vs analytic images
+    assert np.allclose(got.mean(axis=0), 1.0)
+
+
+def test_host_logic_matches_oracle(pkg, host_lib):  # noqa: F811
+    import importlib
+    mod = importlib.import_module("rnb_neus2_b200.albedo_scaling")
+    verts, tris, K, R, Cc, alb, msk = scene()
+    ref = orc_albedo.albedo_scale_ratios(alb, msk, K, R, Cc, verts, tris, NS, seeded_choose(5))
+    got = mod.albedo_scale_ratios_from_arrays(alb, msk, K, R, Cc, verts, tris, NS, choose=seeded_choose(5), raymesh=HostRayMesh(host_lib, verts, tris))
+    assert np.max(np.abs(got - ref)) < 1e-6
+
+
+def test_fewer_masked_pixels_than_samples(pkg, host_lib):  # noqa: F811
+    import importlib
+    mod = importlib.import_module("rnb_neus2_b200.albedo_scaling")
+    verts, tris, K, R, Cc, alb, msk = scene()
+    n_big = int(msk[0].sum()) + 500          # more samples than any view has pixels: every masked pixel is used (:266-270)
+    ref = orc_albedo.albedo_scale_ratios(alb, msk, K, R, Cc, verts, tris, n_big, seeded_choose(1))
+    got = mod.albedo_scale_ratios_from_arrays(alb, msk, K, R, Cc, verts, tris, n_big, choose=seeded_choose(1), raymesh=HostRayMesh(host_lib, verts, tris))
+    assert np.max(np.abs(got - ref)) < 1e-6
+    assert np.max(np.abs(got / expected_factors(GAINS) - 1)) < 0.03
+
+
+def test_mesh_and_camera_readers(pkg, tmp_path):
+    import importlib
+    mod = importlib.import_module("rnb_neus2_b200.albedo_scaling")
+    verts, tris = icosphere(1)
+    obj = tmp_path / "mesh_0.obj"
+    with open(obj, "w") as f:          # the layout rnb_save_mesh / the reference's save_mesh write
+        for v in verts:
+            f.write("v %0.5f %0.5f %0.5f %0.3f %0.3f %0.3f\n" % (v[0], v[1], v[2], 0.5, 0.5, 0.5))
+        for v in verts:
+            f.write("vn %0.5f %0.5f %0.5f\n" % tuple(v))
+        for t in tris:
+            f.write("f %d//%d %d//%d %d//%d\n" % (t[0] + 1, t[0] + 1, t[1] + 1, t[1] + 1, t[2] + 1, t[2] + 1))
+    v2, t2 = mod.load_mesh(obj)
+    assert np.array_equal(t2, tris) and np.max(np.abs(v2 - verts)) < 1e-5
+    ply = tmp_path / "mesh_0.ply"
+    with open(ply, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nelement face %d\nproperty list uchar int vertex_index\nend_header\n" % (len(verts), len(tris)))
+        for v in verts:
+            f.write("%0.5f %0.5f %0.5f\n" % tuple(v))
+        for t in tris:
+            f.write("3 %d %d %d\n" % tuple(t))
+    v3, t3 = mod.load_mesh(ply)
+    assert np.array_equal(t3, tris) and np.max(np.abs(v3 - verts)) < 1e-5
+    # transform.json with n2w: cameras come back in world space
+    K, R, Cc = ring_cameras(3, 32, 24)
+    n2w = np.diag([2.0, 2.0, 2.0, 1.0]); n2w[:3, 3] = [5.0, -1.0, 0.5]
+    frames = []
+    for i in range(3):
+        c2w = np.eye(4); c2w[:3, :3] = R[i]; c2w[:3, 3] = Cc[i][:, 0]
+        frames.append({"albedo_path": "albedos/%05d.png" % i, "normal_path": "normals/%05d.png" % i, "transform_matrix": c2w.tolist(), "intrinsic_matrix": K[i].tolist()})
+    tj = tmp_path / "transform.json"
+    tj.write_text(json.dumps({"w": 32, "h": 24, "n2w": n2w.tolist(), "frames": frames}))
+    names = ["%05d.png" % i for i in range(3)]
+    K2, R2, C2 = mod.load_cameras(tj, names)
+    assert np.allclose(K2, K) and np.allclose(R2, 2.0 * R, atol=1e-6) and np.allclose(C2[:, :, 0], 2.0 * Cc[:, :, 0] + n2w[:3, 3], atol=1e-5)
+    Ko, Ro, Co = orc_albedo.cameras_from_transform(json.loads(tj.read_text()), [n[:-4] for n in names])
+    assert np.array_equal(K2, Ko) and np.array_equal(R2, Ro) and np.array_equal(C2, Co)
+    with pytest.raises(RuntimeError):
+        mod.load_cameras(tj, ["99999.png"])
+    with pytest.raises(ValueError):
+        mod.load_cameras(tmp_path / "cams.txt", names)
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_scale_and_save_albedos(pkg, tmp_path, bits):
+    import importlib
+    import cv2
+    mod = importlib.import_module("rnb_neus2_b200.albedo_scaling")
+    rng = np.random.default_rng(bits)
+    src = tmp_path / "albedos"; dst = tmp_path / "albedos_scaled"; src.mkdir()
+    mx = 2 ** bits - 1
+    imgs = []
+    for i in range(3):
+        a = rng.integers(0, mx + 1, size=(12, 10, 4)).astype(np.uint8 if bits == 8 else np.uint16)
+        cv2.imwrite(str(src / ("%05d.png" % i)), a)          # BGRA on disk
+        imgs.append(a)
+    ratios = np.array([[1.0, 0.5, 0.25], [0.9, 1.1, 2.0], [0.3, 0.3, 0.3]])
+    mod.scale_and_save_albedos(str(src), str(dst), ratios)
+    for i in range(3):
+        out = cv2.imread(str(dst / ("%05d.png" % i)), cv2.IMREAD_UNCHANGED)
+        assert out.dtype == imgs[i].dtype and out.shape == imgs[i].shape
+        rgb = imgs[i][:, :, 2::-1].astype(np.float32) / float(mx)
+        want = (np.clip(rgb * ratios[i], 0.0, 1.0) * float(mx)).astype(out.dtype)          # truncation, like the reference's save_image
+        assert np.array_equal(out[:, :, 2::-1], want)
+        alpha = ((imgs[i][:, :, 3].astype(np.float32) / np.float32(mx)).astype(np.float64) * float(mx)).astype(out.dtype)      # same float32 -> float64 round trip
+        assert np.array_equal(out[:, :, 3], alpha)
+        assert np.max(np.abs(out[:, :, 3].astype(np.int64) - imgs[i][:, :, 3].astype(np.int64))) <= 1

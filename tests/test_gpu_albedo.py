@@ -1,0 +1,135 @@
+"""Albedo-scaling stage on the GPU: the ray/mesh kernel through the C ABI against brute force, and
+compute_albedo_scale_ratios end to end from files against the oracle restatement and the known gains."""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import orc_albedo  # noqa: E402
+from albedo_scene import expected_factors, icosphere, render_views, ring_cameras  # noqa: E402
+from test_raymesh_host import random_rays, two_spheres  # noqa: E402
+from test_albedo_scaling import GAINS, H, NS, V, W, scene, seeded_choose  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("grid_res", [0, 5, 64])
+def test_raymesh_first_hit_vs_bruteforce(pkg, grid_res):
+    verts, tris = two_spheres()
+    rm = pkg.RayMesh(verts, tris, grid_res)
+    o, d = random_rays(3000, 11)
+    t, tri = rm.first_hit(o, d)
+    t_ref, tri_ref = orc_albedo.first_hit(verts, tris, o, d)
+    assert np.array_equal(np.isfinite(t), np.isfinite(t_ref))
+    m = np.isfinite(t_ref)
+    assert m.sum() > 1400
+    assert np.max(np.abs(t[m] - t_ref[m])) < 1e-9          # binary64 on both sides (fused multiply-adds on the device)
+    assert (tri[m] == tri_ref[m]).mean() > 0.995
+    assert np.all(tri[~m] == pkg.RayMesh.NO_TRI)
+    rm.close()
+
+
+def test_raymesh_any_hit_vs_bruteforce(pkg):
+    verts, tris = two_spheres()
+    rm = pkg.RayMesh(verts, tris)
+    o, d = random_rays(3000, 12)
+    t_max = np.random.default_rng(13).uniform(0.5, 5.0, size=o.shape[0])
+    got = rm.any_hit(o, d, t_max)
+    ref = orc_albedo.any_hit(verts, tris, o, d, t_max)
+    assert np.array_equal(got, ref)
+    assert rm.first_hit(np.zeros((0, 3)), np.zeros((0, 3)))[0].shape == (0,)          # empty batch
+    rm.close()
+
+
+def test_raymesh_errors(pkg):
+    verts, tris = icosphere(0)
+    with pytest.raises(pkg.RnbError):
+        pkg.RayMesh(verts, np.array([[0, 1, 99]], np.uint32))
+    with pytest.raises(pkg.RnbError):
+        pkg.RayMesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    rm = pkg.RayMesh(verts, tris)
+    with pytest.raises(ValueError):
+        rm.any_hit(np.zeros((4, 3)), np.ones((4, 3)), np.ones(3))
+    rm.close()
+
+
+def test_ratios_from_arrays_match_oracle(pkg):
+    mod = importlib.import_module("rnb_neus2_b200.albedo_scaling")
+    verts, tris, K, R, Cc, alb, msk = scene()
+    ref = orc_albedo.albedo_scale_ratios(alb, msk, K, R, Cc, verts, tris, NS, seeded_choose(7))
+    got = mod.albedo_scale_ratios_from_arrays(alb, msk, K, R, Cc, verts, tris, NS, choose=seeded_choose(7))
+    assert np.max(np.abs(got - ref)) < 1e-6
+    assert np.max(np.abs(got / expected_factors(GAINS) - 1)) < 0.03
+
+
+def test_compute_albedo_scale_ratios_from_files(pkg, tmp_path):
+    """the reference's call (pipeline.py:150-156): albedo folder + transform.json + the stage-1 mesh file"""
+    import cv2
+    mod = importlib.import_module("rnb_neus2_b200.albedo_scaling")
+    verts, tris, K, R, Cc, alb, msk = scene()
+    adir = tmp_path / "albedos"; adir.mkdir()
+    frames = []
+    for i in range(V):
+        rgba = np.concatenate([alb[i], msk[i][:, :, None]], axis=2)
+        mod.save_image(rgba, adir / ("%05d.png" % i), bit_depth=16)
+        c2w = np.eye(4); c2w[:3, :3] = R[i]; c2w[:3, 3] = Cc[i][:, 0]
+        frames.append({"albedo_path": "albedos/%05d.png" % i, "normal_path": "normals/%05d.png" % i, "transform_matrix": c2w.tolist(), "intrinsic_matrix": K[i].tolist()})
+    (tmp_path / "transform.json").write_text(json.dumps({"w": W, "h": H, "frames": frames}))
+    with open(tmp_path / "mesh_0.obj", "w") as f:
+        for v in verts:
+            f.write("v %0.5f %0.5f %0.5f 0.5 0.5 0.5\n" % tuple(v))
+        for t in tris:
+            f.write("f %d//%d %d//%d %d//%d\n" % (t[0] + 1, t[0] + 1, t[1] + 1, t[1] + 1, t[2] + 1, t[2] + 1))
+    np.random.seed(3)
+    got = mod.compute_albedo_scale_ratios(str(adir), str(tmp_path / "transform.json"), str(tmp_path / "mesh_0.obj"), n_samples=NS)
+    # oracle on what the files hold, same draws
+    names = sorted(os.listdir(adir))
+    imgs = [mod.load_image(adir / n) for n in names]
+    a2 = np.array([im[:, :, :3] for im in imgs]); m2 = np.array([im[:, :, 3] for im in imgs])
+    Ko, Ro, Co = orc_albedo.cameras_from_transform(json.loads((tmp_path / "transform.json").read_text()), [n[:-4] for n in names])
+    v2, t2 = mod.load_mesh(tmp_path / "mesh_0.obj")
+    np.random.seed(3)
+    ref = orc_albedo.albedo_scale_ratios(a2, m2, Ko, Ro, Co, v2, t2, NS, lambda n, k: np.random.choice(n, k, replace=False))
+    assert np.max(np.abs(got - ref)) < 1e-6
+    assert np.max(np.abs(got / expected_factors(GAINS) - 1)) < 0.03
+    # and the second half of the stage: scaled albedos agree across views where the gains differed
+    mod.scale_and_save_albedos(str(adir), str(tmp_path / "albedos_scaled"), got)
+    out = cv2.imread(str(tmp_path / "albedos_scaled" / names[1]), cv2.IMREAD_UNCHANGED)
+    assert out.dtype == np.uint16 and out.shape == (H, W, 4)
+
+
+def test_raymesh_full_size(pkg):
+    """96 views x 2000 rays against a 328 k-triangle sphere: every ray that the analytic sphere stops is stopped by the mesh at the
+    same depth; timing is reported, not asserted."""
+    verts, tris = icosphere(7)
+    assert tris.shape[0] == 20 * 4 ** 7
+    t0 = time.time(); rm = pkg.RayMesh(verts, tris); build_s = time.time() - t0
+    rng = np.random.default_rng(5)
+    n = 96 * 2000
+    o = rng.normal(size=(n, 3)); o = o / np.linalg.norm(o, axis=1)[:, None] * 3.0
+    target = rng.normal(size=(n, 3)); target = target / np.linalg.norm(target, axis=1)[:, None] * rng.uniform(0.0, 1.3, size=(n, 1))
+    d = target - o; d /= np.linalg.norm(d, axis=1)[:, None]
+    rm.first_hit(o[:1000], d[:1000])
+    t0 = time.time(); t, tri = rm.first_hit(o, d); first_s = time.time() - t0
+    b = (o * d).sum(1); disc = b * b - (9.0 - 1.0)
+    ana = np.where(disc > 0, -b - np.sqrt(np.maximum(disc, 0.0)), np.inf)
+    inner = disc > 0.04
+    assert np.all(np.isfinite(t[inner]))
+    assert np.max(np.abs(t[inner] - ana[inner])) < 2e-4          # inscribed polyhedron vs the sphere: sagitta ~ 1e-5, incidence cosine >= 0.2
+    loc = o[inner] + d[inner] * t[inner, None]
+    nd = -loc / np.linalg.norm(loc, axis=1)[:, None]          # towards the centre: must be blocked by the far side
+    t0 = time.time(); blk = rm.any_hit(loc + 1e-2 * nd, nd, np.full(loc.shape[0], 5.0)); any_s = time.time() - t0
+    assert blk.all()
+    out = rm.any_hit(loc - 1e-2 * nd, -nd, np.full(loc.shape[0], 5.0))          # outwards: free
+    assert not out.any()
+    print("raymesh full size: %d triangles, grid %s, build %.3f s, first hit of %d rays %.4f s, occlusion %.4f s" % (tris.shape[0], rm.info(), build_s, n, first_s, any_s))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "raymesh_time.json"), "w") as f:
+        json.dump({"triangles": int(tris.shape[0]), "grid": rm.info(), "build_s": build_s, "rays": n, "first_hit_s": first_s, "any_hit_s": any_s, "any_hit_rays": int(loc.shape[0])}, f)
+    rm.close()

@@ -1,0 +1,97 @@
+"""CPU check of the ray/mesh traversal the CUDA kernel runs (rnb_raymesh.cuh compiled for the host) against brute force over all
+triangles (oracle/orc_albedo.py)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import orc_albedo  # noqa: E402
+from albedo_scene import icosphere  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    src = os.path.join(ROOT, "tests", "cuda", "raymesh_host.cpp"); so = os.path.join(ROOT, "tests", "cuda", "libraymesh_host.so")
+    deps = [src] + [os.path.join(ROOT, "rnb-neus2_b200", "csrc", f) for f in ("rnb_raymesh.cuh", "rnb_raymesh_build.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    return C.CDLL(so)
+
+
+def _trace(L, verts, tris, org, dirs, t_max=None, grid_res=0):
+    n = org.shape[0]
+    t = np.zeros(n); tri = np.zeros(n, np.uint32); res = (C.c_uint32 * 3)()
+    p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+    org = np.ascontiguousarray(org, np.float64); dirs = np.ascontiguousarray(dirs, np.float64)
+    tm = np.ascontiguousarray(t_max, np.float64) if t_max is not None else None
+    L.raymesh_host_trace(p(verts, C.c_float), C.c_uint32(len(verts)), p(tris, C.c_uint32), C.c_uint32(len(tris)), C.c_uint32(grid_res),
+                         p(org, C.c_double), p(dirs, C.c_double), p(tm, C.c_double), C.c_uint32(n), p(t, C.c_double), p(tri, C.c_uint32), res)
+    return t, tri, tuple(res)
+
+
+def two_spheres():
+    v1, f1 = icosphere(3, 1.0); v2, f2 = icosphere(2, 0.35, (1.6, 0.4, 0.2))
+    return np.ascontiguousarray(np.concatenate([v1, v2])), np.ascontiguousarray(np.concatenate([f1, f2 + len(v1)]).astype(np.uint32))
+
+
+def random_rays(n, seed):
+    rng = np.random.default_rng(seed)
+    o = rng.normal(size=(n, 3)); o = o / np.linalg.norm(o, axis=1)[:, None] * rng.uniform(2.0, 4.0, size=(n, 1))
+    target = rng.uniform(-1.3, 1.3, size=(n, 3))
+    d = target - o; d /= np.linalg.norm(d, axis=1)[:, None]
+    o[: n // 8] = rng.uniform(-0.5, 0.5, size=(n // 8, 3))          # some origins inside the big sphere
+    return o, d
+
+
+@pytest.mark.parametrize("grid_res", [0, 4, 37, 128])
+def test_first_hit_matches_bruteforce(host_lib, grid_res):
+    verts, tris = two_spheres()
+    o, d = random_rays(1500, 1)
+    t, tri, res = _trace(host_lib, verts, tris, o, d, None, grid_res)
+    t_ref, tri_ref = orc_albedo.first_hit(verts, tris, o, d)
+    assert np.array_equal(np.isfinite(t), np.isfinite(t_ref))
+    m = np.isfinite(t_ref)
+    assert m.sum() > 700
+    assert np.max(np.abs(t[m] - t_ref[m])) < 1e-9
+    same = tri[m] == tri_ref[m]
+    assert same.mean() > 0.995          # a ray through a shared edge may report either neighbour
+    assert np.all(tri[~m] == orc_albedo.NO_TRI)
+
+
+def test_axis_aligned_and_degenerate_rays(host_lib):
+    verts, tris = two_spheres()
+    o = np.array([[3.0, 0.0, 0.0], [0.0, -3.0, 0.0], [0.0, 0.0, 3.0], [3.0, 3.0, 3.0], [0.0, 0.0, 0.0], [5.0, 0.01, 0.02]])
+    d = np.array([[-1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0], [-1.0, 0.0, 0.0]])
+    t, tri, _ = _trace(host_lib, verts, tris, o, d)
+    t_ref, _ = orc_albedo.first_hit(verts, tris, o, d)
+    assert np.array_equal(np.isfinite(t), np.isfinite(t_ref))
+    m = np.isfinite(t_ref)
+    assert np.allclose(t[m], t_ref[m], atol=1e-9)
+    assert not np.isfinite(t[3])          # pointing away from everything
+
+
+def test_any_hit_matches_bruteforce(host_lib):
+    verts, tris = two_spheres()
+    o, d = random_rays(1500, 2)
+    rng = np.random.default_rng(3)
+    t_max = rng.uniform(0.5, 5.0, size=o.shape[0])
+    _, tri, _ = _trace(host_lib, verts, tris, o, d, t_max)
+    ref = orc_albedo.any_hit(verts, tris, o, d, t_max)
+    got = tri != orc_albedo.NO_TRI
+    assert np.array_equal(got, ref)
+    assert 100 < ref.sum() < 1400
+
+
+def test_unnormalised_directions_scale_the_parameter(host_lib):
+    verts, tris = two_spheres()
+    o, d = random_rays(300, 4)
+    t1, tri1, _ = _trace(host_lib, verts, tris, o, d)
+    t2, tri2, _ = _trace(host_lib, verts, tris, o, d * 2.5)
+    m = np.isfinite(t1)
+    assert np.array_equal(m, np.isfinite(t2))
+    assert np.allclose(t1[m], t2[m] * 2.5, rtol=1e-12)
