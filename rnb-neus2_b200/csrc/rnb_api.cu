@@ -64,16 +64,14 @@ std::string mesh_write(cudaStream_t, const float*, const float*, const float*, c
 
 using namespace rnb;
 
-#ifndef RNB_ASYNC_END_DEFAULT
-#define RNB_ASYNC_END_DEFAULT false
+#ifndef RNB_PRELAUNCH_AT_DEFAULT
+#define RNB_PRELAUNCH_AT_DEFAULT 3      /* A/B on B200 (profiles/r01_ab_prelaunch_at.txt): step 0.822 (0) / 0.847 (1) / 0.832 (2) / 0.809 ms (3) */
 #endif
 #ifndef RNB_SCATTER_AGG_DEFAULT
-#define RNB_SCATTER_AGG_DEFAULT 0u
+#define RNB_SCATTER_AGG_DEFAULT 5u      /* A/B on B200 (profiles/r01_ab_scatter_agg.txt): backward 0.290 -> 0.276 ms at 5 levels, 0.286 at 8 */
 #endif
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-struct rnb_ctx;
-static void settle(rnb_ctx* c);
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(RNB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct rnb_ctx {
@@ -103,14 +101,10 @@ struct rnb_ctx {
 	// pinned batch size the march of step N+1 is launched on a side stream when the backward of step N has finished, so that it
 	// shares the SMs with the (HBM-bound) optimizer / the gradient all-reduce instead of running alone
 	cudaStream_t side = nullptr; cudaEvent_t ev_bwd = nullptr, ev_march = nullptr;
-	// early read-back (RNB_ASYNC_END, single rank, not while profiling): a step's counters and loss sums are final once the loss kernel has
-	// run, so they are copied to the host on a copy stream WHILE the backward runs and rnb_train_step_end waits for that copy only.  The
-	// host is then back in the caller (and queues the next step) while backward + optimizer still execute: no idle gap between steps.
-	// `unsettled` remembers the stream that still carries that work; every entry point that is not a training call drains it first.
-	cudaStream_t copy_st = nullptr; cudaEvent_t ev_loss = nullptr, ev_copy = nullptr; bool async_end = false, early_copy = false;
-	cudaStream_t unsettled = nullptr; bool unsettled_valid = false;
 	// in-memory checkpoint (rnb_checkpoint_save / _restore): one device-side slot of everything a step reads and writes
 	struct Ckpt { void* buf = nullptr; size_t bytes = 0; bool valid = false; uint32_t opt_step, density_ema_step, training_step, rays_per_batch, n_rays_total, measured_before, measured; float lr_factor; Pcg32 rng, density_rng; } ck;
+	int pre_at = RNB_PRELAUNCH_AT_DEFAULT;      // where the next march may start: 0 behind the backward, 1 behind the loss, 2 behind pass A, 3 behind scan/emit (last readers of the ray buffers)
+	bool pre_armed = false;                     // this step will pre-launch (decided before its kernels are queued)
 	bool prelaunch = true; bool pre_valid = false; uint32_t pre_R = 0, pre_nrt = 0; uint64_t pre_rng_state = 0, pre_rng_inc = 0;
 	// last extracted mesh (rnb_marching_cubes*): MeshState verts / vert_normals / vert_colors / indices (testbed.h:418-447), device memory
 	struct Mesh { float *verts = nullptr, *normals = nullptr, *colors = nullptr; uint32_t* indices = nullptr; uint32_t n_verts = 0, n_verts_padded = 0, n_indices = 0; float ms[4] = {0, 0, 0, 0}; } mesh;
@@ -149,7 +143,6 @@ static void prof_resolve(rnb_ctx* c) {      // call after the stream has been sy
 static uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
 
 // a pre-launched march is only usable if nothing it depends on changed: drop it (after it has drained) otherwise
-static void settle(rnb_ctx* c) { if (c && c->unsettled_valid) { cudaStreamSynchronize(c->unsettled); c->unsettled_valid = false; } }
 static void drop_prelaunch(rnb_ctx* c) { if (c->pre_valid) { cudaStreamSynchronize(c->side); c->pre_valid = false; } }
 
 static uint32_t valid_level_for_step(const rnb_ctx* c, int step) {   // grid.h:1430-1437
@@ -271,9 +264,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 		// RNB_NETWORK=mma keeps the mma.sync tile kernels everywhere; default: tcgen05 kernels where they exist
 		if (const char* d = getenv("RNB_BW_DEBUG")) set_bw_debug(atoi(d));
 		if (const char* d = getenv("RNB_PRELAUNCH")) c->prelaunch = atoi(d) != 0;
-		c->async_end = RNB_ASYNC_END_DEFAULT;
-		if (const char* d = getenv("RNB_ASYNC_END")) c->async_end = atoi(d) != 0;
-		CU(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_loss, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+		if (const char* d = getenv("RNB_PRELAUNCH_AT")) c->pre_at = std::min(std::max(atoi(d), 0), 3);
 		c->use_tc = c->use_mma && tc_supported(M) && !(e && std::string(e) == "mma");
 		c->use_tc_bwd = c->use_tc && !(getenv("RNB_BACKWARD") && std::string(getenv("RNB_BACKWARD")) == "mma");     // RNB_BACKWARD=mma: mma.sync backward
 		CU(cudaMalloc(&c->wtc, tc_blob_bytes(M))); CU(cudaMemset(c->wtc, 0, tc_blob_bytes(M)));
@@ -287,7 +278,6 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 }
 
 int rnb_destroy(rnb_ctx* c) {
-	settle(c);
 	if (!c) return RNB_OK;
 	void* ptrs[] = {c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps, c->density_grid, c->density_tmp, c->bitfield, c->mean_acc, c->mean, c->gpos, c->gidx, c->gdens,
 	                c->views_dev, c->ray_n, c->ray_indices, c->numsteps, c->counters, c->n_fwd, c->cbase, c->n_emit, c->ray_geom, c->ts, c->ray_dirw, c->loss_out, c->stats,
@@ -300,14 +290,11 @@ int rnb_destroy(rnb_ctx* c) {
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
 	if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
 	if (c->ev_march) cudaEventDestroy(c->ev_march);
-	if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
-	if (c->ev_loss) cudaEventDestroy(c->ev_loss);
-	if (c->ev_copy) cudaEventDestroy(c->ev_copy);
 	delete c;
 	return RNB_OK;
 }
 
-int rnb_param_layout(rnb_ctx* c, uint64_t out[5]) { settle(c);
+int rnb_param_layout(rnb_ctx* c, uint64_t out[5]) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	out[0] = c->off_sdf; out[1] = c->off_rgb; out[2] = c->M.off_grid; out[3] = c->M.off_var; out[4] = c->M.n_params;
 	return RNB_OK;
@@ -332,7 +319,7 @@ static void builtin_sphere_init(const rnb_ctx* c, std::vector<float>& w) {
 	for (uint32_t o = 1; o < 16; ++o) for (uint32_t i = 0; i < W; ++i) w[(size_t)W * IN + (size_t)o * W + i] = (r.next_float() * 2 - 1) * 0.1f;
 }
 
-int rnb_init_params(rnb_ctx* c, const float* sdf_init, size_t n_sdf_init) { settle(c);
+int rnb_init_params(rnb_ctx* c, const float* sdf_init, size_t n_sdf_init) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	const ModelDev& M = c->M;
 	std::seed_seq seq{c->cfg.seed};                 // trainer.h:54-60
@@ -368,25 +355,25 @@ int rnb_init_params(rnb_ctx* c, const float* sdf_init, size_t n_sdf_init) { sett
 	return RNB_OK;
 }
 
-int rnb_set_params_fp32(rnb_ctx* c, const float* p, size_t n) { settle(c);
+int rnb_set_params_fp32(rnb_ctx* c, const float* p, size_t n) {
 	if (!c || !p || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
 	CU(cudaMemcpy(c->master, p, n * 4, cudaMemcpyHostToDevice));
 	launch_cast_params(0, c->M.n_params, c->master, c->params);
 	CU(cudaDeviceSynchronize());
 	return RNB_OK;
 }
-int rnb_get_params_fp32(rnb_ctx* c, float* p, size_t n) { settle(c);
+int rnb_get_params_fp32(rnb_ctx* c, float* p, size_t n) {
 	if (!c || !p || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
 	CU(cudaMemcpy(p, c->master, n * 4, cudaMemcpyDeviceToHost));
 	return RNB_OK;
 }
-int rnb_export_params_fp16(rnb_ctx* c, uint16_t* host, size_t n, int use_ema) { settle(c);
+int rnb_export_params_fp16(rnb_ctx* c, uint16_t* host, size_t n, int use_ema) {
 	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
 	CU(cudaMemcpy(host, use_ema ? c->ema : c->params, n * 2, cudaMemcpyDeviceToHost));
 	return RNB_OK;
 }
 // Trainer::deserialize (trainer.h:263-275): fp16 params in, fp32 master re-derived, optimizer moments restart
-int rnb_import_params_fp16(rnb_ctx* c, const uint16_t* host, size_t n) { settle(c);
+int rnb_import_params_fp16(rnb_ctx* c, const uint16_t* host, size_t n) {
 	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
 	CU(cudaMemcpy(c->params, host, n * 2, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(c->ema, host, n * 2, cudaMemcpyHostToDevice));
@@ -396,39 +383,39 @@ int rnb_import_params_fp16(rnb_ctx* c, const uint16_t* host, size_t n) { settle(
 	CU(cudaDeviceSynchronize());
 	return RNB_OK;
 }
-int rnb_export_density_grid(rnb_ctx* c, float* host, size_t n, uint32_t* ema_step) { settle(c);
+int rnb_export_density_grid(rnb_ctx* c, float* host, size_t n, uint32_t* ema_step) {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "density grid is 128^3 floats");
 	CU(cudaMemcpy(host, c->density_grid, n * 4, cudaMemcpyDeviceToHost));
 	if (ema_step) *ema_step = c->density_ema_step;
 	return RNB_OK;
 }
-int rnb_get_bitfield(rnb_ctx* c, uint8_t* host, size_t n) { settle(c);
+int rnb_get_bitfield(rnb_ctx* c, uint8_t* host, size_t n) {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "bitfield is 128^3 bytes");
 	CU(cudaMemcpy(host, c->bitfield, n, cudaMemcpyDeviceToHost));
 	return RNB_OK;
 }
-int rnb_set_bitfield(rnb_ctx* c, const uint8_t* host, size_t n) { settle(c);
+int rnb_set_bitfield(rnb_ctx* c, const uint8_t* host, size_t n) {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "bitfield is 128^3 bytes");
 	drop_prelaunch(c);
 	CU(cudaMemcpy(c->bitfield, host, n, cudaMemcpyHostToDevice));
 	return RNB_OK;
 }
-int rnb_get_train_state(rnb_ctx* c, uint32_t out[4]) { settle(c);
+int rnb_get_train_state(rnb_ctx* c, uint32_t out[4]) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	out[0] = c->training_step; out[1] = c->rays_per_batch; out[2] = c->n_rays_total; out[3] = c->measured_before;
 	return RNB_OK;
 }
-int rnb_set_train_state(rnb_ctx* c, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) { settle(c);
+int rnb_set_train_state(rnb_ctx* c, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) {
 	if (c) drop_prelaunch(c);
 	if (!c || rays_per_batch == 0 || rays_per_batch > (1u << 18)) return fail(RNB_ERR_INVALID, "bad train state");
 	c->training_step = training_step; c->rays_per_batch = rays_per_batch; c->n_rays_total = n_rays_total; c->measured_before = measured_before;
 	return ensure_ray_capacity(c, rays_per_batch);
 }
-int rnb_get_rng(rnb_ctx* c, uint64_t out[4]) { settle(c);
+int rnb_get_rng(rnb_ctx* c, uint64_t out[4]) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	out[0] = c->rng.state; out[1] = c->rng.inc; out[2] = c->density_rng.state; out[3] = c->density_rng.inc; return RNB_OK;
 }
-int rnb_set_rng(rnb_ctx* c, const uint64_t in[4]) { settle(c);
+int rnb_set_rng(rnb_ctx* c, const uint64_t in[4]) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	drop_prelaunch(c);
 	c->rng.state = in[0]; c->rng.inc = in[1]; c->density_rng.state = in[2]; c->density_rng.inc = in[3]; return RNB_OK;
@@ -459,8 +446,8 @@ static int set_views(rnb_ctx* c, const rnb_view* views, uint32_t n, bool upload)
 	c->n_views = n;
 	return RNB_OK;
 }
-int rnb_set_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { settle(c); return set_views(c, v, n, false); }
-int rnb_upload_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { settle(c); return set_views(c, v, n, true); }
+int rnb_set_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { return set_views(c, v, n, false); }
+int rnb_upload_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { return set_views(c, v, n, true); }
 
 // ---- dataset ingest -----------------------------------------------------------------------------------------
 // stbi_load_16(path, &w, &h, &comp, 4) as load_nerf uses it (src/nerf_loader.cu:612,653): any PNG -> 16-bit RGBA in host memory
@@ -474,7 +461,7 @@ void rnb_free_host(void* p) { free(p); }
 
 // the image half of load_nerf (src/nerf_loader.cu:556-760): decode every normal / albedo map on host threads into pinned staging
 // and upload; meta[i] carries intrinsics and the camera matrix (pixel pointers ignored; w/h checked against the files when non-zero)
-int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const char* const* normal_paths, const char* const* albedo_paths, uint32_t threads, void* stream) { settle(c);
+int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const char* const* normal_paths, const char* const* albedo_paths, uint32_t threads, void* stream) {
 	if (!c || !meta || !normal_paths || n == 0) return fail(RNB_ERR_INVALID, "no views");
 	std::vector<const char*> paths(2 * (size_t)n, nullptr);
 	for (uint32_t i = 0; i < n; ++i) {
@@ -501,7 +488,7 @@ int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const 
 
 int rnb_set_flags(rnb_ctx* c, const rnb_flags* f) { if (!c || !f) return fail(RNB_ERR_INVALID, "null argument"); c->flags = *f; return RNB_OK; }
 
-int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t ema_step) { settle(c);
+int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t ema_step) {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "density grid is 128^3 floats");
 	drop_prelaunch(c);
 	CU(cudaMemcpy(c->density_grid, host, n * 4, cudaMemcpyHostToDevice));
@@ -542,7 +529,6 @@ static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint3
 	return RNB_OK;
 }
 int rnb_prep(rnb_ctx* c, void* stream) {
-	if (c && c->unsettled_valid && c->unsettled != (cudaStream_t)stream) settle(c);
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	drop_prelaunch(c);
 	if (c->training_step < 256) return density_update(c, (cudaStream_t)stream, GRID_CELLS, 0);
@@ -587,21 +573,19 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt, uin
 	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->ray_n, c->ray_indices, c->numsteps, c->counters),
 	                   launch_emit(st, R, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4),
 	                   launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw)));
-	KT("pass_a_sdf_normal", 2, (net_pack(c, st, c->params), net_pass_a(c, st, vl, c->pos4, c->counters + 1, max_inference)));
+	if (c->pre_armed && c->pre_at == 3) CU(cudaEventRecord(c->ev_bwd, st));      // ray_n / ray_geom / ts have been consumed: the next march may overwrite them
+	// weight blobs for this step's kernels: the mma.sync panel copy only when one of its kernels runs in the step (cross-check paths)
+	const bool all_tc = c->use_tc && c->use_tc_bwd;
+	KT("pass_a_sdf_normal", all_tc ? 2 : 3, ((all_tc ? (void)launch_tc(0, st, c->M, c->params, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm) : net_pack(c, st, c->params)),
+	                                         net_pass_a(c, st, vl, c->pos4, c->counters + 1, max_inference)));
+	if (c->pre_armed && c->pre_at == 2) CU(cudaEventRecord(c->ev_bwd, st));
 	KT("compact", 3, (launch_compact_count(st, R, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd),
 	                 launch_scan_compact(st, c->counters, local_target, c->n_fwd, c->cbase, c->n_emit, c->stats),
 	                 launch_gather_compacted(st, R, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4)));
 	KT("pass_b_forward", 1, net_pass_b(c, st, c->params, vl, c->cpos4, c->counters + 4, c->cap_compact, c->ray_dirw));
 	KT("loss", 2, launch_loss(st, R, c->flags, R, nrt, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
 	            c->out16, c->dout16, c->loss_out, c->stats));
-	if (c->async_end && G == 1 && !c->prof) {      // counters and loss sums are final here: read them back in the shadow of the backward
-		CU(cudaEventRecord(c->ev_loss, st));
-		CU(cudaStreamWaitEvent(c->copy_st, c->ev_loss, 0));
-		CU(cudaMemcpyAsync(c->counters_host, c->counters, 8 * 4, cudaMemcpyDeviceToHost, c->copy_st));
-		CU(cudaMemcpyAsync(c->stats_host, c->stats, 8 * 4, cudaMemcpyDeviceToHost, c->copy_st));
-		CU(cudaEventRecord(c->ev_copy, c->copy_st));
-		c->early_copy = true;
-	}
+	if (c->pre_armed && c->pre_at == 1) CU(cudaEventRecord(c->ev_bwd, st));
 	KT("backward", c->use_mma ? 1 : 9, net_backward(c, st, vl, c->counters + 3, local_target, local_target, c->counters + 3));
 	CU(cudaGetLastError());
 	return RNB_OK;
@@ -628,7 +612,6 @@ int rnb_train_step_begin(rnb_ctx* c, void* stream) {
 	if (!c->views_dev) return fail(RNB_ERR_STATE, "no dataset: call rnb_set_dataset / rnb_upload_dataset first");
 	if (c->in_step) return fail(RNB_ERR_STATE, "rnb_train_step_begin called twice");
 	cudaStream_t st = (cudaStream_t)stream;
-	if (c->unsettled_valid && c->unsettled != st) settle(c);
 	const uint32_t R = c->rays_per_batch;
 	int rc = ensure_ray_capacity(c, R); if (rc) return rc;
 	uint32_t max_inference;                                         // testbed_nerf.cu:3891-3896
@@ -637,15 +620,18 @@ int rnb_train_step_begin(rnb_ctx* c, void* stream) {
 	if (c->training_step == 0) c->n_rays_total = 0;                 // :3906-3911
 	const uint32_t nrt = c->n_rays_total; c->n_rays_total += R;
 	c->step_R = R; c->step_nrt = nrt;
+	// pre-launch the NEXT step's march on the side stream (pinned batch size only: the adaptive controller fixes the next batch size
+	// after this step's counters are read; not on steps that refresh the occupancy grid first; not while profiling stages)
+	{
+		const uint32_t ts_next = c->training_step + 1, skip = std::min(std::max(ts_next / 16u, 1u), 16u);
+		c->pre_armed = c->cfg.pin_rays_per_batch && !c->prof && c->prelaunch && ts_next % skip != 0 && R <= c->cap_rays;
+	}
 	rc = step_front(c, st, R, nrt, max_inference); if (rc) return rc;
 	c->rng.advance();                                               // :4118
 	c->in_step = true;
-	// pre-launch the NEXT step's march behind this step's backward (pinned batch size only: the adaptive controller fixes the next
-	// batch size after this step's counters are read; not on steps that refresh the occupancy grid first; not while profiling stages)
 	{
-		const uint32_t ts_next = c->training_step + 1, skip = std::min(std::max(ts_next / 16u, 1u), 16u);
-		if (c->cfg.pin_rays_per_batch && !c->prof && c->prelaunch && ts_next % skip != 0 && R <= c->cap_rays) {
-			CU(cudaEventRecord(c->ev_bwd, st));
+		if (c->pre_armed) {      // the side stream waits for the point chosen by pre_at (recorded inside step_front, or here: behind the backward)
+			if (c->pre_at == 0) CU(cudaEventRecord(c->ev_bwd, st));
 			CU(cudaStreamWaitEvent(c->side, c->ev_bwd, 0));
 			launch_march(c->side, R, c->cfg.world_size, c->cfg.rank, c->n_rays_total, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts);
 			CU(cudaEventRecord(c->ev_march, c->side));
@@ -665,16 +651,10 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
 	c->in_step = false;
 	// Counters::update_after_training (:3532-3558).  The sample counts are needed on the host for next step's
 	// max_inference and for the batch-size controller; they are small and copied asynchronously.
-	if (c->early_copy) {
-		CU(cudaEventSynchronize(c->ev_copy));
-		c->early_copy = false; c->unsettled = st; c->unsettled_valid = true;
-	} else {
-		CU(cudaMemcpyAsync(c->counters_host, c->counters, 8 * 4, cudaMemcpyDeviceToHost, st));
-		CU(cudaMemcpyAsync(c->stats_host, c->stats, 8 * 4, cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-		c->unsettled_valid = false;
-		prof_resolve(c);
-	}
+	CU(cudaMemcpyAsync(c->counters_host, c->counters, 8 * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(c->stats_host, c->stats, 8 * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	prof_resolve(c);
 	const uint32_t total = c->counters_host[2];
 	c->measured_before = c->counters_host[1]; c->measured = total;
 	const uint32_t R = c->step_R;
@@ -712,7 +692,7 @@ int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
 // step counters, density grid + bitfield, both pcg32 streams, the controller counters.  (The gradient buffer is zero between
 // steps.)  Used by bench.py to time `value` and `e2e` on the SAME training steps; the file-level snapshot of the reference
 // (src/testbed.cu:3280-3390) keeps only the EMA fp16 weights and the density grid and goes through rnb_export_* / rnb_import_*.
-int rnb_checkpoint_save(rnb_ctx* c) { settle(c);
+int rnb_checkpoint_save(rnb_ctx* c) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (c->in_step) return fail(RNB_ERR_STATE, "checkpoint inside a step");
 	drop_prelaunch(c);
@@ -734,7 +714,7 @@ int rnb_checkpoint_save(rnb_ctx* c) { settle(c);
 	k.valid = true;
 	return RNB_OK;
 }
-int rnb_checkpoint_restore(rnb_ctx* c) { settle(c);
+int rnb_checkpoint_restore(rnb_ctx* c) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->ck.valid) return fail(RNB_ERR_STATE, "no checkpoint");
 	if (c->in_step) return fail(RNB_ERR_STATE, "restore inside a step");
@@ -757,14 +737,14 @@ int rnb_checkpoint_restore(rnb_ctx* c) { settle(c);
 	return RNB_OK;
 }
 
-int rnb_profile_enable(rnb_ctx* c, int on) { settle(c);
+int rnb_profile_enable(rnb_ctx* c, int on) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	c->prof = on != 0;
 	if (on) { for (auto& a : c->prof_acc) { a.ms = 0; a.calls = 0; } }
 	return RNB_OK;
 }
 // names_buf receives ';'-separated stage names; ms / calls are parallel arrays of capacity *n (in) and count (out)
-int rnb_profile_read(rnb_ctx* c, char* names_buf, size_t names_cap, double* ms, uint64_t* calls, uint32_t* n) { settle(c);
+int rnb_profile_read(rnb_ctx* c, char* names_buf, size_t names_cap, double* ms, uint64_t* calls, uint32_t* n) {
 	if (!c || !n) return fail(RNB_ERR_INVALID, "null argument");
 	std::string names; uint32_t k = 0;
 	for (auto& a : c->prof_acc) { if (k >= *n) break; names += a.name; names += ';'; ms[k] = a.ms; calls[k] = a.calls; ++k; }
@@ -774,15 +754,15 @@ int rnb_profile_read(rnb_ctx* c, char* names_buf, size_t names_cap, double* ms, 
 }
 int rnb_launch_count(rnb_ctx* c, uint64_t* out) { if (!c || !out) return fail(RNB_ERR_INVALID, "null argument"); *out = c->launches; return RNB_OK; }
 
-int rnb_grad_buffer(rnb_ctx* c, float** g, uint64_t* n) { settle(c); if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *g = c->grads; *n = c->M.n_params; return RNB_OK; }
+int rnb_grad_buffer(rnb_ctx* c, float** g, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *g = c->grads; *n = c->M.n_params; return RNB_OK; }
 // host copies for parity tests: the fp32 gradient accumulators (valid between rnb_train_step_begin and _end) and the per-ray
 // loss terms of the last step (loss_output / ek_loss_output / mask_loss_output of compute_loss_kernel, testbed_nerf.cu:1396-2097)
-int rnb_get_grads_fp32(rnb_ctx* c, float* host, size_t n) { settle(c);
+int rnb_get_grads_fp32(rnb_ctx* c, float* host, size_t n) {
 	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad gradient buffer");
 	CU(cudaMemcpy(host, c->grads, n * 4, cudaMemcpyDeviceToHost));
 	return RNB_OK;
 }
-int rnb_get_ray_losses(rnb_ctx* c, uint32_t cap, uint32_t* ray_idx, float* loss3, uint32_t* n_out) { settle(c);
+int rnb_get_ray_losses(rnb_ctx* c, uint32_t cap, uint32_t* ray_idx, float* loss3, uint32_t* n_out) {
 	if (!c || !ray_idx || !loss3 || !n_out) return fail(RNB_ERR_INVALID, "null argument");
 	uint32_t K = 0; CU(cudaMemcpy(&K, c->counters, 4, cudaMemcpyDeviceToHost));
 	K = std::min(K, std::min(cap, c->cap_rays));
@@ -792,7 +772,7 @@ int rnb_get_ray_losses(rnb_ctx* c, uint32_t cap, uint32_t* ray_idx, float* loss3
 	return RNB_OK;
 }
 // per kept ray of the last step: samples marched and samples kept by the transmittance cut (profiling / tests)
-int rnb_get_ray_counts(rnb_ctx* c, uint32_t cap, uint32_t* marched, uint32_t* kept, uint32_t* n_out) { settle(c);
+int rnb_get_ray_counts(rnb_ctx* c, uint32_t cap, uint32_t* marched, uint32_t* kept, uint32_t* n_out) {
 	if (!c || !marched || !kept || !n_out) return fail(RNB_ERR_INVALID, "null argument");
 	uint32_t K = 0; CU(cudaMemcpy(&K, c->counters, 4, cudaMemcpyDeviceToHost));
 	K = std::min(K, std::min(cap, c->cap_rays));
@@ -803,9 +783,9 @@ int rnb_get_ray_counts(rnb_ctx* c, uint32_t cap, uint32_t* marched, uint32_t* ke
 	*n_out = K;
 	return RNB_OK;
 }
-int rnb_stat_buffer(rnb_ctx* c, float** s, uint64_t* n) { settle(c); if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *s = c->stats; *n = 8; return RNB_OK; }
+int rnb_stat_buffer(rnb_ctx* c, float** s, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *s = c->stats; *n = 8; return RNB_OK; }
 
-int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream) { settle(c);
+int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream) {
 	if (!c || !xyz_dev) return fail(RNB_ERR_INVALID, "null argument");
 	cudaStream_t st = (cudaStream_t)stream;
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
@@ -829,7 +809,7 @@ int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, flo
 // SDF on a lattice — Testbed::get_density_on_grid (src/testbed_nerf.cu:4218-4269: generate_grid_samples_nerf_uniform + NerfNetwork::sdf in
 // 1 M-point batches + grid_samples_half_to_float) in one launch: the lattice positions are generated inside the tcgen05 probe kernel
 // (the reference materialises 12 B per point first: 12.9 GB at 1024^3).  out_dev[x + y rx + z rx ry] = sdf (incl. bias), fp32.
-int rnb_sdf_on_grid(rnb_ctx* c, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float* out_dev, int use_ema, void* stream) { settle(c);
+int rnb_sdf_on_grid(rnb_ctx* c, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float* out_dev, int use_ema, void* stream) {
 	if (!c || !res || !aabb_min || !aabb_max || !out_dev) return fail(RNB_ERR_INVALID, "null argument");
 	if ((uint64_t)res[0] * res[1] * res[2] > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice larger than 2^32 points");
 	if (!c->use_tc) return fail(RNB_ERR_STATE, "rnb_sdf_on_grid needs the tcgen05 network path");
@@ -852,7 +832,6 @@ static void mesh_free(rnb_ctx* c) {
 // (src/marching_cubes.cu:794-822, :722-728, src/testbed_nerf.cu:4193-4216).  with_colors == 0 skips the network pass (colours zero).
 int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh,
                                     int with_colors, int use_ema, void* stream, rnb_mesh_info* info) {
-	settle(c);
 	if (!c || !density_dev || !res || !aabb_min || !aabb_max) return fail(RNB_ERR_INVALID, "null argument");
 	if (res[0] == 0 || res[1] == 0 || res[2] == 0 || res[0] % 16 != 0) return fail(RNB_ERR_INVALID, "lattice x resolution must be a positive multiple of 16");
 	if ((uint64_t)res[0] * res[1] * res[2] > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice larger than 2^32 points");
@@ -902,7 +881,7 @@ int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const 
 }
 
 // Testbed::marching_cubes (src/testbed_nerf.cu:4297-4348): resolution rounded up to multiples of 16, SDF sweep, extraction, normals, colours.
-int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_min[3], const float aabb_max[3], float thresh, int use_ema, void* stream, rnb_mesh_info* info) { settle(c);
+int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_min[3], const float aabb_max[3], float thresh, int use_ema, void* stream, rnb_mesh_info* info) {
 	if (!c || !res_in || !aabb_min || !aabb_max) return fail(RNB_ERR_INVALID, "null argument");
 	const uint32_t res[3] = {next_multiple(res_in[0], 16u), next_multiple(res_in[1], 16u), next_multiple(res_in[2], 16u)};
 	const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
@@ -920,7 +899,7 @@ int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_mi
 	return rc;
 }
 
-int rnb_mesh_buffers(rnb_ctx* c, float** verts, float** normals, float** colors, uint32_t** indices, rnb_mesh_info* info) { settle(c);
+int rnb_mesh_buffers(rnb_ctx* c, float** verts, float** normals, float** colors, uint32_t** indices, rnb_mesh_info* info) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->mesh.verts) return fail(RNB_ERR_STATE, "no mesh: call rnb_marching_cubes first");
 	if (verts) *verts = c->mesh.verts;
@@ -932,7 +911,7 @@ int rnb_mesh_buffers(rnb_ctx* c, float** verts, float** normals, float** colors,
 }
 
 // host copies of the mesh (Testbed::compute_marching_cubes_mesh, src/python_api.cu:99-130); each pointer may be null
-int rnb_mesh_download(rnb_ctx* c, float* verts, float* normals, float* colors, uint32_t* indices) { settle(c);
+int rnb_mesh_download(rnb_ctx* c, float* verts, float* normals, float* colors, uint32_t* indices) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->mesh.verts) return fail(RNB_ERR_STATE, "no mesh: call rnb_marching_cubes first");
 	const size_t vb = (size_t)c->mesh.n_verts_padded * 12;
@@ -956,7 +935,7 @@ int rnb_save_mesh(const float* verts_dev, const float* normals_dev, const float*
 }
 
 // ---- stage-level entry points (host buffers) ------------------------------------------------------------------------
-int rnb_stage_generate(rnb_ctx* c, uint32_t n_rays, uint32_t n_rays_total, uint32_t max_samples, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t counters[2]) { settle(c);
+int rnb_stage_generate(rnb_ctx* c, uint32_t n_rays, uint32_t n_rays_total, uint32_t max_samples, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t counters[2]) {
 	if (!c || !c->views_dev) return fail(RNB_ERR_STATE, "no dataset");
 	if (max_samples > c->max_samples) return fail(RNB_ERR_INVALID, "max_samples exceeds capacity");
 	drop_prelaunch(c);
@@ -1003,7 +982,7 @@ static int upload_coords(rnb_ctx* c, const float* coords, size_t n, float4* dst_
 	return RNB_OK;
 }
 
-int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, float* out16, float* normal) { settle(c);
+int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, float* out16, float* normal) {
 	if (!c || !coords || !out16) return fail(RNB_ERR_INVALID, "null argument");
 	if (n > c->cap_compact) return fail(RNB_ERR_INVALID, "too many samples for one stage call");
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
@@ -1025,7 +1004,6 @@ int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, fl
 
 int rnb_stage_loss(rnb_ctx* c, const float* out16_c, const uint32_t* ray_indices, const uint32_t* n_fwd, const uint32_t* cbase, const uint32_t* n_emit,
                    uint32_t K, uint32_t n_rays, uint32_t n_rays_total, float* dout16, float* loss, float* ek, float* mask) {
-	settle(c);
 	if (!c || !c->views_dev) return fail(RNB_ERR_STATE, "no dataset");
 	int rc = ensure_ray_capacity(c, std::max(K, n_rays)); if (rc) return rc;
 	size_t total = 0; for (uint32_t k = 0; k < K; ++k) total = std::max<size_t>(total, (size_t)cbase[k] + n_fwd[k]);
@@ -1050,7 +1028,7 @@ int rnb_stage_loss(rnb_ctx* c, const float* out16_c, const uint32_t* ray_indices
 	return RNB_OK;
 }
 
-int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, size_t n, uint32_t n_in_rollover, float* grads) { settle(c);
+int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, size_t n, uint32_t n_in_rollover, float* grads) {
 	if (!c || !coords || !dout16 || !grads) return fail(RNB_ERR_INVALID, "null argument");
 	if (n > c->cfg.target_batch_size) return fail(RNB_ERR_INVALID, "too many samples");
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
@@ -1070,7 +1048,7 @@ int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, siz
 	return RNB_OK;
 }
 
-int rnb_stage_optimizer(rnb_ctx* c, const float* grads_host) { settle(c);
+int rnb_stage_optimizer(rnb_ctx* c, const float* grads_host) {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (grads_host) CU(cudaMemcpy(c->grads, grads_host, (size_t)c->M.n_params * 4, cudaMemcpyHostToDevice));
 	int rc = optimizer_step(c, 0); if (rc) return rc;
