@@ -213,6 +213,9 @@ def _shell_bitfield():
     return out
 
 
+DP_MODE_DEFAULT = "allreduce"      # N > 1: "allreduce" (replicated Adam) or "sharded" (reduce-scatter + sharded Adam + all-gather); RNB_DP overrides
+
+
 def _network_path():
     # mirrors the selection in csrc/rnb_api.cu (RNB_NETWORK=simt|mma, RNB_BACKWARD=mma are cross-check paths)
     net = os.environ.get("RNB_NETWORK", "")
@@ -269,12 +272,26 @@ def main():
     dataset_bytes = sum(v["normal"].nbytes for v in views)
 
     grad_t = stat_t = None
+    dp_mode = os.environ.get("RNB_DP", DP_MODE_DEFAULT) if world > 1 else "single"
     if world > 1:
         gp, gn = t.grad_buffer(); sp, sn = t.stat_buffer()
 
         class _Arr:
-            def __init__(self, p, n): self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (p, False), "version": 3}
-        grad_t = torch.as_tensor(_Arr(gp, gn), device="cuda"); stat_t = torch.as_tensor(_Arr(sp, sn), device="cuda")
+            def __init__(self, p, n, ts="<f4"): self.__cuda_array_interface__ = {"shape": (n,), "typestr": ts, "data": (p, False), "version": 3}
+        stat_t = torch.as_tensor(_Arr(sp, sn), device="cuda")
+        if dp_mode == "sharded":
+            # sharded optimizer: reduce-scatter of the fp32 gradients, Adam/EMA on this rank's 1/N of the parameters, all-gather
+            # of the binary16 training parameters.  The arrays are padded to a multiple of 512 elements, so the shards are equal.
+            pp, _, _, npad = t.param_buffers()
+            shard = npad // world
+            assert shard * world == npad and shard % 8 == 0
+            grad_t = torch.as_tensor(_Arr(gp, npad), device="cuda")
+            par_t = torch.as_tensor(_Arr(pp, npad, "<f2"), device="cuda")
+            red_t = torch.zeros(shard, dtype=torch.float32, device="cuda")
+            own_t = torch.zeros(shard, dtype=torch.float16, device="cuda")
+            t.set_optimizer_shard(rank * shard, (rank + 1) * shard, red_t.data_ptr())
+        else:
+            grad_t = torch.as_tensor(_Arr(gp, gn), device="cuda")
 
     def step(want_stats):
         if world == 1:
@@ -284,6 +301,12 @@ def main():
         if ts % skip == 0:
             t.training_prep_nerf()
         t.train_step_begin()
+        if dp_mode == "sharded":
+            dist.reduce_scatter_tensor(red_t, grad_t); dist.all_reduce(stat_t)
+            st = t.train_step_end()
+            own_t.copy_(par_t[rank * shard:(rank + 1) * shard])
+            dist.all_gather_into_tensor(par_t, own_t)         # every rank's next forward sees all updated shards
+            return st
         dist.all_reduce(grad_t); dist.all_reduce(stat_t)      # the single gradient exchange of the step (NCCL over NVLink)
         return t.train_step_end()
 
@@ -354,7 +377,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_global": R, "pretrain_steps": args.pretrain, "samples_per_step": int(ns), "compacted_samples_per_step": int(nc), "live_hash_levels": L,
                        "cache": "working set (hash table 21 MB + gradients 42 MB + optimizer state 170 MB + 1.5 GB images) exceeds L2; no flush needed",
-                       "parallelism": "dp%d ray-sharded (4096 rays + 2^18-sample batch per GPU), fp32 gradient all-reduce" % n_gpus if n_gpus > 1 else "single GPU", "network_path": _network_path(),
+                       "parallelism": ("dp%d ray-sharded (4096 rays + 2^18-sample batch per GPU), " % n_gpus + ("fp32 gradient reduce-scatter + sharded Adam + fp16 parameter all-gather" if dp_mode == "sharded" else "fp32 gradient all-reduce")) if n_gpus > 1 else "single GPU", "network_path": _network_path(),
                        "dataset_upload_s": round(upload_s, 3), "dataset_bytes": dataset_bytes, "scene_render_s": round(gen_s, 1)},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,

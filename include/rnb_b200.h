@@ -182,6 +182,15 @@ int rnb_train_step_begin(rnb_ctx* ctx, void* stream);
 int rnb_train_step_end(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
 int rnb_grad_buffer(rnb_ctx* ctx, float** grads_dev, uint64_t* n);
 int rnb_stat_buffer(rnb_ctx* ctx, float** stats_dev, uint64_t* n);
+/* Sharded optimizer for data parallelism (new; the reference is single-GPU): instead of all-reducing the fp32 gradient buffer and running
+ * Adam/EMA on every rank, rank r owns parameters [begin, end): the caller REDUCE-SCATTERS the gradient buffer (rnb_grad_buffer; the arrays
+ * are allocated and zero up to n_padded, a multiple of 512, so that equal shards exist for every power-of-two world), rnb_train_step_end
+ * updates only the shard (fp32 master weights and Adam moments of the other shards are never touched on this rank) and clears the
+ * whole gradient buffer, and the caller ALL-GATHERS the binary16 training parameters (params_fp16_dev, n_padded elements).  The EMA copy
+ * is maintained per shard: all-gather ema_fp16_dev once before exporting a snapshot / extracting a mesh.
+ * reduced_grads_dev: where the reduced shard lives (end - begin floats; NULL = in place in the gradient buffer).  end == 0 switches back. */
+int rnb_param_buffers(rnb_ctx* ctx, void** params_fp16_dev, void** ema_fp16_dev, uint64_t* n_params, uint64_t* n_padded);
+int rnb_set_optimizer_shard(rnb_ctx* ctx, uint64_t begin, uint64_t end, const float* reduced_grads_dev);
 /* host copies for parity checks: gradient accumulators (fp32, loss-scaled; the reference's Trainer::param_gradients(),
  * trainer.h:240, is the fp16 equivalent) and, per kept ray, its index and (loss, ek_loss, mask_loss) as written by
  * compute_loss_kernel_train_nerf (src/testbed_nerf.cu:1833-1841) */

@@ -46,6 +46,7 @@ struct Oracle {
 	std::vector<float> last_loss, last_ek, last_mask;   // per kept ray, in ray_indices order
 	// data-parallel restatement: rank r of `world` marches rays i == r (mod world); sums[] are all-reduced with the gradients
 	uint32_t world = 1, rank = 0; bool in_step = false; uint32_t step_R = 0;
+	size_t shard_begin = 0, shard_end = 0;      // data-parallel optimizer shard (end == 0: all parameters)
 	double sums[4] = {0, 0, 0, 0};   // loss, ek, mask, compacted samples
 	uint32_t cnt_kept = 0, cnt_samples = 0, cnt_total = 0, cnt_trained = 0;
 };
@@ -151,6 +152,10 @@ void orc_set_train_state(Oracle* o, uint32_t training_step, uint32_t rays_per_ba
 	o->training_step = training_step; o->rays_per_batch = rays_per_batch; o->n_rays_total = n_rays_total; o->measured_before = measured_before; o->pin_rays = pin_rays; o->target_batch = target_batch;
 }
 void orc_set_world(Oracle* o, uint32_t world, uint32_t rank) { o->world = world ? world : 1; o->rank = rank; }
+// data-parallel restatement of the sharded optimizer: Adam/EMA on [begin, end) only; the binary16 training weights of the other
+// shards are installed by the caller from the all-gather (orc_set_half_params)
+void orc_set_opt_shard(Oracle* o, uint64_t begin, uint64_t end) { o->shard_begin = (size_t)begin; o->shard_end = (size_t)end; }
+void orc_set_half_params(Oracle* o, const float* half_widened) { std::memcpy(o->pv.data(), half_widened, o->m.n_params * 4); }
 void orc_set_rng(Oracle* o, uint64_t state, uint64_t inc, uint64_t dstate, uint64_t dinc) { o->rng.state = state; o->rng.inc = inc; o->density_rng.state = dstate; o->density_rng.inc = dinc; }
 void orc_get_rng(Oracle* o, uint64_t* out) { out[0] = o->rng.state; out[1] = o->rng.inc; out[2] = o->density_rng.state; out[3] = o->density_rng.inc; }
 void orc_get_bitfield(Oracle* o, uint8_t* out) { std::memcpy(out, o->bitfield.data(), o->bitfield.size()); }
@@ -311,8 +316,10 @@ void orc_optimizer_step(Oracle* o) {
 	++o->opt_step;
 	const size_t n = o->m.n_params, n_mat = o->m.off_grid;
 	const size_t rgb_b = o->m.off_rgb, rgb_e = o->m.off_grid;
+	const size_t sb = o->shard_end ? o->shard_begin : 0, se = o->shard_end ? std::min(o->shard_end, n) : n;
 	parallel_for(o->threads, n, [&](int, size_t b, size_t e) {
 		for (size_t i = b; i < e; ++i) {
+			if (i < sb || i >= se) continue;
 			float gradient = hq(o->grads[i]) / o->loss_scale;
 			const bool is_mat = i < n_mat;
 			if (!is_mat && gradient == 0) continue;
@@ -334,7 +341,7 @@ void orc_optimizer_step(Oracle* o) {
 	const float d_old = 1 - (float)std::pow(o->ema_decay, o->opt_step - 1);
 	const float d_new = 1.0f / (1 - (float)std::pow(o->ema_decay, o->opt_step));
 	parallel_for(o->threads, n, [&](int, size_t b, size_t e) {
-		for (size_t i = b; i < e; ++i) o->ema[i] = hq((o->ema[i] * o->ema_decay * d_old + o->pv[i] * (1 - o->ema_decay)) * d_new);
+		for (size_t i = b; i < e; ++i) if (i >= sb && i < se) o->ema[i] = hq((o->ema[i] * o->ema_decay * d_old + o->pv[i] * (1 - o->ema_decay)) * d_new);
 	});
 }
 

@@ -45,6 +45,7 @@ void launch_loss(cudaStream_t, uint32_t, const rnb_flags&, uint32_t, uint32_t, u
 struct AdamParams {
 	float base_lr, beta1, beta2, eps, l2, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
 	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf; float log2_beta1, log2_beta2;
+	uint32_t shard_begin, shard_end; const float* gsrc;      // data-parallel optimizer shard (rnb_optim.cu)
 };
 void launch_adam_ema(cudaStream_t, const AdamParams&, float*, __half*, __half*, float*, float*, float*, uint32_t*);
 void launch_cast_params(cudaStream_t, uint32_t, const float*, __half*);
@@ -80,6 +81,8 @@ struct rnb_ctx {
 	// parameters / optimizer state
 	float* master = nullptr; __half* params = nullptr; __half* ema = nullptr; float* grads = nullptr; float* m1 = nullptr; float* m2 = nullptr; uint32_t* steps = nullptr;
 	uint32_t opt_step = 0; float lr_factor = 1.f;
+	size_t np_padded = 0;                              // per-parameter arrays are allocated (and zeroed) up to a multiple of 512 elements: equal shards for any power-of-two world
+	uint32_t shard_begin = 0, shard_end = 0; const float* shard_grads = nullptr;      // rnb_set_optimizer_shard; end == 0: the whole range
 	// occupancy
 	float* density_grid = nullptr; float* density_tmp = nullptr; uint8_t* bitfield = nullptr; double* mean_acc = nullptr; float* mean = nullptr;
 	float4* gpos = nullptr; uint32_t* gidx = nullptr; float* gdens = nullptr;
@@ -237,7 +240,8 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 	if (const char* e = getenv("RNB_SCATTER_AGG")) M.scatter_agg = (uint32_t)std::max(0, atoi(e));
 	M.scatter_agg = std::min(M.scatter_agg, M.n_levels);
 	for (uint32_t i = 0; i < M.scatter_agg; ++i) if (M.res[i] > 1024u) { M.scatter_agg = i; break; }      // the 10-bit cell key
-	const size_t np = M.n_params;
+	const size_t np = ((size_t)M.n_params + 511) / 512 * 512;      // padded capacity (the tail stays zero): collectives over equal shards
+	c->np_padded = np;
 	CU(cudaMalloc(&c->master, np * 4)); CU(cudaMalloc(&c->params, np * 2)); CU(cudaMalloc(&c->ema, np * 2)); CU(cudaMalloc(&c->grads, np * 4));
 	CU(cudaMalloc(&c->m1, np * 4)); CU(cudaMalloc(&c->m2, np * 4)); CU(cudaMalloc(&c->steps, np * 4));
 	CU(cudaMemset(c->master, 0, np * 4)); CU(cudaMemset(c->params, 0, np * 2)); CU(cudaMemset(c->ema, 0, np * 2)); CU(cudaMemset(c->grads, 0, np * 4));
@@ -602,6 +606,7 @@ static int optimizer_step(rnb_ctx* c, cudaStream_t st) {
 	A.ema_debias_new = 1.0f / (1 - (float)std::pow(c->cfg.ema_decay, c->opt_step));
 	A.n_params = c->M.n_params; A.n_matrix = c->M.off_grid; A.rgb_begin = c->off_rgb; A.rgb_end = c->M.off_grid; A.only_sdf = c->flags.only_sdf_training;
 	A.log2_beta1 = (float)std::log2((double)c->cfg.beta1); A.log2_beta2 = (float)std::log2((double)c->cfg.beta2);
+	A.shard_begin = c->shard_end ? c->shard_begin : 0u; A.shard_end = c->shard_end ? std::min(c->shard_end, c->M.n_params) : c->M.n_params; A.gsrc = c->shard_end ? c->shard_grads : nullptr;
 	KT("adam_ema", 1, launch_adam_ema(st, A, c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps));
 	CU(cudaGetLastError());
 	return RNB_OK;
@@ -781,6 +786,23 @@ int rnb_get_ray_counts(rnb_ctx* c, uint32_t cap, uint32_t* marched, uint32_t* ke
 	for (uint32_t k = 0; k < K; ++k) marched[k] = ns[2 * k];
 	CU(cudaMemcpy(kept, c->n_fwd, (size_t)K * 4, cudaMemcpyDeviceToHost));
 	*n_out = K;
+	return RNB_OK;
+}
+// ---- data-parallel optimizer sharding (new) ---------------------------------------------------------------
+int rnb_param_buffers(rnb_ctx* c, void** params_fp16, void** ema_fp16, uint64_t* n_params, uint64_t* n_padded) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (params_fp16) *params_fp16 = c->params;
+	if (ema_fp16) *ema_fp16 = c->ema;
+	if (n_params) *n_params = c->M.n_params;
+	if (n_padded) *n_padded = c->np_padded;
+	return RNB_OK;
+}
+int rnb_set_optimizer_shard(rnb_ctx* c, uint64_t begin, uint64_t end, const float* reduced_grads_dev) {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (c->in_step) return fail(RNB_ERR_STATE, "optimizer shard changed inside a step");
+	if (end == 0) { c->shard_begin = c->shard_end = 0; c->shard_grads = nullptr; return RNB_OK; }
+	if (begin % 8 || end % 8 || begin >= end || end > c->np_padded) return fail(RNB_ERR_INVALID, "optimizer shard must be a non-empty [begin, end) of multiples of 8 inside the padded parameter range");
+	c->shard_begin = (uint32_t)begin; c->shard_end = (uint32_t)end; c->shard_grads = reduced_grads_dev;
 	return RNB_OK;
 }
 int rnb_stat_buffer(rnb_ctx* c, float** s, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *s = c->stats; *n = 8; return RNB_OK; }

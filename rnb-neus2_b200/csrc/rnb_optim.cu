@@ -15,6 +15,9 @@ namespace rnb {
 struct AdamParams {
 	float base_lr, beta1, beta2, eps, l2, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
 	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf; float log2_beta1, log2_beta2;
+	// data-parallel optimizer shard: this rank updates parameters [shard_begin, shard_end) (multiples of 4) from gsrc[i - shard_begin]
+	// (the reduce-scattered gradient sum; NULL: the gradient buffer itself) and only clears the gradient buffer elsewhere
+	uint32_t shard_begin, shard_end; const float* gsrc;
 };
 
 // One thread owns 4 consecutive parameters: every array is moved with one 128-bit (fp32 / u32) or 64-bit (binary16) access.
@@ -45,15 +48,26 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
                                                   float* __restrict__ grads, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
 	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
 	if (i0 >= A.n_params) return;
+	if (i0 < A.shard_begin || i0 >= A.shard_end) {     // another rank's parameters: drop this rank's partial gradient, the weights arrive with the all-gather
+		if (i0 + 4 <= A.n_params) {
+			const float4 g = *reinterpret_cast<const float4*>(grads + i0);
+			if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
+		} else for (uint32_t i = i0; i < A.n_params; ++i) grads[i] = 0.f;
+		return;
+	}
 	if (i0 + 4 <= A.n_params) {
-		const float4 g = *reinterpret_cast<const float4*>(grads + i0);
+		float4 g = *reinterpret_cast<const float4*>(grads + i0);
+		if (A.gsrc) {                                   // the reduced gradient lives in the caller's reduce-scatter output
+			if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
+			g = *reinterpret_cast<const float4*>(A.gsrc + (i0 - A.shard_begin));
+		}
 		uint2 pw = *reinterpret_cast<const uint2*>(params + i0), pe = *reinterpret_cast<const uint2*>(ema + i0);
 		const bool anyg = g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f;
 		const bool mat = i0 < A.n_matrix;
 		if (!anyg && !mat && pw.x == pe.x && pw.y == pe.y) return;
 		__half* wh = reinterpret_cast<__half*>(&pw); __half* eh = reinterpret_cast<__half*>(&pe);
 		if (anyg || mat) {
-			if (anyg) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);     // consumed: ready for the next step's atomics
+			if (anyg && !A.gsrc) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);     // consumed: ready for the next step's atomics
 			const float4 w4 = *reinterpret_cast<const float4*>(master + i0), a4 = *reinterpret_cast<const float4*>(m1 + i0), b4 = *reinterpret_cast<const float4*>(m2 + i0);
 			const uint4 s4 = *reinterpret_cast<const uint4*>(steps + i0);
 			AdamLane S[4] = {{w4.x, a4.x, b4.x, s4.x}, {w4.y, a4.y, b4.y, s4.y}, {w4.z, a4.z, b4.z, s4.z}, {w4.w, a4.w, b4.w, s4.w}};
@@ -74,7 +88,7 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 		*reinterpret_cast<uint2*>(params + i0) = pw; *reinterpret_cast<uint2*>(ema + i0) = pe;
 	} else {
 		for (uint32_t i = i0; i < A.n_params; ++i) {
-			const float g32 = grads[i]; grads[i] = 0.f;
+			const float g32 = A.gsrc ? A.gsrc[i - A.shard_begin] : grads[i]; grads[i] = 0.f;
 			__half wh = params[i];
 			AdamLane S{master[i], m1[i], m2[i], steps[i]};
 			if (adam_one(A, i, g32, S, wh)) { master[i] = S.w; m1[i] = S.m1; m2[i] = S.m2; steps[i] = S.step; }

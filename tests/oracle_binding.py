@@ -225,6 +225,13 @@ class Oracle:
     def set_world(self, world, rank):
         self.L.orc_set_world(self.h, world, rank)
 
+    def set_opt_shard(self, begin, end):
+        self.L.orc_set_opt_shard(self.h, C.c_uint64(begin), C.c_uint64(end))
+
+    def set_half_params(self, hv):
+        hv = np.ascontiguousarray(hv, np.float32); assert hv.size == self.n_params
+        self.L.orc_set_half_params(self.h, _p(hv, C.c_float))
+
     def train_step_begin(self):
         self.L.orc_train_step_begin(self.h)
 

@@ -95,3 +95,67 @@ def test_two_rank_step_matches_single_process():
     cosv = float(gs[mlp].astype(np.float64) @ gd[mlp].astype(np.float64) / (np.linalg.norm(gs[mlp]) * np.linalg.norm(gd[mlp])))
     assert cosv > 0.999, cosv
     assert abs(float(res[0]["sums"][3]) - float(single.get_sums()[3])) < 1e-6     # global compacted count
+
+
+# ---- sharded optimizer: reduce-scatter + Adam on 1/G of the parameters + all-gather of the binary16 weights ----------
+def _worker_sharded(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rep = _make(rank, world, threads=1)          # replicated protocol: all-reduce, Adam everywhere (one thread: the oracle's float atomics
+    shd = _make(rank, world, threads=1)          # sharded protocol                                  arrive in a fixed order, runs are bit-reproducible)
+    n = rep.n_params
+    npad = (n + 511) // 512 * 512; shard = npad // world
+    b, e = rank * shard, min((rank + 1) * shard, n)
+    shd.set_opt_shard(rank * shard, (rank + 1) * shard)
+    out = {"equal_half": [], "equal_loss": []}
+    for step in range(2):
+        rep.train_step_begin()
+        g = torch.from_numpy(rep.get_grads().copy()); s = torch.from_numpy(rep.get_sums().copy())
+        dist.all_reduce(g); dist.all_reduce(s)
+        rep.set_grads(g.numpy()); rep.set_sums(s.numpy())
+        st_r = rep.train_step_end()
+
+        shd.train_step_begin()
+        gl = np.zeros(npad, np.float32); gl[:n] = shd.get_grads()
+        g2 = torch.from_numpy(gl); s2 = torch.from_numpy(shd.get_sums().copy())
+        dist.all_reduce(g2); dist.all_reduce(s2)          # gloo has no reduce-scatter: the shard of the all-reduced sum is the same numbers
+        mine = np.zeros(n, np.float32); mine[b:e] = g2.numpy()[b:e]          # everything outside the shard is dropped, as in the kernel
+        shd.set_grads(mine); shd.set_sums(s2.numpy())
+        st_s = shd.train_step_end()
+        hv = np.zeros(npad, np.float32); hv[:n] = shd.get_params()[1]
+        own = torch.from_numpy(hv[rank * shard:(rank + 1) * shard].copy())
+        parts = [torch.zeros(shard, dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(parts, own)
+        shd.set_half_params(torch.cat(parts).numpy()[:n])
+        out["equal_half"].append(bool(np.array_equal(rep.get_params()[1], shd.get_params()[1])))
+        out["equal_loss"].append(float(st_r.loss) == float(st_s.loss))
+    m_r, _, e_r = rep.get_params(); m_s, _, e_s = shd.get_params()
+    out["own_master_equal"] = bool(np.array_equal(m_r[b:e], m_s[b:e])); out["own_ema_equal"] = bool(np.array_equal(e_r[b:e], e_s[b:e]))
+    out["dbg"] = (int((m_r[b:e] != m_s[b:e]).sum()), int((e_r[b:e] != e_s[b:e]).sum()), b, e, n, int(np.flatnonzero(m_r[b:e] != m_s[b:e])[:1].sum()) if (m_r[b:e] != m_s[b:e]).any() else -1, int(np.isnan(m_r).sum()), int(np.isnan(e_r).sum()))
+    other = np.ones(n, bool); other[b:e] = False
+    out["other_master_untouched"] = bool(np.array_equal(m_s[other], _make(rank, world).get_params()[0][other]))
+    out["changed"] = bool(np.any(m_r != _make(rank, world).get_params()[0]))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_sharded_optimizer_matches_replicated():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=800) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(2):
+        assert all(res[r]["equal_half"]), "training weights differ between the replicated and the sharded protocol"
+        assert all(res[r]["equal_loss"])
+        assert res[r]["own_master_equal"] and res[r]["own_ema_equal"], res[r].get("dbg")
+        assert res[r]["other_master_untouched"] and res[r]["changed"]
