@@ -8,11 +8,15 @@ Follows rnb_neus2/albedo_scaling.py (reference):
   * medians, chained product, normalisation by the mean                 :366-383
   * scale_and_save_albedos                                              :386-436
 
-The reference delegates the two ray/mesh queries to trimesh (`mesh.ray.intersects_location`), which is NOT in this image
-(SURVEY N4): **parity of this stage is unpinned** against a run of the reference.  The restatement is pinned instead by a
-known-answer scene (tests/test_albedo_scaling.py: per-view gains applied to a view-independent texture are recovered) and the
-ray queries by brute force over all triangles in binary64 (Moeller-Trumbore), the published algorithm trimesh's default
-`ray_triangle` engine implements.
+Pinning.  The reference delegates the two ray/mesh queries to trimesh (`mesh.ray.intersects_location`; trimesh 4.x per the
+reference's requirements, NOT in this image).  Everything else of the module IS run here: tests/golden/make_albedo_golden.py
+imports the reference's rnb_neus2/albedo_scaling.py with a stand-in `trimesh` module that has exactly the surface the
+reference uses (`load_mesh(path).ray.intersects_location(...)`) and answers with brute force over all triangles in binary64
+(Moeller-Trumbore, the published algorithm behind trimesh's default `ray_triangle` engine).  The resulting fixture
+(tests/golden/ref_albedo_scaling.npz: ratios for two seeds, cameras, the scaled PNGs) pins this restatement to 1e-9 and the
+product's host logic to 1e-9 / byte-identical files (tests/test_albedo_scaling.py).  **Unpinned: trimesh's own intersector**
+(its tolerance handling on edges and its hit ordering); the known-answer scene (per-view gains applied to a view-independent
+texture are recovered) bounds what that could change.
 
 Only tests/ may import this module.
 """

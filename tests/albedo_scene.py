@@ -70,3 +70,49 @@ def expected_factors(gains):
     inv = 1.0 / np.asarray(gains, dtype=np.float64)
     inv = inv / inv[0]
     return inv / inv.mean(axis=0)
+
+
+# ---- the fixed scene of the albedo-scaling tests, as files (the reference's inputs: albedo folder, transform.json, mesh) --------------
+V, W, H = 8, 96, 80
+GAINS = np.array([[1.0, 1.0, 1.0], [0.8, 0.9, 1.1], [1.2, 0.7, 0.95], [0.9, 1.1, 1.3], [1.05, 0.85, 0.75], [0.7, 1.2, 1.0], [1.3, 1.0, 0.9], [0.95, 0.95, 1.15]])
+
+
+def fixed_scene():
+    verts, tris = icosphere(3)
+    K, R, Cc = ring_cameras(V, W, H)
+    alb, msk = render_views(K, R, Cc, W, H, GAINS)
+    return verts, tris, K, R, Cc, alb, msk
+
+
+def write_scene_files(root):
+    """16-bit RGBA PNGs (alpha = mask) under root/albedos, root/transform.json (with an n2w that is not the identity), root/mesh_0.obj in
+    world space.  Returns the image names and a hash of everything written."""
+    import hashlib
+    import json
+    import os
+    import cv2
+    verts, tris, K, R, Cc, alb, msk = fixed_scene()
+    os.makedirs(os.path.join(root, "albedos"), exist_ok=True)
+    n2w = np.diag([1.5, 1.5, 1.5, 1.0]); n2w[:3, 3] = [0.3, -0.2, 0.1]
+    w2n = np.linalg.inv(n2w)
+    h = hashlib.sha256()
+    names, frames = [], []
+    for i in range(V):
+        rgba = np.concatenate([alb[i], msk[i][:, :, None]], axis=2)
+        img = (np.clip(rgba, 0.0, 1.0) * 65535.0).astype(np.uint16)
+        name = "%05d.png" % i
+        cv2.imwrite(os.path.join(root, "albedos", name), np.ascontiguousarray(np.concatenate([img[:, :, 2::-1], img[:, :, 3:]], axis=2)), [cv2.IMWRITE_PNG_COMPRESSION, 0])
+        h.update(img.tobytes())
+        c2w = np.eye(4); c2w[:3, :3] = R[i]; c2w[:3, 3] = Cc[i][:, 0]
+        c2n = w2n @ c2w                                   # the file holds normalised-space cameras; n2w takes them back to the world
+        frames.append({"albedo_path": "albedos/" + name, "normal_path": "normals/" + name, "transform_matrix": c2n.tolist(), "intrinsic_matrix": K[i].tolist()})
+        names.append(name)
+    tj = json.dumps({"w": W, "h": H, "n2w": n2w.tolist(), "frames": frames})
+    open(os.path.join(root, "transform.json"), "w").write(tj); h.update(tj.encode())
+    with open(os.path.join(root, "mesh_0.obj"), "w") as f:
+        for v in verts:
+            f.write("v %0.5f %0.5f %0.5f 0.500 0.500 0.500\n" % tuple(v))
+        for t in tris:
+            f.write("f %d//%d %d//%d %d//%d\n" % (t[0] + 1, t[0] + 1, t[1] + 1, t[1] + 1, t[2] + 1, t[2] + 1))
+    h.update(open(os.path.join(root, "mesh_0.obj"), "rb").read())
+    return {"names": names, "sha256": h.hexdigest()}

@@ -13,15 +13,10 @@ import orc_albedo  # noqa: E402
 from albedo_scene import expected_factors, icosphere, render_views, ring_cameras  # noqa: E402
 from test_raymesh_host import _trace, host_lib  # noqa: E402,F401
 
-V, W, H, NS = 8, 96, 80, 400
-GAINS = np.array([[1.0, 1.0, 1.0], [0.8, 0.9, 1.1], [1.2, 0.7, 0.95], [0.9, 1.1, 1.3], [1.05, 0.85, 0.75], [0.7, 1.2, 1.0], [1.3, 1.0, 0.9], [0.95, 0.95, 1.15]])
+from albedo_scene import GAINS, H, V, W, fixed_scene as scene, write_scene_files  # noqa: E402
 
-
-def scene():
-    verts, tris = icosphere(3)
-    K, R, Cc = ring_cameras(V, W, H)
-    alb, msk = render_views(K, R, Cc, W, H, GAINS)
-    return verts, tris, K, R, Cc, alb, msk
+NS = 400
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_albedo_scaling.npz")
 
 
 def seeded_choose(seed):
@@ -140,3 +135,57 @@ def test_scale_and_save_albedos(pkg, tmp_path, bits):
         alpha = ((imgs[i][:, :, 3].astype(np.float32) / np.float32(mx)).astype(np.float64) * float(mx)).astype(out.dtype)      # same float32 -> float64 round trip
         assert np.array_equal(out[:, :, 3], alpha)
         assert np.max(np.abs(out[:, :, 3].astype(np.int64) - imgs[i][:, :, 3].astype(np.int64))) <= 1
+
+
+# ---- against the reference's own module (tests/golden/make_albedo_golden.py ran rnb_neus2/albedo_scaling.py with a trimesh stand-in) ----
+def test_oracle_matches_reference_golden(tmp_path):
+    g = np.load(GOLDEN)
+    info = write_scene_files(str(tmp_path))
+    assert np.array_equal(np.frombuffer(bytes.fromhex(info["sha256"]), np.uint8), g["input_sha256"]), "the scene files differ from the ones the fixture was made from"
+    import cv2
+    imgs = []
+    for n in info["names"]:
+        a = cv2.imread(str(tmp_path / "albedos" / n), cv2.IMREAD_UNCHANGED).astype(np.float32) / 65535.0
+        imgs.append(np.concatenate([a[:, :, 2::-1], a[:, :, 3:]], axis=2))
+    alb = np.array([im[:, :, :3] for im in imgs]); msk = np.array([im[:, :, 3] for im in imgs])
+    K, R, Cc = orc_albedo.cameras_from_transform(json.loads((tmp_path / "transform.json").read_text()), [n[:-4] for n in info["names"]])
+    assert np.array_equal(K, g["K"]) and np.array_equal(R, g["R"]) and np.array_equal(Cc, g["C"])
+    verts, tris = [], []
+    for line in open(tmp_path / "mesh_0.obj"):
+        if line.startswith("v "):
+            verts.append([float(x) for x in line.split()[1:4]])
+        elif line.startswith("f "):
+            tris.append([int(t.split("/")[0]) - 1 for t in line.split()[1:4]])
+    verts = np.array(verts, np.float32); tris = np.array(tris, np.uint32)
+    for seed, ns in ((3, 400), (11, 150)):
+        np.random.seed(seed)
+        got = orc_albedo.albedo_scale_ratios(alb, msk, K, R, Cc, verts, tris, ns, lambda n, k: np.random.choice(n, k, replace=False))
+        assert np.max(np.abs(got - g["ratios_seed%d_n%d" % (seed, ns)])) < 1e-9
+
+
+def test_product_matches_reference_golden(pkg, host_lib, tmp_path, monkeypatch):  # noqa: F811
+    """the product's file-level entry points (the two calls of pipeline.py:150-163) with the ray queries served by the host build of the
+    kernel's traversal: ratios, cameras and the scaled images equal what the reference's module produced from the same files"""
+    import hashlib
+    import importlib
+    import cv2
+    mod = importlib.import_module("rnb_neus2_b200.albedo_scaling")
+    g = np.load(GOLDEN)
+    info = write_scene_files(str(tmp_path))
+    class _Bound(HostRayMesh):
+        def __init__(self, v, t):
+            HostRayMesh.__init__(self, host_lib, v, t)
+    monkeypatch.setattr(mod, "RayMesh", _Bound)
+    K, R, Cc = mod.load_cameras(str(tmp_path / "transform.json"), info["names"])
+    assert np.array_equal(K, g["K"]) and np.array_equal(R, g["R"]) and np.array_equal(Cc, g["C"])
+    for seed, ns in ((3, 400), (11, 150)):
+        np.random.seed(seed)
+        got = mod.compute_albedo_scale_ratios(str(tmp_path / "albedos"), str(tmp_path / "transform.json"), str(tmp_path / "mesh_0.obj"), n_samples=ns)
+        assert np.max(np.abs(got - g["ratios_seed%d_n%d" % (seed, ns)])) < 1e-9
+    mod.scale_and_save_albedos(str(tmp_path / "albedos"), str(tmp_path / "scaled"), g["ratios_seed3_n400"])
+    out1 = cv2.imread(str(tmp_path / "scaled" / info["names"][1]), cv2.IMREAD_UNCHANGED)
+    assert np.array_equal(out1, g["scaled_view1"])
+    h = hashlib.sha256()
+    for n in info["names"]:
+        h.update(open(tmp_path / "scaled" / n, "rb").read())
+    assert np.array_equal(np.frombuffer(h.digest(), np.uint8), g["scaled_sha256"]), "scaled PNG files are not byte-identical to the reference's"

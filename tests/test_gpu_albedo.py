@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import orc_albedo  # noqa: E402
 from albedo_scene import expected_factors, icosphere, render_views, ring_cameras  # noqa: E402
 from test_raymesh_host import random_rays, two_spheres  # noqa: E402
-from test_albedo_scaling import GAINS, H, NS, V, W, scene, seeded_choose  # noqa: E402
+from test_albedo_scaling import GAINS, H, NS, V, W, scene, seeded_choose  # noqa: E402,F401
 
 pytestmark = pytest.mark.gpu
 
