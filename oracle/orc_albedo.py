@@ -8,8 +8,8 @@ Follows rnb_neus2/albedo_scaling.py (reference):
   * medians, chained product, normalisation by the mean                 :366-383
   * scale_and_save_albedos                                              :386-436
 
-Pinning.  The reference delegates the two ray/mesh queries to trimesh (`mesh.ray.intersects_location`; trimesh 4.x per the
-reference's requirements, NOT in this image).  Everything else of the module IS run here: tests/golden/make_albedo_golden.py
+Pinning.  The reference delegates the two ray/mesh queries to trimesh (`mesh.ray.intersects_location`; `trimesh`, unpinned in the
+reference's setup.py:14, NOT in this image).  Everything else of the module IS run here: tests/golden/make_albedo_golden.py
 imports the reference's rnb_neus2/albedo_scaling.py with a stand-in `trimesh` module that has exactly the surface the
 reference uses (`load_mesh(path).ray.intersects_location(...)`) and answers with brute force over all triangles in binary64
 (Moeller-Trumbore, the published algorithm behind trimesh's default `ray_triangle` engine).  The resulting fixture
