@@ -36,3 +36,42 @@ def test_error_path_without_gpu_or_bad_config(pkg):
     h = C.c_void_p()
     rc = L.rnb_create(C.byref(cfg), C.byref(h))
     assert rc != 0 and len(L.rnb_last_error()) > 0      # invalid config (or no device): loud failure, never a fallback
+
+
+def test_header_is_plain_c_and_links_from_c(pkg, tmp_path):
+    """the boundary is a C ABI: the header must compile as C99 (and as C++), and a C program using it must link against the library and
+    get the loud failure path without a device / with a bad configuration"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc"); gxx = shutil.which("g++")
+    if not gcc or not gxx:
+        import pytest
+        pytest.skip("no host compiler")
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "cabi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "rnb_b200.h"
+int main(void) {
+	rnb_config cfg; rnb_flags fl; rnb_ctx* ctx = 0; rnb_raymesh* rm = 0;
+	rnb_default_config(&cfg); rnb_default_flags(&fl);
+	if (rnb_abi_version() != RNB_ABI_VERSION) return 2;
+	cfg.n_levels = 40;                                   /* invalid: more levels than the library supports */
+	if (rnb_create(&cfg, &ctx) == RNB_OK) return 3;
+	if (strlen(rnb_last_error()) == 0) return 4;
+	if (rnb_train(0, 0, 0) == RNB_OK) return 5;           /* null context */
+	if (rnb_raymesh_create(0, 0, 0, 0, 0, &rm) == RNB_OK) return 6;
+	if (rnb_raymesh_destroy(0) != RNB_OK) return 7;
+	printf("abi %u ok\n", rnb_abi_version());
+	return 0;
+}
+''')
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
+    exe = tmp_path / "cabi"
+    libdir = os.path.join(ROOT, "rnb-neus2_b200")
+    subprocess.check_call([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lrnb_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "abi 1 ok" in out.stdout
