@@ -48,7 +48,8 @@ int rnb_raymesh_destroy(rnb_raymesh* r);
 int rnb_raymesh_create(const float* verts, uint32_t n_verts, const uint32_t* indices, uint32_t n_tris, uint32_t grid_res, rnb_raymesh** out) {
 	if (!verts || !indices || !out) return rnb_set_error_(RNB_ERR_INVALID, "null argument");
 	if (n_verts == 0 || n_tris == 0) return rnb_set_error_(RNB_ERR_INVALID, "empty mesh");
-	for (uint32_t i = 0; i < 3 * n_tris; ++i) if (indices[i] >= n_verts) return rnb_set_error_(RNB_ERR_INVALID, "triangle index out of range");
+	for (size_t i = 0; i < (size_t)3 * n_tris; ++i) if (indices[i] >= n_verts) return rnb_set_error_(RNB_ERR_INVALID, "triangle index out of range");
+	for (size_t i = 0; i < (size_t)3 * n_verts; ++i) if (!std::isfinite(verts[i])) return rnb_set_error_(RNB_ERR_INVALID, "mesh vertex is not finite");
 	int dev_count = 0;
 	if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return rnb_set_error_(RNB_ERR_CUDA, "no CUDA device: the ray/mesh queries have no CPU path");
 	HostGrid H;

@@ -95,3 +95,26 @@ def test_unnormalised_directions_scale_the_parameter(host_lib):
     m = np.isfinite(t1)
     assert np.array_equal(m, np.isfinite(t2))
     assert np.allclose(t1[m], t2[m] * 2.5, rtol=1e-12)
+
+
+def test_c_abi_argument_checks_without_a_device(pkg):
+    """rnb_raymesh_create validates its arguments before it touches the device, and has no CPU path behind it"""
+    import torch
+    L = pkg.lib()
+    verts, tris = icosphere(1)
+    h = C.c_void_p()
+    p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+    INVALID, CUDA = 1, None
+    bad_idx = tris.copy(); bad_idx[3, 1] = len(verts)
+    nan_v = verts.copy(); nan_v[5, 2] = np.nan
+    cases = [(None, 0, None, 0), (verts, len(verts), None, 0), (verts, len(verts), tris, 0), (verts, 0, tris, len(tris)), (verts, len(verts), bad_idx, len(tris)), (nan_v, len(verts), tris, len(tris))]
+    for v, nv, t, nt in cases:
+        rc = L.rnb_raymesh_create(p(v, C.c_float) if v is not None else None, C.c_uint32(nv), p(t, C.c_uint32) if t is not None else None, C.c_uint32(nt), C.c_uint32(0), C.byref(h))
+        assert rc != 0 and len(L.rnb_last_error()) > 0
+    assert b"not finite" in L.rnb_last_error()
+    if not torch.cuda.is_available():
+        rc = L.rnb_raymesh_create(p(verts, C.c_float), C.c_uint32(len(verts)), p(tris, C.c_uint32), C.c_uint32(len(tris)), C.c_uint32(0), C.byref(h))
+        assert rc != 0 and b"no CPU path" in L.rnb_last_error()
+    assert L.rnb_raymesh_intersect(None, None, None, None, C.c_uint32(4), None, None, None) != 0
+    assert L.rnb_raymesh_info(None, None, None) != 0
+    assert L.rnb_raymesh_destroy(None) == 0
