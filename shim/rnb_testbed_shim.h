@@ -1,0 +1,213 @@
+// rnb_testbed_shim.h — the reference-side binding of librnb_b200.so, as code that COMPILES against the reference's own headers.
+//
+// A maintainer of RobinBruneau/RNb-NeuS2 includes this file at the top of src/testbed.cu and src/testbed_nerf.cu (after testbed.h) and
+// adds six one-line calls behind `#ifdef NGP_USE_RNB_B200` (INTEGRATION.md §2 lists them; oracle/shim_patch.py applies exactly those to
+// a scratch copy of the two files and `make -C oracle -f Makefile.ref shim` builds oracle/_ref/bin/testbed_rnb from it — the reference
+// sources themselves are never modified or copied into this repository).
+//
+//   Testbed::reset_network()            ... end:    rnb_shim::on_reset_network(*this);
+//   Testbed::load_nerf()                ... end:    rnb_shim::on_dataset(*this);
+//   Testbed::train(batch)               ... start:  if (m_testbed_mode == ETestbedMode::Nerf && rnb_shim::train(*this)) { update_loss_graph(); return; }
+//   Testbed::compute_and_save_marching_cubes_mesh(...) start:  if (... rnb_shim::compute_and_save_mesh(*this, filename, res3d, aabb, thresh, unwrap_it)) return;
+//   Testbed::save_snapshot(...)         ... start:  rnb_shim::push_state(*this);
+//   Testbed::load_snapshot(...)         ... end:    rnb_shim::pull_state(*this);
+//
+// Design: the library owns the training state while training runs; `push_state` copies it into the reference's own objects (trainer
+// parameters, density grid + bitfield, step counters) so that EVERY stock consumer — snapshot writer, renderer, the stock marching
+// cubes — keeps working on trained weights without knowing about the library; `pull_state` goes the other way after a snapshot load.
+// One Testbed per process (./build/testbed), hence one context.
+#pragma once
+#ifdef NGP_USE_RNB_B200
+
+#include <rnb_b200.h>
+#include <neural-graphics-primitives/testbed.h>
+#include <neural-graphics-primitives/nerf_network.h>
+#include <tiny-cuda-nn/common.h>
+#include <tiny-cuda-nn/trainer.h>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace rnb_shim {
+
+inline rnb_ctx*& ctx() { static rnb_ctx* c = nullptr; return c; }
+inline bool& state_dirty() { static bool d = false; return d; }          // the library holds newer weights than the reference's trainer
+
+inline void check(int rc) {      // CUDA_CHECK_THROW behaviour: a failing call ends the run with the library's message
+	if (rc != RNB_OK) throw std::runtime_error{std::string{"rnb_b200: "} + rnb_last_error()};
+}
+
+inline uint32_t grid_cells() { return ngp::NERF_GRIDSIZE() * ngp::NERF_GRIDSIZE() * ngp::NERF_GRIDSIZE(); }
+
+// --- dataset: device pointers stay owned by the reference's loader (metadata_normal / metadata_albedo, nerf_loader.h:88-89) -----------
+inline void on_dataset(ngp::Testbed& t) {
+	if (!ctx() || t.m_testbed_mode != ngp::ETestbedMode::Nerf) return;
+	const auto& ds = t.m_nerf.training.dataset;
+	if (ds.n_images == 0 || ds.metadata_normal.size() < ds.n_images || t.m_nerf.training.transforms.size() < ds.n_images) return;
+	std::vector<rnb_view> views(ds.n_images);
+	for (size_t i = 0; i < views.size(); ++i) {
+		const auto& mn = ds.metadata_normal[i];
+		views[i].normal_px = mn.pixels;
+		views[i].albedo_px = i < ds.metadata_albedo.size() ? ds.metadata_albedo[i].pixels : nullptr;
+		views[i].w = mn.resolution.x(); views[i].h = mn.resolution.y();
+		views[i].fx = mn.focal_length.x(); views[i].fy = mn.focal_length.y();
+		views[i].cx = mn.principal_point.x(); views[i].cy = mn.principal_point.y();
+		std::memcpy(views[i].xform, t.m_nerf.training.transforms[i].start.data(), 12 * sizeof(float));      // Eigen 3x4, column-major
+	}
+	check(rnb_set_dataset(ctx(), views.data(), (uint32_t)views.size()));
+}
+
+// --- network: same configuration, and the reference's OWN initial parameters (no second initialiser to keep in sync) ----------------
+inline void on_reset_network(ngp::Testbed& t) {
+	if (t.m_testbed_mode != ngp::ETestbedMode::Nerf) return;
+	using json = nlohmann::json;
+	const json& cfgj = t.m_network_config;
+	const json& enc = cfgj.contains("encoding") ? cfgj["encoding"] : json::object();
+	const json& net = cfgj.contains("network") ? cfgj["network"] : json::object();
+	const json& rgb = cfgj.contains("rgb_network") ? cfgj["rgb_network"] : json::object();
+	rnb_config cfg; rnb_default_config(&cfg);
+	cfg.n_levels = enc.value("n_levels", 14u);
+	cfg.log2_hashmap_size = enc.value("log2_hashmap_size", 19u);
+	cfg.base_resolution = t.m_base_grid_resolution;
+	cfg.per_level_scale = t.m_per_level_scale;
+	cfg.top_resolution = enc.value("top_resolution", 2048.0f);
+	cfg.base_valid_level_scale = enc.value("base_valid_level_scale", 0.2f);
+	cfg.valid_level_scale = enc.value("valid_level_scale", 0.02f);
+	cfg.base_training_step = enc.value("base_training_step", 100u);
+	cfg.sdf_n_neurons = net.value("n_neurons", 64u);
+	cfg.sdf_n_hidden_layers = net.value("n_hidden_layers", 1u);
+	cfg.sdf_bias = net.value("sdf_bias", -0.1f);
+	cfg.rgb_n_neurons = rgb.value("n_neurons", 64u);
+	cfg.rgb_n_hidden_layers = rgb.value("n_hidden_layers", 2u);
+	// optimizer: Ema(ExponentialDecay(Adam)) as in configs/nerf/base.json:5-29 — walk the nesting, take what each level defines
+	const json* o = cfgj.contains("optimizer") ? &cfgj["optimizer"] : nullptr;
+	while (o) {
+		const std::string otype = o->value("otype", std::string{});
+		if (otype == "Ema") cfg.ema_decay = o->value("decay", cfg.ema_decay);
+		else if (otype == "ExponentialDecay") {
+			cfg.lr_decay_start = o->value("decay_start", cfg.lr_decay_start);
+			cfg.lr_decay_interval = o->value("decay_interval", cfg.lr_decay_interval);
+			cfg.lr_decay_base = o->value("decay_base", cfg.lr_decay_base);
+		} else if (otype == "Adam") {
+			cfg.learning_rate = o->value("learning_rate", cfg.learning_rate);
+			cfg.beta1 = o->value("beta1", cfg.beta1); cfg.beta2 = o->value("beta2", cfg.beta2);
+			cfg.epsilon = o->value("epsilon", cfg.epsilon); cfg.l2_reg = o->value("l2_reg", cfg.l2_reg);
+		}
+		o = o->contains("nested") ? &(*o)["nested"] : nullptr;
+	}
+	cfg.seed = t.m_seed;
+	cfg.rays_per_batch = t.m_nerf.training.counters_rgb.rays_per_batch;
+	cfg.pin_rays_per_batch = 0;                                    // the reference's adaptive controller stays in charge
+	cfg.density_grid_decay = t.m_nerf.training.density_grid_decay;
+	if (ctx()) { rnb_destroy(ctx()); ctx() = nullptr; }
+	check(rnb_create(&cfg, &ctx()));
+	// initial parameters: whatever the reference's Trainer just initialised (fp32 master copy), in the same order (nerf_network.h:539-583)
+	uint64_t layout[5]; check(rnb_param_layout(ctx(), layout));
+	const size_t n = t.m_network->n_params();
+	if (n != layout[4]) throw std::runtime_error{"rnb_b200: parameter count differs from the reference network (" + std::to_string(n) + " vs " + std::to_string(layout[4]) + ")"};
+	std::vector<float> w(n);
+	CUDA_CHECK_THROW(cudaMemcpy(w.data(), t.m_trainer->params_full_precision(), n * sizeof(float), cudaMemcpyDeviceToHost));
+	check(rnb_set_params_fp32(ctx(), w.data(), n));
+	state_dirty() = false;
+	on_dataset(t);
+}
+
+inline rnb_flags flags_of(ngp::Testbed& t) {
+	rnb_flags f; rnb_default_flags(&f);
+	f.apply_L2 = t.m_apply_L2; f.apply_supernormal = t.m_apply_supernormal; f.apply_rgbplus = t.m_apply_rgbplus; f.apply_relu = t.m_apply_relu;
+	f.apply_bce = t.m_apply_bce; f.light_opti = t.m_light_opti; f.no_albedo = t.m_no_albedo;
+	f.mask_loss_weight = t.m_mask_loss_weight; f.ek_loss_weight = t.m_ek_loss_weight;
+	f.cos_anneal_ratio = t.m_nerf_network->cos_anneal_ratio();
+	return f;
+}
+
+// --- one call of Testbed::train: occupancy refresh cadence + train_nerf + optimizer step (src/testbed.cu:2776-2872) -----------------
+inline bool train(ngp::Testbed& t) {
+	if (!ctx()) return false;
+	rnb_flags f = flags_of(t);
+	check(rnb_set_flags(ctx(), &f));
+	rnb_step_stats st;
+	check(rnb_train(ctx(), t.m_training_stream, &st));              // returns with the stream synchronised, like the reference
+	state_dirty() = true;
+	t.m_training_step = st.training_step;
+	t.m_canonical_training_step = (int)st.training_step;
+	t.m_nerf_network->m_training_step = st.training_step;
+	t.m_loss_scalar.update(st.loss); t.m_ek_loss_scalar.update(st.ek_loss); t.m_mask_loss_scalar.update(st.mask_loss);
+	auto& c = t.m_nerf.training.counters_rgb;
+	c.rays_per_batch = st.rays_per_batch_next;
+	c.measured_batch_size = st.n_samples_compacted;
+	c.measured_batch_size_before_compaction = st.n_samples;
+	c.n_rays_total += st.n_rays;
+	if (st.n_samples_compacted == 0) {
+		tlog::warning() << "Nerf training generated 0 samples. Aborting training.";
+		t.m_train = false;
+	}
+	return true;
+}
+
+// --- library -> reference objects: after this every stock consumer (snapshot, renderer, stock marching cubes) sees the trained state ---
+inline void push_state(ngp::Testbed& t) {
+	if (!ctx() || !state_dirty()) return;
+	using precision_t = tcnn::network_precision_t;
+	static_assert(sizeof(precision_t) == 2, "the library exchanges binary16 parameters");
+	const size_t n = t.m_network->n_params();
+	std::vector<uint16_t> h(n);
+	check(rnb_export_params_fp16(ctx(), h.data(), n, /*use_ema=*/1));
+	CUDA_CHECK_THROW(cudaMemcpy(t.m_trainer->params_inference(), h.data(), n * 2, cudaMemcpyHostToDevice));
+	check(rnb_export_params_fp16(ctx(), h.data(), n, /*use_ema=*/0));
+	CUDA_CHECK_THROW(cudaMemcpy(t.m_trainer->params(), h.data(), n * 2, cudaMemcpyHostToDevice));
+	std::vector<float> w(n);
+	check(rnb_get_params_fp32(ctx(), w.data(), n));
+	CUDA_CHECK_THROW(cudaMemcpy(t.m_trainer->params_full_precision(), w.data(), n * 4, cudaMemcpyHostToDevice));
+	const uint32_t cells = grid_cells();
+	std::vector<float> grid(cells); uint32_t ema_step = 0;
+	check(rnb_export_density_grid(ctx(), grid.data(), cells, &ema_step));
+	if (t.m_nerf.density_grid.size() < cells) t.m_nerf.density_grid.resize(cells);
+	CUDA_CHECK_THROW(cudaMemcpy(t.m_nerf.density_grid.data(), grid.data(), (size_t)cells * 4, cudaMemcpyHostToDevice));
+	t.m_nerf.density_grid_ema_step = ema_step;
+	std::vector<uint8_t> bits(cells);                                // 8 mips x 128^3 bits
+	check(rnb_get_bitfield(ctx(), bits.data(), cells));
+	const size_t nb = std::min<size_t>(t.m_nerf.density_grid_bitfield.size(), bits.size());
+	if (nb) CUDA_CHECK_THROW(cudaMemcpy(t.m_nerf.density_grid_bitfield.data(), bits.data(), nb, cudaMemcpyHostToDevice));
+	uint32_t ts[4]; check(rnb_get_train_state(ctx(), ts));
+	t.m_training_step = ts[0];
+	state_dirty() = false;
+}
+
+// --- reference objects -> library: after Testbed::load_snapshot --------------------------------------------------------------------
+inline void pull_state(ngp::Testbed& t) {
+	if (!ctx() || t.m_testbed_mode != ngp::ETestbedMode::Nerf) return;
+	const size_t n = t.m_network->n_params();
+	std::vector<uint16_t> h(n);
+	CUDA_CHECK_THROW(cudaMemcpy(h.data(), t.m_trainer->params(), n * 2, cudaMemcpyDeviceToHost));
+	check(rnb_import_params_fp16(ctx(), h.data(), n));               // Adam moments restart, as in the reference (trainer.h:263-275)
+	const uint32_t cells = grid_cells();
+	if (t.m_nerf.density_grid.size() >= cells) {
+		std::vector<float> grid(cells);
+		CUDA_CHECK_THROW(cudaMemcpy(grid.data(), t.m_nerf.density_grid.data(), (size_t)cells * 4, cudaMemcpyDeviceToHost));
+		check(rnb_import_density_grid(ctx(), grid.data(), cells, t.m_nerf.density_grid_ema_step));
+	}
+	const auto& c = t.m_nerf.training.counters_rgb;
+	check(rnb_set_train_state(ctx(), (uint32_t)t.m_training_step, c.rays_per_batch, c.n_rays_total, c.measured_batch_size_before_compaction));
+	state_dirty() = false;
+}
+
+// --- Testbed::compute_and_save_marching_cubes_mesh (src/testbed.cu:369-381): sweep + extraction + text on the GPU -----------------------
+inline bool compute_and_save_mesh(ngp::Testbed& t, const char* filename, Eigen::Vector3i res3d, const ngp::BoundingBox& aabb, float thresh, bool unwrap_it) {
+	if (!ctx()) return false;
+	if (unwrap_it) { push_state(t); return false; }                  // the unwrap / texture variant stays with the reference, on the trained weights
+	if (thresh == std::numeric_limits<float>::max()) thresh = t.m_mesh.thresh;
+	const uint32_t r[3] = {(uint32_t)res3d.x(), (uint32_t)res3d.y(), (uint32_t)res3d.z()};      // rounded up to multiples of 16 inside, like :4298-4300
+	rnb_mesh_info mi;
+	check(rnb_marching_cubes(ctx(), r, aabb.min.data(), aabb.max.data(), thresh, /*use_ema=*/1, t.m_inference_stream, &mi));
+	float *v = nullptr, *nrm = nullptr, *col = nullptr; uint32_t* idx = nullptr;
+	check(rnb_mesh_buffers(ctx(), &v, &nrm, &col, &idx, nullptr));
+	const auto& ds = t.m_nerf.training.dataset;
+	check(rnb_save_mesh(v, nrm, col, idx, mi.n_verts_padded, mi.n_indices, filename, ds.scale, ds.offset.data(), ds.n2w_s, ds.n2w_t.data(), ds.from_na ? 1 : 0, t.m_inference_stream, nullptr));
+	return true;
+}
+
+} // namespace rnb_shim
+#endif // NGP_USE_RNB_B200
