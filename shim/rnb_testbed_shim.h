@@ -120,6 +120,8 @@ inline rnb_flags flags_of(ngp::Testbed& t) {
 	f.apply_bce = t.m_apply_bce; f.light_opti = t.m_light_opti; f.no_albedo = t.m_no_albedo;
 	f.mask_loss_weight = t.m_mask_loss_weight; f.ek_loss_weight = t.m_ek_loss_weight;
 	f.cos_anneal_ratio = t.m_nerf_network->cos_anneal_ratio();
+	// --fractional-training warm-up (Testbed::frame, src/testbed.cu:1886-1895): geometry only, the colour MLP is frozen
+	f.only_sdf_training = (t.m_fractional_training && t.m_training_step < t.m_fractional) ? 1 : 0;
 	return f;
 }
 
