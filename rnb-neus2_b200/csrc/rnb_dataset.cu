@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 #include <thread>
@@ -24,8 +25,10 @@ namespace rnb {
 static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
 // Decodes `path` into out (w * h * 4 uint16, caller-provided through alloc(w, h)).  Returns "" or an error message.
+constexpr uint32_t PNG_MAX_DIM = 1u << 24;      // stb_image's STBI_MAX_DIMENSIONS: larger headers are treated as corrupt, never allocated for
+
 template <typename Alloc>
-static std::string decode_png_rgba16(const char* path, uint32_t* w_out, uint32_t* h_out, Alloc alloc) {
+static std::string decode_png_rgba16_impl(const char* path, uint32_t* w_out, uint32_t* h_out, Alloc alloc) {
 	FILE* f = fopen(path, "rb");
 	if (!f) return std::string("image not found: ") + path;
 	std::vector<uint8_t> file;
@@ -56,12 +59,16 @@ static std::string decode_png_rgba16(const char* path, uint32_t* w_out, uint32_t
 		o += 12 + (size_t)len;
 	}
 	if (w == 0 || h == 0 || ctype < 0) return std::string("PNG without IHDR: ") + path;
+	if (w > PNG_MAX_DIM || h > PNG_MAX_DIM) return std::string("PNG too large (corrupt header?): ") + path;
 	if (interlace) return std::string("interlaced PNG is not supported: ") + path;
 	int channels;
 	switch (ctype) { case 0: channels = 1; break; case 2: channels = 3; break; case 3: channels = 1; break; case 4: channels = 2; break; case 6: channels = 4; break;
 		default: return std::string("bad PNG colour type: ") + path; }
 	if (!((depth == 8 || depth == 16) && ctype != 3) && !(ctype == 3 && depth == 8)) return std::string("unsupported PNG bit depth: ") + path;
 	const size_t bpp = (size_t)channels * depth / 8, stride = (size_t)w * bpp;
+	// a deflate stream expands at most 1032:1: a header that promises more pixels than the compressed data can hold is corrupt, and
+	// must not drive an allocation
+	if ((stride + 1) * (size_t)h > idat.size() * 1032 + 1024) return std::string("corrupt PNG data: ") + path;
 	std::vector<uint8_t> raw((stride + 1) * h);
 	{
 		uLongf dl = (uLongf)raw.size();
@@ -124,6 +131,13 @@ static std::string decode_png_rgba16(const char* path, uint32_t* w_out, uint32_t
 	return "";
 }
 
+// the C ABI never lets an exception out: allocation failures of the decoder's scratch vectors become an error string
+template <typename Alloc>
+static std::string decode_png_rgba16(const char* path, uint32_t* w_out, uint32_t* h_out, Alloc alloc) {
+	try { return decode_png_rgba16_impl(path, w_out, h_out, alloc); }
+	catch (const std::exception& ex) { return std::string("out of memory while decoding ") + path + " (" + ex.what() + ")"; }
+}
+
 std::string load_png_rgba16_host(const char* path, uint32_t* w, uint32_t* h, uint16_t** pixels) {
 	*pixels = nullptr;
 	uint16_t* buf = nullptr;
@@ -142,6 +156,7 @@ static std::string png_size(const char* path, uint32_t* w, uint32_t* h) {
 	if (got != sizeof(hd) || memcmp(hd, sig, 8) != 0 || memcmp(hd + 12, "IHDR", 4) != 0) return std::string("not a PNG file: ") + path;
 	*w = be32(hd + 16); *h = be32(hd + 20);
 	if (*w == 0 || *h == 0) return std::string("PNG without IHDR: ") + path;
+	if (*w > PNG_MAX_DIM || *h > PNG_MAX_DIM) return std::string("PNG too large (corrupt header?): ") + path;
 	return "";
 }
 

@@ -161,3 +161,15 @@ def test_axis_conventions_and_aabb(tmp_path):
     assert v["normal_path"].endswith(os.path.join("n", "0.png")) and v["albedo_path"] is None and v["cx"] == np.float32(0.5) and v["cy"] == np.float32(0.5)
     with pytest.raises(ValueError, match="No training images"):
         json.dump({"w": 1, "h": 1, "frames": []}, open(tmp_path / "transform.json", "w")); ds.load_transforms(str(tmp_path))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_png_decoder_survives_corrupt_files(tmp_path, seed):
+    """2 x 600 corrupt PNGs (tests/fuzz/png_fuzz.py) through the C ABI in a child process: it must exit normally — a hostile IHDR once
+    drove a std::bad_alloc out of the library and aborted the process"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz", "png_fuzz.py"), str(seed), str(tmp_path), "600"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr[-600:])
+    assert "rejected" in r.stdout and int(r.stdout.split("rejected")[1].split()[0]) > 400
