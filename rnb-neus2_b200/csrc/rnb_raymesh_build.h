@@ -25,18 +25,22 @@ inline void build_grid(const float* verts, uint32_t n_verts, const uint32_t* ind
 	const double pad = 1e-3 * ext;
 	if (grid_res == 0) grid_res = (uint32_t)std::lround(std::sqrt((double)n_tris / 6.0));
 	grid_res = std::min(std::max(grid_res, 4u), 320u);
-	const double h = (ext + 2 * pad) / grid_res;
 	GridView& G = H.view;
-	size_t n_cells = 1;
-	for (int a = 0; a < 3; ++a) {
-		G.bmin[a] = lo[a] - pad;
-		G.res[a] = std::max(1, (int)std::ceil((hi[a] - lo[a] + 2 * pad) / h));
-		G.cell[a] = h; G.inv_cell[a] = 1.0 / h;
-		n_cells *= (size_t)G.res[a];
-	}
 	G.n_tris = n_tris;
 	H.tri_verts.resize((size_t)n_tris * 9);
 	for (uint32_t t = 0; t < n_tris; ++t) for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) H.tri_verts[(size_t)t * 9 + 3 * k + a] = verts[3 * (size_t)indices[3 * t + k] + a];
+	size_t n_cells = 1;
+	auto lay_out = [&](uint32_t r) {
+		const double h = (ext + 2 * pad) / r;
+		n_cells = 1;
+		for (int a = 0; a < 3; ++a) {
+			G.bmin[a] = lo[a] - pad;
+			G.res[a] = std::max(1, (int)std::ceil((hi[a] - lo[a] + 2 * pad) / h));
+			G.cell[a] = h; G.inv_cell[a] = 1.0 / h;
+			n_cells *= (size_t)G.res[a];
+		}
+	};
+	lay_out(grid_res);
 	// cell range of a triangle: its bounding box, inflated so that hits computed a rounding error outside a cell are still found there
 	const double slack = 1e-6 * ext;
 	auto range = [&](uint32_t t, int32_t c0[3], int32_t c1[3]) {
@@ -47,6 +51,18 @@ inline void build_grid(const float* verts, uint32_t n_verts, const uint32_t* ind
 			c1[a] = std::min(std::max((int32_t)std::floor((mx - G.bmin[a]) * G.inv_cell[a]), 0), G.res[a] - 1);
 		}
 	};
+	// a few triangles much larger than a cell (a ground plane next to a scanned object) would be referenced from every cell they span:
+	// coarsen the grid until the reference list is at most a small multiple of the triangle count
+	for (;;) {
+		size_t refs = 0;
+		for (uint32_t t = 0; t < n_tris; ++t) {
+			int32_t c0[3], c1[3]; range(t, c0, c1);
+			refs += (size_t)(c1[0] - c0[0] + 1) * (size_t)(c1[1] - c0[1] + 1) * (size_t)(c1[2] - c0[2] + 1);
+		}
+		if (refs <= std::max<size_t>((size_t)64 * n_tris, (size_t)1 << 22) || grid_res <= 4) break;
+		grid_res = std::max(4u, grid_res / 2);
+		lay_out(grid_res);
+	}
 	H.cell_start.assign(n_cells + 1, 0u);
 	for (uint32_t t = 0; t < n_tris; ++t) {
 		int32_t c0[3], c1[3]; range(t, c0, c1);

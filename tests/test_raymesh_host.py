@@ -118,3 +118,23 @@ def test_c_abi_argument_checks_without_a_device(pkg):
     assert L.rnb_raymesh_intersect(None, None, None, None, C.c_uint32(4), None, None, None) != 0
     assert L.rnb_raymesh_info(None, None, None) != 0
     assert L.rnb_raymesh_destroy(None) == 0
+
+
+def test_large_triangles_coarsen_the_grid(host_lib):
+    """60 triangles that span the whole box next to a finely tessellated object: at 320^3 cells each of them would be referenced from
+    millions of cells (2 G references); the grid is coarsened until the list is bounded, and the answers stay those of brute force"""
+    v1, f1 = icosphere(4, 0.05)                                              # 5120 small triangles
+    rng = np.random.default_rng(9)
+    big = rng.uniform(-40, 40, size=(180, 3)).astype(np.float32)
+    verts = np.ascontiguousarray(np.concatenate([v1, big])); n = len(v1)
+    tris = np.ascontiguousarray(np.concatenate([f1, n + np.arange(180).reshape(60, 3)]).astype(np.uint32))
+    o = rng.uniform(-30, 30, size=(400, 3))
+    tgt = rng.uniform(-5, 5, size=(400, 3)); tgt[:100] = rng.uniform(-0.05, 0.05, size=(100, 3))
+    d = tgt - o; d /= np.linalg.norm(d, axis=1)[:, None]
+    t, tri, res = _trace(host_lib, verts, tris, o, d, None, 320)
+    assert max(res) <= 80, res                                               # 320 -> 160 -> 80: the bounding boxes of the 60 triangles then cover < 4 M cells
+    t_ref, tri_ref = orc_albedo.first_hit(verts, tris, o, d)
+    assert np.array_equal(np.isfinite(t), np.isfinite(t_ref)) and np.isfinite(t_ref).sum() > 100
+    m = np.isfinite(t_ref)
+    assert np.max(np.abs(t[m] - t_ref[m])) < 1e-8
+    assert (tri[m] == tri_ref[m]).mean() > 0.99
