@@ -200,11 +200,29 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 	if (cfg->rgb_n_hidden_layers < 1 || cfg->rgb_n_hidden_layers > 2) return fail(RNB_ERR_INVALID, "rgb network: 1 or 2 hidden layers");
 	if ((cfg->sdf_n_neurons != 32 && cfg->sdf_n_neurons != 64) || (cfg->rgb_n_neurons != 32 && cfg->rgb_n_neurons != 64)) return fail(RNB_ERR_INVALID, "n_neurons must be 32 or 64");
 	if (cfg->world_size < 1 || cfg->rank >= cfg->world_size) return fail(RNB_ERR_INVALID, "bad rank / world_size");
+	{   // values that would otherwise reach the device as shifts past the word size, zero divisors or NaN resolutions
+		auto pos = [](float v) { return std::isfinite(v) && v > 0.f; };
+		auto unit = [](float v) { return std::isfinite(v) && v >= 0.f && v < 1.f; };
+		if (cfg->log2_hashmap_size < 4 || cfg->log2_hashmap_size > 24) return fail(RNB_ERR_INVALID, "log2_hashmap_size must be in 4..24");
+		if (cfg->base_resolution < 2 || cfg->base_resolution > 4096) return fail(RNB_ERR_INVALID, "base_resolution must be in 2..4096");
+		if (cfg->per_level_scale > 0.f ? !(std::isfinite(cfg->per_level_scale) && cfg->per_level_scale <= 16.f)
+		                               : (cfg->n_levels > 1 && !(pos(cfg->top_resolution) && cfg->top_resolution >= (float)cfg->base_resolution && cfg->top_resolution <= 65536.f)))
+			return fail(RNB_ERR_INVALID, "per_level_scale must be in (0, 16], or top_resolution in [base_resolution, 65536] to derive it");
+		if (std::isnan(cfg->per_level_scale)) return fail(RNB_ERR_INVALID, "per_level_scale is NaN");
+		if (cfg->target_batch_size < cfg->world_size || cfg->target_batch_size > (1u << 24)) return fail(RNB_ERR_INVALID, "target_batch_size must be in world_size..2^24");
+		if (cfg->rays_per_batch < 1 || cfg->rays_per_batch > (1u << 18)) return fail(RNB_ERR_INVALID, "rays_per_batch must be in 1..2^18 (the reference's cap, testbed_nerf.cu:3555)");
+		if (!pos(cfg->loss_scale)) return fail(RNB_ERR_INVALID, "loss_scale must be positive");
+		if (!(std::isfinite(cfg->learning_rate) && cfg->learning_rate >= 0.f) || !unit(cfg->beta1) || !unit(cfg->beta2) || !pos(cfg->epsilon) || !(std::isfinite(cfg->l2_reg) && cfg->l2_reg >= 0.f))
+			return fail(RNB_ERR_INVALID, "optimizer: learning_rate >= 0, beta1 / beta2 in [0, 1), epsilon > 0, l2_reg >= 0");
+		if (!unit(cfg->ema_decay) || (cfg->lr_decay_interval && !pos(cfg->lr_decay_base))) return fail(RNB_ERR_INVALID, "optimizer: ema_decay in [0, 1), lr_decay_base > 0");
+		if (!(pos(cfg->density_grid_decay) && cfg->density_grid_decay <= 1.f)) return fail(RNB_ERR_INVALID, "density_grid_decay must be in (0, 1]");
+		if (!std::isfinite(cfg->sdf_bias) || !std::isfinite(cfg->base_valid_level_scale) || !std::isfinite(cfg->valid_level_scale)) return fail(RNB_ERR_INVALID, "non-finite sdf_bias / valid_level_scale");
+	}
 	int dev = 0; CU(cudaGetDevice(&dev));
 	rnb_ctx* c = new rnb_ctx();
 	c->cfg = *cfg; rnb_default_flags(&c->flags);
-	if (c->cfg.per_level_scale <= 0.f && c->cfg.n_levels > 1)
-		c->cfg.per_level_scale = std::exp(std::log(c->cfg.top_resolution * 1.0f / (float)c->cfg.base_resolution) / (c->cfg.n_levels - 1));   // src/testbed.cu:2321
+	if (c->cfg.per_level_scale <= 0.f)
+		c->cfg.per_level_scale = c->cfg.n_levels > 1 ? std::exp(std::log(c->cfg.top_resolution * 1.0f / (float)c->cfg.base_resolution) / (c->cfg.n_levels - 1)) : 1.0f;   // src/testbed.cu:2321
 	ModelDev& M = c->M; memset(&M, 0, sizeof(M));
 	M.n_levels = cfg->n_levels; M.n_enc = 2 * cfg->n_levels; M.sdf_width = cfg->sdf_n_neurons; M.rgb_width = cfg->rgb_n_neurons; M.sdf_bias = cfg->sdf_bias;
 	uint32_t offset = 0;

@@ -75,3 +75,25 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "abi 1 ok" in out.stdout
+
+
+def test_create_rejects_configurations_that_would_misbehave_on_the_device(pkg):
+    """shifts past the word size, zero divisors, NaN resolutions: stopped in rnb_create with RNB_ERR_INVALID and a message, before any
+    device call (valid configurations get past the checks and fail here only for the missing device)"""
+    import torch
+    L = pkg.lib()
+    bad = [dict(log2_hashmap_size=40), dict(log2_hashmap_size=0), dict(base_resolution=0), dict(target_batch_size=0), dict(target_batch_size=1 << 31),
+           dict(rays_per_batch=0), dict(rays_per_batch=1 << 19), dict(top_resolution=-5.0), dict(top_resolution=float("nan")), dict(per_level_scale=float("nan")),
+           dict(per_level_scale=64.0), dict(loss_scale=0.0), dict(beta1=1.0), dict(beta2=-0.1), dict(epsilon=0.0), dict(ema_decay=1.0), dict(learning_rate=float("inf")),
+           dict(density_grid_decay=0.0), dict(sdf_bias=float("nan")), dict(world_size=4, target_batch_size=2)]
+    for kw in bad:
+        h = C.c_void_p()
+        rc = L.rnb_create(C.byref(pkg.default_config(**kw)), C.byref(h))
+        assert rc == -1 and len(L.rnb_last_error()) > 0, kw
+    if not torch.cuda.is_available():
+        good = [dict(), dict(n_levels=1), dict(per_level_scale=1.3819), dict(n_levels=8, log2_hashmap_size=14, sdf_n_neurons=32, rgb_n_neurons=32, rgb_n_hidden_layers=1, rays_per_batch=128),
+                dict(world_size=8, rank=7, target_batch_size=(1 << 18) * 8), dict(lr_decay_interval=0, lr_decay_base=0.0), dict(ema_decay=0.0, l2_reg=0.0, learning_rate=0.0)]
+        for kw in good:
+            h = C.c_void_p()
+            rc = L.rnb_create(C.byref(pkg.default_config(**kw)), C.byref(h))
+            assert rc == -2, (kw, L.rnb_last_error())          # RNB_ERR_CUDA: no device in this container, and no fallback
