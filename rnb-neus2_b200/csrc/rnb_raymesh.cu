@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 #include "../../include/rnb_b200.h"
@@ -53,7 +54,8 @@ int rnb_raymesh_create(const float* verts, uint32_t n_verts, const uint32_t* ind
 	int dev_count = 0;
 	if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return rnb_set_error_(RNB_ERR_CUDA, "no CUDA device: the ray/mesh queries have no CPU path");
 	HostGrid H;
-	build_grid(verts, n_verts, indices, n_tris, grid_res, H);
+	try { build_grid(verts, n_verts, indices, n_tris, grid_res, H); }      // no exception leaves the C ABI
+	catch (const std::exception& ex) { return rnb_set_error_(RNB_ERR_NOMEM, (std::string("building the cell grid failed: ") + ex.what()).c_str()); }
 	rnb_raymesh* r = new rnb_raymesh();
 	struct Guard { rnb_raymesh* r; ~Guard() { if (r) rnb_raymesh_destroy(r); } } guard{r};      // released on success
 	r->view = H.view; r->n_refs = H.cell_tris.size();
