@@ -73,6 +73,10 @@ using namespace rnb;
 #endif
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+// every multi-statement entry point is a function-try-block: no C++ exception (std::bad_alloc from a scratch vector, std::length_error)
+// crosses the C ABI; it becomes a status code with the message in rnb_last_error()
+#define RNB_API_CATCH catch (const std::bad_alloc&) { return fail(RNB_ERR_NOMEM, "out of host memory"); } \
+                      catch (const std::exception& ex_) { return fail(RNB_ERR_INVALID, std::string("internal error: ") + ex_.what()); }
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(RNB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct rnb_ctx {
@@ -192,7 +196,7 @@ void rnb_default_flags(rnb_flags* f) {
 	f->apply_L2 = 1; f->apply_rgbplus = 1; f->no_albedo = 1; f->mask_loss_weight = 1.0f; f->ek_loss_weight = 0.01f; f->cos_anneal_ratio = 1.0f; f->light_mode = -1;
 }
 
-int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
+int rnb_create(const rnb_config* cfg, rnb_ctx** out) try {
 	if (!cfg || !out) return fail(RNB_ERR_INVALID, "null argument");
 	if (cfg->abi_version != RNB_ABI_VERSION) return fail(RNB_ERR_INVALID, "ABI version mismatch");
 	if (cfg->n_levels < 1 || cfg->n_levels > 14) return fail(RNB_ERR_INVALID, "n_levels must be in 1..14 (SDF-MLP input width must be 32 or 48, nerf_network.h:594-604)");
@@ -297,9 +301,9 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) {
 	{ Pcg32 t = c->rng; c->density_rng = Pcg32(t.next_uint()); }     // src/testbed.cu:2223,2236,2490
 	*out = c;
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
-int rnb_destroy(rnb_ctx* c) {
+int rnb_destroy(rnb_ctx* c) try {
 	if (!c) return RNB_OK;
 	void* ptrs[] = {c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps, c->density_grid, c->density_tmp, c->bitfield, c->mean_acc, c->mean, c->gpos, c->gidx, c->gdens,
 	                c->views_dev, c->ray_n, c->ray_indices, c->numsteps, c->counters, c->n_fwd, c->cbase, c->n_emit, c->ray_geom, c->ts, c->ray_dirw, c->loss_out, c->stats,
@@ -314,13 +318,13 @@ int rnb_destroy(rnb_ctx* c) {
 	if (c->ev_march) cudaEventDestroy(c->ev_march);
 	delete c;
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
-int rnb_param_layout(rnb_ctx* c, uint64_t out[5]) {
+int rnb_param_layout(rnb_ctx* c, uint64_t out[5]) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	out[0] = c->off_sdf; out[1] = c->off_rgb; out[2] = c->M.off_grid; out[3] = c->M.off_var; out[4] = c->M.n_params;
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 // Built-in geometric initialisation used when the reference's utils/mlp_weights*.txt is not supplied: a bias-free
 // one-hidden-layer ReLU network whose output 0 approximates |x - 0.5| * k (sum of ReLUs over random directions).
@@ -341,7 +345,7 @@ static void builtin_sphere_init(const rnb_ctx* c, std::vector<float>& w) {
 	for (uint32_t o = 1; o < 16; ++o) for (uint32_t i = 0; i < W; ++i) w[(size_t)W * IN + (size_t)o * W + i] = (r.next_float() * 2 - 1) * 0.1f;
 }
 
-int rnb_init_params(rnb_ctx* c, const float* sdf_init, size_t n_sdf_init) {
+int rnb_init_params(rnb_ctx* c, const float* sdf_init, size_t n_sdf_init) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	const ModelDev& M = c->M;
 	std::seed_seq seq{c->cfg.seed};                 // trainer.h:54-60
@@ -375,27 +379,27 @@ int rnb_init_params(rnb_ctx* c, const float* sdf_init, size_t n_sdf_init) {
 	c->opt_step = 0; c->lr_factor = 1.f;
 	CU(cudaDeviceSynchronize());
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
-int rnb_set_params_fp32(rnb_ctx* c, const float* p, size_t n) {
+int rnb_set_params_fp32(rnb_ctx* c, const float* p, size_t n) try {
 	if (!c || !p || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
 	CU(cudaMemcpy(c->master, p, n * 4, cudaMemcpyHostToDevice));
 	launch_cast_params(0, c->M.n_params, c->master, c->params);
 	CU(cudaDeviceSynchronize());
 	return RNB_OK;
-}
-int rnb_get_params_fp32(rnb_ctx* c, float* p, size_t n) {
+} RNB_API_CATCH
+int rnb_get_params_fp32(rnb_ctx* c, float* p, size_t n) try {
 	if (!c || !p || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
 	CU(cudaMemcpy(p, c->master, n * 4, cudaMemcpyDeviceToHost));
 	return RNB_OK;
-}
-int rnb_export_params_fp16(rnb_ctx* c, uint16_t* host, size_t n, int use_ema) {
+} RNB_API_CATCH
+int rnb_export_params_fp16(rnb_ctx* c, uint16_t* host, size_t n, int use_ema) try {
 	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
 	CU(cudaMemcpy(host, use_ema ? c->ema : c->params, n * 2, cudaMemcpyDeviceToHost));
 	return RNB_OK;
-}
+} RNB_API_CATCH
 // Trainer::deserialize (trainer.h:263-275): fp16 params in, fp32 master re-derived, optimizer moments restart
-int rnb_import_params_fp16(rnb_ctx* c, const uint16_t* host, size_t n) {
+int rnb_import_params_fp16(rnb_ctx* c, const uint16_t* host, size_t n) try {
 	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
 	CU(cudaMemcpy(c->params, host, n * 2, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(c->ema, host, n * 2, cudaMemcpyHostToDevice));
@@ -404,44 +408,44 @@ int rnb_import_params_fp16(rnb_ctx* c, const uint16_t* host, size_t n) {
 	c->opt_step = 0; c->lr_factor = 1.f;
 	CU(cudaDeviceSynchronize());
 	return RNB_OK;
-}
-int rnb_export_density_grid(rnb_ctx* c, float* host, size_t n, uint32_t* ema_step) {
+} RNB_API_CATCH
+int rnb_export_density_grid(rnb_ctx* c, float* host, size_t n, uint32_t* ema_step) try {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "density grid is 128^3 floats");
 	CU(cudaMemcpy(host, c->density_grid, n * 4, cudaMemcpyDeviceToHost));
 	if (ema_step) *ema_step = c->density_ema_step;
 	return RNB_OK;
-}
-int rnb_get_bitfield(rnb_ctx* c, uint8_t* host, size_t n) {
+} RNB_API_CATCH
+int rnb_get_bitfield(rnb_ctx* c, uint8_t* host, size_t n) try {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "bitfield is 128^3 bytes");
 	CU(cudaMemcpy(host, c->bitfield, n, cudaMemcpyDeviceToHost));
 	return RNB_OK;
-}
-int rnb_set_bitfield(rnb_ctx* c, const uint8_t* host, size_t n) {
+} RNB_API_CATCH
+int rnb_set_bitfield(rnb_ctx* c, const uint8_t* host, size_t n) try {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "bitfield is 128^3 bytes");
 	drop_prelaunch(c);
 	CU(cudaMemcpy(c->bitfield, host, n, cudaMemcpyHostToDevice));
 	return RNB_OK;
-}
-int rnb_get_train_state(rnb_ctx* c, uint32_t out[4]) {
+} RNB_API_CATCH
+int rnb_get_train_state(rnb_ctx* c, uint32_t out[4]) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	out[0] = c->training_step; out[1] = c->rays_per_batch; out[2] = c->n_rays_total; out[3] = c->measured_before;
 	return RNB_OK;
-}
-int rnb_set_train_state(rnb_ctx* c, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) {
+} RNB_API_CATCH
+int rnb_set_train_state(rnb_ctx* c, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) try {
 	if (c) drop_prelaunch(c);
 	if (!c || rays_per_batch == 0 || rays_per_batch > (1u << 18)) return fail(RNB_ERR_INVALID, "bad train state");
 	c->training_step = training_step; c->rays_per_batch = rays_per_batch; c->n_rays_total = n_rays_total; c->measured_before = measured_before;
 	return ensure_ray_capacity(c, rays_per_batch);
-}
-int rnb_get_rng(rnb_ctx* c, uint64_t out[4]) {
+} RNB_API_CATCH
+int rnb_get_rng(rnb_ctx* c, uint64_t out[4]) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	out[0] = c->rng.state; out[1] = c->rng.inc; out[2] = c->density_rng.state; out[3] = c->density_rng.inc; return RNB_OK;
-}
-int rnb_set_rng(rnb_ctx* c, const uint64_t in[4]) {
+} RNB_API_CATCH
+int rnb_set_rng(rnb_ctx* c, const uint64_t in[4]) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	drop_prelaunch(c);
 	c->rng.state = in[0]; c->rng.inc = in[1]; c->density_rng.state = in[2]; c->density_rng.inc = in[3]; return RNB_OK;
-}
+} RNB_API_CATCH
 
 static int set_views(rnb_ctx* c, const rnb_view* views, uint32_t n, bool upload) {
 	if (!c || !views || n == 0) return fail(RNB_ERR_INVALID, "no views");
@@ -473,17 +477,17 @@ int rnb_upload_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { return set_v
 
 // ---- dataset ingest -----------------------------------------------------------------------------------------
 // stbi_load_16(path, &w, &h, &comp, 4) as load_nerf uses it (src/nerf_loader.cu:612,653): any PNG -> 16-bit RGBA in host memory
-int rnb_load_png_rgba16(const char* path, uint32_t* w, uint32_t* h, uint16_t** pixels_host) {
+int rnb_load_png_rgba16(const char* path, uint32_t* w, uint32_t* h, uint16_t** pixels_host) try {
 	if (!path || !w || !h || !pixels_host) return fail(RNB_ERR_INVALID, "null argument");
 	const std::string e = load_png_rgba16_host(path, w, h, pixels_host);
 	if (!e.empty()) return fail(RNB_ERR_INVALID, e);
 	return RNB_OK;
-}
+} RNB_API_CATCH
 void rnb_free_host(void* p) { free(p); }
 
 // the image half of load_nerf (src/nerf_loader.cu:556-760): decode every normal / albedo map on host threads into pinned staging
 // and upload; meta[i] carries intrinsics and the camera matrix (pixel pointers ignored; w/h checked against the files when non-zero)
-int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const char* const* normal_paths, const char* const* albedo_paths, uint32_t threads, void* stream) {
+int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const char* const* normal_paths, const char* const* albedo_paths, uint32_t threads, void* stream) try {
 	if (!c || !meta || !normal_paths || n == 0) return fail(RNB_ERR_INVALID, "no views");
 	std::vector<const char*> paths(2 * (size_t)n, nullptr);
 	for (uint32_t i = 0; i < n; ++i) {
@@ -506,11 +510,11 @@ int rnb_load_dataset_images(rnb_ctx* c, const rnb_view* meta, uint32_t n, const 
 	if (rc != RNB_OK) { cudaFree(arena); return rc; }
 	c->owned.push_back(arena);                                  // the context owns the uploaded pixels (freed by the next dataset call / rnb_destroy)
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 int rnb_set_flags(rnb_ctx* c, const rnb_flags* f) { if (!c || !f) return fail(RNB_ERR_INVALID, "null argument"); c->flags = *f; return RNB_OK; }
 
-int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t ema_step) {
+int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t ema_step) try {
 	if (!c || !host || n != GRID_CELLS) return fail(RNB_ERR_INVALID, "density grid is 128^3 floats");
 	drop_prelaunch(c);
 	CU(cudaMemcpy(c->density_grid, host, n * 4, cudaMemcpyHostToDevice));
@@ -520,7 +524,7 @@ int rnb_import_density_grid(rnb_ctx* c, const float* host, size_t n, uint32_t em
 	launch_grid_finish(0, 0, c->gidx, c->gdens, 1.0f, c->density_grid, c->density_tmp, c->mean_acc, c->mean, c->bitfield);
 	CU(cudaDeviceSynchronize());
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 static void net_density(rnb_ctx* c, cudaStream_t st, uint32_t vl, uint32_t n) {
 	if (c->use_tc) {
@@ -550,12 +554,12 @@ static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint3
 	CU(cudaGetLastError());
 	return RNB_OK;
 }
-int rnb_prep(rnb_ctx* c, void* stream) {
+int rnb_prep(rnb_ctx* c, void* stream) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	drop_prelaunch(c);
 	if (c->training_step < 256) return density_update(c, (cudaStream_t)stream, GRID_CELLS, 0);
 	return density_update(c, (cudaStream_t)stream, GRID_CELLS / 4, GRID_CELLS / 4);
-}
+} RNB_API_CATCH
 
 // network stage dispatch: tensor-core tile kernels (default) or the CUDA-core kernels
 static void net_pack(rnb_ctx* c, cudaStream_t st, const __half* P) {
@@ -630,7 +634,7 @@ static int optimizer_step(rnb_ctx* c, cudaStream_t st) {
 	return RNB_OK;
 }
 
-int rnb_train_step_begin(rnb_ctx* c, void* stream) {
+int rnb_train_step_begin(rnb_ctx* c, void* stream) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->views_dev) return fail(RNB_ERR_STATE, "no dataset: call rnb_set_dataset / rnb_upload_dataset first");
 	if (c->in_step) return fail(RNB_ERR_STATE, "rnb_train_step_begin called twice");
@@ -663,9 +667,9 @@ int rnb_train_step_begin(rnb_ctx* c, void* stream) {
 		}
 	}
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
-int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
+int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->in_step) return fail(RNB_ERR_STATE, "rnb_train_step_end without begin");
 	cudaStream_t st = (cudaStream_t)stream;
@@ -693,14 +697,14 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
 		stats->n_samples_trained = c->counters_host[3]; stats->rays_per_batch_next = c->rays_per_batch; stats->training_step = c->training_step; stats->density_grid_updated = 0;
 	}
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
-int rnb_train_step(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
+int rnb_train_step(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	int rc = rnb_train_step_begin(c, stream); if (rc) return rc;
 	return rnb_train_step_end(c, stream, stats);
-}
+} RNB_API_CATCH
 
-int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
+int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	const uint32_t skip = std::min(std::max(c->training_step / 16u, 1u), 16u);     // src/testbed.cu:2805-2806
 	uint32_t updated = 0;
@@ -708,14 +712,14 @@ int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) {
 	int rc = rnb_train_step(c, stream, stats);
 	if (!rc && stats) stats->density_grid_updated = updated;
 	return rc;
-}
+} RNB_API_CATCH
 
 // ---- in-memory checkpoint / resume (one slot, device side) -------------------------------------------------------------
 // Everything Testbed::train reads and writes between steps: fp32 master / fp16 / EMA parameters, Adam moments and per-parameter
 // step counters, density grid + bitfield, both pcg32 streams, the controller counters.  (The gradient buffer is zero between
 // steps.)  Used by bench.py to time `value` and `e2e` on the SAME training steps; the file-level snapshot of the reference
 // (src/testbed.cu:3280-3390) keeps only the EMA fp16 weights and the density grid and goes through rnb_export_* / rnb_import_*.
-int rnb_checkpoint_save(rnb_ctx* c) {
+int rnb_checkpoint_save(rnb_ctx* c) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (c->in_step) return fail(RNB_ERR_STATE, "checkpoint inside a step");
 	drop_prelaunch(c);
@@ -736,8 +740,8 @@ int rnb_checkpoint_save(rnb_ctx* c) {
 	k.n_rays_total = c->n_rays_total; k.measured_before = c->measured_before; k.measured = c->measured; k.rng = c->rng; k.density_rng = c->density_rng;
 	k.valid = true;
 	return RNB_OK;
-}
-int rnb_checkpoint_restore(rnb_ctx* c) {
+} RNB_API_CATCH
+int rnb_checkpoint_restore(rnb_ctx* c) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->ck.valid) return fail(RNB_ERR_STATE, "no checkpoint");
 	if (c->in_step) return fail(RNB_ERR_STATE, "restore inside a step");
@@ -758,34 +762,34 @@ int rnb_checkpoint_restore(rnb_ctx* c) {
 	c->opt_step = k.opt_step; c->lr_factor = k.lr_factor; c->density_ema_step = k.density_ema_step; c->training_step = k.training_step; c->rays_per_batch = k.rays_per_batch;
 	c->n_rays_total = k.n_rays_total; c->measured_before = k.measured_before; c->measured = k.measured; c->rng = k.rng; c->density_rng = k.density_rng;
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
-int rnb_profile_enable(rnb_ctx* c, int on) {
+int rnb_profile_enable(rnb_ctx* c, int on) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	c->prof = on != 0;
 	if (on) { for (auto& a : c->prof_acc) { a.ms = 0; a.calls = 0; } }
 	return RNB_OK;
-}
+} RNB_API_CATCH
 // names_buf receives ';'-separated stage names; ms / calls are parallel arrays of capacity *n (in) and count (out)
-int rnb_profile_read(rnb_ctx* c, char* names_buf, size_t names_cap, double* ms, uint64_t* calls, uint32_t* n) {
+int rnb_profile_read(rnb_ctx* c, char* names_buf, size_t names_cap, double* ms, uint64_t* calls, uint32_t* n) try {
 	if (!c || !n) return fail(RNB_ERR_INVALID, "null argument");
 	std::string names; uint32_t k = 0;
 	for (auto& a : c->prof_acc) { if (k >= *n) break; names += a.name; names += ';'; ms[k] = a.ms; calls[k] = a.calls; ++k; }
 	*n = k;
 	if (names_buf && names_cap) { strncpy(names_buf, names.c_str(), names_cap - 1); names_buf[names_cap - 1] = 0; }
 	return RNB_OK;
-}
+} RNB_API_CATCH
 int rnb_launch_count(rnb_ctx* c, uint64_t* out) { if (!c || !out) return fail(RNB_ERR_INVALID, "null argument"); *out = c->launches; return RNB_OK; }
 
 int rnb_grad_buffer(rnb_ctx* c, float** g, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *g = c->grads; *n = c->M.n_params; return RNB_OK; }
 // host copies for parity tests: the fp32 gradient accumulators (valid between rnb_train_step_begin and _end) and the per-ray
 // loss terms of the last step (loss_output / ek_loss_output / mask_loss_output of compute_loss_kernel, testbed_nerf.cu:1396-2097)
-int rnb_get_grads_fp32(rnb_ctx* c, float* host, size_t n) {
+int rnb_get_grads_fp32(rnb_ctx* c, float* host, size_t n) try {
 	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad gradient buffer");
 	CU(cudaMemcpy(host, c->grads, n * 4, cudaMemcpyDeviceToHost));
 	return RNB_OK;
-}
-int rnb_get_ray_losses(rnb_ctx* c, uint32_t cap, uint32_t* ray_idx, float* loss3, uint32_t* n_out) {
+} RNB_API_CATCH
+int rnb_get_ray_losses(rnb_ctx* c, uint32_t cap, uint32_t* ray_idx, float* loss3, uint32_t* n_out) try {
 	if (!c || !ray_idx || !loss3 || !n_out) return fail(RNB_ERR_INVALID, "null argument");
 	uint32_t K = 0; CU(cudaMemcpy(&K, c->counters, 4, cudaMemcpyDeviceToHost));
 	K = std::min(K, std::min(cap, c->cap_rays));
@@ -793,9 +797,9 @@ int rnb_get_ray_losses(rnb_ctx* c, uint32_t cap, uint32_t* ray_idx, float* loss3
 	CU(cudaMemcpy(loss3, c->loss_out, (size_t)K * 12, cudaMemcpyDeviceToHost));
 	*n_out = K;
 	return RNB_OK;
-}
+} RNB_API_CATCH
 // per kept ray of the last step: samples marched and samples kept by the transmittance cut (profiling / tests)
-int rnb_get_ray_counts(rnb_ctx* c, uint32_t cap, uint32_t* marched, uint32_t* kept, uint32_t* n_out) {
+int rnb_get_ray_counts(rnb_ctx* c, uint32_t cap, uint32_t* marched, uint32_t* kept, uint32_t* n_out) try {
 	if (!c || !marched || !kept || !n_out) return fail(RNB_ERR_INVALID, "null argument");
 	uint32_t K = 0; CU(cudaMemcpy(&K, c->counters, 4, cudaMemcpyDeviceToHost));
 	K = std::min(K, std::min(cap, c->cap_rays));
@@ -805,27 +809,27 @@ int rnb_get_ray_counts(rnb_ctx* c, uint32_t cap, uint32_t* marched, uint32_t* ke
 	CU(cudaMemcpy(kept, c->n_fwd, (size_t)K * 4, cudaMemcpyDeviceToHost));
 	*n_out = K;
 	return RNB_OK;
-}
+} RNB_API_CATCH
 // ---- data-parallel optimizer sharding (new) ---------------------------------------------------------------
-int rnb_param_buffers(rnb_ctx* c, void** params_fp16, void** ema_fp16, uint64_t* n_params, uint64_t* n_padded) {
+int rnb_param_buffers(rnb_ctx* c, void** params_fp16, void** ema_fp16, uint64_t* n_params, uint64_t* n_padded) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (params_fp16) *params_fp16 = c->params;
 	if (ema_fp16) *ema_fp16 = c->ema;
 	if (n_params) *n_params = c->M.n_params;
 	if (n_padded) *n_padded = c->np_padded;
 	return RNB_OK;
-}
-int rnb_set_optimizer_shard(rnb_ctx* c, uint64_t begin, uint64_t end, const float* reduced_grads_dev) {
+} RNB_API_CATCH
+int rnb_set_optimizer_shard(rnb_ctx* c, uint64_t begin, uint64_t end, const float* reduced_grads_dev) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (c->in_step) return fail(RNB_ERR_STATE, "optimizer shard changed inside a step");
 	if (end == 0) { c->shard_begin = c->shard_end = 0; c->shard_grads = nullptr; return RNB_OK; }
 	if (begin % 8 || end % 8 || begin >= end || end > c->np_padded) return fail(RNB_ERR_INVALID, "optimizer shard must be a non-empty [begin, end) of multiples of 8 inside the padded parameter range");
 	c->shard_begin = (uint32_t)begin; c->shard_end = (uint32_t)end; c->shard_grads = reduced_grads_dev;
 	return RNB_OK;
-}
+} RNB_API_CATCH
 int rnb_stat_buffer(rnb_ctx* c, float** s, uint64_t* n) { if (!c) return fail(RNB_ERR_INVALID, "null ctx"); *s = c->stats; *n = 8; return RNB_OK; }
 
-int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream) {
+int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, float* normal_dev, float* density_dev, int use_ema, void* stream) try {
 	if (!c || !xyz_dev) return fail(RNB_ERR_INVALID, "null argument");
 	cudaStream_t st = (cudaStream_t)stream;
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
@@ -844,12 +848,12 @@ int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, flo
 	CU(cudaFreeAsync(tmp, st));
 	CU(cudaGetLastError());
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 // SDF on a lattice — Testbed::get_density_on_grid (src/testbed_nerf.cu:4218-4269: generate_grid_samples_nerf_uniform + NerfNetwork::sdf in
 // 1 M-point batches + grid_samples_half_to_float) in one launch: the lattice positions are generated inside the tcgen05 probe kernel
 // (the reference materialises 12 B per point first: 12.9 GB at 1024^3).  out_dev[x + y rx + z rx ry] = sdf (incl. bias), fp32.
-int rnb_sdf_on_grid(rnb_ctx* c, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float* out_dev, int use_ema, void* stream) {
+int rnb_sdf_on_grid(rnb_ctx* c, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float* out_dev, int use_ema, void* stream) try {
 	if (!c || !res || !aabb_min || !aabb_max || !out_dev) return fail(RNB_ERR_INVALID, "null argument");
 	if ((uint64_t)res[0] * res[1] * res[2] > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice larger than 2^32 points");
 	if (!c->use_tc) return fail(RNB_ERR_STATE, "rnb_sdf_on_grid needs the tcgen05 network path");
@@ -860,7 +864,7 @@ int rnb_sdf_on_grid(rnb_ctx* c, const uint32_t res[3], const float aabb_min[3], 
 	launch_tc_sdf_grid(st, c->M, P, c->wtc, vl, res, aabb_min, aabb_max, out_dev, c->n_sm);
 	CU(cudaGetLastError());
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 // ---- mesh extraction ----------------------------------------------------------------------------------------
 static void mesh_free(rnb_ctx* c) {
@@ -871,7 +875,7 @@ static void mesh_free(rnb_ctx* c) {
 // marching_cubes_gpu + compute_mesh_1ring + compute_mesh_vertex_colors on a caller-provided lattice of SDF values
 // (src/marching_cubes.cu:794-822, :722-728, src/testbed_nerf.cu:4193-4216).  with_colors == 0 skips the network pass (colours zero).
 int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh,
-                                    int with_colors, int use_ema, void* stream, rnb_mesh_info* info) {
+                                    int with_colors, int use_ema, void* stream, rnb_mesh_info* info) try {
 	if (!c || !density_dev || !res || !aabb_min || !aabb_max) return fail(RNB_ERR_INVALID, "null argument");
 	if (res[0] == 0 || res[1] == 0 || res[2] == 0 || res[0] % 16 != 0) return fail(RNB_ERR_INVALID, "lattice x resolution must be a positive multiple of 16");
 	if ((uint64_t)res[0] * res[1] * res[2] > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice larger than 2^32 points");
@@ -918,10 +922,10 @@ int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const 
 		for (int k = 0; k < 4; ++k) info->stage_ms[k] = m.ms[k];
 	}
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 // Testbed::marching_cubes (src/testbed_nerf.cu:4297-4348): resolution rounded up to multiples of 16, SDF sweep, extraction, normals, colours.
-int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_min[3], const float aabb_max[3], float thresh, int use_ema, void* stream, rnb_mesh_info* info) {
+int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_min[3], const float aabb_max[3], float thresh, int use_ema, void* stream, rnb_mesh_info* info) try {
 	if (!c || !res_in || !aabb_min || !aabb_max) return fail(RNB_ERR_INVALID, "null argument");
 	const uint32_t res[3] = {next_multiple(res_in[0], 16u), next_multiple(res_in[1], 16u), next_multiple(res_in[2], 16u)};
 	const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
@@ -937,9 +941,9 @@ int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_mi
 	if (rc == RNB_OK) { cudaEventElapsedTime(&c->mesh.ms[0], es[0], es[1]); if (info) info->stage_ms[0] = c->mesh.ms[0]; }
 	cudaEventDestroy(es[0]); cudaEventDestroy(es[1]);
 	return rc;
-}
+} RNB_API_CATCH
 
-int rnb_mesh_buffers(rnb_ctx* c, float** verts, float** normals, float** colors, uint32_t** indices, rnb_mesh_info* info) {
+int rnb_mesh_buffers(rnb_ctx* c, float** verts, float** normals, float** colors, uint32_t** indices, rnb_mesh_info* info) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->mesh.verts) return fail(RNB_ERR_STATE, "no mesh: call rnb_marching_cubes first");
 	if (verts) *verts = c->mesh.verts;
@@ -948,10 +952,10 @@ int rnb_mesh_buffers(rnb_ctx* c, float** verts, float** normals, float** colors,
 	if (indices) *indices = c->mesh.indices;
 	if (info) { info->n_verts = c->mesh.n_verts; info->n_verts_padded = c->mesh.n_verts_padded; info->n_indices = c->mesh.n_indices; info->res[0] = info->res[1] = info->res[2] = 0; for (int k = 0; k < 4; ++k) info->stage_ms[k] = c->mesh.ms[k]; }
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 // host copies of the mesh (Testbed::compute_marching_cubes_mesh, src/python_api.cu:99-130); each pointer may be null
-int rnb_mesh_download(rnb_ctx* c, float* verts, float* normals, float* colors, uint32_t* indices) {
+int rnb_mesh_download(rnb_ctx* c, float* verts, float* normals, float* colors, uint32_t* indices) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->mesh.verts) return fail(RNB_ERR_STATE, "no mesh: call rnb_marching_cubes first");
 	const size_t vb = (size_t)c->mesh.n_verts_padded * 12;
@@ -960,11 +964,11 @@ int rnb_mesh_download(rnb_ctx* c, float* verts, float* normals, float* colors, u
 	if (colors) CU(cudaMemcpy(colors, c->mesh.colors, vb, cudaMemcpyDeviceToHost));
 	if (indices) CU(cudaMemcpy(indices, c->mesh.indices, (size_t)c->mesh.n_indices * 4, cudaMemcpyDeviceToHost));
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 // save_mesh (src/marching_cubes.cu:824-982) on device arrays; no context needed
 int rnb_save_mesh(const float* verts_dev, const float* normals_dev, const float* colors_dev, const uint32_t* indices_dev, uint32_t n_verts, uint32_t n_indices, const char* path,
-                  float nerf_scale, const float nerf_offset[3], float n2w_s, const float n2w_t[3], int invert_normals, void* stream, uint64_t* bytes_written) {
+                  float nerf_scale, const float nerf_offset[3], float n2w_s, const float n2w_t[3], int invert_normals, void* stream, uint64_t* bytes_written) try {
 	if (!path || !nerf_offset || !n2w_t) return fail(RNB_ERR_INVALID, "null argument");
 	if ((n_verts && (!verts_dev || !normals_dev || !colors_dev)) || (n_indices && !indices_dev)) return fail(RNB_ERR_INVALID, "null mesh array");
 	if (n_indices % 3) return fail(RNB_ERR_INVALID, "index count is not a multiple of 3");
@@ -972,10 +976,10 @@ int rnb_save_mesh(const float* verts_dev, const float* normals_dev, const float*
 	const std::string e = mesh_write((cudaStream_t)stream, verts_dev, normals_dev, colors_dev, indices_dev, n_verts, n_indices, path, nerf_scale, nerf_offset, n2w_s, n2w_t, invert_normals, bytes_written, &launches);
 	if (!e.empty()) return fail(RNB_ERR_CUDA, e);
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 // ---- stage-level entry points (host buffers) ------------------------------------------------------------------------
-int rnb_stage_generate(rnb_ctx* c, uint32_t n_rays, uint32_t n_rays_total, uint32_t max_samples, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t counters[2]) {
+int rnb_stage_generate(rnb_ctx* c, uint32_t n_rays, uint32_t n_rays_total, uint32_t max_samples, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t counters[2]) try {
 	if (!c || !c->views_dev) return fail(RNB_ERR_STATE, "no dataset");
 	if (max_samples > c->max_samples) return fail(RNB_ERR_INVALID, "max_samples exceeds capacity");
 	drop_prelaunch(c);
@@ -1006,7 +1010,7 @@ int rnb_stage_generate(rnb_ctx* c, uint32_t n_rays, uint32_t n_rays_total, uint3
 		}
 	}
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 static int upload_coords(rnb_ctx* c, const float* coords, size_t n, float4* dst_pos, float** dirw_out) {
 	std::vector<float4> p4(n); std::vector<float> dw(n * 3);
@@ -1022,7 +1026,7 @@ static int upload_coords(rnb_ctx* c, const float* coords, size_t n, float4* dst_
 	return RNB_OK;
 }
 
-int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, float* out16, float* normal) {
+int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, float* out16, float* normal) try {
 	if (!c || !coords || !out16) return fail(RNB_ERR_INVALID, "null argument");
 	if (n > c->cap_compact) return fail(RNB_ERR_INVALID, "too many samples for one stage call");
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
@@ -1040,10 +1044,10 @@ int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, fl
 	if (normal) { CU(cudaMemcpy(normal, nrm_dev, n * 12, cudaMemcpyDeviceToHost)); cudaFree(nrm_dev); }
 	cudaFree(dirw);
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 int rnb_stage_loss(rnb_ctx* c, const float* out16_c, const uint32_t* ray_indices, const uint32_t* n_fwd, const uint32_t* cbase, const uint32_t* n_emit,
-                   uint32_t K, uint32_t n_rays, uint32_t n_rays_total, float* dout16, float* loss, float* ek, float* mask) {
+                   uint32_t K, uint32_t n_rays, uint32_t n_rays_total, float* dout16, float* loss, float* ek, float* mask) try {
 	if (!c || !c->views_dev) return fail(RNB_ERR_STATE, "no dataset");
 	int rc = ensure_ray_capacity(c, std::max(K, n_rays)); if (rc) return rc;
 	size_t total = 0; for (uint32_t k = 0; k < K; ++k) total = std::max<size_t>(total, (size_t)cbase[k] + n_fwd[k]);
@@ -1066,9 +1070,9 @@ int rnb_stage_loss(rnb_ctx* c, const float* out16_c, const uint32_t* ray_indices
 	CU(cudaMemcpy(lo.data(), c->loss_out, (size_t)K * 12, cudaMemcpyDeviceToHost));
 	for (uint32_t k = 0; k < K; ++k) { loss[k] = lo[3 * k]; ek[k] = lo[3 * k + 1]; mask[k] = lo[3 * k + 2]; }
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
-int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, size_t n, uint32_t n_in_rollover, float* grads) {
+int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, size_t n, uint32_t n_in_rollover, float* grads) try {
 	if (!c || !coords || !dout16 || !grads) return fail(RNB_ERR_INVALID, "null argument");
 	if (n > c->cfg.target_batch_size) return fail(RNB_ERR_INVALID, "too many samples");
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
@@ -1086,14 +1090,14 @@ int rnb_stage_backward(rnb_ctx* c, const float* coords, const float* dout16, siz
 	CU(cudaMemset(c->grads, 0, (size_t)c->M.n_params * 4));
 	cudaFree(nin); cudaFree(dirw);
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
-int rnb_stage_optimizer(rnb_ctx* c, const float* grads_host) {
+int rnb_stage_optimizer(rnb_ctx* c, const float* grads_host) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (grads_host) CU(cudaMemcpy(c->grads, grads_host, (size_t)c->M.n_params * 4, cudaMemcpyHostToDevice));
 	int rc = optimizer_step(c, 0); if (rc) return rc;
 	CU(cudaDeviceSynchronize());
 	return RNB_OK;
-}
+} RNB_API_CATCH
 
 } // extern "C"
