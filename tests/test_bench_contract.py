@@ -34,3 +34,19 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     assert p.returncode != 0
     assert "CUDA" in (p.stderr + p.stdout)
     assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
+
+
+def test_network_path_label_follows_the_kernel_selection(monkeypatch):
+    """config.network_path names the kernels the library selects from the same environment variables (csrc/rnb_api.cu)"""
+    import importlib
+    bench = importlib.import_module("bench")
+    for var in ("RNB_NETWORK", "RNB_BACKWARD"):
+        monkeypatch.delenv(var, raising=False)
+    assert bench._network_path() == "tcgen05 forward + tcgen05 backward"
+    monkeypatch.setenv("RNB_BACKWARD", "mma")
+    assert bench._network_path() == "tcgen05 forward + mma.sync backward"
+    monkeypatch.setenv("RNB_NETWORK", "mma")
+    assert "mma.sync" in bench._network_path() and "cross-check" in bench._network_path()
+    monkeypatch.setenv("RNB_NETWORK", "simt")
+    assert "CUDA-core" in bench._network_path()
+    assert bench.DP_MODE_DEFAULT == "allreduce"          # the measured default at N = 2 (DESIGN.md §9)
