@@ -107,6 +107,10 @@ inline void on_reset_network(ngp::Testbed& t) {
 	uint64_t layout[5]; check(rnb_param_layout(ctx(), layout));
 	const size_t n = t.m_network->n_params();
 	if (n != layout[4]) throw std::runtime_error{"rnb_b200: parameter count differs from the reference network (" + std::to_string(n) + " vs " + std::to_string(layout[4]) + ")"};
+	// binary16 copy first (training + inference parameters, Adam state cleared), then the exact fp32 master weights on top
+	std::vector<uint16_t> h16(n);
+	CUDA_CHECK_THROW(cudaMemcpy(h16.data(), t.m_trainer->params(), n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+	check(rnb_import_params_fp16(ctx(), h16.data(), n));
 	std::vector<float> w(n);
 	CUDA_CHECK_THROW(cudaMemcpy(w.data(), t.m_trainer->params_full_precision(), n * sizeof(float), cudaMemcpyDeviceToHost));
 	check(rnb_set_params_fp32(ctx(), w.data(), n));
