@@ -116,3 +116,33 @@ def write_scene_files(root):
             f.write("f %d//%d %d//%d %d//%d\n" % (t[0] + 1, t[0] + 1, t[1] + 1, t[1] + 1, t[2] + 1, t[2] + 1))
     h.update(open(os.path.join(root, "mesh_0.obj"), "rb").read())
     return {"names": names, "sha256": h.hexdigest()}
+
+
+# ---- input of the prepare stage: the standard dict of the reference's dataloaders (dataloaders/base.py) over files on disk ------------
+def write_prepare_inputs(root):
+    """normal maps (16-bit RGB PNG), albedos (8-bit for odd views, 16-bit otherwise, none for view 5), 8-bit masks, view 6 without its
+    normal file (must be skipped), landmarks on the sphere; returns the data dict"""
+    import os
+    import cv2
+    verts, tris, K, R, Cc, alb, msk = fixed_scene()
+    src = os.path.join(root, "src"); os.makedirs(src, exist_ok=True)
+    rng = np.random.default_rng(21)
+    views = []
+    for i in range(V):
+        nrm = (np.clip(rng.normal(0.5, 0.2, size=(H, W, 3)), 0, 1) * 65535).astype(np.uint16) * (msk[i][:, :, None] > 0)
+        npath = os.path.join(src, "n%02d.png" % i)
+        if i != 6:
+            cv2.imwrite(npath, nrm)
+        apath = None
+        if i != 5:
+            apath = os.path.join(src, "a%02d.png" % i)
+            a = np.clip(alb[i][:, :, ::-1], 0, 1)
+            cv2.imwrite(apath, (a * 255).astype(np.uint8) if i % 2 else (a * 65535).astype(np.uint16))
+        mpath = os.path.join(src, "m%02d.png" % i)
+        cv2.imwrite(mpath, (msk[i] * 255).astype(np.uint8))
+        c2w = np.eye(4); c2w[:3, :3] = R[i]; c2w[:3, 3] = Cc[i][:, 0] * 37.0 + np.array([120.0, -40.0, 15.0])      # an unnormalised world
+        K4 = np.eye(4); K4[:3, :3] = K[i]
+        views.append({"c2w": c2w, "K": K4, "normal_path": npath, "albedo_path": apath, "mask_path": mpath if i != 2 else None, "pose_id": str(i)})
+    lm = rng.normal(size=(500, 3)); lm = lm / np.linalg.norm(lm, axis=1)[:, None] * 37.0 + np.array([120.0, -40.0, 15.0])
+    lm[:5] *= 3.0                                                    # outliers for the percentile cut
+    return {"views": views, "landmarks": lm, "image_width": W, "image_height": H, "scale_mat": None}
