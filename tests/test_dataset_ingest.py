@@ -173,3 +173,16 @@ def test_png_decoder_survives_corrupt_files(tmp_path, seed):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz", "png_fuzz.py"), str(seed), str(tmp_path), "600"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr[-600:])
     assert "rejected" in r.stdout and int(r.stdout.split("rejected")[1].split()[0]) > 400
+
+
+def test_most_compressible_image_is_not_mistaken_for_a_hostile_header(tmp_path):
+    """the decoder refuses headers that promise more pixels than deflate's 1032:1 bound allows for the compressed data; a constant
+    full-size map at maximum compression (ratio ~1028:1) is the closest legitimate file"""
+    import cv2
+    pkg = rnb_loader.load_package()
+    for val in (0, 65535):
+        p = str(tmp_path / ("const%d.png" % val))
+        cv2.imwrite(p, np.full((1200, 1600, 4), val, np.uint16), [cv2.IMWRITE_PNG_COMPRESSION, 9])
+        assert (1600 * 8 + 1) * 1200 / os.path.getsize(p) > 800
+        a = pkg.load_png_rgba16(p)
+        assert a.shape == (1200, 1600, 4) and int(a.min()) == val and int(a.max()) == val
