@@ -58,7 +58,7 @@ static void dump_host(const std::string& name, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
 	if (argc < 5) {
-		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--time-from K] [--pin-rays N] [--mesh RES] [--save-snapshot FILE] [--load-snapshot FILE]\n");
+		fprintf(stderr, "usage: ref_harness <scene_dir> <network_config.json> <out_dir> <n_steps> [--no-albedo] [--supernormal] [--opti-lights] [--l1] [--no-rgbplus] [--dump-every K | --dump-steps a,b,c] [--time-only] [--time-from K] [--pin-rays N] [--mesh RES] [--save-snapshot FILE] [--load-snapshot FILE] [--print-every K]\n");
 		return 1;
 	}
 	char buf[PATH_MAX]; ssize_t cnt = readlink("/proc/self/exe", buf, PATH_MAX);
@@ -67,7 +67,7 @@ int main(int argc, char** argv) {
 	g_out = argv[3];
 	const int n_steps = atoi(argv[4]);
 	bool no_albedo = false, supernormal = false, opti = false, l1 = false, rgbplus = true, time_only = false;
-	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps; int time_from = -1; int mesh_res = 0; std::string save_snapshot, load_snapshot;
+	int dump_every = 1; uint32_t pin_rays = 0; std::vector<int> dump_steps; int time_from = -1; int mesh_res = 0; int print_every = 50; std::string save_snapshot, load_snapshot;
 	for (int i = 5; i < argc; ++i) {
 		std::string a = argv[i];
 		if (a == "--no-albedo") no_albedo = true; else if (a == "--supernormal") supernormal = true; else if (a == "--opti-lights") opti = true;
@@ -76,6 +76,7 @@ int main(int argc, char** argv) {
 		else if (a == "--pin-rays" && i + 1 < argc) pin_rays = (uint32_t)atoi(argv[++i]);
 		else if (a == "--time-from" && i + 1 < argc) time_from = atoi(argv[++i]);
 		else if (a == "--mesh" && i + 1 < argc) mesh_res = atoi(argv[++i]);
+		else if (a == "--print-every" && i + 1 < argc) print_every = std::max(1, atoi(argv[++i]));
 		else if (a == "--save-snapshot" && i + 1 < argc) save_snapshot = argv[++i];
 		else if (a == "--load-snapshot" && i + 1 < argc) load_snapshot = argv[++i];
 		else if (a == "--dump-steps" && i + 1 < argc) { std::string l = argv[++i]; size_t p0 = 0; while (p0 < l.size()) { size_t q = l.find(',', p0); if (q == std::string::npos) q = l.size(); dump_steps.push_back(atoi(l.substr(p0, q - p0).c_str())); p0 = q + 1; } }
@@ -168,7 +169,7 @@ int main(int argc, char** argv) {
 			memcpy(&o[6], sc, 12);
 			dump_host(tag + "_out_counters.bin", o, sizeof(o));
 		}
-		if (k % 50 == 0 || k == n_steps - 1)
+		if (k % print_every == 0 || k == n_steps - 1)
 			printf("ref step %d rays %u samples %u compacted %u loss %g  %.3f ms\n", k, R, tr.counters_rgb.measured_batch_size_before_compaction, tr.counters_rgb.measured_batch_size, tb.m_loss_scalar.val(), ms);
 	}
 	if (!time_only) dump_state("final");

@@ -458,11 +458,14 @@ void orc_train_step_end(Oracle* o, OrcStats* st) {
 	++o->training_step;
 	o->in_step = false;
 	const uint32_t total = o->cnt_total, R = o->step_R;
-	o->measured_before = o->cnt_samples; o->measured = total;
+	if (o->cnt_samples == 0 || total == 0) { o->measured_before = 0; o->measured = 0; }      // Counters::update_after_training, testbed_nerf.cu:3540-3542
+	else { o->measured_before = o->cnt_samples; o->measured = total; }
 	const float f = (float)o->sums[3] / (float)o->target_batch;     // sums[3] is the global compacted count after the all-reduce
 	if (st) { st->loss = (float)o->sums[0] * f; st->ek_loss = (float)o->sums[1] * f; st->mask_loss = (float)o->sums[2] * f; st->n_rays_kept = o->cnt_kept; st->n_samples = o->cnt_samples; st->n_compacted = total; st->n_emitted = o->cnt_trained; }
-	if (!o->pin_rays && total > 0) {
-		uint32_t r = (uint32_t)((float)R * (float)o->target_batch / (float)total);
+	// data parallel: sums[3] is the all-reduced compacted count, so that every rank derives the same next batch size
+	const uint32_t total_global = o->world > 1 ? (uint32_t)(o->sums[3] + 0.5) : total;
+	if (!o->pin_rays && total_global > 0 && (o->world > 1 || o->cnt_samples != 0)) {
+		uint32_t r = (uint32_t)((float)R * (float)o->target_batch / (float)total_global);
 		o->rays_per_batch = std::min(next_multiple(r, 128u), 1u << 18);
 	}
 	if (st) st->rays_per_batch_next = o->rays_per_batch;

@@ -224,6 +224,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) try {
 	}
 	int dev = 0; CU(cudaGetDevice(&dev));
 	rnb_ctx* c = new rnb_ctx();
+	struct Guard { rnb_ctx* p; ~Guard() { if (p) rnb_destroy(p); } } guard{c};      // any early return below releases what has been allocated so far
 	c->cfg = *cfg; rnb_default_flags(&c->flags);
 	if (c->cfg.per_level_scale <= 0.f)
 		c->cfg.per_level_scale = c->cfg.n_levels > 1 ? std::exp(std::log(c->cfg.top_resolution * 1.0f / (float)c->cfg.base_resolution) / (c->cfg.n_levels - 1)) : 1.0f;   // src/testbed.cu:2321
@@ -299,6 +300,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) try {
 	int rc = ensure_ray_capacity(c, c->rays_per_batch); if (rc) return rc;
 	c->rng = Pcg32(cfg->seed);
 	{ Pcg32 t = c->rng; c->density_rng = Pcg32(t.next_uint()); }     // src/testbed.cu:2223,2236,2490
+	guard.p = nullptr;
 	*out = c;
 	return RNB_OK;
 } RNB_API_CATCH
@@ -449,27 +451,39 @@ int rnb_set_rng(rnb_ctx* c, const uint64_t in[4]) try {
 
 static int set_views(rnb_ctx* c, const rnb_view* views, uint32_t n, bool upload) {
 	if (!c || !views || n == 0) return fail(RNB_ERR_INVALID, "no views");
+	// validate everything first, build the new allocations and the new view table in locals, and only then swap them into the context:
+	// a failure leaves the previous dataset installed and intact (nothing the old ViewDev table points at has been freed)
+	for (uint32_t i = 0; i < n; ++i) if (!views[i].normal_px || views[i].w <= 0 || views[i].h <= 0) return fail(RNB_ERR_INVALID, "view without normal map");
 	drop_prelaunch(c);
-	for (void* p : c->owned) cudaFree(p);
-	c->owned.clear();
+	std::vector<void*> fresh;
+	auto release = [&]() { for (void* p : fresh) cudaFree(p); fresh.clear(); };
 	std::vector<ViewDev> vd(n);
 	for (uint32_t i = 0; i < n; ++i) {
 		const rnb_view& v = views[i];
-		if (!v.normal_px || v.w <= 0 || v.h <= 0) return fail(RNB_ERR_INVALID, "view without normal map");
 		const size_t bytes = (size_t)v.w * v.h * 8;
 		const void* np = v.normal_px; const void* ap = v.albedo_px;
 		if (upload) {
-			void* d = nullptr; CU(cudaMalloc(&d, bytes)); c->owned.push_back(d); CU(cudaMemcpy(d, v.normal_px, bytes, cudaMemcpyHostToDevice)); np = d;
-			if (v.albedo_px) { void* a = nullptr; CU(cudaMalloc(&a, bytes)); c->owned.push_back(a); CU(cudaMemcpy(a, v.albedo_px, bytes, cudaMemcpyHostToDevice)); ap = a; }
+			for (int k = 0; k < 2; ++k) {
+				const void* src = k == 0 ? v.normal_px : v.albedo_px;
+				if (!src) continue;
+				void* d = nullptr;
+				cudaError_t e = cudaMalloc(&d, bytes);
+				if (e == cudaSuccess) { fresh.push_back(d); e = cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice); }
+				if (e != cudaSuccess) { release(); return fail(e == cudaErrorMemoryAllocation ? RNB_ERR_NOMEM : RNB_ERR_CUDA, std::string("dataset upload: ") + cudaGetErrorString(e)); }
+				(k == 0 ? np : ap) = d;
+			}
 		}
 		vd[i].normal_px = (const uint2*)np; vd[i].albedo_px = (const uint2*)ap; vd[i].w = v.w; vd[i].h = v.h;
 		vd[i].fx = v.fx; vd[i].fy = v.fy; vd[i].cx = v.cx; vd[i].cy = v.cy;
 		memcpy(vd[i].xform, v.xform, sizeof(v.xform));
 	}
-	cudaFree(c->views_dev); c->views_dev = nullptr;
-	CU(cudaMalloc(&c->views_dev, n * sizeof(ViewDev)));
-	CU(cudaMemcpy(c->views_dev, vd.data(), n * sizeof(ViewDev), cudaMemcpyHostToDevice));
-	c->n_views = n;
+	ViewDev* table = nullptr;
+	cudaError_t e = cudaMalloc(&table, n * sizeof(ViewDev));
+	if (e == cudaSuccess) e = cudaMemcpy(table, vd.data(), n * sizeof(ViewDev), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { cudaFree(table); release(); return fail(RNB_ERR_CUDA, std::string("dataset view table: ") + cudaGetErrorString(e)); }
+	for (void* p : c->owned) cudaFree(p);
+	cudaFree(c->views_dev);
+	c->owned = std::move(fresh); c->views_dev = table; c->n_views = n;
 	return RNB_OK;
 }
 int rnb_set_dataset(rnb_ctx* c, const rnb_view* v, uint32_t n) { return set_views(c, v, n, false); }
@@ -683,10 +697,17 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	CU(cudaStreamSynchronize(st));
 	prof_resolve(c);
 	const uint32_t total = c->counters_host[2];
-	c->measured_before = c->counters_host[1]; c->measured = total;
 	const uint32_t R = c->step_R;
-	if (!c->cfg.pin_rays_per_batch && total > 0) {
-		uint32_t r = (uint32_t)((float)R * (float)c->cfg.target_batch_size / (float)total);
+	// data parallel: every rank must derive the SAME next batch size, so the controller is driven by the all-reduced compacted count
+	// (stats[3], summed over ranks together with the losses by the caller) against the global target; single GPU: the local count
+	const uint32_t total_global = c->cfg.world_size > 1 ? (uint32_t)(c->stats_host[3] + 0.5f) : total;
+	if (c->counters_host[1] == 0 || total == 0) {      // Counters::update_after_training zeroes both and leaves rays_per_batch alone (:3540-3542)
+		c->measured_before = 0; c->measured = 0;
+	} else {
+		c->measured_before = c->counters_host[1]; c->measured = total;
+	}
+	if (!c->cfg.pin_rays_per_batch && total_global > 0 && (c->cfg.world_size > 1 || c->counters_host[1] != 0)) {
+		uint32_t r = (uint32_t)((float)R * (float)c->cfg.target_batch_size / (float)total_global);
 		c->rays_per_batch = std::min(next_multiple(r, 128u), 1u << 18);
 	}
 	if (stats) {

@@ -65,15 +65,17 @@ def load_transforms(path):
         x = nerf_matrix_to_ngp(m, scale, offset, from_na, from_mitsuba)
         K = fr["intrinsic_matrix"]
 
-        def img(key):
-            p = fr.get(key, "")
+        def img(key, required):
+            p = fr.get(key, "") or ""
             if p == "":
+                if required:      # the reference falls back to a per-part default name (nerf_loader.cu:588-592) that the RNb pipeline never writes
+                    raise ValueError("transform.json frame %d has no %s" % (i, key))
                 return None
             p = os.path.join(base, p)
             if os.path.splitext(p)[1] == "":
                 p += ".png"
-            return p.replace("\\\\", "/")
-        views.append(dict(normal_path=img("normal_path"), albedo_path=img("albedo_path"), w=int(w), h=int(h),
+            return p.replace("\\", "/")             # every single backslash, like replace(..., '\\', '/') in nerf_loader.cu:604,645
+        views.append(dict(normal_path=img("normal_path", True), albedo_path=img("albedo_path", False), w=int(w), h=int(h),
                           fx=f32(K[0][0]), fy=f32(K[1][1]), cx=f32(K[0][2]) / f32(w), cy=f32(K[1][2]) / f32(h),
                           xform=x.T.reshape(-1).copy()))           # column-major 3x4, as rnb_view.xform
     return dict(views=views, scale=float(scale), offset=tuple(float(v) for v in offset), aabb_scale=int(j.get("aabb_scale", 1)), from_na=from_na,

@@ -186,3 +186,18 @@ def test_most_compressible_image_is_not_mistaken_for_a_hostile_header(tmp_path):
         assert (1600 * 8 + 1) * 1200 / os.path.getsize(p) > 800
         a = pkg.load_png_rgba16(p)
         assert a.shape == (1200, 1600, 4) and int(a.min()) == val and int(a.max()) == val
+
+
+def test_transform_json_windows_paths_and_missing_normal(tmp_path):
+    """replace(path, '\\\\', '/') converts EVERY backslash (ref:src/nerf_loader.cu:604,645); a frame without a normal map is a clear error, an empty
+    albedo path means "no albedo map" (None), never an AttributeError further down"""
+    fr = {"normal_path": "normals\\sub\\00000.png", "albedo_path": "", "transform_matrix": np.eye(4).tolist(), "intrinsic_matrix": [[10, 0, 2], [0, 10, 2], [0, 0, 1]]}
+    tj = {"w": 4, "h": 4, "aabb_scale": 1, "scale": 0.5, "offset": [0.5] * 3, "from_na": True, "frames": [fr]}
+    (tmp_path / "transform.json").write_text(json.dumps(tj))
+    m = ds.load_transforms(str(tmp_path))
+    assert m["views"][0]["normal_path"].endswith("normals/sub/00000.png") and "\\" not in m["views"][0]["normal_path"]
+    assert m["views"][0]["albedo_path"] is None
+    fr["normal_path"] = ""
+    (tmp_path / "transform.json").write_text(json.dumps(tj))
+    with pytest.raises(ValueError, match="normal_path"):
+        ds.load_transforms(str(tmp_path))

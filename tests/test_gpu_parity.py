@@ -6,7 +6,7 @@ plus an element-wise bound of two binary16 ulps, because one rounding flip of a 
 """
 import numpy as np
 import pytest
-from common import SMALL, MID, make_pair, rel_err
+from common import SMALL, MID, FULL, make_pair, rel_err
 from oracle_binding import default_flags as orc_flags
 
 pytestmark = pytest.mark.gpu
@@ -68,7 +68,9 @@ def test_march_empty_and_full_occupancy(pkg, small_scene):
             assert np.array_equal(a["coords"][:n].view(np.uint32), b["coords"][:n].view(np.uint32))
 
 
-@pytest.mark.parametrize("cfg,step", [(SMALL, 0), (MID, 0), (MID, 300)])
+# FULL = the shipped default network (L=14, T=2^19: levels 0-4 dense incl. the non-power-of-two resolutions 34 / 50 / 72, levels 5-13 hashed);
+# steps 0 / 300 / 700 have 14 / 7 / 14 live levels (grid.h:1430-1437)
+@pytest.mark.parametrize("cfg,step", [(SMALL, 0), (MID, 0), (MID, 300), (FULL, 0), (FULL, 300), (FULL, 700)])
 def test_network_forward(pkg, cfg, step):
     o, t = make_pair(pkg, cfg, seed_params=1)
     t.set_train_state(step, 512); vl = o.valid_level(step)
@@ -127,13 +129,24 @@ def test_loss_and_output_gradients(pkg, small_scene, flagset):
     assert np.all(d[~emitted] == 0)
 
 
-@pytest.mark.parametrize("cfg,step", [(SMALL, 0), (MID, 0), (MID, 200)])
-def test_network_backward_first_and_second_order(pkg, cfg, step):
+def ray_like_coords(rs, n_rays, per_ray):
+    """consecutive lattice points of rays (dt = sqrt(3)/1024), the order compacted samples have in a training step: adjacent samples share
+    coarse cells, which is what the warp-aggregated scatter and the paired 16-byte reductions of the backward rely on"""
+    o = rs.uniform(0.2, 0.8, (n_rays, 1, 3)); d = rs.randn(n_rays, 1, 3); d /= np.linalg.norm(d, axis=2, keepdims=True)
+    tt = (np.arange(per_ray) - per_ray / 2)[None, :, None] * (np.sqrt(3.0) / 1024)
+    pos = np.clip(o + d * tt, 0.0, 1.0).reshape(-1, 3)
+    c = rs.rand(n_rays * per_ray, 7).astype(np.float32)
+    c[:, :3] = pos.astype(np.float32)
+    return c
+
+
+@pytest.mark.parametrize("cfg,step,raylike", [(SMALL, 0, False), (MID, 0, False), (MID, 200, False), (FULL, 0, False), (FULL, 300, True), (FULL, 700, True), (FULL, 700, False)])
+def test_network_backward_first_and_second_order(pkg, cfg, step, raylike):
     o, t = make_pair(pkg, cfg, seed_params=4)
     t.set_train_state(step, 512); vl = o.valid_level(step)
     rs = np.random.RandomState(9)
     n = 4096
-    coords = rs.rand(n, 7).astype(np.float32)
+    coords = ray_like_coords(rs, 32, 128) if raylike else rs.rand(n, 7).astype(np.float32)
     dout = (rs.randn(n, 16) * 0.05).astype(np.float16).astype(np.float32)
     dout[:, 11:] = 0
     n_in = 3000                                          # roll-over multiplicities differ across the batch
@@ -149,8 +162,34 @@ def test_network_backward_first_and_second_order(pkg, cfg, step):
     assert np.array_equal(g[sl["grid"]] != 0, g_ref[sl["grid"]] != 0) or rel_err((g[sl["grid"]] != 0).astype(float), (g_ref[sl["grid"]] != 0).astype(float)) < 1e-3
 
 
-def test_optimizer_adam_ema_sparse_rule(pkg):
-    o, t = make_pair(pkg, SMALL, seed_params=6)
+@pytest.mark.parametrize("agg,pair", [(0, 0), (0, 1), (5, 0), (8, 1)])
+def test_backward_scatter_variants_agree(pkg, agg, pair, monkeypatch):
+    """The warp-aggregated scatter (RNB_SCATTER_AGG levels) and the paired 16-byte reductions (RNB_SCATTER_PAIR) are re-orderings of the
+    same sums: every setting must give the default setting's gradients (fp32 accumulation order differs: 1e-5) on the default network with
+    ray-ordered samples, and the same set of touched entries."""
+    rs = np.random.RandomState(21)
+    coords = ray_like_coords(rs, 48, 96)
+    n = coords.shape[0]
+    dout = (rs.randn(n, 16) * 0.05).astype(np.float16).astype(np.float32); dout[:, 11:] = 0
+    res = []
+    for env in (None, (agg, pair)):
+        if env is None:
+            monkeypatch.delenv("RNB_SCATTER_AGG", raising=False); monkeypatch.delenv("RNB_SCATTER_PAIR", raising=False)
+        else:
+            monkeypatch.setenv("RNB_SCATTER_AGG", str(env[0])); monkeypatch.setenv("RNB_SCATTER_PAIR", str(env[1]))
+        o, t = make_pair(pkg, FULL, seed_params=4)
+        t.set_train_state(700, 512)
+        res.append(t.stage_backward(coords, dout, n - 500).copy())
+        del t, o
+    g0, g1 = res
+    assert np.linalg.norm(g0) > 0
+    assert rel_err(g1, g0) < 1e-5, rel_err(g1, g0)
+    assert np.array_equal(g1 != 0, g0 != 0)
+
+
+@pytest.mark.parametrize("cfg", [SMALL, FULL])
+def test_optimizer_adam_ema_sparse_rule(pkg, cfg):
+    o, t = make_pair(pkg, cfg, seed_params=6)
     rs = np.random.RandomState(1)
     for it in range(3):
         g = np.zeros(o.n_params, np.float32)
