@@ -2,16 +2,18 @@
 """bench.py — training rays/s of the NeuS2 / RNb-NeuS2 inner loop on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path through the C ABI
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference on the host cores
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the unmodified reference CUDA build (oracle/_ref) on one GPU, else the CPU restatement
 
-Workload (N=1): BASELINE.json configs[1] — 96 views 1600x1200, normals only (--no-albedo), shipped default network
-(L=14, F=2, T=2^19, SDF MLP 1x64, colour MLP 2x64), 4096 rays/step pinned.  DiLiGenT-MV is not available offline, so
-the views are a synthetic analytic ellipsoid rendered on the host (rnb-neus2_b200/scene.py) and uploaded once, like the
-reference's nerf_loader does.  One "step" = Testbed::train: occupancy-grid refresh when due + sample generation +
-two network passes + loss + backward + Adam/EMA.
-Prints ONE JSON line on rank 0.
+Workload: the north_star target — a synthetic 96-view 1600x1200 normal + albedo scene (DiLiGenT-MV is not available offline: analytic ellipsoid
+with a procedural albedo, rnb-neus2_b200/scene.py), shipped default network (L=14, F=2, T=2^19, SDF MLP 1x64, colour MLP 2x64), RGB+ reflectance
+loss, 4096 rays/step per GPU pinned, timed after 700 training steps so that all 14 hash levels are live (grid.h:1430-1437) and the occupancy grid
+is past its 256-step bootstrap.  `--workload normals` is BASELINE configs[1] (--no-albedo).  One "step" = Testbed::train: occupancy-grid refresh
+when due + sample generation + two network passes + loss + backward + (N > 1: one binary16 gradient all-reduce inside the library) + Adam/EMA.
+Prints ONE JSON line on rank 0; further operating points (normals-only, the adaptive batch-size controller the drop-in binary runs,
+N > 1: BASELINE configs[3] = 16,384 rays/step strong-sharded) ride in `records`.
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -26,7 +28,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "training_rays_per_second"
 UNIT = "rays/s"
 RAYS_PER_STEP = 4096
-WORKLOAD = "synthetic-ellipsoid 96 views 1600x1200 normals-only, hashgrid L=14 T=2^19 F=2, SDF MLP 1x64, colour MLP 2x64, 4096 rays/step pinned"
+NETWORK = "hashgrid L=14 T=2^19 F=2, SDF MLP 1x64, colour MLP 2x64"
+WORKLOADS = {
+    "albedo": "synthetic-ellipsoid 96 views 1600x1200 normals+albedo (RGB+ reflectance loss), " + NETWORK + ", 4096 rays/step pinned",
+    "normals": "synthetic-ellipsoid 96 views 1600x1200 normals-only, " + NETWORK + ", 4096 rays/step pinned",
+}
+WORKLOAD = WORKLOADS["albedo"]
+PRETRAIN_DEFAULT = 700
 
 
 def peaks():
@@ -129,11 +137,12 @@ def run_reference_cuda(args):
     work = "/tmp/rnb_bench_ref"
     scene_dir = os.path.join(work, "scene"); dump = os.path.join(work, "dump"); os.makedirs(dump, exist_ok=True)
     t0 = time.time()
-    views, _ = build_views(args.views, args.width, args.height, False)
+    albedo = args.workload == "albedo"
+    views, _ = build_views(args.views, args.width, args.height, albedo)
     ref_scene.write_scene(scene_dir, views, workers=min(16, os.cpu_count() or 4))
     scene_s = time.time() - t0
     n = args.pretrain + args.warmup + args.steps
-    cmd = [REF_HARNESS, scene_dir + "/", os.path.join(ROOT, "oracle", "_ref", "configs", "nerf", "base.json"), dump, str(n), "--no-albedo", "--time-only",
+    cmd = [REF_HARNESS, scene_dir + "/", os.path.join(ROOT, "oracle", "_ref", "configs", "nerf", "base.json"), dump, str(n)] + ([] if albedo else ["--no-albedo"]) + ["--time-only",
            "--pin-rays", str(RAYS_PER_STEP), "--time-from", str(args.pretrain + args.warmup)]
     clocks = ClockSampler(0); clocks.start()
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -144,7 +153,7 @@ def run_reference_cuda(args):
     val = float(meta["rays_per_second"]); ms = float(meta["timed_ms"]) / max(int(meta["timed_steps"]), 1)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 1, "steps": int(meta["timed_steps"]), "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp16 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pretrain_steps": args.pretrain, "scene_write_s": round(scene_s, 1),
+            "config": {"workload": WORKLOADS[args.workload], "pretrain_steps": args.pretrain, "scene_write_s": round(scene_s, 1),
                        "note": "unmodified reference CUDA path (Testbed::train, tiny-cuda-nn; sm_100 SASS from oracle/Makefile.ref) on ONE B200 of this box, light draw pinned (oracle/ref_prelude.h), "
                                "rays/step pinned by overwriting the controller output; per-step CUDA events around Testbed::train incl. its occupancy refreshes; the reference has no CPU or multi-GPU path"},
             "clocks": clk,
@@ -166,11 +175,12 @@ def run_reference(args):
     build_oracle()
     threads = os.cpu_count() or 1
     w, h, n_views = 1600, 1200, 96
-    views, gen_s = build_views(n_views, w, h, False)
+    albedo = args.workload == "albedo"
+    views, gen_s = build_views(n_views, w, h, albedo)
     o = Oracle(threads=threads, **FULL)
     o.init_params(1337, None)
     o.set_views(views)
-    o.set_flags(default_flags(no_albedo=1))
+    o.set_flags(default_flags(no_albedo=0 if albedo else 1))
     rays = 512        # bounded sample of the 4096-ray step: every stage scales linearly in rays
     o.set_train_state(training_step=1, rays_per_batch=rays, pin_rays=1)
     o.set_bitfield(_shell_bitfield())
@@ -184,7 +194,7 @@ def run_reference(args):
     val = rays * k / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": args.warmup, "ms_per_step": dt / k * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference algorithm (oracle/), occupancy = analytic surface shell, bounded sample"},
+            "config": {"workload": WORKLOADS[args.workload], "note": "CPU restatement of the reference algorithm (oracle/), occupancy = analytic surface shell, bounded sample"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": "%d rays/step x %d steps (of 4096 rays/step), %d samples/step" % (rays, k, st.n_samples)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -213,7 +223,7 @@ def _shell_bitfield():
     return out
 
 
-DP_MODE_DEFAULT = "allreduce"      # N > 1: "allreduce" (replicated Adam) or "sharded" (reduce-scatter + sharded Adam + all-gather); RNB_DP overrides
+DP_MODE_DEFAULT = "allreduce"      # N > 1: "allreduce" (one binary16 all-reduce, replicated Adam) or "sharded" (reduce-scatter + sharded Adam + all-gather); RNB_DP overrides
 
 
 def _network_path():
@@ -226,24 +236,56 @@ def _network_path():
     return "tcgen05 forward + tcgen05 backward"
 
 
+def live_levels(step, n_levels=14):
+    """hash levels a training step touches (progressive training, grid.h:1430-1437)"""
+    import math
+    if step <= 0:
+        return n_levels
+    return int(min(n_levels, math.ceil(0.2 * n_levels + 0.02 * max(0, step - 100)) + 1))
+
+
+def algorithmic_work(L, ns, nc, n_params):
+    """SURVEY §8(d) / DESIGN §7, per stage: hash gather 8 corners x 4 B per live level and sample; merged first + second order scatter as a
+    read-modify-write of 8 corners x 4 B (the reference's binary16 gradient format) = 64 B per level; sample rows in / out; optimizer 8 B per
+    parameter (lower bound: gradient read + EMA, +34 B per touched parameter not counted).  MLP flops = 2 x MACs of the layers a stage runs."""
+    alg = {"march": 4.0 * ns, "scan_emit": 20.0 * ns, "pass_a_sdf_normal": (32.0 * L + 24.0) * ns, "compact": 24.0 * nc + 8.0 * ns, "pass_b_forward": (32.0 * L + 48.0) * nc, "loss": 64.0 * nc,
+           "backward": ((32.0 + 64.0) * L + 48.0) * nc, "adam_ema": 8.0 * n_params}
+    flops = {"pass_a_sdf_normal": 10368.0 * ns, "pass_b_forward": 26752.0 * nc, "backward": 84000.0 * nc}
+    return alg, flops
+
+
+def _traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the newest committed ncu --set full capture (profiles/rNN_traffic.json)"""
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            v = json.load(open(f)).get(kernel)
+            if v is not None:
+                return v, os.path.basename(f)
+        except Exception:
+            pass
+    return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--pretrain", type=int, default=300, help="untimed training steps before warm-up so that the occupancy grid is past its 256-step bootstrap (BASELINE.md §3)")
+    ap.add_argument("--workload", default="albedo", choices=sorted(WORKLOADS), help="albedo: the north_star target (normals + albedo, RGB+ loss); normals: BASELINE configs[1] (--no-albedo)")
+    ap.add_argument("--pretrain", type=int, default=PRETRAIN_DEFAULT, help="untimed training steps before warm-up: all 14 hash levels live (step > 560), occupancy grid past its 256-step bootstrap")
     ap.add_argument("--views", type=int, default=96)
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-records", action="store_true", help="only the headline workload (skip the normals-only / adaptive / strong-scaling records)")
     ap.add_argument("--cpu-port", action="store_true", help="--impl reference: time the CPU restatement instead of the reference CUDA build")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
-    # stdout carries exactly one JSON line: everything libraries print (NCCL banner, torch warnings) goes to stderr until then
+    # stdout carries exactly one JSON line: everything libraries print (NCCL banner / NCCL_DEBUG output, torch warnings) goes to stderr until then
     sys.stdout.flush()
     _saved_stdout = os.dup(1); os.dup2(2, 1)
     import numpy as np
@@ -256,108 +298,74 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("RNB_NCCL_DEBUG", "NONE")      # keep stdout to the single JSON line (NCCL prints its version banner there otherwise)
-        import torch.distributed as dist
+        import torch.distributed as dist          # plumbing only (unique-id broadcast, barriers, max over ranks); the gradient exchange is inside the library
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
-    R = RAYS_PER_STEP * n_gpus                      # weak scaling: 4096 rays per GPU per step, global batch R
-    views, gen_s = build_views(args.views, args.width, args.height, False)
-    # weak scaling with the per-GPU work fixed: 4096 rays AND a 2^18-sample training batch per GPU (the reference's target_batch_size is a
-    # global cap; leaving it at 2^18 for N GPUs would shrink every rank's network passes by N and read as super-linear scaling)
-    cfg = pkg.default_config(rays_per_batch=R, pin_rays_per_batch=1, world_size=world, rank=rank, target_batch_size=(1 << 18) * n_gpus)
-    flags_kw = dict(no_albedo=1)
-    t = pkg.Testbed(cfg, pkg.default_flags(**flags_kw))
-    t.init_params()
-    t0 = time.time(); t.load_training_data(views); upload_s = time.time() - t0
-    dataset_bytes = sum(v["normal"].nbytes for v in views)
-
-    grad_t = stat_t = None
+    albedo = args.workload == "albedo"
+    views, gen_s = build_views(args.views, args.width, args.height, albedo)
+    dataset_bytes = sum(v["normal"].nbytes + (v["albedo"].nbytes if v["albedo"] is not None else 0) for v in views)
+    flags_kw = dict(no_albedo=0 if albedo else 1)
     dp_mode = os.environ.get("RNB_DP", DP_MODE_DEFAULT) if world > 1 else "single"
     if world > 1:
-        gp, gn = t.grad_buffer(); sp, sn = t.stat_buffer()
+        os.environ["RNB_DP"] = dp_mode
 
-        class _Arr:
-            def __init__(self, p, n, ts="<f4"): self.__cuda_array_interface__ = {"shape": (n,), "typestr": ts, "data": (p, False), "version": 3}
-        stat_t = torch.as_tensor(_Arr(sp, sn), device="cuda")
-        if dp_mode == "sharded":
-            # sharded optimizer: reduce-scatter of the fp32 gradients, Adam/EMA on this rank's 1/N of the parameters, all-gather
-            # of the binary16 training parameters.  The arrays are padded to a multiple of 512 elements, so the shards are equal.
-            pp, _, _, npad = t.param_buffers()
-            shard = npad // world
-            assert shard * world == npad and shard % 8 == 0
-            grad_t = torch.as_tensor(_Arr(gp, npad), device="cuda")
-            par_t = torch.as_tensor(_Arr(pp, npad, "<f2"), device="cuda")
-            red_t = torch.zeros(shard, dtype=torch.float32, device="cuda")
-            own_t = torch.zeros(shard, dtype=torch.float16, device="cuda")
-            t.set_optimizer_shard(rank * shard, (rank + 1) * shard, red_t.data_ptr())
-        else:
-            grad_t = torch.as_tensor(_Arr(gp, gn), device="cuda")
+    def make_testbed(rays_global, target_global, pin=1, fl=None):
+        cfg = pkg.default_config(rays_per_batch=rays_global, pin_rays_per_batch=pin, world_size=world, rank=rank, target_batch_size=target_global)
+        tb = pkg.Testbed(cfg, pkg.default_flags(**(fl or flags_kw)))
+        tb.init_params()
+        t0 = time.time(); tb.load_training_data(views); up = time.time() - t0
+        if world > 1:
+            ids = [pkg.Testbed.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, 0)
+            tb.comm_init(ids[0])
+        return tb, up
 
-    def step(want_stats):
-        if world == 1:
-            return t.train(want_stats=want_stats)
-        ts = t.get_train_state()[0]
-        skip = min(max(ts // 16, 1), 16)
-        if ts % skip == 0:
-            t.training_prep_nerf()
-        t.train_step_begin()
-        if dp_mode == "sharded":
-            dist.reduce_scatter_tensor(red_t, grad_t); dist.all_reduce(stat_t)
-            st = t.train_step_end()
-            own_t.copy_(par_t[rank * shard:(rank + 1) * shard])
-            dist.all_gather_into_tensor(par_t, own_t)         # every rank's next forward sees all updated shards
-            return st
-        dist.all_reduce(grad_t); dist.all_reduce(stat_t)      # the single gradient exchange of the step (NCCL over NVLink)
-        return t.train_step_end()
-
-    for _ in range(args.pretrain + args.warmup):
-        step(False)
-    torch.cuda.synchronize()
-
-    def timed(k, want_stats):
+    def timed(tb, k, want_stats):
         if dist: dist.barrier()
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        l0 = t.launch_count()
+        l0 = tb.launch_count()
         e0.record()
-        last = None
+        last = None; rays = 0
         for _ in range(k):
-            last = step(want_stats)
+            last = tb.train(want_stats=want_stats)
+            if want_stats: rays += int(last.n_rays)
         e1.record()
         torch.cuda.synchronize()
         if dist: dist.barrier()
         ms = e0.elapsed_time(e1)
         if dist:
             tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
-        return ms, t.launch_count() - l0, last
+        return ms, tb.launch_count() - l0, last, rays
 
+    # ---- headline: weak scaling with the per-GPU work fixed: 4096 rays AND a 2^18-sample training batch per GPU (the reference's target_batch_size
+    # is a global cap; leaving it at 2^18 for N GPUs would shrink every rank's network passes by N and read as super-linear scaling)
+    R = RAYS_PER_STEP * n_gpus
+    t, upload_s = make_testbed(R, (1 << 18) * n_gpus)
+    for _ in range(args.pretrain + args.warmup):
+        t.train(want_stats=False)
+    torch.cuda.synchronize()
     # value, e2e and the per-stage pass are all taken on the SAME training steps: the state after warm-up is checkpointed on the device
     # and restored between the passes (the cost of a step changes with the training step: live hash levels, samples per ray)
     t.checkpoint_save()
     clocks = ClockSampler(local_rank); clocks.start()
-    ms, launches, _ = timed(args.steps, False)
+    ms, launches, _, _ = timed(t, args.steps, False)          # no per-step read-back: rnb_train returns without host synchronisation
     clk = clocks.stop()
-    # end to end through the public call with the per-step read-back of the loss scalars / counters
     t.checkpoint_restore()
-    ms_e2e, _, last = timed(args.steps, True)
-    # per-stage device timing for the roofline (events on the launching stream; separate pass so that `value` is undisturbed)
+    ms_e2e, _, last, _ = timed(t, args.steps, True)            # end to end through the public call with the per-step read-back of the loss scalars / counters
     t.checkpoint_restore()
-    t.profile_enable(True)
-    timed(args.steps, True)
+    t.profile_enable(True)                                     # per-stage device timing for the roofline (events on the launching stream; separate pass so that `value` is undisturbed)
+    timed(t, args.steps, True)
     prof = t.profile_read(); t.profile_enable(False)
 
     value = R * args.steps / (ms * 1e-3)
     e2e = R * args.steps / (ms_e2e * 1e-3)
     hbm_peak, peak_src, tf_peak = peaks()
-    # Per-stage device time (CUDA events on the launching stream) and algorithmic work: hash gather 8 corners x 4 B
-    # per live level, scatter = read-modify-write of 8 corners x 8 B (fp32 pairs), rows in/out; MLP flops = 2 x MACs of the layers run.
     per_stage = {k: v[0] / max(v[1], 1) for k, v in prof.items()}
     ns, nc = last.n_samples, last.n_samples_trained
     ts_now = t.get_train_state()[0]
-    L = int(min(14, np.ceil(0.2 * 14 + 0.02 * max(0, ts_now - 100)) + 1)) if ts_now > 0 else 14
-    alg = {"march": 4.0 * ns, "scan_emit": 20.0 * ns, "pass_a_sdf_normal": (32.0 * L + 24.0) * ns, "compact": 24.0 * nc + 8.0 * ns, "pass_b_forward": (32.0 * L + 60.0) * nc, "loss": 64.0 * nc,
-           "backward": (32.0 * L + 2 * 64.0 * L + 48.0) * nc, "adam_ema": 8.0 * t.n_params}
-    flops = {"pass_a_sdf_normal": 8192.0 * ns, "pass_b_forward": 24576.0 * nc, "backward": 84000.0 * nc}
+    L = live_levels(ts_now)
+    alg, flops = algorithmic_work(L, ns, nc, t.n_params)
     stages = {}
     for k, msk in per_stage.items():
         row = {"ms": round(msk, 4)}
@@ -366,29 +374,74 @@ def main():
         if k in flops:
             row["TFLOPs"] = round(flops[k] / (msk * 1e-3) / 1e12, 2); row["tensor_frac"] = round(flops[k] / (msk * 1e-3) / 1e12 / tf_peak, 5)
         stages[k] = row
-    dom = max((k for k in per_stage if k != "grid_update"), key=lambda k: per_stage[k])
+    comm_stages = ("grid_update", "grad_pack", "grad_exchange", "param_allgather")
+    dom = max((k for k in per_stage if k not in comm_stages), key=lambda k: per_stage[k])
     ach = alg.get(dom, 0.0) / (per_stage[dom] * 1e-3) / 1e9
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture (profiles/)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom)
-    except Exception:
-        pass
+    traffic, traffic_src = _traffic(dom)
+    step_bytes = sum(alg[k] for k in alg if k in per_stage)
+    step_flops = sum(flops[k] for k in flops if k in per_stage)
+    if n_gpus > 1:
+        par = "dp%d ray-sharded (4096 rays + 2^18-sample batch per GPU); gradient exchange inside the library (rnb_comm_init): " % n_gpus + (
+            "binary16 reduce-scatter + sharded Adam + binary16 parameter all-gather" if dp_mode == "sharded" else "ONE binary16 all-reduce of the 21 MB gradient buffer (+ 8 floats of statistics in the same NCCL group)")
+    else:
+        par = "single GPU"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_global": R, "pretrain_steps": args.pretrain, "samples_per_step": int(ns), "compacted_samples_per_step": int(nc), "live_hash_levels": L,
-                       "cache": "working set (hash table 21 MB + gradients 42 MB + optimizer state 170 MB + 1.5 GB images) exceeds L2; no flush needed",
-                       "parallelism": ("dp%d ray-sharded (4096 rays + 2^18-sample batch per GPU), " % n_gpus + ("fp32 gradient reduce-scatter + sharded Adam + fp16 parameter all-gather" if dp_mode == "sharded" else "fp32 gradient all-reduce")) if n_gpus > 1 else "single GPU", "network_path": _network_path(),
+            "config": {"workload": WORKLOADS[args.workload], "rays_per_step_global": R, "pretrain_steps": args.pretrain, "training_step_at_end": int(ts_now), "samples_per_step": int(ns), "compacted_samples_per_step": int(nc),
+                       "live_hash_levels": L,
+                       "cache": "working set (hash table 21 MB + gradients 42 MB + optimizer state 170 MB + %.1f GB images) exceeds L2; no flush needed" % (dataset_bytes / 1e9),
+                       "parallelism": par, "network_path": _network_path(),
                        "dataset_upload_s": round(upload_s, 3), "dataset_bytes": dataset_bytes, "scene_render_s": round(gen_s, 1)},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,
-                    "note": "rnb_train through the C ABI with per-step stats read-back; dataset resident after one upload (%.2f s for %d MB from host memory), as in the reference" % (upload_s, dataset_bytes >> 20)},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "note": "achieved = algorithmic bytes of the stage / its CUDA-event time; the hash table (21 MB) and gradient buffer (42 MB) are L2 resident, so DRAM traffic (ncu) is far below the algorithmic bytes",
+                    "note": "rnb_train through the C ABI with per-step stats read-back (host waits for every step); `value` = the same steps without read-back (no host synchronisation); "
+                            "dataset resident after one upload (%.2f s for %d MB from host memory), as in the reference" % (upload_s, dataset_bytes >> 20)},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "note": "achieved = algorithmic bytes of the stage (SURVEY 8(d): 32 B gather + 64 B scatter per sample-level, rows in/out) / its CUDA-event time; the hash table (21 MB) and "
+                                 "the gradient buffer (42 MB) are L2 resident, so DRAM traffic (ncu) is far below the algorithmic bytes",
+                         "step": {"alg_GBps": round(step_bytes / (ms / args.steps * 1e-3) / 1e9, 1), "hbm_frac": round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm_peak, 4),
+                                  "TFLOPs": round(step_flops / (ms / args.steps * 1e-3) / 1e12, 2), "tensor_frac": round(step_flops / (ms / args.steps * 1e-3) / 1e12 / tf_peak, 5)},
                          "stages": stages}}
+    if world > 1:
+        line["config"]["nccl"] = t.comm_info()
+
+    # ---- CPU baseline beside it: the oracle (CPU port of the reference algorithm) on all host cores from the same trained state, bounded sample
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        t.checkpoint_restore()
         threads = os.cpu_count() or 1
-        v, info = cpu_baseline_from_state(t, views, flags_kw, threads, 3, 512)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": "3 steps x 512 rays from the same training state (%s)" % json.dumps(info)}
+        cs, cr = 6, 2048
+        v, info = cpu_baseline_from_state(t, views, flags_kw, threads, cs, cr)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": "%d steps x %d rays (of 4096 rays/step) from the same trained state (%s)" % (cs, cr, json.dumps(info))}
+
+    # ---- further operating points (shorter windows) ------------------------------------------------------------------------------
+    if not args.no_records:
+        records = {}
+        k2 = max(20, args.steps // 3)
+        # (1) the other loss configuration on the same trained state and the same steps (the flag only changes the loss kernel and the colour-MLP gradient)
+        if albedo:
+            t.checkpoint_restore()
+            t.set_flags(pkg.default_flags(no_albedo=1))
+            m2, _, _, _ = timed(t, k2, False)
+            t.set_flags(pkg.default_flags(**flags_kw))
+            records["normals"] = {"workload": WORKLOADS["normals"], "value": R * k2 / (m2 * 1e-3), "unit": UNIT, "ms_per_step": m2 / k2, "steps": k2, "note": "same trained state and steps, --no-albedo loss"}
+        # (2) the adaptive batch-size controller (pin_rays_per_batch = 0): what shim/rnb_testbed_shim.h and therefore ./build/testbed run; the controller holds
+        # the compacted sample count at 2^18 per GPU, rays/step follow the scene; the host waits for the counters every step like the reference
+        ta, _ = make_testbed(R, (1 << 18) * n_gpus, pin=0)
+        for _ in range(args.pretrain + args.warmup):
+            ta.train(want_stats=False)
+        m3, _, la, rays3 = timed(ta, k2, True)
+        records["adaptive_controller"] = {"workload": WORKLOADS[args.workload].replace("4096 rays/step pinned", "rays/step set by the controller (2^18 compacted samples per step and GPU)"),
+                                          "value": rays3 / (m3 * 1e-3), "unit": UNIT, "ms_per_step": m3 / k2, "steps": k2, "rays_per_step_last": int(la.n_rays), "samples_per_step_last": int(la.n_samples),
+                                          "compacted_per_step_last": int(la.n_samples_compacted)}
+        # (3) N > 1: BASELINE configs[3] — 16,384 rays/step in total, strong-sharded over the GPUs, global 2^18-sample budget as in the reference
+        if world > 1:
+            tsx, _ = make_testbed(16384, 1 << 18)
+            for _ in range(args.pretrain + args.warmup):
+                tsx.train(want_stats=False)
+            m4, _, _, _ = timed(tsx, k2, False)
+            records["strong_16384_rays"] = {"workload": WORKLOADS[args.workload].replace("4096 rays/step pinned", "16384 rays/step in total, ray-sharded over %d GPUs" % n_gpus), "scaling": "strong",
+                                            "value": 16384 * k2 / (m4 * 1e-3), "unit": UNIT, "ms_per_step": m4 / k2, "steps": k2}
+        line["records"] = records
     sys.stdout.flush(); os.dup2(_saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line)); sys.stdout.flush()

@@ -148,6 +148,13 @@ int rnb_get_bitfield(rnb_ctx* ctx, uint8_t* host, size_t n /* 128^3 (8 mips x 12
 int rnb_set_bitfield(rnb_ctx* ctx, const uint8_t* host, size_t n);
 int rnb_get_train_state(rnb_ctx* ctx, uint32_t out[4] /* training_step, rays_per_batch, n_rays_total, measured_before_compaction */);
 int rnb_set_train_state(rnb_ctx* ctx, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before_compaction);
+/* Testbed::load_snapshot restores m_training_step but neither m_canonical_training_step (testbed.h:907; reset_network zeroes it, src/testbed.cu:2451)
+ * nor Training::n_images_for_training_prev (testbed.h:578).  Both steer the occupancy refresh: cadence and bootstrap mode follow the canonical step
+ * (src/testbed.cu:2805-2806, src/testbed_nerf.cu:4133), and a refresh that sees an image count different from the previous one starts from an EMPTY
+ * grid (:3446-3452).  A stage-2 process of run_pipeline.py therefore discards the snapshot's grid at its first step and rebuilds it from one full sweep.
+ * rnb_set_train_state leaves canonical == training_step (a state in the middle of a run); a caller that mirrors load_snapshot passes the reference's
+ * own two values here afterwards (shim: pull_state).  n_images_prev == 0xffffffff: adopt the current dataset (never empty the grid on that account). */
+int rnb_set_canonical_state(rnb_ctx* ctx, uint32_t canonical_training_step, uint32_t n_images_prev);
 int rnb_get_rng(rnb_ctx* ctx, uint64_t out[4] /* m_rng state, inc, density_grid_rng state, inc */);
 int rnb_set_rng(rnb_ctx* ctx, const uint64_t in[4]);
 
@@ -170,17 +177,35 @@ int rnb_set_flags(rnb_ctx* ctx, const rnb_flags* flags);
 /* replaces Testbed::training_prep_nerf (src/testbed_nerf.cu:4125-4138): one occupancy-grid refresh. */
 int rnb_prep(rnb_ctx* ctx, void* stream);
 /* replaces Testbed::train_nerf (src/testbed_nerf.cu:3560-3668): generate samples, forward, loss, backward,
- * optimizer step, counters.  stats may be NULL (no host synchronisation). */
+ * optimizer step, counters.  stats may be NULL: with a pinned batch size the call then returns without any host synchronisation (the clamp
+ * of the next step's sample budget stays on the device); the adaptive controller needs the compacted count on the host and waits for it,
+ * as the reference does after every step (src/testbed_nerf.cu:3535-3551, src/testbed.cu:2866). */
 int rnb_train_step(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
 /* replaces Testbed::train (src/testbed.cu:2776-2872): progressive-level update, prep cadence, train_nerf. */
 int rnb_train(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
 
 /* data-parallel split of rnb_train_step: [begin: everything up to and including backward] -> the caller all-reduces
- * rnb_grad_buffer (sum, fp32, n_params elements) and rnb_counter_buffer (sum, uint32 x 8 / float) over its communicator
+ * rnb_grad_buffer (sum, fp32, n_params elements) and rnb_stat_buffer (sum, 8 floats: loss sums and sample counts) over its communicator
  * -> [end: optimizer + controller].  The reference has no collective; this is where one goes (trainer.h:78-84). */
 int rnb_train_step_begin(rnb_ctx* ctx, void* stream);
 int rnb_train_step_end(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
 int rnb_grad_buffer(rnb_ctx* ctx, float** grads_dev, uint64_t* n);
+/* Data parallelism behind the boundary (new; the reference is single-GPU, its gradient buffer between backward and optimizer_step is one contiguous
+ * binary16 array: trainer.h:78-84, src/testbed_nerf.cu:4068 -> :3624).  With a communicator installed and rnb_config.world_size > 1,
+ * rnb_train_step / rnb_train do the exchange themselves on the caller's stream: the fp32 accumulators are rounded to binary16 once, summed
+ * with ONE ncclAllReduce (21 MB at the default configuration) grouped with the 8 floats of loss sums / counts, and Adam / EMA consume the sum.
+ * Environment RNB_DP=sharded selects reduce-scatter -> optimizer on 1 / world of the parameters -> all-gather of the binary16 parameters.
+ * NCCL is opened at run time (dlopen of libnccl.so.2), so single-GPU users have no dependency on it.
+ *   rnb_comm_unique_id: ncclGetUniqueId on one rank; the caller's launcher carries the 128 bytes to the other ranks (file, socket, MPI, torchrun store)
+ *   rnb_comm_init:      ncclCommInitRank(world_size, id, rank) on the current device, communicator owned by the context
+ *   rnb_comm_adopt:     use a caller-owned ncclComm_t (its size and rank must equal rnb_config's)
+ *   rnb_comm_info:      out = { communicator installed, NCCL version code, sharded optimizer, world_size } */
+#define RNB_COMM_ID_BYTES 128
+int rnb_comm_unique_id(uint8_t id_out[RNB_COMM_ID_BYTES]);
+int rnb_comm_init(rnb_ctx* ctx, const uint8_t id[RNB_COMM_ID_BYTES]);
+int rnb_comm_adopt(rnb_ctx* ctx, void* nccl_comm);
+int rnb_comm_destroy(rnb_ctx* ctx);
+int rnb_comm_info(rnb_ctx* ctx, uint32_t out[4]);
 int rnb_stat_buffer(rnb_ctx* ctx, float** stats_dev, uint64_t* n);
 /* Sharded optimizer for data parallelism (new; the reference is single-GPU): instead of all-reducing the fp32 gradient buffer and running
  * Adam/EMA on every rank, rank r owns parameters [begin, end): the caller REDUCE-SCATTERS the gradient buffer (rnb_grad_buffer; the arrays

@@ -39,6 +39,9 @@ struct Oracle {
 	// training state
 	uint32_t training_step = 0, rays_per_batch = 4096, n_rays_total = 0, target_batch = 1u << 18;
 	uint32_t measured_before = 0, measured = 0; int pin_rays = 1;
+	// Testbed::m_canonical_training_step (testbed.h:907; 0 after load_snapshot -> reset_network, src/testbed.cu:2451; = training step after every step,
+	// testbed_nerf.cu:3646) and Training::n_images_for_training_prev (testbed.h:578; ~0u = adopt the current image count)
+	uint32_t canonical_step = 0, n_images_prev = ~0u;
 	Flags flags;
 	std::vector<View> views;
 	// scratch kept for inspection
@@ -150,7 +153,10 @@ void orc_set_views(Oracle* o, const View* v, uint32_t n) { o->views.assign(v, v 
 void orc_set_flags(Oracle* o, const Flags* f) { o->flags = *f; }
 void orc_set_train_state(Oracle* o, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before, int pin_rays, uint32_t target_batch) {
 	o->training_step = training_step; o->rays_per_batch = rays_per_batch; o->n_rays_total = n_rays_total; o->measured_before = measured_before; o->pin_rays = pin_rays; o->target_batch = target_batch;
+	o->canonical_step = training_step;
 }
+// the two members Testbed::load_snapshot does not restore (src/testbed.cu:3333-3390)
+void orc_set_canonical_state(Oracle* o, uint32_t canonical_step, uint32_t n_images_prev) { o->canonical_step = canonical_step; o->n_images_prev = n_images_prev; }
 void orc_set_world(Oracle* o, uint32_t world, uint32_t rank) { o->world = world ? world : 1; o->rank = rank; }
 // data-parallel restatement of the sharded optimizer: Adam/EMA on [begin, end) only; the binary16 training weights of the other
 // shards are installed by the caller from the all-gather (orc_set_half_params)
@@ -349,7 +355,12 @@ void orc_optimizer_step(Oracle* o) {
 // kernels :585-614,616-635,655-685,693-740.  With aabb_scale 1 there is one cascade of densities; mips are OR-pooled.
 void orc_density_update(Oracle* o, uint32_t n_uniform, uint32_t n_nonuniform, uint32_t valid_level) {
 	const uint32_t NE = GRIDSIZE * GRIDSIZE * GRIDSIZE;
-	if (o->training_step == 0) { o->density_ema_step = 0; std::fill(o->density_grid.begin(), o->density_grid.end(), 0.f); }
+	if (o->n_images_prev == ~0u) o->n_images_prev = (uint32_t)o->views.size();
+	if (o->training_step == 0 || (uint32_t)o->views.size() != o->n_images_prev) {      // testbed_nerf.cu:3446-3452
+		o->n_images_prev = (uint32_t)o->views.size();
+		if (o->training_step == 0) o->density_ema_step = 0;
+		std::fill(o->density_grid.begin(), o->density_grid.end(), 0.f);
+	}
 	std::vector<float> tmp(NE, 0.f);
 	const uint32_t n_total = n_uniform + n_nonuniform;
 	std::vector<float> pos((size_t)n_total * 3); std::vector<uint32_t> idxs(n_total);
@@ -405,11 +416,11 @@ float orc_density_mean(Oracle* o) { return o->density_mean; }
 
 // training_prep_nerf cadence (src/testbed.cu:2805-2806, testbed_nerf.cu:4125-4138)
 int orc_prep_if_due(Oracle* o) {
-	uint32_t skip = std::min(std::max(o->training_step / 16u, 1u), 16u);
-	if (o->training_step % skip != 0) return 0;
+	uint32_t skip = std::min(std::max(o->canonical_step / 16u, 1u), 16u);      // src/testbed.cu:2805-2806
+	if (o->canonical_step % skip != 0) return 0;
 	uint32_t vl = valid_level_for_step(o->m, (int)o->training_step);
 	const uint32_t NE = GRIDSIZE * GRIDSIZE * GRIDSIZE;
-	if (o->training_step < 256) orc_density_update(o, NE, 0, vl); else orc_density_update(o, NE / 4, NE / 4, vl);
+	if (o->canonical_step < 256) orc_density_update(o, NE, 0, vl); else orc_density_update(o, NE / 4, NE / 4, vl);      // testbed_nerf.cu:4133
 	return 1;
 }
 
@@ -424,7 +435,7 @@ void orc_train_step_begin(Oracle* o) {
 	uint32_t max_inference;
 	if (o->measured_before == 0) { o->measured_before = max_inference = max_samples; }
 	else max_inference = next_multiple(std::min(o->measured_before, max_samples), 128u);
-	if (o->training_step == 0) o->n_rays_total = 0;
+	if (o->training_step == 0 || o->canonical_step == 0) o->n_rays_total = 0;      // testbed_nerf.cu:3906
 	const uint32_t nrt = o->n_rays_total; o->n_rays_total += R;
 	o->ray_indices.assign(R, 0); o->rays.assign((size_t)R * 6, 0.f); o->numsteps.assign((size_t)R * 2, 0); o->coords.resize((size_t)max_inference * 7);
 	uint32_t counters[2];
@@ -456,6 +467,7 @@ void orc_train_step_begin(Oracle* o) {
 void orc_train_step_end(Oracle* o, OrcStats* st) {
 	orc_optimizer_step(o);
 	++o->training_step;
+	o->canonical_step = o->training_step;
 	o->in_step = false;
 	const uint32_t total = o->cnt_total, R = o->step_R;
 	if (o->cnt_samples == 0 || total == 0) { o->measured_before = 0; o->measured = 0; }      // Counters::update_after_training, testbed_nerf.cu:3540-3542

@@ -52,8 +52,8 @@ class StepStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "rnb_last_error", "rnb_abi_version", "rnb_create", "rnb_destroy", "rnb_default_config", "rnb_default_flags", "rnb_param_layout", "rnb_init_params",
     "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
-    "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
-    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_stat_buffer", "rnb_param_buffers", "rnb_set_optimizer_shard", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf", "rnb_sdf_on_grid",
+    "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_set_canonical_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
+    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_comm_unique_id", "rnb_comm_init", "rnb_comm_adopt", "rnb_comm_destroy", "rnb_comm_info", "rnb_stat_buffer", "rnb_param_buffers", "rnb_set_optimizer_shard", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf", "rnb_sdf_on_grid",
     "rnb_load_png_rgba16", "rnb_free_host", "rnb_load_dataset_images", "rnb_marching_cubes", "rnb_marching_cubes_from_density", "rnb_mesh_buffers", "rnb_mesh_download", "rnb_save_mesh",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
     "rnb_raymesh_create", "rnb_raymesh_destroy", "rnb_raymesh_info", "rnb_raymesh_intersect",
@@ -206,6 +206,7 @@ class Testbed:
         self.off_sdf, self.off_rgb, self.off_grid, self.off_var, self.n_params = [int(x) for x in lay]
         self._keep = []
         self.last_measured_batch_size = 0; self.last_loss = 0.0       # of the last step whose statistics were read (snapshot fields)
+        self._n_images_prev = 0; self._n_views = 0                    # Training::n_images_for_training_prev of this "process" (testbed.h:578)
         if flags is not None:
             self.set_flags(flags)
 
@@ -274,6 +275,10 @@ class Testbed:
     def set_train_state(self, training_step, rays_per_batch, n_rays_total=0, measured_before=0):
         self._chk(self.L.rnb_set_train_state(self.h, training_step, rays_per_batch, n_rays_total, measured_before))
 
+    def set_canonical_state(self, canonical_training_step, n_images_prev):
+        """The two members Testbed::load_snapshot does not restore: m_canonical_training_step and n_images_for_training_prev (rnb_b200.h)."""
+        self._chk(self.L.rnb_set_canonical_state(self.h, canonical_training_step, n_images_prev))
+
     def get_rng(self):
         o = (C.c_uint64 * 4)(); self._chk(self.L.rnb_get_rng(self.h, o)); return [int(x) for x in o]
 
@@ -303,11 +308,13 @@ class Testbed:
         """views: list of dict(normal=uint16[h,w,4], albedo=uint16[h,w,4]|None, fx, fy, cx, cy, xform[12]) in host memory."""
         arr = self._views(views, False)
         self._chk(self.L.rnb_upload_dataset(self.h, arr, len(views)))
+        self._n_views = len(views)
         self._keep = []
 
     def set_dataset_device(self, views):
         arr = self._views(views, True)
         self._chk(self.L.rnb_set_dataset(self.h, arr, len(views)))
+        self._n_views = len(views)
 
     def set_flags(self, flags):
         self.flags = flags
@@ -316,6 +323,7 @@ class Testbed:
     # --- training (Testbed::train / training_prep_nerf / train_nerf) ---
     def training_prep_nerf(self, stream=None):
         self._chk(self.L.rnb_prep(self.h, C.c_void_p(stream)))
+        self._n_images_prev = self._n_views
 
     def train_nerf(self, stream=None, want_stats=True):
         st = StepStats()
@@ -325,6 +333,7 @@ class Testbed:
     def train(self, stream=None, want_stats=True):
         st = StepStats()
         self._chk(self.L.rnb_train(self.h, C.c_void_p(stream), C.byref(st) if want_stats else None))
+        self._n_images_prev = self._n_views          # the first Testbed::train of a process always refreshes the occupancy grid (canonical step 0)
         if want_stats:
             self.last_measured_batch_size = int(st.n_samples_compacted); self.last_loss = float(st.loss)
         return st
@@ -337,6 +346,29 @@ class Testbed:
         self._chk(self.L.rnb_train_step_end(self.h, C.c_void_p(stream), C.byref(st)))
         self.last_measured_batch_size = int(st.n_samples_compacted); self.last_loss = float(st.loss)
         return st
+
+    # --- data parallelism behind the boundary (rnb_comm_*) ---
+    @staticmethod
+    def comm_unique_id():
+        """ncclGetUniqueId through the library (call on ONE rank and carry the 128 bytes to the others)."""
+        buf = (C.c_uint8 * 128)()
+        rc = lib().rnb_comm_unique_id(buf)
+        if rc != 0:
+            raise RnbError(lib().rnb_last_error().decode())
+        return bytes(buf)
+
+    def comm_init(self, unique_id):
+        """ncclCommInitRank(world_size, id, rank) on the current device; afterwards train() / train_nerf() exchange the gradients themselves."""
+        assert len(unique_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._chk(self.L.rnb_comm_init(self.h, buf))
+
+    def comm_destroy(self):
+        self._chk(self.L.rnb_comm_destroy(self.h))
+
+    def comm_info(self):
+        o = (C.c_uint32 * 4)(); self._chk(self.L.rnb_comm_info(self.h, o))
+        return dict(installed=bool(o[0]), nccl_version=int(o[1]), sharded=bool(o[2]), world_size=int(o[3]))
 
     def grad_buffer(self):
         p = C.POINTER(C.c_float)(); n = C.c_uint64()
@@ -415,6 +447,7 @@ class Testbed:
         normals = (C.c_char_p * n)(*[v["normal_path"].encode() for v in meta["views"]])
         albedos = (C.c_char_p * n)(*[(v["albedo_path"].encode() if v["albedo_path"] else None) for v in meta["views"]])
         self._chk(self.L.rnb_load_dataset_images(self.h, arr, n, normals, albedos, int(threads), C.c_void_p(stream)))
+        self._n_views = n
         self.dataset = meta
         return meta
 
@@ -444,6 +477,9 @@ class Testbed:
         if d["density_grid"].size:
             self.import_density_grid(d["density_grid"], 0)
         self.set_train_state(d["training_step"], d["rays_per_batch"], 0, d["measured_batch_size_before_compaction"])
+        # neither the canonical step nor the image count of the last occupancy refresh is in the file: the reference resumes with canonical step 0 and
+        # (in the process that loads the snapshot before it ever trained) with n_images_for_training_prev 0, so its first step rebuilds the grid from empty
+        self.set_canonical_state(0, self._n_images_prev)
         self.last_measured_batch_size = d["measured_batch_size"]
         return cfg
 

@@ -14,11 +14,14 @@
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
+#include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges are no-ops unless a profiler (nsys / ncu --nvtx) is attached
+#include <nccl.h>      // types and prototypes only: libnccl.so.2 is opened at run time by rnb_comm_* (single-GPU users never need it)
 
 namespace rnb {
 // rnb_march.cu
 void launch_march(cudaStream_t, uint32_t, uint32_t, uint32_t, uint32_t, Pcg32, const ViewDev*, uint32_t, const uint8_t*, uint32_t*, float*, float*);
-void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, uint32_t*, uint32_t*, uint32_t*);
+void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*);
 void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, const float*, const float*, float4*);
 // rnb_network_simt.cu
 void launch_forward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, int, const float4*, const uint32_t*, uint32_t, const float*, __half*, float*, float*, float*);
@@ -30,6 +33,7 @@ size_t mma_pack_u32(const ModelDev&);
 void launch_mma(int, cudaStream_t, const ModelDev&, const __half*, uint32_t*, uint32_t, const float4*, const uint32_t*, uint32_t, const float*, __half*, const __half*, uint32_t, uint32_t, const uint32_t*, float*, int);
 bool tc_supported(const ModelDev&);
 void set_bw_debug(int);
+void set_bw_scatter_groups(int);
 void launch_tc_sdf_grid(cudaStream_t, const ModelDev&, const __half*, const uint8_t*, uint32_t, const uint32_t[3], const float[3], const float[3], float*, int);
 void launch_tc_backward(cudaStream_t, const ModelDev&, const __half*, const uint8_t*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, float*, int);
 size_t tc_blob_bytes(const ModelDev&);
@@ -46,7 +50,9 @@ struct AdamParams {
 	float base_lr, beta1, beta2, eps, l2, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
 	uint32_t n_params, n_matrix, rgb_begin, rgb_end; int only_sdf; float log2_beta1, log2_beta2;
 	uint32_t shard_begin, shard_end; const float* gsrc;      // data-parallel optimizer shard (rnb_optim.cu)
+	const __half* gsrc16;                                   // binary16 gradient exchange (rnb_optim.cu)
 };
+void launch_pack_grads(cudaStream_t, uint32_t, float*, __half*);
 void launch_adam_ema(cudaStream_t, const AdamParams&, float*, __half*, __half*, float*, float*, float*, uint32_t*);
 void launch_cast_params(cudaStream_t, uint32_t, const float*, __half*);
 void launch_widen_params(cudaStream_t, uint32_t, const __half*, float*);
@@ -79,6 +85,36 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
                       catch (const std::exception& ex_) { return fail(RNB_ERR_INVALID, std::string("internal error: ") + ex_.what()); }
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(RNB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
+// ---- NCCL, opened at run time ---------------------------------------------------------------------------------------------
+// The single-GPU library has no link-time dependency on NCCL.  rnb_comm_* dlopen libnccl.so.2: inside a process that has already loaded
+// one (PyTorch bundles its own) the loader hands back that copy, otherwise the system library.
+struct NcclApi {
+	void* handle = nullptr;
+	decltype(&ncclGetUniqueId) GetUniqueId = nullptr; decltype(&ncclCommInitRank) CommInitRank = nullptr; decltype(&ncclCommDestroy) CommDestroy = nullptr;
+	decltype(&ncclAllReduce) AllReduce = nullptr; decltype(&ncclReduceScatter) ReduceScatter = nullptr; decltype(&ncclAllGather) AllGather = nullptr;
+	decltype(&ncclGroupStart) GroupStart = nullptr; decltype(&ncclGroupEnd) GroupEnd = nullptr; decltype(&ncclGetErrorString) GetErrorString = nullptr;
+	decltype(&ncclCommCount) CommCount = nullptr; decltype(&ncclCommUserRank) CommUserRank = nullptr; decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+static NcclApi* nccl_api() {
+	static NcclApi api; static bool tried = false;
+	if (tried) return api.handle ? &api : nullptr;
+	tried = true;
+	const char* names[] = {"libnccl.so.2", "libnccl.so"};
+	for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+	if (!api.handle) return nullptr;
+	bool ok = true;
+	auto sym = [&](const char* n) { void* p = dlsym(api.handle, n); if (!p) ok = false; return p; };
+	api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId"); api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+	api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy"); api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+	api.ReduceScatter = (decltype(api.ReduceScatter))sym("ncclReduceScatter"); api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+	api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart"); api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+	api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString"); api.CommCount = (decltype(api.CommCount))sym("ncclCommCount");
+	api.CommUserRank = (decltype(api.CommUserRank))sym("ncclCommUserRank"); api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+	if (!ok) { dlclose(api.handle); api.handle = nullptr; return nullptr; }
+	return &api;
+}
+#define NC(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(RNB_ERR_CUDA, std::string(#x) + ": " + N->GetErrorString(r_)); } while (0)
+
 struct rnb_ctx {
 	rnb_config cfg; rnb_flags flags; ModelDev M;
 	uint32_t off_sdf = 0, off_rgb = 0;
@@ -100,16 +136,25 @@ struct rnb_ctx {
 	float4 *pos4 = nullptr, *cpos4 = nullptr;
 	__half *outA = nullptr, *out16 = nullptr, *dout16 = nullptr, *bw_scratch = nullptr; float* bw_front = nullptr;
 	uint32_t* counters_host = nullptr; float* stats_host = nullptr;   // pinned
+	cudaEvent_t ev_counters = nullptr; bool counters_pending = false;  // asynchronous read-back of the step counters (rnb_train_step_end without stats)
+	// data parallelism behind the boundary (rnb_comm_*): one NCCL communicator per context, binary16 gradient exchange buffer
+	ncclComm_t comm = nullptr; bool comm_owned = false; __half* grads16 = nullptr; int dp_sharded = 0;
+	const __half* xch16 = nullptr; uint32_t xch_begin = 0, xch_end = 0;      // result of this step's gradient exchange, consumed by rnb_train_step_end
 	// training state
 	Pcg32 rng, density_rng;
 	uint32_t training_step = 0, rays_per_batch = 4096, n_rays_total = 0, measured_before = 0, measured = 0;
+	// Testbed::m_canonical_training_step (testbed.h:907): drives the occupancy-refresh cadence and mode (src/testbed.cu:2805-2806, testbed_nerf.cu:4133)
+	// and the n_rays_total reset (:3906); it equals the training step after every step (:3646) but is 0 after load_snapshot (reset_network, src/testbed.cu:2451).
+	// n_images_prev = Training::n_images_for_training_prev (testbed.h:578): a refresh that sees another image count starts from an empty grid (:3446-3452);
+	// ~0u = "adopt the current dataset" (a context that continues a run whose state was imported piecewise)
+	uint32_t canonical_step = 0, n_images_prev = ~0u;
 	uint32_t step_R = 0, step_nrt = 0; bool in_step = false;
 	// software pipelining of the ray march (it reads only the bitfield, the dataset and the rng, never the parameters): with a
 	// pinned batch size the march of step N+1 is launched on a side stream when the backward of step N has finished, so that it
 	// shares the SMs with the (HBM-bound) optimizer / the gradient all-reduce instead of running alone
 	cudaStream_t side = nullptr; cudaEvent_t ev_bwd = nullptr, ev_march = nullptr;
 	// in-memory checkpoint (rnb_checkpoint_save / _restore): one device-side slot of everything a step reads and writes
-	struct Ckpt { void* buf = nullptr; size_t bytes = 0; bool valid = false; uint32_t opt_step, density_ema_step, training_step, rays_per_batch, n_rays_total, measured_before, measured; float lr_factor; Pcg32 rng, density_rng; } ck;
+	struct Ckpt { void* buf = nullptr; size_t bytes = 0; bool valid = false; uint32_t opt_step, density_ema_step, training_step, rays_per_batch, n_rays_total, measured_before, measured, canonical_step, n_images_prev; float lr_factor; Pcg32 rng, density_rng; } ck;
 	int pre_at = RNB_PRELAUNCH_AT_DEFAULT;      // where the next march may start: 0 behind the backward, 1 behind the loss, 2 behind pass A, 3 behind scan/emit (last readers of the ray buffers)
 	bool pre_armed = false;                     // this step will pre-launch (decided before its kernels are queued)
 	bool prelaunch = true; bool pre_valid = false; uint32_t pre_R = 0, pre_nrt = 0; uint64_t pre_rng_state = 0, pre_rng_inc = 0;
@@ -145,12 +190,30 @@ static void prof_resolve(rnb_ctx* c) {      // call after the stream has been sy
 	}
 	c->prof_pending.clear();
 }
-#define KT(name, nk, call) do { prof_begin(c, st, name); call; prof_end(c, st); c->launches += (nk); } while (0)
+// every stage of the step is an NVTX range ("rnb/<stage>") around its launches: `ncu --nvtx --nvtx-include "rnb/backward/"` and nsys timelines
+// select stages by name (the reference has no tracing hooks beyond wall-clock EMAs)
+struct NvtxRange { explicit NvtxRange(const char* n) { char b[64]; snprintf(b, sizeof(b), "rnb/%s", n); nvtxRangePushA(b); } ~NvtxRange() { nvtxRangePop(); } };
+#define KT(name, nk, call) do { NvtxRange nvtx_(name); prof_begin(c, st, name); call; prof_end(c, st); c->launches += (nk); } while (0)
 
 static uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
 
 // a pre-launched march is only usable if nothing it depends on changed: drop it (after it has drained) otherwise
 static void drop_prelaunch(rnb_ctx* c) { if (c->pre_valid) { cudaStreamSynchronize(c->side); c->pre_valid = false; } }
+
+// host mirror of the step counters.  update_after_training's rule (:3540-3545): both measured sizes are zeroed by a step without samples
+static void apply_counters(rnb_ctx* c) {
+	const uint32_t before = c->counters_host[1], total = c->counters_host[2];
+	if (before == 0 || total == 0) { c->measured_before = 0; c->measured = 0; } else { c->measured_before = before; c->measured = total; }
+}
+// rnb_train_step_end without stats leaves the read-back of the counters in flight: whoever needs the host copy waits for it here
+static void pull_counters(rnb_ctx* c) {
+	if (!c->counters_pending) return;
+	cudaEventSynchronize(c->ev_counters);
+	apply_counters(c);
+	c->counters_pending = false;
+}
+// the clamp of the next step's sample budget lives on the device (counters[5]); host-side state changes are pushed to it
+static cudaError_t push_measured(rnb_ctx* c) { return cudaMemcpy(c->counters + 5, &c->measured_before, 4, cudaMemcpyHostToDevice); }
 
 static uint32_t valid_level_for_step(const rnb_ctx* c, int step) {   // grid.h:1430-1437
 	if (step <= 0) return c->cfg.n_levels;
@@ -282,6 +345,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) try {
 	CU(cudaMalloc(&c->counters, 16 * 4)); CU(cudaMemset(c->counters, 0, 16 * 4));
 	CU(cudaMalloc(&c->stats, 8 * 4)); CU(cudaMemset(c->stats, 0, 8 * 4));
 	CU(cudaMallocHost(&c->counters_host, 16 * 4)); CU(cudaMallocHost(&c->stats_host, 8 * 4));
+	CU(cudaEventCreateWithFlags(&c->ev_counters, cudaEventDisableTiming));
 	CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_march, cudaEventDisableTiming));
 	{
 		cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev)); c->n_sm = prop.multiProcessorCount;
@@ -290,6 +354,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) try {
 		CU(cudaMalloc(&c->wpack, mma_pack_u32(M) * 4)); CU(cudaMemset(c->wpack, 0, mma_pack_u32(M) * 4));
 		// RNB_NETWORK=mma keeps the mma.sync tile kernels everywhere; default: tcgen05 kernels where they exist
 		if (const char* d = getenv("RNB_BW_DEBUG")) set_bw_debug(atoi(d));
+		if (const char* d = getenv("RNB_BW_SCATTER_WG")) set_bw_scatter_groups(atoi(d));      // scatter warpgroups of the tcgen05 backward (1 default, 2)
 		if (const char* d = getenv("RNB_PRELAUNCH")) c->prelaunch = atoi(d) != 0;
 		if (const char* d = getenv("RNB_PRELAUNCH_AT")) c->pre_at = std::min(std::max(atoi(d), 0), 3);
 		c->use_tc = c->use_mma && tc_supported(M) && !(e && std::string(e) == "mma");
@@ -318,6 +383,9 @@ int rnb_destroy(rnb_ctx* c) try {
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
 	if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
 	if (c->ev_march) cudaEventDestroy(c->ev_march);
+	if (c->ev_counters) cudaEventDestroy(c->ev_counters);
+	cudaFree(c->grads16);
+	if (c->comm && c->comm_owned) { if (NcclApi* N = nccl_api()) N->CommDestroy(c->comm); }
 	delete c;
 	return RNB_OK;
 } RNB_API_CATCH
@@ -430,14 +498,26 @@ int rnb_set_bitfield(rnb_ctx* c, const uint8_t* host, size_t n) try {
 } RNB_API_CATCH
 int rnb_get_train_state(rnb_ctx* c, uint32_t out[4]) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	pull_counters(c);
 	out[0] = c->training_step; out[1] = c->rays_per_batch; out[2] = c->n_rays_total; out[3] = c->measured_before;
 	return RNB_OK;
 } RNB_API_CATCH
 int rnb_set_train_state(rnb_ctx* c, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) try {
 	if (c) drop_prelaunch(c);
 	if (!c || rays_per_batch == 0 || rays_per_batch > (1u << 18)) return fail(RNB_ERR_INVALID, "bad train state");
+	pull_counters(c);
 	c->training_step = training_step; c->rays_per_batch = rays_per_batch; c->n_rays_total = n_rays_total; c->measured_before = measured_before;
+	CU(push_measured(c));
+	c->canonical_step = training_step;                 // a state in the middle of a run; rnb_set_canonical_state says otherwise (snapshot load)
 	return ensure_ray_capacity(c, rays_per_batch);
+} RNB_API_CATCH
+// the two members Testbed::load_snapshot does NOT restore (see rnb_ctx): the reference resumes stage 2 with m_canonical_training_step == 0 and, in a
+// fresh process, n_images_for_training_prev == 0, so its first Testbed::train refreshes the occupancy grid at once, in bootstrap mode, from an EMPTIED grid
+int rnb_set_canonical_state(rnb_ctx* c, uint32_t canonical_training_step, uint32_t n_images_prev) try {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	drop_prelaunch(c);
+	c->canonical_step = canonical_training_step; c->n_images_prev = n_images_prev;
+	return RNB_OK;
 } RNB_API_CATCH
 int rnb_get_rng(rnb_ctx* c, uint64_t out[4]) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
@@ -552,8 +632,10 @@ static void net_density(rnb_ctx* c, cudaStream_t st, uint32_t vl, uint32_t n) {
 
 // ---- occupancy refresh: training_prep_nerf / update_density_grid_nerf --------------------------------------------
 static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint32_t n_nonuniform) {
-	if (c->training_step == 0) {
-		c->density_ema_step = 0;
+	if (c->n_images_prev == ~0u) c->n_images_prev = c->n_views;
+	if (c->training_step == 0 || c->n_views != c->n_images_prev) {      // testbed_nerf.cu:3446-3452
+		c->n_images_prev = c->n_views;
+		if (c->training_step == 0) c->density_ema_step = 0;
 		CU(cudaMemsetAsync(c->density_grid, 0, GRID_CELLS * 4, st));
 	}
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
@@ -571,7 +653,7 @@ static int density_update(rnb_ctx* c, cudaStream_t st, uint32_t n_uniform, uint3
 int rnb_prep(rnb_ctx* c, void* stream) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	drop_prelaunch(c);
-	if (c->training_step < 256) return density_update(c, (cudaStream_t)stream, GRID_CELLS, 0);
+	if (c->canonical_step < 256) return density_update(c, (cudaStream_t)stream, GRID_CELLS, 0);      // testbed_nerf.cu:4133
 	return density_update(c, (cudaStream_t)stream, GRID_CELLS / 4, GRID_CELLS / 4);
 } RNB_API_CATCH
 
@@ -599,7 +681,8 @@ static void net_backward(rnb_ctx* c, cudaStream_t st, uint32_t vl, const uint32_
 // ---- one training step ----------------------------------------------------------------------------------------------
 // counters (device, uint32): [0] kept rays  [1] samples before compaction  [2] compacted (untruncated)  [3] trained = min([2], target)
 //                            [4] samples forwarded in pass B  [5] samples before compaction of the previous step
-static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt, uint32_t max_inference) {
+static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt) {
+	const uint32_t max_inference = c->max_samples;      // capacity; the clamp to last step's sample count happens on the device (k_scan_rays, counters[5] -> counters[6])
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
 	const ModelDev& M = c->M;
 	const uint32_t G = c->cfg.world_size, local_target = c->cfg.target_batch_size / G;
@@ -610,14 +693,14 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt, uin
 		drop_prelaunch(c);
 		KT("march", 1, launch_march(st, R, G, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts));
 	}
-	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->ray_n, c->ray_indices, c->numsteps, c->counters),
+	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->counters + 5, c->ray_n, c->ray_indices, c->numsteps, c->counters),
 	                   launch_emit(st, R, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4),
 	                   launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw)));
 	if (c->pre_armed && c->pre_at == 3) CU(cudaEventRecord(c->ev_bwd, st));      // ray_n / ray_geom / ts have been consumed: the next march may overwrite them
 	// weight blobs for this step's kernels: the mma.sync panel copy only when one of its kernels runs in the step (cross-check paths)
 	const bool all_tc = c->use_tc && c->use_tc_bwd;
 	KT("pass_a_sdf_normal", all_tc ? 2 : 3, ((all_tc ? (void)launch_tc(0, st, c->M, c->params, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm) : net_pack(c, st, c->params)),
-	                                         net_pass_a(c, st, vl, c->pos4, c->counters + 1, max_inference)));
+	                                         net_pass_a(c, st, vl, c->pos4, c->counters + 6, max_inference)));
 	if (c->pre_armed && c->pre_at == 2) CU(cudaEventRecord(c->ev_bwd, st));
 	KT("compact", 3, (launch_compact_count(st, R, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd),
 	                 launch_scan_compact(st, c->counters, local_target, c->n_fwd, c->cbase, c->n_emit, c->stats),
@@ -631,7 +714,7 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt, uin
 	return RNB_OK;
 }
 
-static int optimizer_step(rnb_ctx* c, cudaStream_t st) {
+static int optimizer_step(rnb_ctx* c, cudaStream_t st, const __half* gsrc16 = nullptr, uint32_t sh_begin = 0, uint32_t sh_end = 0) {
 	if (c->opt_step == 0) c->lr_factor = 1.0f;      // exponential_decay.h:61-72
 	if (c->opt_step >= c->cfg.lr_decay_start && c->cfg.lr_decay_interval && (c->opt_step - c->cfg.lr_decay_start) % c->cfg.lr_decay_interval == 0) c->lr_factor *= c->cfg.lr_decay_base;
 	++c->opt_step;
@@ -643,6 +726,8 @@ static int optimizer_step(rnb_ctx* c, cudaStream_t st) {
 	A.n_params = c->M.n_params; A.n_matrix = c->M.off_grid; A.rgb_begin = c->off_rgb; A.rgb_end = c->M.off_grid; A.only_sdf = c->flags.only_sdf_training;
 	A.log2_beta1 = (float)std::log2((double)c->cfg.beta1); A.log2_beta2 = (float)std::log2((double)c->cfg.beta2);
 	A.shard_begin = c->shard_end ? c->shard_begin : 0u; A.shard_end = c->shard_end ? std::min(c->shard_end, c->M.n_params) : c->M.n_params; A.gsrc = c->shard_end ? c->shard_grads : nullptr;
+	if (gsrc16 && sh_end) { A.shard_begin = sh_begin; A.shard_end = std::min(sh_end, c->M.n_params); A.gsrc = nullptr; }      // sharded optimizer on the library's own communicator
+	A.gsrc16 = gsrc16;
 	KT("adam_ema", 1, launch_adam_ema(st, A, c->master, c->params, c->ema, c->grads, c->m1, c->m2, c->steps));
 	CU(cudaGetLastError());
 	return RNB_OK;
@@ -655,10 +740,7 @@ int rnb_train_step_begin(rnb_ctx* c, void* stream) try {
 	cudaStream_t st = (cudaStream_t)stream;
 	const uint32_t R = c->rays_per_batch;
 	int rc = ensure_ray_capacity(c, R); if (rc) return rc;
-	uint32_t max_inference;                                         // testbed_nerf.cu:3891-3896
-	if (c->measured_before == 0) { c->measured_before = max_inference = c->max_samples; }
-	else max_inference = next_multiple(std::min(c->measured_before, c->max_samples), 128u);
-	if (c->training_step == 0) c->n_rays_total = 0;                 // :3906-3911
+	if (c->training_step == 0 || c->canonical_step == 0) c->n_rays_total = 0;      // :3906-3911
 	const uint32_t nrt = c->n_rays_total; c->n_rays_total += R;
 	c->step_R = R; c->step_nrt = nrt;
 	// pre-launch the NEXT step's march on the side stream (pinned batch size only: the adaptive controller fixes the next batch size
@@ -667,7 +749,7 @@ int rnb_train_step_begin(rnb_ctx* c, void* stream) try {
 		const uint32_t ts_next = c->training_step + 1, skip = std::min(std::max(ts_next / 16u, 1u), 16u);
 		c->pre_armed = c->cfg.pin_rays_per_batch && !c->prof && c->prelaunch && ts_next % skip != 0 && R <= c->cap_rays;
 	}
-	rc = step_front(c, st, R, nrt, max_inference); if (rc) return rc;
+	rc = step_front(c, st, R, nrt); if (rc) return rc;
 	c->rng.advance();                                               // :4118
 	c->in_step = true;
 	{
@@ -687,25 +769,37 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (!c->in_step) return fail(RNB_ERR_STATE, "rnb_train_step_end without begin");
 	cudaStream_t st = (cudaStream_t)stream;
-	int rc = optimizer_step(c, st); if (rc) return rc;
+	int rc = c->xch16 ? optimizer_step(c, st, c->xch16, c->xch_begin, c->xch_end) : optimizer_step(c, st); if (rc) return rc;
+	if (c->xch16 && c->xch_end) {      // sharded: every rank's next forward needs all updated shards of the binary16 training parameters
+		NcclApi* N = nccl_api();
+		const size_t shard = c->np_padded / c->cfg.world_size;
+		KT("param_allgather", 1, rc = (int)N->AllGather(c->params + (size_t)c->cfg.rank * shard, c->params, shard, ncclHalf, c->comm, st));
+		if (rc) return fail(RNB_ERR_CUDA, std::string("ncclAllGather: ") + N->GetErrorString((ncclResult_t)rc));
+	}
+	c->xch16 = nullptr; c->xch_begin = c->xch_end = 0;
 	++c->training_step;
+	c->canonical_step = c->training_step;              // testbed_nerf.cu:3646 (static scene: no global-movement phase)
 	c->in_step = false;
-	// Counters::update_after_training (:3532-3558).  The sample counts are needed on the host for next step's
-	// max_inference and for the batch-size controller; they are small and copied asynchronously.
+	// Counters::update_after_training (:3532-3558).  The clamp of the next step's sample budget stays on the device (k_scan_compact -> counters[5]
+	// -> k_scan_rays), so with a pinned batch size nothing of this step is needed on the host before the next one is queued: without `stats`
+	// the call returns with the read-back in flight (pull_counters) — no host synchronisation.  The adaptive controller sizes the next
+	// launch from the compacted count and therefore waits, like the reference does every step (:3535-3551, src/testbed.cu:2866).
 	CU(cudaMemcpyAsync(c->counters_host, c->counters, 8 * 4, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(c->stats_host, c->stats, 8 * 4, cudaMemcpyDeviceToHost, st));
+	const uint32_t R = c->step_R;
+	if (!stats && c->cfg.pin_rays_per_batch && !c->prof) {
+		CU(cudaEventRecord(c->ev_counters, st));
+		c->counters_pending = true;
+		return RNB_OK;
+	}
 	CU(cudaStreamSynchronize(st));
+	c->counters_pending = false;
 	prof_resolve(c);
 	const uint32_t total = c->counters_host[2];
-	const uint32_t R = c->step_R;
 	// data parallel: every rank must derive the SAME next batch size, so the controller is driven by the all-reduced compacted count
-	// (stats[3], summed over ranks together with the losses by the caller) against the global target; single GPU: the local count
+	// (stats[3], summed over ranks together with the losses) against the global target; single GPU: the local count
 	const uint32_t total_global = c->cfg.world_size > 1 ? (uint32_t)(c->stats_host[3] + 0.5f) : total;
-	if (c->counters_host[1] == 0 || total == 0) {      // Counters::update_after_training zeroes both and leaves rays_per_batch alone (:3540-3542)
-		c->measured_before = 0; c->measured = 0;
-	} else {
-		c->measured_before = c->counters_host[1]; c->measured = total;
-	}
+	apply_counters(c);
 	if (!c->cfg.pin_rays_per_batch && total_global > 0 && (c->cfg.world_size > 1 || c->counters_host[1] != 0)) {
 		uint32_t r = (uint32_t)((float)R * (float)c->cfg.target_batch_size / (float)total_global);
 		c->rays_per_batch = std::min(next_multiple(r, 128u), 1u << 18);
@@ -720,16 +814,97 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	return RNB_OK;
 } RNB_API_CATCH
 
+// ---- data parallelism behind the boundary ----------------------------------------------------------------------------------
+// The reference is single-GPU; its gradient buffer is one contiguous binary16 array between backward and optimizer_step (trainer.h:78-84,
+// testbed_nerf.cu:4068 -> :3624): that is where the collective goes.  Rays i = rank (mod world) are marched by this context (rnb_config);
+// after the backward the fp32 accumulators are rounded to binary16 ONCE (the reference's gradient format), summed over the ranks with one
+// ncclAllReduce on the caller's stream (21 MB instead of the 42 MB of the fp32 buffer; in-switch reduction on NVSwitch systems), together with
+// the 8 floats of loss sums / sample counts in the same NCCL group, and Adam/EMA read the binary16 sum.  RNB_DP=sharded: reduce-scatter ->
+// Adam/EMA on 1/world of the parameters -> all-gather of the binary16 training parameters (same bytes on the wire, 1/world of the optimizer).
+int rnb_comm_unique_id(uint8_t id_out[RNB_COMM_ID_BYTES]) try {
+	if (!id_out) return fail(RNB_ERR_INVALID, "null argument");
+	NcclApi* N = nccl_api(); if (!N) return fail(RNB_ERR_STATE, "libnccl.so.2 not found");
+	static_assert(RNB_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "id size");
+	ncclUniqueId id; NC(N->GetUniqueId(&id));
+	memcpy(id_out, id.internal, RNB_COMM_ID_BYTES);
+	return RNB_OK;
+} RNB_API_CATCH
+static int comm_buffers(rnb_ctx* c) {
+	if (!c->grads16) { CU(cudaMalloc(&c->grads16, c->np_padded * 2)); CU(cudaMemset(c->grads16, 0, c->np_padded * 2)); }
+	const char* e = getenv("RNB_DP");
+	c->dp_sharded = (e && std::string(e) == "sharded" && c->np_padded % ((size_t)c->cfg.world_size * 8) == 0) ? 1 : 0;
+	return RNB_OK;
+}
+int rnb_comm_init(rnb_ctx* c, const uint8_t id_in[RNB_COMM_ID_BYTES]) try {
+	if (!c || !id_in) return fail(RNB_ERR_INVALID, "null argument");
+	if (c->comm) return fail(RNB_ERR_STATE, "communicator already set");
+	if (c->in_step) return fail(RNB_ERR_STATE, "communicator changed inside a step");
+	NcclApi* N = nccl_api(); if (!N) return fail(RNB_ERR_STATE, "libnccl.so.2 not found");
+	ncclUniqueId id; memcpy(id.internal, id_in, RNB_COMM_ID_BYTES);
+	NC(N->CommInitRank(&c->comm, (int)c->cfg.world_size, id, (int)c->cfg.rank));
+	c->comm_owned = true;
+	return comm_buffers(c);
+} RNB_API_CATCH
+int rnb_comm_adopt(rnb_ctx* c, void* nccl_comm) try {
+	if (!c || !nccl_comm) return fail(RNB_ERR_INVALID, "null argument");
+	if (c->comm) return fail(RNB_ERR_STATE, "communicator already set");
+	NcclApi* N = nccl_api(); if (!N) return fail(RNB_ERR_STATE, "libnccl.so.2 not found");
+	int n = 0, r = -1; NC(N->CommCount((ncclComm_t)nccl_comm, &n)); NC(N->CommUserRank((ncclComm_t)nccl_comm, &r));
+	if ((uint32_t)n != c->cfg.world_size || (uint32_t)r != c->cfg.rank) return fail(RNB_ERR_INVALID, "communicator size / rank differ from rnb_config.world_size / rank");
+	c->comm = (ncclComm_t)nccl_comm; c->comm_owned = false;
+	return comm_buffers(c);
+} RNB_API_CATCH
+int rnb_comm_destroy(rnb_ctx* c) try {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (c->in_step) return fail(RNB_ERR_STATE, "communicator changed inside a step");
+	if (c->comm && c->comm_owned) { NcclApi* N = nccl_api(); CU(cudaDeviceSynchronize()); if (N) N->CommDestroy(c->comm); }
+	c->comm = nullptr; c->comm_owned = false;
+	return RNB_OK;
+} RNB_API_CATCH
+int rnb_comm_info(rnb_ctx* c, uint32_t out[4]) try {
+	if (!c || !out) return fail(RNB_ERR_INVALID, "null argument");
+	NcclApi* N = nccl_api(); int v = 0; if (N) N->GetVersion(&v);
+	out[0] = c->comm ? 1u : 0u; out[1] = (uint32_t)v; out[2] = (uint32_t)c->dp_sharded; out[3] = c->cfg.world_size;
+	return RNB_OK;
+} RNB_API_CATCH
+
+// between rnb_train_step_begin and rnb_train_step_end
+static int exchange_gradients(rnb_ctx* c, cudaStream_t st) {
+	NcclApi* N = nccl_api(); if (!N) return fail(RNB_ERR_STATE, "libnccl.so.2 not found");
+	const uint32_t np = (uint32_t)c->np_padded;
+	KT("grad_pack", 1, launch_pack_grads(st, np, c->grads, c->grads16));
+	CU(cudaGetLastError());
+	prof_begin(c, st, "grad_exchange");
+	NC(N->GroupStart());
+	if (c->dp_sharded) {
+		const size_t shard = c->np_padded / c->cfg.world_size;
+		NC(N->ReduceScatter(c->grads16, c->grads16 + (size_t)c->cfg.rank * shard, shard, ncclHalf, ncclSum, c->comm, st));
+		c->xch16 = c->grads16 + (size_t)c->cfg.rank * shard; c->xch_begin = (uint32_t)(c->cfg.rank * shard); c->xch_end = (uint32_t)((c->cfg.rank + 1) * shard);
+	} else {
+		NC(N->AllReduce(c->grads16, c->grads16, np, ncclHalf, ncclSum, c->comm, st));
+		c->xch16 = c->grads16; c->xch_begin = 0; c->xch_end = 0;
+	}
+	NC(N->AllReduce(c->stats, c->stats, 8, ncclFloat, ncclSum, c->comm, st));
+	NC(N->GroupEnd());
+	prof_end(c, st); c->launches += 1;
+	return RNB_OK;
+}
+
 int rnb_train_step(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	int rc = rnb_train_step_begin(c, stream); if (rc) return rc;
+	if (c->cfg.world_size > 1) {
+		if (!c->comm) { c->in_step = false; return fail(RNB_ERR_STATE, "world_size > 1: call rnb_comm_init / rnb_comm_adopt first, or drive rnb_train_step_begin / _end with your own collective"); }
+		rc = exchange_gradients(c, (cudaStream_t)stream); if (rc) { c->in_step = false; return rc; }
+	}
 	return rnb_train_step_end(c, stream, stats);
 } RNB_API_CATCH
 
 int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
-	const uint32_t skip = std::min(std::max(c->training_step / 16u, 1u), 16u);     // src/testbed.cu:2805-2806
+	NvtxRange nvtx_("train");
+	const uint32_t skip = std::min(std::max(c->canonical_step / 16u, 1u), 16u);    // src/testbed.cu:2805-2806
 	uint32_t updated = 0;
-	if (c->training_step % skip == 0) { int rc = rnb_prep(c, stream); if (rc) return rc; updated = 1; }
+	if (c->canonical_step % skip == 0) { int rc = rnb_prep(c, stream); if (rc) return rc; updated = 1; }
 	int rc = rnb_train_step(c, stream, stats);
 	if (!rc && stats) stats->density_grid_updated = updated;
 	return rc;
@@ -744,6 +919,7 @@ int rnb_checkpoint_save(rnb_ctx* c) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
 	if (c->in_step) return fail(RNB_ERR_STATE, "checkpoint inside a step");
 	drop_prelaunch(c);
+	pull_counters(c);
 	const size_t np = c->M.n_params, need = np * 20 + (size_t)GRID_CELLS * 4 + GRID_CELLS;
 	if (c->ck.bytes < need) { cudaFree(c->ck.buf); c->ck.buf = nullptr; CU(cudaMalloc(&c->ck.buf, need)); c->ck.bytes = need; }
 	CU(cudaDeviceSynchronize());
@@ -759,6 +935,7 @@ int rnb_checkpoint_save(rnb_ctx* c) try {
 	auto& k = c->ck;
 	k.opt_step = c->opt_step; k.lr_factor = c->lr_factor; k.density_ema_step = c->density_ema_step; k.training_step = c->training_step; k.rays_per_batch = c->rays_per_batch;
 	k.n_rays_total = c->n_rays_total; k.measured_before = c->measured_before; k.measured = c->measured; k.rng = c->rng; k.density_rng = c->density_rng;
+	k.canonical_step = c->canonical_step; k.n_images_prev = c->n_images_prev;
 	k.valid = true;
 	return RNB_OK;
 } RNB_API_CATCH
@@ -767,6 +944,7 @@ int rnb_checkpoint_restore(rnb_ctx* c) try {
 	if (!c->ck.valid) return fail(RNB_ERR_STATE, "no checkpoint");
 	if (c->in_step) return fail(RNB_ERR_STATE, "restore inside a step");
 	drop_prelaunch(c);
+	pull_counters(c);
 	CU(cudaDeviceSynchronize());
 	const size_t np = c->M.n_params;
 	const uint8_t* b = (const uint8_t*)c->ck.buf;
@@ -782,6 +960,8 @@ int rnb_checkpoint_restore(rnb_ctx* c) try {
 	const auto& k = c->ck;
 	c->opt_step = k.opt_step; c->lr_factor = k.lr_factor; c->density_ema_step = k.density_ema_step; c->training_step = k.training_step; c->rays_per_batch = k.rays_per_batch;
 	c->n_rays_total = k.n_rays_total; c->measured_before = k.measured_before; c->measured = k.measured; c->rng = k.rng; c->density_rng = k.density_rng;
+	c->canonical_step = k.canonical_step; c->n_images_prev = k.n_images_prev;
+	CU(push_measured(c));
 	return RNB_OK;
 } RNB_API_CATCH
 
@@ -1006,7 +1186,7 @@ int rnb_stage_generate(rnb_ctx* c, uint32_t n_rays, uint32_t n_rays_total, uint3
 	drop_prelaunch(c);
 	int rc = ensure_ray_capacity(c, n_rays); if (rc) return rc;
 	launch_march(0, n_rays, c->cfg.world_size, c->cfg.rank, n_rays_total, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts);
-	launch_scan_rays(0, n_rays, max_samples, c->ray_n, c->ray_indices, c->numsteps, c->counters);
+	launch_scan_rays(0, n_rays, max_samples, nullptr, c->ray_n, c->ray_indices, c->numsteps, c->counters);
 	launch_emit(0, n_rays, c->counters, c->cfg.world_size, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4);
 	CU(cudaDeviceSynchronize());
 	uint32_t cnt[2]; CU(cudaMemcpy(cnt, c->counters, 8, cudaMemcpyDeviceToHost));

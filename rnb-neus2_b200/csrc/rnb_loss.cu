@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(1024) k_scan_compact(uint32_t* __restrict__ co
 	}
 	if (tid == 0) {
 		counters[2] = carry; counters[3] = min(carry, max_compacted); counters[4] = fwd_end;
+		counters[5] = (carry == 0u || counters[1] == 0u) ? 0u : counters[1];      // measured_batch_size_before_compaction for the next step's clamp (Counters::update_after_training :3540-3545)
 		if (stats) { stats[3] = (float)carry; stats[4] = (float)counters[1]; stats[5] = (float)K; }   // float copies: summed across ranks with the losses
 	}
 }

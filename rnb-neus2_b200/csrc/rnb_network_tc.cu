@@ -58,6 +58,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 	uint32_t done = 0;
 	while (!done) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+// named barrier over the first `N` threads' worth of warps that execute it (the scatter warps of the backward never do)
+template <int ID, int N>
+__device__ __forceinline__ void bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -531,6 +539,16 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
 	for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// two single columns of this thread's lane (one wait for both)
+__device__ __forceinline__ void tmem_ld1x2(uint32_t ta, uint32_t tb, uint32_t& a, uint32_t& b) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(a) : "r"(ta) : "memory");
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(b) : "r"(tb) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // gather for the backward: the MLP input row goes to the X tile in shared memory (it is a weight-gradient operand), dy/dx to TMEM.
 // Two threads share one sample: `half` 0 gathers levels 0-7 (X chunks 0,1), `half` 1 levels 8-15 (chunks 2,3).
 __device__ __forceinline__ void gather_row_bwd(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint8_t* __restrict__ xtile, uint32_t tcol_dy, int row, int half) {
@@ -566,27 +584,43 @@ __device__ __forceinline__ void gather_row_bwd(const ModelDev& M, const __half* 
 	}
 }
 
-// 256 threads: thread pair (t, t + 128) shares sample row t of the 128-sample tile (and TMEM lane t: a warp reaches the lane
-// quarter warp % 4).  The pair splits the gather / V / scatter by hash levels and every 64-wide epilogue by column halves, which
-// doubles the warps per SM of this one-CTA-per-SM kernel.
-template <int SW, bool RGB3>
-__global__ void __launch_bounds__(2 * TILE, 1) k_backward_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
+// Warp-specialised: 256 CHAIN threads + 128 * NSC SCATTER threads.
+//   chain:   thread pair (t, t + 128) shares sample row t of the 128-sample tile (and TMEM lane t: a warp reaches the lane quarter
+//            warp % 4).  The pair splits the gather / V by hash levels and every 64-wide epilogue by column halves.  After the last
+//            stage of a tile the pair leaves the tile's d(enc) and dsdf/d(enc) as packed binary16 words in a 32-column TMEM mailbox
+//            (+ position, g_n and the live flag in shared memory), arrives on `bar_full` and goes on with the NEXT tile;
+//   scatter: warpgroup j (thread = sample, same TMEM lane) waits on `bar_full`, issues the merged first + second order reductions of the
+//            levels l = j (mod NSC) and arrives on `bar_empty`: the LSU-bound scatter of tile n runs under the tensor-core chain of
+//            tile n + 1 instead of after it (ncu before the split: 1 CTA / SM, issue-active 30 %, nothing saturated).
+//   Registers are rebalanced with setmaxnreg (the chain warps need ~200, the scatter warps ~100).
+template <int NSC> struct BwRegs;
+// setmaxnreg.inc can only take what the CTA's own warps have released with setmaxnreg.dec: with the launch allocation A = 65536 / threads rounded
+// down to 8 (168 at 384 threads, 128 at 512), NSC * (A - SCAT) >= 2 * (CHAIN - A) must hold or the second chain warpgroup waits forever
+template <> struct BwRegs<1> { static constexpr int LAUNCH = 168, CHAIN = 200, SCAT = 104; };     // frees 64 * 128 = 8192, takes 2 * 32 * 128 = 8192
+template <> struct BwRegs<2> { static constexpr int LAUNCH = 128, CHAIN = 168, SCAT = 88; };      // frees 2 * 40 * 128, takes 2 * 40 * 128
+static_assert(1 * (BwRegs<1>::LAUNCH - BwRegs<1>::SCAT) >= 2 * (BwRegs<1>::CHAIN - BwRegs<1>::LAUNCH), "register hand-over does not balance");
+static_assert(2 * (BwRegs<2>::LAUNCH - BwRegs<2>::SCAT) >= 2 * (BwRegs<2>::CHAIN - BwRegs<2>::LAUNCH), "register hand-over does not balance");
+template <int SW, bool RGB3, int NSC>
+__global__ void __launch_bounds__((2 + NSC) * TILE, 1) k_backward_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
                                                              const float4* __restrict__ pos4, const __half* __restrict__ dout16, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
                                                              uint32_t n_roll, uint32_t n_batch, const uint32_t* __restrict__ n_in_ptr, float* __restrict__ G) {
 	using B = Blob<SW>;
 	constexpr uint32_t T32 = TILE * 64, TW = TILE * SW * 2, T16 = TILE * 32;        // tile bytes: 32-, SW-, 16-wide
 	constexpr uint32_t XB = (B::END + 127u) & ~127u, VB = XB + T32, RB = VB + T32, HB = RB + T32, TMB = HB + TW, DHB = TMB + TW, F1B = DHB + TW,
-	                   H1B = F1B + TW, DH1B = H1B + TW, H2B = DH1B + TW, DH2B = H2B + TW, DYB = DH2B + TW, DCB = DYB + T16, E0B = DCB + T16, EXB = E0B + T16, SM_END = EXB + TILE * 32;
+	                   H1B = F1B + TW, DH1B = H1B + TW, H2B = DH1B + TW, DH2B = H2B + TW, DYB = DH2B + TW, DCB = DYB + T16, E0B = DCB + T16, EXB = E0B + T16, SCB = EXB + TILE * 32,
+	                   SM_END = SCB + TILE * 32;          // SCB: hand-off record of the scatter warps [8][128] floats: x y z gn0 gn1 gn2 live
 	// TMEM columns
 	constexpr uint32_t C_D = 0, C_D2 = 64, C_16 = 128, C_GIN = 144, C_32 = 176, C_DY = 208;            // chain accumulators, gin (kept for the scatter), dR / dU, dy/dx (14 levels x 8 columns, 6 used)
 	constexpr uint32_t A_W1 = 320, A_W2T = 352, A_C1 = 368, A_C2 = 400, A_C3T = 464;                   // weight-gradient accumulators (M = 64)
+	constexpr uint32_t C_MB = 480;                                      // mailbox of the scatter warps: [480,496) d(enc), [496,512) dsdf/d(enc), one packed binary16 pair per level
 	constexpr int NH = SW / 32;                                         // column halves of a hidden row that carry data (SW = 32: only half 0)
+	constexpr int NT = (2 + NSC) * TILE;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint32_t tmem_slot;
-	__shared__ __align__(8) uint64_t bar, bar_dw;
-	const int tid = threadIdx.x, warp = tid >> 5, half = tid >> 7, row_t = tid & (TILE - 1);
-	for (uint32_t i = tid; i < B::END / 16; i += 2 * TILE) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
-	for (uint32_t i = tid; i < (SM_END - XB) / 16; i += 2 * TILE) reinterpret_cast<uint4*>(smem + XB)[i] = make_uint4(0u, 0u, 0u, 0u);
+	__shared__ __align__(8) uint64_t bar, bar_dw, bar_full, bar_empty;
+	const int tid = threadIdx.x, warp = tid >> 5, half = tid >> 7, row_t = tid & (TILE - 1);      // half: 0 / 1 chain, >= 2 scatter warpgroup half - 2
+	for (uint32_t i = tid; i < B::END / 16; i += NT) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
+	for (uint32_t i = tid; i < (SM_END - XB) / 16; i += NT) reinterpret_cast<uint4*>(smem + XB)[i] = make_uint4(0u, 0u, 0u, 0u);
 	__syncthreads();
 	if (half == 0) {   // E0: column 0 = 1 (column sums through the tensor core)
 		const __half2 one = __halves2half2(__float2half_rn(1.f), __float2half_rn(0.f));
@@ -594,11 +628,40 @@ __global__ void __launch_bounds__(2 * TILE, 1) k_backward_tc(ModelDev M, const _
 	}
 	fence_async_smem();
 	if (warp == 0) tmem_alloc<512>(&tmem_slot);
-	if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar_dw, 1); }
+	if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar_dw, 1); mbar_init(&bar_full, 2 * TILE); mbar_init(&bar_empty, NSC * TILE); }
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem = tmem_slot, trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+	float* scr = reinterpret_cast<float*>(smem + SCB);
+	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
+	const uint32_t n_tiles = (n + TILE - 1) / TILE;
+	const uint32_t L = M.n_levels, n_live = min(L, valid_level + 1u);
+	if (half >= 2) {
+		// ---- scatter warps -------------------------------------------------------------------------------------------------
+		reg_dec<BwRegs<NSC>::SCAT>();
+		const uint32_t j = (uint32_t)half - 2u;
+		uint32_t ph = 0;
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+			mbar_wait(&bar_full, ph); ph ^= 1;
+			tc_fence_after();
+			const float px = scr[row_t], py = scr[TILE + row_t], pz = scr[2 * TILE + row_t];
+			const float g0 = scr[3 * TILE + row_t], g1 = scr[4 * TILE + row_t], g2 = scr[5 * TILE + row_t];
+			const bool live = scr[6 * TILE + row_t] != 0.f;
+			#pragma unroll 1
+			for (uint32_t l = j; l < n_live; l += NSC) {
+				uint32_t wd, wg;
+				tmem_ld1x2(trow + C_MB + l, trow + C_MB + 16 + l, wd, wg);          // tcgen05.ld is warp-collective: executed by every lane, live or not
+				const float2 du = __half22float2(*reinterpret_cast<const __half2*>(&wd)), gi = __half22float2(*reinterpret_cast<const __half2*>(&wg));
+				if (l < M.scatter_agg) scatter_level_agg(M, G, l, live, px, py, pz, du.x, du.y, gi.x, gi.y, g0, g1, g2);      // warp-uniform branch
+				else if (live) scatter_level(M, G, l, px, py, pz, du.x, du.y, gi.x, gi.y, g0, g1, g2);
+			}
+			tc_fence_before();
+			mbar_arrive(&bar_empty);
+		}
+	} else {
+	// ---- chain warps ------------------------------------------------------------------------------------------------------
+	reg_inc<BwRegs<NSC>::CHAIN>();
 	const float* w2r = reinterpret_cast<const float*>(smem + B::W2R);
 	float* ex = reinterpret_cast<float*>(smem + EXB);                   // pair exchange: [0,128) sdf part of half 0, [128,256) half 1, [256 + 3 * (128 h + row)] normal parts
 	const uint32_t sW1 = smem_u32(smem + B::W1), sW2 = smem_u32(smem + B::W2), sC1 = smem_u32(smem + B::C1), sC2 = smem_u32(smem + B::C2), sC3 = smem_u32(smem + B::C3);
@@ -608,16 +671,13 @@ __global__ void __launch_bounds__(2 * TILE, 1) k_backward_tc(ModelDev M, const _
 	constexpr uint32_t PS = TILE * 16;                                   // panel stride of every 128-row tile
 	constexpr uint32_t ID_W = make_idesc(128, SW, 0, 0), ID_16 = make_idesc(128, 16, 0, 0), ID_T32 = make_idesc(128, 32, 0, 1), ID_TW = make_idesc(128, SW, 0, 1);
 	constexpr uint32_t IDG_16 = make_idesc(64, 16, 1, 1), IDG_32 = make_idesc(64, 32, 1, 1), IDG_W = make_idesc(64, SW, 1, 1);
-	const uint32_t n = n_ptr ? min(*n_ptr, n_max) : n_max;
 	const uint32_t n_in = n_in_ptr ? *n_in_ptr : n;
-	const uint32_t n_tiles = (n + TILE - 1) / TILE;
 	const float inv_nb = 1.0f / (float)n_batch;
-	const uint32_t L = M.n_levels, n_live = min(L, valid_level + 1u);
 	const uint32_t l_begin = 8u * (uint32_t)half, l_end = l_begin + 8u;      // this thread's hash levels (and u' words)
-	uint32_t phase = 0, phase_dw = 0;
+	uint32_t phase = 0, phase_dw = 0, phase_mb = 0;
 	float var_acc = 0.f;
 	bool first = true;
-	auto issue_begin = [&]() { tmem_st_wait(); fence_async_smem(); tc_fence_before(); __syncthreads(); };
+	auto issue_begin = [&]() { tmem_st_wait(); fence_async_smem(); tc_fence_before(); bar_sync<1, 2 * TILE>(); };
 	auto issue_end = [&]() { mbar_wait(&bar, phase); phase ^= 1; tc_fence_after(); };
 	// chain layer: D[128 x N] = A(smem tile, K-major, K = 16 * ksteps) . B
 	auto chain = [&](uint32_t d_col, uint32_t sA, int ksteps, uint32_t sB, uint32_t b_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc) {
@@ -746,7 +806,7 @@ __global__ void __launch_bounds__(2 * TILE, 1) k_backward_tc(ModelDev M, const _
 				*reinterpret_cast<uint4*>(smem + RB + 1 * PS + row_t * 16) = make_uint4(r[4], r[5], r[6], r[7]);
 			}
 		}
-		__syncthreads();
+		bar_sync<1, 2 * TILE>();
 		if (half == 0) {   // r' chunk 2: x y z n0 n1 n2 0 0
 			const float* qa = ex + 2 * TILE + 3 * row_t; const float* qb = ex + 2 * TILE + 3 * (TILE + row_t);
 			const float n0 = qa[0] + qb[0], n1 = qa[1] + qb[1], n2 = qa[2] + qb[2];
@@ -857,14 +917,25 @@ __global__ void __launch_bounds__(2 * TILE, 1) k_backward_tc(ModelDev M, const _
 			umma_commit(&bar_dw);
 		}
 		issue_end();
-		// ---- merged first + second order hash scatter, this thread's levels, one at a time (values re-read from TMEM)
-		#pragma unroll 1
-		for (uint32_t l = l_begin; l < min(l_end, n_live); ++l) {
-			float du0, du1, g0, g1;
-			tmem_ld2(trow + C_32 + 2 * l, du0, du1);          // tcgen05.ld is warp-collective: executed by every lane, live or not
-			tmem_ld2(trow + C_GIN + 2 * l, g0, g1);
-			if (l < M.scatter_agg) scatter_level_agg(M, G, l, live, p.x, p.y, p.z, hq(du0), hq(du1), hq(g0), hq(g1), gn[0], gn[1], gn[2]);      // warp-uniform branch
-			else if (live) scatter_level(M, G, l, p.x, p.y, p.z, hq(du0), hq(du1), hq(g0), hq(g1), gn[0], gn[1], gn[2]);
+		// ---- hand-off to the scatter warps: d(enc) and dsdf/d(enc) of this thread's levels as packed binary16 words into the mailbox
+		{
+			if (!first) { mbar_wait(&bar_empty, phase_mb); phase_mb ^= 1; tc_fence_after(); }      // the previous tile's reductions have been issued
+			float du[16], gi[16];
+			tmem_ld16(trow + C_32 + half * 16, du);
+			tmem_ld16(trow + C_GIN + half * 16, gi);
+			uint32_t a[8], b[8];
+			#pragma unroll
+			for (int i = 0; i < 8; ++i) { a[i] = pack_h2(du[2 * i], du[2 * i + 1]); b[i] = pack_h2(gi[2 * i], gi[2 * i + 1]); }
+			tmem_st8(trow + C_MB + half * 8, a);
+			tmem_st8(trow + C_MB + 16 + half * 8, b);
+			if (half == 0) {
+				scr[row_t] = p.x; scr[TILE + row_t] = p.y; scr[2 * TILE + row_t] = p.z;
+				scr[3 * TILE + row_t] = gn[0]; scr[4 * TILE + row_t] = gn[1]; scr[5 * TILE + row_t] = gn[2];
+				scr[6 * TILE + row_t] = live ? 1.f : 0.f;
+			}
+			tmem_st_wait();
+			tc_fence_before();
+			mbar_arrive(&bar_full);
 		}
 		first = false;
 	}
@@ -925,6 +996,7 @@ __global__ void __launch_bounds__(2 * TILE, 1) k_backward_tc(ModelDev M, const _
 	}
 	for (int o = 16; o; o >>= 1) var_acc += __shfl_xor_sync(0xffffffffu, var_acc, o);
 	if ((tid & 31) == 0 && var_acc != 0.f) atomicAdd(&G[M.off_var], var_acc);
+	}      // chain warps
 	tc_fence_before();
 	__syncthreads();
 	if (warp == 0) tmem_free<512>(tmem);
@@ -972,22 +1044,33 @@ static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __h
 	}
 }
 
+static int g_bw_scatter_groups = 1;      // RNB_BW_SCATTER_WG=1|2: scatter warpgroups of the backward (A/B knob)
+void set_bw_scatter_groups(int n) { g_bw_scatter_groups = n == 2 ? 2 : 1; }
+
+template <int SW, bool RGB3, int NSC>
+static void launch_tc_backward_cfg(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
+                                   uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
+	using namespace tc;
+	using B = Blob<SW>;
+	const size_t smem = ((B::END + 127u) & ~127u) + 3 * (TILE * 64) + 8 * (TILE * SW * 2) + 3 * (TILE * 32) + TILE * 32 /* pair exchange */ + TILE * 32 /* scatter hand-off */
+	                    + 8192 /* M = 64 products of a 32-wide tile read 4 panels past it */;
+	const uint32_t grid = std::min<uint32_t>((n_max + TILE - 1) / TILE, (uint32_t)n_sm);
+	static bool attr = false;
+	if (!attr) { cudaFuncSetAttribute(k_backward_tc<SW, RGB3, NSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+	k_backward_tc<SW, RGB3, NSC><<<grid, (2 + NSC) * TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+}
+
 template <int SW>
 static void launch_tc_backward_sw(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
                                   uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
-	using namespace tc;
-	using B = Blob<SW>;
 	if (!n_max) return;
-	const size_t smem = ((B::END + 127u) & ~127u) + 3 * (TILE * 64) + 8 * (TILE * SW * 2) + 3 * (TILE * 32) + TILE * 32 /* pair exchange */ + 8192 /* M = 64 products of a 32-wide tile read 4 panels past it */;
-	const uint32_t grid = std::min<uint32_t>((n_max + TILE - 1) / TILE, (uint32_t)n_sm);
-	if (M.n_rgb_layers == 3) {
-		static bool attr = false;
-		if (!attr) { cudaFuncSetAttribute(k_backward_tc<SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-		k_backward_tc<SW, true><<<grid, 2 * TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+	const bool rgb3 = M.n_rgb_layers == 3;
+	if (g_bw_scatter_groups == 2) {
+		if (rgb3) launch_tc_backward_cfg<SW, true, 2>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
+		else launch_tc_backward_cfg<SW, false, 2>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
 	} else {
-		static bool attr = false;
-		if (!attr) { cudaFuncSetAttribute(k_backward_tc<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-		k_backward_tc<SW, false><<<grid, 2 * TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+		if (rgb3) launch_tc_backward_cfg<SW, true, 1>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
+		else launch_tc_backward_cfg<SW, false, 1>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
 	}
 }
 void launch_tc_backward(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,

@@ -18,6 +18,9 @@ struct AdamParams {
 	// data-parallel optimizer shard: this rank updates parameters [shard_begin, shard_end) (multiples of 4) from gsrc[i - shard_begin]
 	// (the reduce-scattered gradient sum; NULL: the gradient buffer itself) and only clears the gradient buffer elsewhere
 	uint32_t shard_begin, shard_end; const float* gsrc;
+	// binary16 gradient exchange (data parallel behind the C ABI): the all-reduced / reduce-scattered gradient sum as binary16 (gsrc16[i - shard_begin]);
+	// the fp32 accumulators have already been cleared by k_pack_grads, so this pass does not touch them
+	const __half* gsrc16;
 };
 
 // One thread owns 4 consecutive parameters: every array is moved with one 128-bit (fp32 / u32) or 64-bit (binary16) access.
@@ -49,6 +52,7 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
 	if (i0 >= A.n_params) return;
 	if (i0 < A.shard_begin || i0 >= A.shard_end) {     // another rank's parameters: drop this rank's partial gradient, the weights arrive with the all-gather
+		if (A.gsrc16) return;
 		if (i0 + 4 <= A.n_params) {
 			const float4 g = *reinterpret_cast<const float4*>(grads + i0);
 			if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -56,7 +60,12 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 		return;
 	}
 	if (i0 + 4 <= A.n_params) {
-		float4 g = *reinterpret_cast<const float4*>(grads + i0);
+		float4 g;
+		if (A.gsrc16) {
+			const uint2 h = *reinterpret_cast<const uint2*>(A.gsrc16 + (i0 - A.shard_begin));
+			const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+			g = make_float4(lo.x, lo.y, hi.x, hi.y);
+		} else g = *reinterpret_cast<const float4*>(grads + i0);
 		if (A.gsrc) {                                   // the reduced gradient lives in the caller's reduce-scatter output
 			if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
 			g = *reinterpret_cast<const float4*>(A.gsrc + (i0 - A.shard_begin));
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 		if (!anyg && !mat && pw.x == pe.x && pw.y == pe.y) return;
 		__half* wh = reinterpret_cast<__half*>(&pw); __half* eh = reinterpret_cast<__half*>(&pe);
 		if (anyg || mat) {
-			if (anyg && !A.gsrc) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);     // consumed: ready for the next step's atomics
+			if (anyg && !A.gsrc && !A.gsrc16) *reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f);     // consumed: ready for the next step's atomics
 			const float4 w4 = *reinterpret_cast<const float4*>(master + i0), a4 = *reinterpret_cast<const float4*>(m1 + i0), b4 = *reinterpret_cast<const float4*>(m2 + i0);
 			const uint4 s4 = *reinterpret_cast<const uint4*>(steps + i0);
 			AdamLane S[4] = {{w4.x, a4.x, b4.x, s4.x}, {w4.y, a4.y, b4.y, s4.y}, {w4.z, a4.z, b4.z, s4.z}, {w4.w, a4.w, b4.w, s4.w}};
@@ -88,7 +97,8 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 		*reinterpret_cast<uint2*>(params + i0) = pw; *reinterpret_cast<uint2*>(ema + i0) = pe;
 	} else {
 		for (uint32_t i = i0; i < A.n_params; ++i) {
-			const float g32 = A.gsrc ? A.gsrc[i - A.shard_begin] : grads[i]; grads[i] = 0.f;
+			const float g32 = A.gsrc16 ? __half2float(A.gsrc16[i - A.shard_begin]) : (A.gsrc ? A.gsrc[i - A.shard_begin] : grads[i]);
+			if (!A.gsrc16) grads[i] = 0.f;
 			__half wh = params[i];
 			AdamLane S{master[i], m1[i], m2[i], steps[i]};
 			if (adam_one(A, i, g32, S, wh)) { master[i] = S.w; m1[i] = S.m1; m2[i] = S.m2; steps[i] = S.step; }
@@ -96,6 +106,23 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 			ema[i] = __float2half_rn((__half2float(ema[i]) * A.ema_decay * A.ema_debias_old + __half2float(wh) * (1 - A.ema_decay)) * A.ema_debias_new);
 		}
 	}
+}
+
+// fp32 gradient accumulators -> binary16 (the reference's gradient format, trainer.h:78-84) for the data-parallel exchange; clears the accumulators.
+// n is a multiple of 8 (the arrays are padded to 512 elements).  One thread moves 8 parameters: two 128-bit loads, one 128-bit store.
+__global__ void __launch_bounds__(256) k_pack_grads(uint32_t n, float* __restrict__ grads, __half* __restrict__ out) {
+	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+	if (i0 >= n) return;
+	const float4 a = *reinterpret_cast<const float4*>(grads + i0), b = *reinterpret_cast<const float4*>(grads + i0 + 4);
+	const bool nz = a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f || b.x != 0.f || b.y != 0.f || b.z != 0.f || b.w != 0.f;
+	uint4 h = make_uint4(0u, 0u, 0u, 0u);
+	if (nz) {
+		__half2 t;
+		t = __floats2half2_rn(a.x, a.y); h.x = *reinterpret_cast<uint32_t*>(&t); t = __floats2half2_rn(a.z, a.w); h.y = *reinterpret_cast<uint32_t*>(&t);
+		t = __floats2half2_rn(b.x, b.y); h.z = *reinterpret_cast<uint32_t*>(&t); t = __floats2half2_rn(b.z, b.w); h.w = *reinterpret_cast<uint32_t*>(&t);
+		*reinterpret_cast<float4*>(grads + i0) = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(grads + i0 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	*reinterpret_cast<uint4*>(out + i0) = h;
 }
 
 __global__ void k_cast_params(uint32_t n, const float* __restrict__ master, __half* __restrict__ params) {
@@ -188,6 +215,7 @@ __global__ void k_bitfield_pool(const uint8_t* __restrict__ prev, uint8_t* __res
 void launch_adam_ema(cudaStream_t st, const AdamParams& A, float* master, __half* params, __half* ema, float* grads, float* m1, float* m2, uint32_t* steps) {
 	k_adam_ema<<<((A.n_params + 3) / 4 + 255) / 256, 256, 0, st>>>(A, master, params, ema, grads, m1, m2, steps);
 }
+void launch_pack_grads(cudaStream_t st, uint32_t n_padded, float* grads, __half* out) { k_pack_grads<<<(n_padded / 8 + 255) / 256, 256, 0, st>>>(n_padded, grads, out); }
 void launch_cast_params(cudaStream_t st, uint32_t n, const float* master, __half* params) { k_cast_params<<<(n + 255) / 256, 256, 0, st>>>(n, master, params); }
 void launch_widen_params(cudaStream_t st, uint32_t n, const __half* params, float* master) { k_widen_params<<<(n + 255) / 256, 256, 0, st>>>(n, params, master); }
 void launch_init_grid(cudaStream_t st, Pcg32 rng, uint64_t n, float* out) {

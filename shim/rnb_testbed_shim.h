@@ -139,6 +139,7 @@ inline bool train(ngp::Testbed& t) {
 	state_dirty() = true;
 	t.m_training_step = st.training_step;
 	t.m_canonical_training_step = (int)st.training_step;
+	if (st.density_grid_updated) t.m_nerf.training.n_images_for_training_prev = t.m_nerf.training.n_images_for_training;      // update_density_grid_nerf :3447
 	t.m_nerf_network->m_training_step = st.training_step;
 	t.m_loss_scalar.update(st.loss); t.m_ek_loss_scalar.update(st.ek_loss); t.m_mask_loss_scalar.update(st.mask_loss);
 	auto& c = t.m_nerf.training.counters_rgb;
@@ -197,6 +198,8 @@ inline void pull_state(ngp::Testbed& t) {
 	}
 	const auto& c = t.m_nerf.training.counters_rgb;
 	check(rnb_set_train_state(ctx(), (uint32_t)t.m_training_step, c.rays_per_batch, c.n_rays_total, c.measured_batch_size_before_compaction));
+	// what load_snapshot does NOT restore: the canonical step (0 after reset_network) and the image count of the last occupancy refresh
+	check(rnb_set_canonical_state(ctx(), (uint32_t)t.m_canonical_training_step, (uint32_t)t.m_nerf.training.n_images_for_training_prev));
 	state_dirty() = false;
 }
 

@@ -154,6 +154,9 @@ class Oracle:
     def set_train_state(self, training_step=0, rays_per_batch=4096, n_rays_total=0, measured_before=0, pin_rays=1, target_batch=1 << 18):
         self.L.orc_set_train_state(self.h, training_step, rays_per_batch, n_rays_total, measured_before, pin_rays, target_batch)
 
+    def set_canonical_state(self, canonical_step, n_images_prev):
+        self.L.orc_set_canonical_state(self.h, canonical_step, n_images_prev)
+
     def get_rng(self):
         o = np.zeros(4, np.uint64); self.L.orc_get_rng(self.h, _p(o, C.c_uint64)); return [int(x) for x in o]
 

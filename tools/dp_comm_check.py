@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""N-GPU check of data parallelism BEHIND the C ABI (rnb_comm_init + rnb_train): the library's own NCCL communicator, binary16 gradient
+exchange (all-reduce, and RNB_DP=sharded: reduce-scatter + sharded Adam + parameter all-gather), against the round-1 protocol (fp32 all-reduce
+driven from outside through rnb_train_step_begin / _end with torch.distributed) and against a single-GPU run of the same global batch.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_comm_check.py
+Float atomics make single steps differ in the last bits, so comparisons are tolerances with a second identical run as the yardstick."""
+import json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import torch.distributed as dist
+import rnb_loader, bench
+
+K = int(os.environ.get("RNB_CHECK_STEPS", "40"))
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+pkg = rnb_loader.load_package()
+views, _ = bench.build_views(12, 320, 240, True)
+R, TARGET = 1024, 1 << 18      # compacted samples stay below the budget: no per-rank truncation, the shards add up to the single-GPU batch
+
+
+class _Arr:
+    def __init__(self, p, n, ts="<f4"): self.__cuda_array_interface__ = {"shape": (n,), "typestr": ts, "data": (p, False), "version": 3}
+
+
+def make(w, r, pin=1):
+    cfg = pkg.default_config(rays_per_batch=R, pin_rays_per_batch=pin, world_size=w, rank=r, target_batch_size=TARGET)
+    t = pkg.Testbed(cfg, pkg.default_flags(no_albedo=0, light_mode=-2))
+    t.init_params(); t.load_training_data(views)
+    return t
+
+
+def bcast_id():
+    ids = [pkg.Testbed.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, 0)
+    return ids[0]
+
+
+def finish(t, losses, rays=None):
+    torch.cuda.synchronize()
+    pp, _, n, npad = t.param_buffers()
+    p = torch.as_tensor(_Arr(pp, npad, "<f2"), device="cuda")[:n].clone()
+    gp, gn = t.grad_buffer()
+    g = torch.as_tensor(_Arr(gp, gn), device="cuda").abs().max().item()
+    ref = p.clone(); dist.broadcast(ref, 0)
+    flag = torch.tensor([1 if torch.equal(ref, p) else 0], device="cuda"); dist.all_reduce(flag)
+    return dict(p=p.float(), losses=losses, identical=int(flag.item()) == world, grad_max=g, rays=rays)
+
+
+def run_external():          # round-1 protocol: fp32 all-reduce from outside
+    t = make(world, rank)
+    gp, gn = t.grad_buffer(); sp, sn = t.stat_buffer()
+    grad_t = torch.as_tensor(_Arr(gp, gn), device="cuda"); stat_t = torch.as_tensor(_Arr(sp, sn), device="cuda")
+    losses = []
+    for _ in range(K):
+        ts = t.get_train_state()[0]
+        if ts % min(max(ts // 16, 1), 16) == 0:
+            t.training_prep_nerf()
+        t.train_step_begin(); dist.all_reduce(grad_t); dist.all_reduce(stat_t)
+        losses.append(float(t.train_step_end().loss))
+    return finish(t, losses)
+
+
+def run_library(mode, pin=1):
+    os.environ["RNB_DP"] = mode
+    t = make(world, rank, pin)
+    t.comm_init(bcast_id())
+    info = t.comm_info()
+    losses = []; rays = []
+    for _ in range(K):
+        st = t.train()
+        losses.append(float(st.loss)); rays.append(int(st.rays_per_batch_next))
+    out = finish(t, losses, rays); out["info"] = info
+    t.comm_destroy()
+    return out
+
+
+def run_single():            # the same global batch on one GPU (every rank runs it: identical by construction)
+    t = make(1, 0)
+    losses = [float(t.train().loss) for _ in range(K)]
+    torch.cuda.synchronize()
+    pp, _, n, npad = t.param_buffers()
+    return dict(p=torch.as_tensor(_Arr(pp, npad, "<f2"), device="cuda")[:n].clone().float(), losses=losses)
+
+
+rel = lambda x, y: float((x - y).norm() / y.norm())
+s1 = run_single(); s2 = run_single()
+e = run_external()
+a = run_library("allreduce"); a2 = run_library("allreduce")
+sh = run_library("sharded")
+ad = run_library("allreduce", pin=0)          # adaptive controller under data parallelism: every rank must derive the same batch sizes
+rays_t = torch.tensor(ad["rays"], device="cuda", dtype=torch.int64); r0 = rays_t.clone(); dist.broadcast(r0, 0)
+same_rays = torch.tensor([1 if torch.equal(r0, rays_t) else 0], device="cuda"); dist.all_reduce(same_rays)
+out = {"world": world, "steps": K, "nccl": a["info"], "sharded_info": sh["info"],
+       "single_run_to_run": rel(s2["p"], s1["p"]),
+       "external_fp32_vs_single": rel(e["p"], s1["p"]), "library_fp16_vs_single": rel(a["p"], s1["p"]), "library_fp16_run_to_run": rel(a2["p"], a["p"]),
+       "library_sharded_vs_single": rel(sh["p"], s1["p"]), "library_sharded_vs_allreduce": rel(sh["p"], a["p"]),
+       "ranks_identical": {"external": e["identical"], "allreduce": a["identical"], "sharded": sh["identical"], "adaptive": ad["identical"]},
+       "grad_buffer_abs_max_after": {"external": e["grad_max"], "allreduce": a["grad_max"], "sharded": sh["grad_max"]},
+       "loss_first_last": {k: [v["losses"][0], v["losses"][-1]] for k, v in (("single", s1), ("external", e), ("allreduce", a), ("sharded", sh), ("adaptive", ad))},
+       "adaptive_rays_same_on_all_ranks": int(same_rays.item()) == world, "adaptive_rays_tail": ad["rays"][-5:]}
+yard = max(out["single_run_to_run"], out["library_fp16_run_to_run"], 1e-4)
+ok = (all(out["ranks_identical"].values()) and all(v == 0.0 for v in out["grad_buffer_abs_max_after"].values()) and out["adaptive_rays_same_on_all_ranks"]
+      and out["library_fp16_vs_single"] <= max(8 * yard, 5e-3) and out["library_sharded_vs_allreduce"] <= max(8 * yard, 5e-3)
+      and abs(a["losses"][-1] - s1["losses"][-1]) <= 0.1 * abs(s1["losses"][-1]) + 1e-6 and a["info"]["installed"] and sh["info"]["sharded"])
+out["ok"] = bool(ok)
+if rank == 0:
+    print(json.dumps(out))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "dp_comm_check_n%d.json" % world), "w"), indent=1)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

@@ -6,7 +6,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEFAULT_LIB = os.path.join(ROOT, "rnb-neus2_b200", "librnb_b200.so")
 PAT = collections.OrderedDict([("UTCHMMA", r"\bUTC\w*MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTCBAR", r"\bUTCBAR"), ("UBLKCP/UTMA", r"\bUBLKCP|\bUTMALDG|\bUTMASTG"),
-                               ("HMMA", r"\bHMMA"), ("REDG", r"\bREDG?\."), ("REDG.x2", r"\bREDG?\.\S*F32x2"), ("REDG.x4", r"\bREDG?\.\S*F32x4"), ("REDUX", r"\bREDUX"), ("SHFL", r"\bSHFL\."), ("LDG", r"\bLDG\."), ("instr", r"^\s+/\*[0-9a-f]{4,}\*/")])
+                               ("HMMA", r"\bHMMA"), ("REDG", r"\bREDG?\."), ("REDG.x2", r"\bREDG?\.\S*F32x2"), ("REDG.x4", r"\bREDG?\.\S*F32x4"), ("REDUX", r"\bREDUX"), ("SHFL", r"\bSHFL\."), ("LDG", r"\bLDG\."), ("USETMAXREG", r"\bUSETMAXREG"), ("SYNCS", r"\bSYNCS\."), ("instr", r"^\s+/\*[0-9a-f]{4,}\*/")])
 
 
 def demangle(names):
