@@ -424,6 +424,24 @@ def main():
             m2, _, _, _ = timed(t, k2, False)
             t.set_flags(pkg.default_flags(**flags_kw))
             records["normals"] = {"workload": WORKLOADS["normals"], "value": R * k2 / (m2 * 1e-3), "unit": UNIT, "ms_per_step": m2 / k2, "steps": k2, "note": "same trained state and steps, --no-albedo loss"}
+        # (1b) BASELINE configs[4]: --supernormal (identity light basis, normals + Eikonal) on the same state, and the mesh-resolution-1024 extraction
+        # (SDF sweep over the 1024^3 lattice on the tcgen05 probe kernel + marching cubes + normals + colours; device times from CUDA events)
+        t.checkpoint_restore()
+        t.set_flags(pkg.default_flags(no_albedo=1, apply_supernormal=1))
+        m5, _, _, _ = timed(t, k2, False)
+        t.set_flags(pkg.default_flags(**flags_kw))
+        records["supernormal"] = {"workload": WORKLOADS["normals"].replace("normals-only", "normals-only --supernormal"), "value": R * k2 / (m5 * 1e-3), "unit": UNIT, "ms_per_step": m5 / k2, "steps": k2}
+        if n_gpus == 1:
+            try:
+                t.checkpoint_restore()
+                torch.cuda.synchronize(); t0 = time.time()
+                mi = t.marching_cubes(1024)
+                torch.cuda.synchronize()
+                records["mesh_1024"] = {"wall_s": round(time.time() - t0, 4), "n_vertices": int(mi["n_verts"]), "n_triangles": int(mi["n_indices"]) // 3,
+                                        "stage_ms": mi["stage_ms"],
+                                        "lattice_points": 1024 ** 3, "note": "Testbed::marching_cubes at --resolution 1024 on the trained state (EMA weights)"}
+            except Exception as ex:      # noqa: BLE001
+                records["mesh_1024"] = {"error": str(ex)[:200]}
         # (2) the adaptive batch-size controller (pin_rays_per_batch = 0): what shim/rnb_testbed_shim.h and therefore ./build/testbed run; the controller holds
         # the compacted sample count at 2^18 per GPU, rays/step follow the scene; the host waits for the counters every step like the reference
         ta, _ = make_testbed(R, (1 << 18) * n_gpus, pin=0)

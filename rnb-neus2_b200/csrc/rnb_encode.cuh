@@ -91,15 +91,23 @@ __device__ __forceinline__ __half2 encode_level_packed(const ModelDev& M, const 
 // per level.  Arithmetic identical to encode_level_packed().
 struct LevelLoads { uint32_t raw[8]; float fx, fy, fz; };
 
-__device__ __forceinline__ void level_issue(const ModelDev& M, const __half* __restrict__ P, uint32_t l, float x, float y, float z, LevelLoads& Q) {
+// stab / n_stage_levels (optional): the first n_stage_levels levels of the table staged in shared memory by the CTA (rnb_network_tc.cu: one bulk-async
+// copy per CTA); their corner reads are shared-memory loads.  The branch is uniform (it depends on the level only).
+__device__ __forceinline__ void level_issue(const ModelDev& M, const __half* __restrict__ P, uint32_t l, float x, float y, float z, LevelLoads& Q,
+                                            const uint32_t* __restrict__ stab = nullptr, uint32_t n_stage_levels = 0) {
 	const uint32_t off = M.offsets[l];
 	const uint32_t* grid = reinterpret_cast<const uint32_t*>(P + M.off_grid);
 	const uint32_t hsz = M.offsets[l + 1] - off, res = M.res[l];
 	const LevelGeom g = level_geom(M.scale[l], x, y, z);
 	uint32_t e[8];
 	corner_entries((M.hashed_mask >> l) & 1u, hsz, res, g, e);
-	#pragma unroll
-	for (int c = 0; c < 8; ++c) Q.raw[c] = __ldg(grid + (e[c] + off));
+	if (l < n_stage_levels) {
+		#pragma unroll
+		for (int c = 0; c < 8; ++c) Q.raw[c] = stab[e[c] + off];
+	} else {
+		#pragma unroll
+		for (int c = 0; c < 8; ++c) Q.raw[c] = __ldg(grid + (e[c] + off));
+	}
 	Q.fx = g.fx; Q.fy = g.fy; Q.fz = g.fz;
 }
 

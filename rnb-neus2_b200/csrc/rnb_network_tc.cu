@@ -66,6 +66,11 @@ template <int R>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+// bulk-async (TMA engine, 1-D) global -> shared copy that completes on an mbarrier: cp.async.bulk, sizes multiples of 16 bytes
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -169,7 +174,8 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
 }
 
 template <bool WITH_DY>
-__device__ __forceinline__ void gather_row_to_tmem(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint32_t tcol, float* __restrict__ dyS, int tid) {
+__device__ __forceinline__ void gather_row_to_tmem(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint32_t tcol, float* __restrict__ dyS, int tid,
+                                                   const uint32_t* __restrict__ stab = nullptr, uint32_t n_stage_levels = 0) {
 	const uint32_t L = M.n_levels;
 	const uint32_t n_live = min(L, valid_level + 1u);          // levels > valid_level are zero (progressive training, grid.h:193-210)
 	const __half2 exy = __halves2half2(__hsub(__float2half_rn(x), __float2half_rn(0.5f)), __hsub(__float2half_rn(y), __float2half_rn(0.5f)));   // fill_positions_view_with_fixed_offset
@@ -180,7 +186,7 @@ __device__ __forceinline__ void gather_row_to_tmem(const ModelDev& M, const __ha
 		if (b < n_live) {
 			LevelLoads Q[4];
 			#pragma unroll
-			for (uint32_t i = 0; i < 4; ++i) if (b + i < n_live) level_issue(M, P, b + i, x, y, z, Q[i]);
+			for (uint32_t i = 0; i < 4; ++i) if (b + i < n_live) level_issue(M, P, b + i, x, y, z, Q[i], stab, n_stage_levels);
 			#pragma unroll
 			for (uint32_t i = 0; i < 4; ++i) {
 				if (b + i < n_live) {
@@ -218,23 +224,36 @@ struct GridSpec { uint32_t rx, ry, rz; float inv[3], ext[3], mn[3]; };
 template <int SW, int MODE>
 __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
                                                     const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
-                                                    __half* __restrict__ outA, float* __restrict__ sdf_out, float* __restrict__ dens_out, GridSpec gs) {
+                                                    __half* __restrict__ outA, float* __restrict__ sdf_out, float* __restrict__ dens_out, GridSpec gs, uint32_t n_stage_levels) {
 	using B = Blob<SW>;
 	constexpr bool NORMAL = MODE == 0;
 	constexpr uint32_t DYB = (B::SDF_END + 127u) & ~127u;               // dy/dx [84][128] fp32 (pass A only)
+	constexpr uint32_t STB = DYB + (NORMAL ? 84u * TILE * 4u : 0u);     // the first n_stage_levels (dense, coarse) levels of the hash table, staged once per CTA
 	constexpr int TMEM_COLS = 128;
 	constexpr uint32_t C_ACC = 0, C_IN = 64, C_TM = 64, C_GIN = 96;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint32_t tmem_slot;
-	__shared__ __align__(8) uint64_t bar;
+	__shared__ __align__(8) uint64_t bar, bar_stage;
 	const int tid = threadIdx.x, warp = tid >> 5;
 	for (uint32_t i = tid; i < B::SDF_END / 16; i += TILE) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wtc) + i);
 	fence_async_smem();                                                  // weights: generic-proxy stores -> visible to the tensor core
 	if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_slot);
-	if (tid == 0) mbar_init(&bar, 1);
+	if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar_stage, 1); }
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
+	const uint32_t* stab = reinterpret_cast<const uint32_t*>(smem + STB);
+	if (n_stage_levels) {
+		// levels [0, n_stage_levels) are contiguous at the start of the table (16^3 and 24^3 entries of 4 bytes at the default configuration: 16 KB + 54 KB):
+		// one thread hands the copy to the bulk-async engine in 32 KB pieces, everybody waits on the transaction barrier before the first gather
+		const uint32_t bytes = M.offsets[n_stage_levels] * 4u;
+		if (tid == 0) {
+			mbar_expect_tx(&bar_stage, bytes);
+			const uint8_t* src = reinterpret_cast<const uint8_t*>(P + M.off_grid);
+			for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(smem + STB + o, src + o, min(32768u, bytes - o), &bar_stage);
+		}
+		mbar_wait(&bar_stage, 0);
+	}
 	const uint32_t tmem = tmem_slot, trow = tmem + ((uint32_t)(warp * 32) << 16);
 	const float* w2r = reinterpret_cast<const float*>(smem + B::W2R);
 	float* dyS = reinterpret_cast<float*>(smem + DYB);
@@ -253,7 +272,7 @@ __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __
 			p = make_float4(__fmaf_rn(__fmul_rn((float)ix, gs.inv[0]), gs.ext[0], gs.mn[0]), __fmaf_rn(__fmul_rn((float)iy, gs.inv[1]), gs.ext[1], gs.mn[1]),
 			                __fmaf_rn(__fmul_rn((float)iz, gs.inv[2]), gs.ext[2], gs.mn[2]), 0.f);
 		} else p = pos4[min(row, n - 1)];
-		gather_row_to_tmem<NORMAL>(M, P, valid_level, p.x, p.y, p.z, trow + C_IN, dyS, tid);
+		gather_row_to_tmem<NORMAL>(M, P, valid_level, p.x, p.y, p.z, trow + C_IN, dyS, tid, stab, n_stage_levels);
 		tmem_st_wait();
 		tc_fence_before();
 		__syncthreads();
@@ -597,7 +616,7 @@ template <int NSC> struct BwRegs;
 // setmaxnreg.inc can only take what the CTA's own warps have released with setmaxnreg.dec: with the launch allocation A = 65536 / threads rounded
 // down to 8 (168 at 384 threads, 128 at 512), NSC * (A - SCAT) >= 2 * (CHAIN - A) must hold or the second chain warpgroup waits forever
 template <> struct BwRegs<1> { static constexpr int LAUNCH = 168, CHAIN = 200, SCAT = 104; };     // frees 64 * 128 = 8192, takes 2 * 32 * 128 = 8192
-template <> struct BwRegs<2> { static constexpr int LAUNCH = 128, CHAIN = 168, SCAT = 88; };      // frees 2 * 40 * 128, takes 2 * 40 * 128
+template <> struct BwRegs<2> { static constexpr int LAUNCH = 128, CHAIN = 184, SCAT = 72; };      // frees 2 * 56 * 128, takes 2 * 56 * 128 (SASS: the scatter code uses 65 registers, the chain 180)
 static_assert(1 * (BwRegs<1>::LAUNCH - BwRegs<1>::SCAT) >= 2 * (BwRegs<1>::CHAIN - BwRegs<1>::LAUNCH), "register hand-over does not balance");
 static_assert(2 * (BwRegs<2>::LAUNCH - BwRegs<2>::SCAT) >= 2 * (BwRegs<2>::CHAIN - BwRegs<2>::LAUNCH), "register hand-over does not balance");
 template <int SW, bool RGB3, int NSC>
@@ -1010,6 +1029,25 @@ bool tc_supported(const ModelDev& M) {
 }
 size_t tc_blob_bytes(const ModelDev&) { return 65536; }
 
+// Coarse levels staged in shared memory by the SDF kernels (bulk-async copy per CTA).  RNB_STAGE_LEVELS=n overrides; default: the probe / lattice
+// kernels (no dy/dx scratch: shared memory is free) stage as many leading levels as fit in 72 KB (levels 0-1 at the default configuration), pass A
+// stages none — its 43 KB of dy/dx scratch per CTA already limits it to 4 CTAs per SM and the A/B (profiles/r02_ab_stage_levels.txt) decides.
+static uint32_t stage_levels_for(const ModelDev& M, bool pass_a) {
+	int want = pass_a ? 0 : 16;
+	if (const char* e = getenv(pass_a ? "RNB_STAGE_LEVELS_A" : "RNB_STAGE_LEVELS")) want = atoi(e);
+	uint32_t n = 0;
+	while (n < M.n_levels && (int)n < want && M.offsets[n + 1] * 4u <= 72u * 1024u) ++n;
+	return n;
+}
+
+// persistent grids: as many CTAs as are resident at once with this much dynamic shared memory (a second wave would run at the tail with part of the machine)
+template <typename K>
+static uint32_t resident_ctas(K kernel, int threads, size_t smem, int n_sm, uint32_t cap_per_sm) {
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+	return (uint32_t)n_sm * std::min<uint32_t>((uint32_t)per_sm, cap_per_sm);
+}
+
 template <int SW>
 static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __half* P, uint8_t* wtc, uint32_t vl, const float4* pos4, const uint32_t* n_ptr, uint32_t n_max,
                          __half* outA, float* sdf_out, float* dens_out, int n_sm, const float* ray_dirw) {
@@ -1020,10 +1058,13 @@ static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __h
 	constexpr uint32_t DYB = (B::SDF_END + 127u) & ~127u;
 	const uint32_t tiles = (n_max + TILE - 1) / TILE;
 	if (what == 1) {
-		const size_t smem = DYB + 84 * TILE * 4;
-		static bool attr = false;
-		if (!attr) { cudaFuncSetAttribute(k_sdf_tc<SW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-		k_sdf_tc<SW, 0><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr, GridSpec{});
+		const uint32_t nst = stage_levels_for(M, true);
+		const size_t smem = DYB + 84 * TILE * 4 + (nst ? M.offsets[nst] * 4u : 0u);
+		static size_t attr = 0;
+		if (attr < smem) { cudaFuncSetAttribute(k_sdf_tc<SW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+		static uint32_t ctas = 0; static size_t ctas_for = ~(size_t)0;
+		if (ctas_for != smem) { ctas = resident_ctas(k_sdf_tc<SW, 0>, TILE, smem, n_sm, 4); ctas_for = smem; }
+		k_sdf_tc<SW, 0><<<std::min<uint32_t>(tiles, ctas), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr, GridSpec{}, nst);
 	} else if (what == 3) {
 		const size_t smem = ((B::END + 127u) & ~127u) + 84 * TILE * 4;
 		const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)n_sm * 3);
@@ -1039,8 +1080,13 @@ static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __h
 	} else if (what == 4) {
 		return;      // backward: see launch_tc_backward
 	} else {
-		const size_t smem = DYB;
-		k_sdf_tc<SW, 1><<<std::min<uint32_t>(tiles, (uint32_t)n_sm * 4), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, nullptr, sdf_out, dens_out, GridSpec{});
+		const uint32_t nst = stage_levels_for(M, false);
+		const size_t smem = DYB + (nst ? M.offsets[nst] * 4u : 0u);
+		static size_t attr = 0;
+		if (attr < smem) { cudaFuncSetAttribute(k_sdf_tc<SW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+		static uint32_t ctas = 0; static size_t ctas_for = ~(size_t)0;
+		if (ctas_for != smem) { ctas = resident_ctas(k_sdf_tc<SW, 1>, TILE, smem, n_sm, 4); ctas_for = smem; }
+		k_sdf_tc<SW, 1><<<std::min<uint32_t>(tiles, ctas), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, nullptr, sdf_out, dens_out, GridSpec{}, nst);
 	}
 }
 
@@ -1086,9 +1132,19 @@ void launch_tc_sdf_grid(cudaStream_t st, const ModelDev& M, const __half* P, con
 	for (int d = 0; d < 3; ++d) { gs.inv[d] = 1.f / (float)res[d]; gs.ext[d] = mx[d] - mn[d]; gs.mn[d] = mn[d]; }
 	const uint64_t n64 = (uint64_t)res[0] * res[1] * res[2];
 	if (!n64) return;
-	const uint32_t n = (uint32_t)n64, tiles = (n + TILE - 1) / TILE, grid = std::min<uint32_t>(tiles, (uint32_t)n_sm * 4);
-	if (M.sdf_width == 64) k_sdf_tc<64, 2><<<grid, TILE, (Blob<64>::SDF_END + 127u) & ~127u, st>>>(M, P, wtc, vl, nullptr, nullptr, n, nullptr, sdf_out, nullptr, gs);
-	else k_sdf_tc<32, 2><<<grid, TILE, (Blob<32>::SDF_END + 127u) & ~127u, st>>>(M, P, wtc, vl, nullptr, nullptr, n, nullptr, sdf_out, nullptr, gs);
+	const uint32_t n = (uint32_t)n64, tiles = (n + TILE - 1) / TILE;
+	const uint32_t nst = stage_levels_for(M, false);
+	const size_t stage_bytes = nst ? M.offsets[nst] * 4u : 0u;
+	static size_t attr64 = 0, attr32 = 0;
+	if (M.sdf_width == 64) {
+		const size_t smem = ((Blob<64>::SDF_END + 127u) & ~127u) + stage_bytes;
+		if (attr64 < smem) { cudaFuncSetAttribute(k_sdf_tc<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr64 = smem; }
+		k_sdf_tc<64, 2><<<std::min<uint32_t>(tiles, resident_ctas(k_sdf_tc<64, 2>, TILE, smem, n_sm, 4)), TILE, smem, st>>>(M, P, wtc, vl, nullptr, nullptr, n, nullptr, sdf_out, nullptr, gs, nst);
+	} else {
+		const size_t smem = ((Blob<32>::SDF_END + 127u) & ~127u) + stage_bytes;
+		if (attr32 < smem) { cudaFuncSetAttribute(k_sdf_tc<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr32 = smem; }
+		k_sdf_tc<32, 2><<<std::min<uint32_t>(tiles, resident_ctas(k_sdf_tc<32, 2>, TILE, smem, n_sm, 4)), TILE, smem, st>>>(M, P, wtc, vl, nullptr, nullptr, n, nullptr, sdf_out, nullptr, gs, nst);
+	}
 }
 
 // what: 0 pack weights, 1 pass A (outA = 4 halfs per sample), 2 SDF probe (sdf_out / dens_out), 3 full forward (outA = 16 halfs per sample, needs ray_dirw)

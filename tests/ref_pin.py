@@ -226,6 +226,18 @@ def main():
         probe["cuda_vs_ref"] = {"albedo_raw": rel_err(co[:, 0:3], pout[:, 0:3]), "sdf": rel_err(co[:, 3], pout[:, 3]), "normal": rel_err(co[:, 4:7], pout[:, 4:7]), "variance": rel_err(co[:, 7], pout[:, 7])}
     summary["probe"] = probe
     print(json.dumps({"probe": probe}))
+    if args.config == "full":
+        # sparse probe fixture for the default network (tests/golden/ref_full_probe.npz): the reference's outputs at 1024 probe points together with the
+        # MLP weights and ONLY the hash entries those points read (found as the non-zero entries of a backward pass with a constant output gradient)
+        npb = 1024
+        dprobe = np.zeros((npb, 16), np.float32); dprobe[:, :11] = 0.01
+        gtouch = o.network_backward(pc[:npb], dprobe, npb, 1 << 18, vl)
+        sel = np.nonzero(gtouch[o.off_grid:o.off_var])[0]
+        sel = np.unique(np.concatenate([sel & ~np.int64(1), sel | 1])).astype(np.uint32)          # whole entries (2 features)
+        np.savez_compressed(os.path.join(args.out, "golden_full_probe.npz"), coords=pc[:npb].astype(np.float32), ref_out_fp16=rd("probe_out_fp16.bin", np.uint16).reshape(-1, 16)[:npb],
+                            mlp_fp16=pf[:o.off_grid].astype(np.float16), var=pf[o.off_var:].astype(np.float32), grid_idx=sel, grid_val_fp16=pf[o.off_grid + sel.astype(np.int64)].astype(np.float16),
+                            state=stf, valid_level=np.array([vl], np.uint32))
+        print(json.dumps({"full_probe_fixture": {"points": npb, "grid_params_kept": int(sel.size), "valid_level": int(vl)}}))
     json.dump(summary, open(os.path.join(args.out, "summary_%s%s.json" % (args.config, "_alb" if args.albedo else "")), "w"), indent=1)
     if golden:
         flat = {}

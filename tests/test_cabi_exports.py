@@ -97,3 +97,15 @@ def test_create_rejects_configurations_that_would_misbehave_on_the_device(pkg):
             h = C.c_void_p()
             rc = L.rnb_create(C.byref(pkg.default_config(**kw)), C.byref(h))
             assert rc == -2, (kw, L.rnb_last_error())          # RNB_ERR_CUDA: no device in this container, and no fallback
+
+
+def test_communicator_entry_points_reject_misuse(pkg):
+    """rnb_comm_*: NCCL is opened at run time; null contexts / ids are refused with a message and nothing crashes without a device"""
+    L = pkg.lib()
+    ident = (C.c_uint8 * 128)()
+    assert L.rnb_comm_init(None, ident) == -1 and b"null" in L.rnb_last_error()
+    assert L.rnb_comm_adopt(None, None) == -1
+    assert L.rnb_comm_destroy(None) == -1
+    assert L.rnb_comm_info(None, None) == -1
+    assert L.rnb_comm_unique_id(None) == -1
+    assert L.rnb_set_canonical_state(None, 0, 0) == -1
