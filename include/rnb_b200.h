@@ -199,13 +199,17 @@ int rnb_grad_buffer(rnb_ctx* ctx, float** grads_dev, uint64_t* n);
  *   rnb_comm_unique_id: ncclGetUniqueId on one rank; the caller's launcher carries the 128 bytes to the other ranks (file, socket, MPI, torchrun store)
  *   rnb_comm_init:      ncclCommInitRank(world_size, id, rank) on the current device, communicator owned by the context
  *   rnb_comm_adopt:     use a caller-owned ncclComm_t (its size and rank must equal rnb_config's)
- *   rnb_comm_info:      out = { communicator installed, NCCL version code, sharded optimizer, world_size } */
+ *   rnb_comm_info:      out = { communicator installed, NCCL version code, sharded optimizer, world_size }
+ * Approximation kept from round 1: the 2^18-sample truncation and the roll-over multiplicity are applied per rank on target / world samples (the exact
+ * global prefix over interleaved rays would need two more small collectives per step); with the adaptive controller the budget is met, not exceeded. */
 #define RNB_COMM_ID_BYTES 128
 int rnb_comm_unique_id(uint8_t id_out[RNB_COMM_ID_BYTES]);
 int rnb_comm_init(rnb_ctx* ctx, const uint8_t id[RNB_COMM_ID_BYTES]);
 int rnb_comm_adopt(rnb_ctx* ctx, void* nccl_comm);
 int rnb_comm_destroy(rnb_ctx* ctx);
 int rnb_comm_info(rnb_ctx* ctx, uint32_t out[4]);
+/* sharded optimizer only (collective; no-op otherwise): gather the per-shard EMA (inference) parameters before rnb_export_params_fp16(use_ema) / a mesh extraction */
+int rnb_comm_sync_ema(rnb_ctx* ctx, void* stream);
 int rnb_stat_buffer(rnb_ctx* ctx, float** stats_dev, uint64_t* n);
 /* Sharded optimizer for data parallelism (new; the reference is single-GPU): instead of all-reducing the fp32 gradient buffer and running
  * Adam/EMA on every rank, rank r owns parameters [begin, end): the caller REDUCE-SCATTERS the gradient buffer (rnb_grad_buffer; the arrays

@@ -53,7 +53,7 @@ EXPORTED_SYMBOLS = [
     "rnb_last_error", "rnb_abi_version", "rnb_create", "rnb_destroy", "rnb_default_config", "rnb_default_flags", "rnb_param_layout", "rnb_init_params",
     "rnb_set_params_fp32", "rnb_get_params_fp32", "rnb_export_params_fp16", "rnb_import_params_fp16", "rnb_export_density_grid", "rnb_import_density_grid",
     "rnb_get_bitfield", "rnb_set_bitfield", "rnb_get_train_state", "rnb_set_train_state", "rnb_set_canonical_state", "rnb_get_rng", "rnb_set_rng", "rnb_set_dataset", "rnb_upload_dataset",
-    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_comm_unique_id", "rnb_comm_init", "rnb_comm_adopt", "rnb_comm_destroy", "rnb_comm_info", "rnb_stat_buffer", "rnb_param_buffers", "rnb_set_optimizer_shard", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf", "rnb_sdf_on_grid",
+    "rnb_set_flags", "rnb_prep", "rnb_train_step", "rnb_train", "rnb_train_step_begin", "rnb_train_step_end", "rnb_grad_buffer", "rnb_comm_unique_id", "rnb_comm_init", "rnb_comm_adopt", "rnb_comm_destroy", "rnb_comm_info", "rnb_comm_sync_ema", "rnb_stat_buffer", "rnb_param_buffers", "rnb_set_optimizer_shard", "rnb_get_grads_fp32", "rnb_get_ray_losses", "rnb_get_ray_counts", "rnb_checkpoint_save", "rnb_checkpoint_restore", "rnb_profile_enable", "rnb_profile_read", "rnb_launch_count", "rnb_eval_sdf", "rnb_sdf_on_grid",
     "rnb_load_png_rgba16", "rnb_free_host", "rnb_load_dataset_images", "rnb_marching_cubes", "rnb_marching_cubes_from_density", "rnb_mesh_buffers", "rnb_mesh_download", "rnb_save_mesh",
     "rnb_stage_generate", "rnb_stage_forward", "rnb_stage_loss", "rnb_stage_backward", "rnb_stage_optimizer",
     "rnb_raymesh_create", "rnb_raymesh_destroy", "rnb_raymesh_info", "rnb_raymesh_intersect",

@@ -136,7 +136,7 @@ struct rnb_ctx {
 	float4 *pos4 = nullptr, *cpos4 = nullptr;
 	__half *outA = nullptr, *out16 = nullptr, *dout16 = nullptr, *bw_scratch = nullptr; float* bw_front = nullptr;
 	uint32_t* counters_host = nullptr; float* stats_host = nullptr;   // pinned
-	cudaEvent_t ev_counters = nullptr; bool counters_pending = false;  // asynchronous read-back of the step counters (rnb_train_step_end without stats)
+	cudaEvent_t ev_counters = nullptr; bool counters_pending = false; bool async_end = true;      // RNB_ASYNC_END=0: wait for every step even without stats (A/B)  // asynchronous read-back of the step counters (rnb_train_step_end without stats)
 	// data parallelism behind the boundary (rnb_comm_*): one NCCL communicator per context, binary16 gradient exchange buffer
 	ncclComm_t comm = nullptr; bool comm_owned = false; __half* grads16 = nullptr; int dp_sharded = 0;
 	const __half* xch16 = nullptr; uint32_t xch_begin = 0, xch_end = 0;      // result of this step's gradient exchange, consumed by rnb_train_step_end
@@ -356,6 +356,7 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) try {
 		if (const char* d = getenv("RNB_BW_DEBUG")) set_bw_debug(atoi(d));
 		if (const char* d = getenv("RNB_BW_SCATTER_WG")) set_bw_scatter_groups(atoi(d));      // scatter warpgroups of the tcgen05 backward (1 default, 2)
 		if (const char* d = getenv("RNB_PRELAUNCH")) c->prelaunch = atoi(d) != 0;
+		if (const char* d = getenv("RNB_ASYNC_END")) c->async_end = atoi(d) != 0;
 		if (const char* d = getenv("RNB_PRELAUNCH_AT")) c->pre_at = std::min(std::max(atoi(d), 0), 3);
 		c->use_tc = c->use_mma && tc_supported(M) && !(e && std::string(e) == "mma");
 		c->use_tc_bwd = c->use_tc && !(getenv("RNB_BACKWARD") && std::string(getenv("RNB_BACKWARD")) == "mma");     // RNB_BACKWARD=mma: mma.sync backward
@@ -787,7 +788,7 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	CU(cudaMemcpyAsync(c->counters_host, c->counters, 8 * 4, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(c->stats_host, c->stats, 8 * 4, cudaMemcpyDeviceToHost, st));
 	const uint32_t R = c->step_R;
-	if (!stats && c->cfg.pin_rays_per_batch && !c->prof) {
+	if (!stats && c->cfg.pin_rays_per_batch && !c->prof && c->async_end) {
 		CU(cudaEventRecord(c->ev_counters, st));
 		c->counters_pending = true;
 		return RNB_OK;
@@ -859,6 +860,16 @@ int rnb_comm_destroy(rnb_ctx* c) try {
 	if (c->in_step) return fail(RNB_ERR_STATE, "communicator changed inside a step");
 	if (c->comm && c->comm_owned) { NcclApi* N = nccl_api(); CU(cudaDeviceSynchronize()); if (N) N->CommDestroy(c->comm); }
 	c->comm = nullptr; c->comm_owned = false;
+	return RNB_OK;
+} RNB_API_CATCH
+// sharded optimizer only: the EMA (inference) parameters are maintained per shard; before a snapshot export or a mesh extraction every rank
+// calls this once (collective) to gather all shards.  No-op with the all-reduce protocol.
+int rnb_comm_sync_ema(rnb_ctx* c, void* stream) try {
+	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (!c->comm || !c->dp_sharded) return RNB_OK;
+	NcclApi* N = nccl_api(); if (!N) return fail(RNB_ERR_STATE, "libnccl.so.2 not found");
+	const size_t shard = c->np_padded / c->cfg.world_size;
+	NC(N->AllGather(c->ema + (size_t)c->cfg.rank * shard, c->ema, shard, ncclHalf, c->comm, (cudaStream_t)stream));
 	return RNB_OK;
 } RNB_API_CATCH
 int rnb_comm_info(rnb_ctx* c, uint32_t out[4]) try {

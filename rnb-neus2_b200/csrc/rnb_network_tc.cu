@@ -1040,12 +1040,15 @@ static uint32_t stage_levels_for(const ModelDev& M, bool pass_a) {
 	return n;
 }
 
-// persistent grids: as many CTAs as are resident at once with this much dynamic shared memory (a second wave would run at the tail with part of the machine)
+// persistent grids: as many CTAs as are resident at once with this much dynamic shared memory (a second wave would run at the tail with part of the
+// machine).  Own arithmetic (227 KB per SM, 1 KB reserved per CTA): cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 2 for a kernel that runs
+// 4 CTAs per SM (r2d session: pass A 0.20 -> 0.46 ms with a grid sized by it); the TMEM budget (128 of 512 columns per CTA) caps it at 4.
 template <typename K>
 static uint32_t resident_ctas(K kernel, int threads, size_t smem, int n_sm, uint32_t cap_per_sm) {
-	int per_sm = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-	return (uint32_t)n_sm * std::min<uint32_t>((uint32_t)per_sm, cap_per_sm);
+	(void)kernel; (void)threads;
+	const size_t per_cta = smem + 1024 + 256;
+	const uint32_t per_sm = (uint32_t)std::max<size_t>(1, (227u * 1024u) / per_cta);
+	return (uint32_t)n_sm * std::min<uint32_t>(per_sm, cap_per_sm);
 }
 
 template <int SW>

@@ -235,10 +235,11 @@ def test_oracle_matches_reference_full_network_all_levels_live():
     from oracle_binding import Oracle
     from common import FULL
     g = np.load(FULL_PROBE)
-    assert int(g["valid_level"][0]) == 13                       # valid_level 13 = all 14 levels enabled (grid.h:193-210)
+    vl = int(g["valid_level"][0])
+    assert vl >= 13                                            # valid_level >= 13: all 14 levels enabled (grid.h:193-210, 1430-1437)
     o = Oracle(threads=4, **FULL)
     o.set_params(_full_probe_params(o, g))
-    out, _ = o.network_forward(g["coords"], 13)
+    out, _ = o.network_forward(g["coords"], vl)
     ref = g["ref_out_fp16"].view(np.float16).astype(np.float32)
     e = _probe_errors(out, ref)
     # the reference accumulates every layer in binary16 (wmma, OUT_T = __half), the oracle in fp32 with binary16 rounding per layer: SDF / normal within
