@@ -334,17 +334,24 @@ def main():
             tb.comm_init(ids[0])
         return tb, up
 
+    # the training stream: created with a priority above the lowest, so that the library's side stream (lowest priority: the march of the next step,
+    # launched one step ahead) only fills what the step's own kernels leave free (RNB_BENCH_STREAM=default: the legacy default stream)
+    if os.environ.get("RNB_BENCH_STREAM", "high") == "default":
+        tstream = torch.cuda.current_stream(); sh = None
+    else:
+        tstream = torch.cuda.Stream(priority=-1); sh = tstream.cuda_stream
+
     def timed(tb, k, want_stats):
         if dist: dist.barrier()
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         l0 = tb.launch_count()
-        e0.record()
+        e0.record(tstream)
         last = None; rays = 0
         for _ in range(k):
-            last = tb.train(want_stats=want_stats)
+            last = tb.train(stream=sh, want_stats=want_stats)
             if want_stats: rays += int(last.n_rays)
-        e1.record()
+        e1.record(tstream)
         torch.cuda.synchronize()
         if dist: dist.barrier()
         ms = e0.elapsed_time(e1)
@@ -357,7 +364,7 @@ def main():
     R = RAYS_PER_STEP * n_gpus
     t, upload_s = make_testbed(R, (1 << 18) * n_gpus)
     for _ in range(args.pretrain + args.warmup):
-        t.train(want_stats=False)
+        t.train(stream=sh, want_stats=False)
     torch.cuda.synchronize()
     # value, e2e and the per-stage pass are all taken on the SAME training steps: the state after warm-up is checkpointed on the device
     # and restored between the passes (the cost of a step changes with the training step: live hash levels, samples per ray)
@@ -404,7 +411,7 @@ def main():
             "config": {"workload": WORKLOADS[args.workload], "rays_per_step_global": R, "pretrain_steps": args.pretrain, "training_step_at_end": int(ts_now), "samples_per_step": int(ns), "compacted_samples_per_step": int(nc),
                        "live_hash_levels": L,
                        "cache": "working set (hash table 21 MB + gradients 42 MB + optimizer state 170 MB + %.1f GB images) exceeds L2; no flush needed" % (dataset_bytes / 1e9),
-                       "parallelism": par, "network_path": _network_path(),
+                       "parallelism": par, "network_path": _network_path(), "stream": "caller's stream with priority -1 (library side stream: lowest priority)" if sh is not None else "legacy default stream",
                        "dataset_upload_s": round(upload_s, 3), "dataset_bytes": dataset_bytes, "scene_render_s": round(gen_s, 1)},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,
@@ -460,7 +467,7 @@ def main():
         # the compacted sample count at 2^18 per GPU, rays/step follow the scene; the host waits for the counters every step like the reference
         ta, _ = make_testbed(R, (1 << 18) * n_gpus, pin=0)
         for _ in range(args.pretrain + args.warmup):
-            ta.train(want_stats=False)
+            ta.train(stream=sh, want_stats=False)
         m3, _, la, rays3 = timed(ta, k2, True)
         records["adaptive_controller"] = {"workload": WORKLOADS[args.workload].replace("4096 rays/step pinned", "rays/step set by the controller (2^18 compacted samples per step and GPU)"),
                                           "value": rays3 / (m3 * 1e-3), "unit": UNIT, "ms_per_step": m3 / k2, "steps": k2, "rays_per_step_last": int(la.n_rays), "samples_per_step_last": int(la.n_samples),
@@ -469,7 +476,7 @@ def main():
         if world > 1:
             tsx, _ = make_testbed(16384, 1 << 18)
             for _ in range(args.pretrain + args.warmup):
-                tsx.train(want_stats=False)
+                tsx.train(stream=sh, want_stats=False)
             m4, _, _, _ = timed(tsx, k2, False)
             records["strong_16384_rays"] = {"workload": WORKLOADS[args.workload].replace("4096 rays/step pinned", "16384 rays/step in total, ray-sharded over %d GPUs" % n_gpus), "scaling": "strong",
                                             "value": 16384 * k2 / (m4 * 1e-3), "unit": UNIT, "ms_per_step": m4 / k2, "steps": k2}

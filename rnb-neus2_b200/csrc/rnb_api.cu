@@ -20,7 +20,7 @@
 
 namespace rnb {
 // rnb_march.cu
-void launch_march(cudaStream_t, uint32_t, uint32_t, uint32_t, uint32_t, Pcg32, const ViewDev*, uint32_t, const uint8_t*, uint32_t*, float*, float*);
+void launch_march(cudaStream_t, uint32_t, uint32_t, uint32_t, uint32_t, Pcg32, const ViewDev*, uint32_t, const uint8_t*, uint32_t*, float*, float*, uint32_t = 0);
 void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*);
 void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, const float*, const float*, float4*);
 // rnb_network_simt.cu
@@ -155,7 +155,10 @@ struct rnb_ctx {
 	cudaStream_t side = nullptr; cudaEvent_t ev_bwd = nullptr, ev_march = nullptr;
 	// in-memory checkpoint (rnb_checkpoint_save / _restore): one device-side slot of everything a step reads and writes
 	struct Ckpt { void* buf = nullptr; size_t bytes = 0; bool valid = false; uint32_t opt_step, density_ema_step, training_step, rays_per_batch, n_rays_total, measured_before, measured, canonical_step, n_images_prev; float lr_factor; Pcg32 rng, density_rng; } ck;
+	uint32_t pre_ctas_per_sm = 0;               // size of the pre-launched march (CTAs of 256 threads per SM; 0 = one warp per ray at once); RNB_PRELAUNCH_CTAS (A/B: capping it is slower, profiles/r02_ab_async_prelaunch.txt)
 	int pre_at = RNB_PRELAUNCH_AT_DEFAULT;      // where the next march may start: 0 behind the backward, 1 behind the loss, 2 behind pass A, 3 behind scan/emit (last readers of the ray buffers)
+	int pre_at_env = -1;                        // RNB_PRELAUNCH_AT; unset: 3 when the host waits for every step, 2 when it runs ahead (profiles/r02_ab_async_prelaunch.txt)
+	bool step_waits = true;                     // this step's rnb_train_step_end will synchronise (stats requested / adaptive controller)
 	bool pre_armed = false;                     // this step will pre-launch (decided before its kernels are queued)
 	bool prelaunch = true; bool pre_valid = false; uint32_t pre_R = 0, pre_nrt = 0; uint64_t pre_rng_state = 0, pre_rng_inc = 0;
 	// last extracted mesh (rnb_marching_cubes*): MeshState verts / vert_normals / vert_colors / indices (testbed.h:418-447), device memory
@@ -346,7 +349,11 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) try {
 	CU(cudaMalloc(&c->stats, 8 * 4)); CU(cudaMemset(c->stats, 0, 8 * 4));
 	CU(cudaMallocHost(&c->counters_host, 16 * 4)); CU(cudaMallocHost(&c->stats_host, 8 * 4));
 	CU(cudaEventCreateWithFlags(&c->ev_counters, cudaEventDisableTiming));
-	CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_march, cudaEventDisableTiming));
+	{   // the side stream has the LOWEST priority: when the caller trains on a stream of higher priority, the pre-launched march only takes what the step's own kernels leave free
+		int prio_lo = 0, prio_hi = 0; CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CU(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_lo));
+	}
+	CU(cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_march, cudaEventDisableTiming));
 	{
 		cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev)); c->n_sm = prop.multiProcessorCount;
 		const char* e = getenv("RNB_NETWORK");        // "simt" selects the CUDA-core kernels (cross-check path)
@@ -357,7 +364,8 @@ int rnb_create(const rnb_config* cfg, rnb_ctx** out) try {
 		if (const char* d = getenv("RNB_BW_SCATTER_WG")) set_bw_scatter_groups(atoi(d));      // scatter warpgroups of the tcgen05 backward (1 default, 2)
 		if (const char* d = getenv("RNB_PRELAUNCH")) c->prelaunch = atoi(d) != 0;
 		if (const char* d = getenv("RNB_ASYNC_END")) c->async_end = atoi(d) != 0;
-		if (const char* d = getenv("RNB_PRELAUNCH_AT")) c->pre_at = std::min(std::max(atoi(d), 0), 3);
+		if (const char* d = getenv("RNB_PRELAUNCH_CTAS")) c->pre_ctas_per_sm = (uint32_t)std::max(0, atoi(d));
+		if (const char* d = getenv("RNB_PRELAUNCH_AT")) c->pre_at_env = std::min(std::max(atoi(d), 0), 3);
 		c->use_tc = c->use_mma && tc_supported(M) && !(e && std::string(e) == "mma");
 		c->use_tc_bwd = c->use_tc && !(getenv("RNB_BACKWARD") && std::string(getenv("RNB_BACKWARD")) == "mma");     // RNB_BACKWARD=mma: mma.sync backward
 		CU(cudaMalloc(&c->wtc, tc_blob_bytes(M))); CU(cudaMemset(c->wtc, 0, tc_blob_bytes(M)));
@@ -749,6 +757,10 @@ int rnb_train_step_begin(rnb_ctx* c, void* stream) try {
 	{
 		const uint32_t ts_next = c->training_step + 1, skip = std::min(std::max(ts_next / 16u, 1u), 16u);
 		c->pre_armed = c->cfg.pin_rays_per_batch && !c->prof && c->prelaunch && ts_next % skip != 0 && R <= c->cap_rays;
+		// With a host that waits for every step the march's launch reaches the device ~0.1 ms into the step and fills the gaps behind pass A by itself;
+		// when the host runs ahead it is eligible the moment its event fires: behind scan/emit it would take the SMs before pass A is resident
+		// (pass A and the backward use every register of an SM), so it is released behind pass A instead, beside the small compaction / loss kernels
+		c->pre_at = c->pre_at_env >= 0 ? c->pre_at_env : (c->step_waits ? 3 : 2);
 	}
 	rc = step_front(c, st, R, nrt); if (rc) return rc;
 	c->rng.advance();                                               // :4118
@@ -757,7 +769,7 @@ int rnb_train_step_begin(rnb_ctx* c, void* stream) try {
 		if (c->pre_armed) {      // the side stream waits for the point chosen by pre_at (recorded inside step_front, or here: behind the backward)
 			if (c->pre_at == 0) CU(cudaEventRecord(c->ev_bwd, st));
 			CU(cudaStreamWaitEvent(c->side, c->ev_bwd, 0));
-			launch_march(c->side, R, c->cfg.world_size, c->cfg.rank, c->n_rays_total, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts);
+			launch_march(c->side, R, c->cfg.world_size, c->cfg.rank, c->n_rays_total, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts, (uint32_t)c->n_sm * c->pre_ctas_per_sm);
 			CU(cudaEventRecord(c->ev_march, c->side));
 			c->launches += 1;
 			c->pre_valid = true; c->pre_R = R; c->pre_nrt = c->n_rays_total; c->pre_rng_state = c->rng.state; c->pre_rng_inc = c->rng.inc;
@@ -902,7 +914,10 @@ static int exchange_gradients(rnb_ctx* c, cudaStream_t st) {
 }
 
 int rnb_train_step(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
-	int rc = rnb_train_step_begin(c, stream); if (rc) return rc;
+	if (c) c->step_waits = stats != nullptr || !c->cfg.pin_rays_per_batch || !c->async_end;
+	int rc = rnb_train_step_begin(c, stream);
+	if (c) c->step_waits = true;
+	if (rc) return rc;
 	if (c->cfg.world_size > 1) {
 		if (!c->comm) { c->in_step = false; return fail(RNB_ERR_STATE, "world_size > 1: call rnb_comm_init / rnb_comm_adopt first, or drive rnb_train_step_begin / _end with your own collective"); }
 		rc = exchange_gradients(c, (cudaStream_t)stream); if (rc) { c->in_step = false; return rc; }

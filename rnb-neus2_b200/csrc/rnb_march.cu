@@ -6,6 +6,7 @@
 // DDA skip rule (:301-323) is resolved with ballots, and the accepted t values are written once.  Sample slots are then
 // handed out by an ordered scan (deterministic) instead of atomicAdd arrival order (:1352,1359).
 #include "rnb_common.cuh"
+#include <algorithm>
 
 namespace rnb {
 
@@ -70,11 +71,13 @@ __device__ __forceinline__ RaySetup ray_setup(uint32_t i, uint32_t n_rays, uint3
 __global__ void __launch_bounds__(256) k_march(uint32_t n_rays, uint32_t world, uint32_t rank, uint32_t n_rays_total, Pcg32 rng,
                                                const ViewDev* __restrict__ views, uint32_t n_views, const uint8_t* __restrict__ bitfield,
                                                uint32_t* __restrict__ ray_n, float* __restrict__ ray_geom /*9 per global ray: o, d_un, dir*/, float* __restrict__ ts) {
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	// grid-stride over rays (one warp per ray at a time): the launch of the NEXT step's march, which shares the SMs with the network kernels of the
+	// current step, is sized to one CTA per SM so that it cannot keep their CTAs from becoming resident (launch_march: `max_ctas`)
+	const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp * world + rank < n_rays; warp += n_warps) {
 	const uint32_t i = warp * world + rank;
-	if (i >= n_rays) return;
 	const RaySetup r = ray_setup(i, n_rays, n_rays_total, rng, views, n_views);
-	if (!r.valid) { if (lane == 0) ray_n[i] = 0; return; }
+	if (!r.valid) { if (lane == 0) ray_n[i] = 0; continue; }
 	if (lane < 9) {
 		const float g[9] = {r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, r.dx, r.dy, r.dz};
 		ray_geom[(size_t)i * 9 + lane] = g[lane];
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(256) k_march(uint32_t n_rays, uint32_t world, 
 		}
 	}
 	if (lane == 0) ray_n[i] = nsamp;
+	}
 }
 
 // Ordered hand-out of sample slots: base = exclusive prefix of numsteps over rays (what the reference's atomicAdd counter
@@ -202,10 +206,12 @@ __global__ void __launch_bounds__(256) k_emit(const uint32_t* __restrict__ count
 }
 
 void launch_march(cudaStream_t st, uint32_t n_rays, uint32_t world, uint32_t rank, uint32_t n_rays_total, Pcg32 rng, const ViewDev* views, uint32_t n_views,
-                  const uint8_t* bitfield, uint32_t* ray_n, float* ray_geom, float* ts) {
+                  const uint8_t* bitfield, uint32_t* ray_n, float* ray_geom, float* ts, uint32_t max_ctas) {
 	const uint32_t n_local = (n_rays + world - 1 - rank) / world;
 	if (!n_local) return;
-	k_march<<<(n_local * 32 + 255) / 256, 256, 0, st>>>(n_rays, world, rank, n_rays_total, rng, views, n_views, bitfield, ray_n, ray_geom, ts);
+	uint32_t grid = (n_local * 32 + 255) / 256;
+	if (max_ctas) grid = std::min(grid, max_ctas);
+	k_march<<<grid, 256, 0, st>>>(n_rays, world, rank, n_rays_total, rng, views, n_views, bitfield, ray_n, ray_geom, ts);
 }
 void launch_scan_rays(cudaStream_t st, uint32_t n_rays, uint32_t max_samples, const uint32_t* prev, const uint32_t* ray_n, uint32_t* ray_indices, uint32_t* numsteps, uint32_t* counters) {
 	k_scan_rays<<<1, 1024, 0, st>>>(n_rays, max_samples, prev, ray_n, ray_indices, numsteps, counters);

@@ -1029,11 +1029,12 @@ bool tc_supported(const ModelDev& M) {
 }
 size_t tc_blob_bytes(const ModelDev&) { return 65536; }
 
-// Coarse levels staged in shared memory by the SDF kernels (bulk-async copy per CTA).  RNB_STAGE_LEVELS=n overrides; default: the probe / lattice
-// kernels (no dy/dx scratch: shared memory is free) stage as many leading levels as fit in 72 KB (levels 0-1 at the default configuration), pass A
-// stages none — its 43 KB of dy/dx scratch per CTA already limits it to 4 CTAs per SM and the A/B (profiles/r02_ab_stage_levels.txt) decides.
+// Coarse levels staged in shared memory by the SDF kernels (one bulk-async copy per CTA): the gather design BASELINE.json's north_star names.
+// Built, measured on B200 (profiles/r02_ab_stage_levels.txt) and left OFF: staging levels 0-1 (70 KB) in the probe kernel drops it from 4 to 3 CTAs per SM
+// and copies 31 MB per launch for tables that the L1 already serves — the occupancy refresh went 0.39 -> 0.73 ms; level 0 (16 KB) in pass A: 0.179 -> 0.192 ms.
+// RNB_STAGE_LEVELS=n (probe / lattice kernels) and RNB_STAGE_LEVELS_A=n (pass A) switch it on.
 static uint32_t stage_levels_for(const ModelDev& M, bool pass_a) {
-	int want = pass_a ? 0 : 16;
+	int want = 0;
 	if (const char* e = getenv(pass_a ? "RNB_STAGE_LEVELS_A" : "RNB_STAGE_LEVELS")) want = atoi(e);
 	uint32_t n = 0;
 	while (n < M.n_levels && (int)n < want && M.offsets[n + 1] * 4u <= 72u * 1024u) ++n;
@@ -1093,8 +1094,8 @@ static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __h
 	}
 }
 
-static int g_bw_scatter_groups = 1;      // RNB_BW_SCATTER_WG=1|2: scatter warpgroups of the backward (A/B knob)
-void set_bw_scatter_groups(int n) { g_bw_scatter_groups = n == 2 ? 2 : 1; }
+static int g_bw_scatter_groups = 2;      // RNB_BW_SCATTER_WG=1|2: scatter warpgroups of the backward (A/B on B200, profiles/r02_ab_backward_ws.txt: 0.254 ms with 1, 0.231 ms with 2 at 14 live levels)
+void set_bw_scatter_groups(int n) { g_bw_scatter_groups = n == 1 ? 1 : 2; }
 
 template <int SW, bool RGB3, int NSC>
 static void launch_tc_backward_cfg(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
