@@ -9,6 +9,7 @@
 // Occupancy grid: update_density_grid_nerf / update_density_grid_mean_and_bitfield (src/testbed_nerf.cu:3424-3517) and
 // kernels :585-614,616-635,655-685,693-740.
 #include "rnb_common.cuh"
+#include <algorithm>
 
 namespace rnb {
 
@@ -21,6 +22,8 @@ struct AdamParams {
 	// binary16 gradient exchange (data parallel behind the C ABI): the all-reduced / reduce-scattered gradient sum as binary16 (gsrc16[i - shard_begin]);
 	// the fp32 accumulators have already been cleared by k_pack_grads, so this pass does not touch them
 	const __half* gsrc16;
+	// this launch covers parameters [first, last) only (chunked exchange: Adam on chunk k runs while chunk k + 1 is still being all-reduced); multiples of 4
+	uint32_t first, last;
 };
 
 // One thread owns 4 consecutive parameters: every array is moved with one 128-bit (fp32 / u32) or 64-bit (binary16) access.
@@ -49,8 +52,8 @@ __device__ __forceinline__ bool adam_one(const AdamParams& A, uint32_t i, float 
 
 __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restrict__ master, __half* __restrict__ params, __half* __restrict__ ema,
                                                   float* __restrict__ grads, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
-	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-	if (i0 >= A.n_params) return;
+	const uint32_t i0 = A.first + (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (i0 >= A.n_params || i0 >= A.last) return;
 	if (i0 < A.shard_begin || i0 >= A.shard_end) {     // another rank's parameters: drop this rank's partial gradient, the weights arrive with the all-gather
 		if (A.gsrc16) return;
 		if (i0 + 4 <= A.n_params) {
@@ -213,7 +216,9 @@ __global__ void k_bitfield_pool(const uint8_t* __restrict__ prev, uint8_t* __res
 }
 
 void launch_adam_ema(cudaStream_t st, const AdamParams& A, float* master, __half* params, __half* ema, float* grads, float* m1, float* m2, uint32_t* steps) {
-	k_adam_ema<<<((A.n_params + 3) / 4 + 255) / 256, 256, 0, st>>>(A, master, params, ema, grads, m1, m2, steps);
+	const uint32_t end = std::min(A.last, A.n_params);
+	if (end <= A.first) return;
+	k_adam_ema<<<((end - A.first + 3) / 4 + 255) / 256, 256, 0, st>>>(A, master, params, ema, grads, m1, m2, steps);
 }
 void launch_pack_grads(cudaStream_t st, uint32_t n_padded, float* grads, __half* out) { k_pack_grads<<<(n_padded / 8 + 255) / 256, 256, 0, st>>>(n_padded, grads, out); }
 void launch_cast_params(cudaStream_t st, uint32_t n, const float* master, __half* params) { k_cast_params<<<(n + 255) / 256, 256, 0, st>>>(n, master, params); }

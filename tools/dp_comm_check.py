@@ -96,14 +96,17 @@ same_rays = torch.tensor([1 if torch.equal(r0, rays_t) else 0], device="cuda"); 
 out = {"world": world, "steps": K, "nccl": a["info"], "sharded_info": sh["info"],
        "single_run_to_run": rel(s2["p"], s1["p"]),
        "external_fp32_vs_single": rel(e["p"], s1["p"]), "library_fp16_vs_single": rel(a["p"], s1["p"]), "library_fp16_run_to_run": rel(a2["p"], a["p"]),
-       "library_sharded_vs_single": rel(sh["p"], s1["p"]), "library_sharded_vs_allreduce": rel(sh["p"], a["p"]),
+       "library_sharded_vs_single": rel(sh["p"], s1["p"]), "library_sharded_vs_allreduce": rel(sh["p"], a["p"]), "library_fp16_vs_external_fp32": rel(a["p"], e["p"]),
        "ranks_identical": {"external": e["identical"], "allreduce": a["identical"], "sharded": sh["identical"], "adaptive": ad["identical"]},
        "grad_buffer_abs_max_after": {"external": e["grad_max"], "allreduce": a["grad_max"], "sharded": sh["grad_max"]},
        "loss_first_last": {k: [v["losses"][0], v["losses"][-1]] for k, v in (("single", s1), ("external", e), ("allreduce", a), ("sharded", sh), ("adaptive", ad))},
        "adaptive_rays_same_on_all_ranks": int(same_rays.item()) == world, "adaptive_rays_tail": ad["rays"][-5:]}
 yard = max(out["single_run_to_run"], out["library_fp16_run_to_run"], 1e-4)
 ok = (all(out["ranks_identical"].values()) and all(v == 0.0 for v in out["grad_buffer_abs_max_after"].values()) and out["adaptive_rays_same_on_all_ranks"]
-      and out["library_fp16_vs_single"] <= max(8 * yard, 5e-3) and out["library_sharded_vs_allreduce"] <= max(8 * yard, 5e-3)
+      # same data-parallel semantics, different exchange: binary16 all-reduce inside the library vs fp32 all-reduce from outside
+      and out["library_fp16_vs_external_fp32"] <= max(8 * yard, 5e-3) and out["library_sharded_vs_allreduce"] <= max(8 * yard, 5e-3)
+      # vs ONE GPU on the same global batch: the roll-over multiplicity is applied per rank, so the trajectories drift apart by a few per cent
+      and out["library_fp16_vs_single"] <= 0.1 and abs(out["library_fp16_vs_single"] - out["external_fp32_vs_single"]) <= 0.01
       and abs(a["losses"][-1] - s1["losses"][-1]) <= 0.1 * abs(s1["losses"][-1]) + 1e-6 and a["info"]["installed"] and sh["info"]["sharded"])
 out["ok"] = bool(ok)
 if rank == 0:

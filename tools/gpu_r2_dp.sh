@@ -2,6 +2,7 @@
 # N-GPU session (gpurun --gpus N): canary, data-parallel check of the library-owned communicator, bench at N GPUs (all-reduce and sharded)
 N=${2:-2}; O=gpurun_out/${1:-r2dp}_n$N; mkdir -p $O
 bash tools/gpu_canary.sh 150 || exit 1
+export RNB_BENCH_CACHE=/dev/shm/rnb_bench_cache
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 if [ "${3:-check}" == "check" ]; then
   RNB_CHECK_STEPS=30 timeout 600 $TR --master-port 29611 tools/dp_comm_check.py > $O/dp_comm_check.log 2>&1; echo "dp_comm_check rc=$?"; grep -E "^\{" $O/dp_comm_check.log | tail -1 | cut -c1-1500
