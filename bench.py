@@ -237,7 +237,7 @@ def _shell_bitfield():
     return out
 
 
-DP_MODE_DEFAULT = "allreduce"      # N > 1: "allreduce" (one binary16 all-reduce, replicated Adam) or "sharded" (reduce-scatter + sharded Adam + all-gather); RNB_DP overrides
+DP_MODE_DEFAULT = "sharded"        # N > 1: "sharded" (binary16 reduce-scatter + Adam on 1/N of the parameters + parameter all-gather) or "allreduce" (one binary16 all-reduce, replicated Adam); RNB_DP overrides
 
 
 def _network_path():

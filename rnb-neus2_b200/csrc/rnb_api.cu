@@ -21,7 +21,7 @@
 namespace rnb {
 // rnb_march.cu
 void launch_march(cudaStream_t, uint32_t, uint32_t, uint32_t, uint32_t, Pcg32, const ViewDev*, uint32_t, const uint8_t*, uint32_t*, float*, float*, uint32_t = 0);
-void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*);
+void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t = 1, uint32_t = 0);
 void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, const float*, const float*, float4*);
 // rnb_network_simt.cu
 void launch_forward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, int, const float4*, const uint32_t*, uint32_t, const float*, __half*, float*, float*, float*);
@@ -140,6 +140,7 @@ struct rnb_ctx {
 	cudaEvent_t ev_counters = nullptr; bool counters_pending = false; bool async_end = true;      // RNB_ASYNC_END=0: wait for every step even without stats (A/B)  // asynchronous read-back of the step counters (rnb_train_step_end without stats)
 	// data parallelism behind the boundary (rnb_comm_*): one NCCL communicator per context, binary16 gradient exchange buffer
 	ncclComm_t comm = nullptr; bool comm_owned = false; __half* grads16 = nullptr; int dp_sharded = 0;
+	bool ema_stale = false;      // sharded optimizer: the EMA copy of the other ranks' shards is out of date until rnb_comm_sync_ema
 	const __half* xch16 = nullptr; uint32_t xch_begin = 0, xch_end = 0;      // result of this step's gradient exchange, consumed by rnb_train_step_end
 	// chunked all-reduce on a communication stream, pipelined with Adam / EMA on the caller's stream (RNB_DP_CHUNKS; default 1 = one all-reduce on the caller's stream: at N = 2 four chunks cost 0.898 ms per step against 0.835, profiles/r02_dp_n2.txt)
 	static constexpr uint32_t MAX_CHUNKS = 16;
@@ -222,6 +223,9 @@ static void pull_counters(rnb_ctx* c) {
 // the clamp of the next step's sample budget lives on the device (counters[5]); host-side state changes are pushed to it
 static cudaError_t push_measured(rnb_ctx* c) { return cudaMemcpy(c->counters + 5, &c->measured_before, 4, cudaMemcpyHostToDevice); }
 
+// sharded optimizer: readers of the inference (EMA) parameters must not see a copy whose foreign shards are stale — fail loudly instead
+#define RNB_EMA_READY(c, use_ema) do { if ((use_ema) && (c)->ema_stale) return fail(RNB_ERR_STATE, "sharded optimizer: the EMA parameters of the other ranks' shards are stale; call rnb_comm_sync_ema (collective) first"); } while (0)
+
 static uint32_t valid_level_for_step(const rnb_ctx* c, int step) {   // grid.h:1430-1437
 	if (step <= 0) return c->cfg.n_levels;
 	float v = c->cfg.base_valid_level_scale * (float)c->cfg.n_levels + c->cfg.valid_level_scale * (float)std::max(0, (int)((uint32_t)step - c->cfg.base_training_step));
@@ -230,7 +234,9 @@ static uint32_t valid_level_for_step(const rnb_ctx* c, int step) {   // grid.h:1
 
 static int ensure_ray_capacity(rnb_ctx* c, uint32_t R) {
 	if (R <= c->cap_rays) return 0;
-	uint32_t cap = std::max(R, 4096u);
+	// grow with head-room: the adaptive controller moves the batch size by a few rays per step, and a reallocation is a device synchronisation
+	// (N = 8 adaptive record of session r2dp: 4.4 ms per step while the capacity followed the batch size ray by ray)
+	uint32_t cap = std::min(std::max(R + R / 2, 4096u), 1u << 18);
 	cudaFree(c->ray_n); cudaFree(c->ray_indices); cudaFree(c->numsteps); cudaFree(c->n_fwd); cudaFree(c->cbase); cudaFree(c->n_emit);
 	cudaFree(c->ray_geom); cudaFree(c->ts); cudaFree(c->ray_dirw); cudaFree(c->loss_out);
 	CU(cudaMalloc(&c->ray_n, cap * 4)); CU(cudaMalloc(&c->ray_indices, cap * 4)); CU(cudaMalloc(&c->numsteps, cap * 8));
@@ -481,6 +487,7 @@ int rnb_get_params_fp32(rnb_ctx* c, float* p, size_t n) try {
 } RNB_API_CATCH
 int rnb_export_params_fp16(rnb_ctx* c, uint16_t* host, size_t n, int use_ema) try {
 	if (!c || !host || n != c->M.n_params) return fail(RNB_ERR_INVALID, "bad parameter buffer");
+	RNB_EMA_READY(c, use_ema);
 	CU(cudaMemcpy(host, use_ema ? c->ema : c->params, n * 2, cudaMemcpyDeviceToHost));
 	return RNB_OK;
 } RNB_API_CATCH
@@ -709,7 +716,7 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt) {
 		drop_prelaunch(c);
 		KT("march", 1, launch_march(st, R, G, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts));
 	}
-	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->counters + 5, c->ray_n, c->ray_indices, c->numsteps, c->counters),
+	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->counters + 5, c->ray_n, c->ray_indices, c->numsteps, c->counters, G, c->cfg.rank),
 	                   launch_emit(st, R, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4),
 	                   launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw)));
 	if (c->pre_armed && c->pre_at == 3) CU(cudaEventRecord(c->ev_bwd, st));      // ray_n / ray_geom / ts have been consumed: the next march may overwrite them
@@ -805,6 +812,7 @@ int rnb_train_step_end(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	if (c->xch16 && c->xch_end) {      // sharded: every rank's next forward needs all updated shards of the binary16 training parameters
 		NcclApi* N = nccl_api();
 		const size_t shard = c->np_padded / c->cfg.world_size;
+		c->ema_stale = true;
 		KT("param_allgather", 1, rc = (int)N->AllGather(c->params + (size_t)c->cfg.rank * shard, c->params, shard, ncclHalf, c->comm, st));
 		if (rc) return fail(RNB_ERR_CUDA, std::string("ncclAllGather: ") + N->GetErrorString((ncclResult_t)rc));
 	}
@@ -863,8 +871,10 @@ int rnb_comm_unique_id(uint8_t id_out[RNB_COMM_ID_BYTES]) try {
 } RNB_API_CATCH
 static int comm_buffers(rnb_ctx* c) {
 	if (!c->grads16) { CU(cudaMalloc(&c->grads16, c->np_padded * 2)); CU(cudaMemset(c->grads16, 0, c->np_padded * 2)); }
+	// default: sharded optimizer (reduce-scatter -> Adam / EMA on 1 / world of the parameters -> all-gather of the binary16 parameters): 0.825 vs 0.835 ms per
+	// step at N = 2 and 0.857 vs 0.929 ms at N = 8 against the single all-reduce (profiles/r02_dp_n2.txt, r02_dp_n8.txt).  RNB_DP=allreduce selects the latter.
 	const char* e = getenv("RNB_DP");
-	c->dp_sharded = (e && std::string(e) == "sharded" && c->np_padded % ((size_t)c->cfg.world_size * 8) == 0) ? 1 : 0;
+	c->dp_sharded = (!(e && std::string(e) == "allreduce") && c->np_padded % ((size_t)c->cfg.world_size * 8) == 0) ? 1 : 0;
 	if (const char* d = getenv("RNB_DP_CHUNKS")) c->dp_chunks = (uint32_t)std::min<int>(std::max(atoi(d), 1), (int)rnb_ctx::MAX_CHUNKS);
 	if (!c->comm_stream) {
 		int prio_lo = 0, prio_hi = 0; CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -908,6 +918,7 @@ int rnb_comm_sync_ema(rnb_ctx* c, void* stream) try {
 	NcclApi* N = nccl_api(); if (!N) return fail(RNB_ERR_STATE, "libnccl.so.2 not found");
 	const size_t shard = c->np_padded / c->cfg.world_size;
 	NC(N->AllGather(c->ema + (size_t)c->cfg.rank * shard, c->ema, shard, ncclHalf, c->comm, (cudaStream_t)stream));
+	c->ema_stale = false;
 	return RNB_OK;
 } RNB_API_CATCH
 int rnb_comm_info(rnb_ctx* c, uint32_t out[4]) try {
@@ -1107,6 +1118,7 @@ int rnb_eval_sdf(rnb_ctx* c, const float* xyz_dev, size_t n, float* sdf_dev, flo
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
 	float4* tmp = nullptr;
 	const size_t CH = 1u << 20;
+	RNB_EMA_READY(c, use_ema);
 	const __half* P = use_ema ? c->ema : c->params;
 	if (c->use_tc && !normal_dev) launch_tc(0, st, c->M, P, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm);     // weight blob of the requested parameter set (re-packed by the next training step)
 	CU(cudaMallocAsync(&tmp, CH * 16, st));
@@ -1131,6 +1143,7 @@ int rnb_sdf_on_grid(rnb_ctx* c, const uint32_t res[3], const float aabb_min[3], 
 	if (!c->use_tc) return fail(RNB_ERR_STATE, "rnb_sdf_on_grid needs the tcgen05 network path");
 	cudaStream_t st = (cudaStream_t)stream;
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
+	RNB_EMA_READY(c, use_ema);
 	const __half* P = use_ema ? c->ema : c->params;
 	launch_tc(0, st, c->M, P, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm);
 	launch_tc_sdf_grid(st, c->M, P, c->wtc, vl, res, aabb_min, aabb_max, out_dev, c->n_sm);
@@ -1168,7 +1181,8 @@ int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const 
 	if (with_colors && m.n_verts_padded) {
 		// the padding vertices (zeros) go through the network as well, as in the reference
 		const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
-		const __half* P = use_ema ? c->ema : c->params;
+	RNB_EMA_READY(c, use_ema);
+	const __half* P = use_ema ? c->ema : c->params;
 		const uint32_t CH = c->cap_compact;
 		float* dirw = nullptr;
 		CU(cudaMalloc(&dirw, (size_t)std::min(CH, m.n_verts_padded) * 12));
@@ -1304,6 +1318,7 @@ int rnb_stage_forward(rnb_ctx* c, const float* coords, size_t n, int use_ema, fl
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
 	float* dirw = nullptr;
 	int rc = upload_coords(c, coords, n, c->cpos4, &dirw); if (rc) return rc;
+	RNB_EMA_READY(c, use_ema);
 	const __half* P = use_ema ? c->ema : c->params;
 	net_pack(c, 0, P);
 	net_pass_b(c, 0, P, vl, c->cpos4, nullptr, (uint32_t)n, dirw);

@@ -153,17 +153,20 @@ __global__ void __launch_bounds__(256) k_march(uint32_t n_rays, uint32_t world, 
 // prev (optional, device): last step's sample count; the sample budget of this step is clamped to it like train_nerf_step does on the host
 // (max_inference, testbed_nerf.cu:3891-3896): 0 -> the whole buffer, else next_multiple(min(prev, capacity), 128).  Keeping the clamp on the device
 // means no step ever needs last step's counters on the host.
+// Data parallel: only rays i = rank (mod world) were marched by this rank; the scan walks those (in ray order), not the global ray array.
 __global__ void __launch_bounds__(1024) k_scan_rays(uint32_t n_rays, uint32_t max_samples, const uint32_t* __restrict__ prev, const uint32_t* __restrict__ ray_n,
-                                                    uint32_t* __restrict__ ray_indices, uint32_t* __restrict__ numsteps /*2 per kept ray*/, uint32_t* __restrict__ counters /*[0]=kept,[1]=samples,[6]=samples to forward*/) {
+                                                    uint32_t* __restrict__ ray_indices, uint32_t* __restrict__ numsteps /*2 per kept ray*/, uint32_t* __restrict__ counters /*[0]=kept,[1]=samples,[6]=samples to forward*/,
+                                                    uint32_t world, uint32_t rank) {
 	__shared__ uint32_t s_a[32], s_b[32];
 	__shared__ uint32_t carry_n, carry_k;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	if (prev) { const uint32_t p = *prev; if (p) max_samples = min(max_samples, (min(p, max_samples) + 127u) / 128u * 128u); }
 	if (tid == 0) { carry_n = 0; carry_k = 0; }
 	__syncthreads();
-	for (uint32_t c0 = 0; c0 < n_rays; c0 += 1024) {
-		const uint32_t i = c0 + tid;
-		const uint32_t n = i < n_rays ? ray_n[i] : 0;
+	const uint32_t n_local = (n_rays + world - 1 - rank) / world;
+	for (uint32_t c0 = 0; c0 < n_local; c0 += 1024) {
+		const uint32_t li = c0 + tid, i = li * world + rank;
+		const uint32_t n = (li < n_local && i < n_rays) ? ray_n[i] : 0;
 		uint32_t a = n;
 		#pragma unroll
 		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, a, o); if ((int)lane >= o) a += v; }
@@ -213,8 +216,8 @@ void launch_march(cudaStream_t st, uint32_t n_rays, uint32_t world, uint32_t ran
 	if (max_ctas) grid = std::min(grid, max_ctas);
 	k_march<<<grid, 256, 0, st>>>(n_rays, world, rank, n_rays_total, rng, views, n_views, bitfield, ray_n, ray_geom, ts);
 }
-void launch_scan_rays(cudaStream_t st, uint32_t n_rays, uint32_t max_samples, const uint32_t* prev, const uint32_t* ray_n, uint32_t* ray_indices, uint32_t* numsteps, uint32_t* counters) {
-	k_scan_rays<<<1, 1024, 0, st>>>(n_rays, max_samples, prev, ray_n, ray_indices, numsteps, counters);
+void launch_scan_rays(cudaStream_t st, uint32_t n_rays, uint32_t max_samples, const uint32_t* prev, const uint32_t* ray_n, uint32_t* ray_indices, uint32_t* numsteps, uint32_t* counters, uint32_t world, uint32_t rank) {
+	k_scan_rays<<<1, 1024, 0, st>>>(n_rays, max_samples, prev, ray_n, ray_indices, numsteps, counters, world ? world : 1u, rank);
 }
 void launch_emit(cudaStream_t st, uint32_t n_rays_upper, const uint32_t* counters, uint32_t world, const uint32_t* ray_indices, const uint32_t* numsteps, const float* ray_geom, const float* ts, float4* pos4) {
 	if (!n_rays_upper) return;

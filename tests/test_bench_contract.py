@@ -49,4 +49,4 @@ def test_network_path_label_follows_the_kernel_selection(monkeypatch):
     assert "mma.sync" in bench._network_path() and "cross-check" in bench._network_path()
     monkeypatch.setenv("RNB_NETWORK", "simt")
     assert "CUDA-core" in bench._network_path()
-    assert bench.DP_MODE_DEFAULT == "allreduce"          # the measured default at N = 2
+    assert bench.DP_MODE_DEFAULT == "sharded"            # the measured default at N = 2 and N = 8 (profiles/r02_dp_n*.txt)
