@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  See orc_common.h for scope and parity status ("parity unpinned").
+// ORACLE — TEST INFRASTRUCTURE ONLY.  See orc_common.h for scope and parity status (pinned against the reference build run on B200).
 //
 // C entry points (ctypes) over the CPU restatement.  Stage functions mirror the reference call graph of
 // Testbed::train -> training_prep_nerf / train_nerf -> train_nerf_step (src/testbed.cu:2776-2872,
