@@ -36,8 +36,8 @@ def test_cited_files_exist():
 
 
 def test_readme_headline_matches_the_bench_record():
-    rec = json.load(open(os.path.join(ROOT, "profiles", "r01_final2_bench.json")))
-    ref = json.load(open(os.path.join(ROOT, "profiles", "r01_final2_bench_reference_arm.json")))
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r02_final_bench.json")))
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r02_final_bench_reference_arm.json")))
     readme = open(os.path.join(ROOT, "README.md")).read()
     assert "%.2f M rays/s" % (rec["value"] / 1e6) in readme
     assert "%.2f M end to end" % (rec["e2e"]["value"] / 1e6) in readme
@@ -45,3 +45,5 @@ def test_readme_headline_matches_the_bench_record():
     assert "%.2f M rays/s for the reference" % (ref["value"] / 1e6) in readme
     assert rec["roofline"]["kernel"] == "backward" and 0 < rec["roofline"]["frac"] < 1
     assert rec["cpu_baseline"]["kind"] == "port" and rec["gpu_launches"] > 0 and rec["clocks"]["reasons"] == []
+    assert "normals+albedo" in rec["config"]["workload"] and rec["config"]["live_hash_levels"] == 14 and rec["config"]["workload"] == ref["config"]["workload"]
+    assert set(rec["records"]) >= {"normals", "supernormal", "mesh_1024", "adaptive_controller"}

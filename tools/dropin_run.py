@@ -133,19 +133,29 @@ def write_rnb_input(out_dir, views):
         nm = v["normal"]
         cv2.imwrite(os.path.join(out_dir, "normal", "%03d.png" % i), np.ascontiguousarray(nm[..., [2, 1, 0]]))       # cv2 stores BGR: file order stays RGB
         cv2.imwrite(os.path.join(out_dir, "mask", "%03d.png" % i), (nm[..., 3] > 0).astype(np.uint8) * 255)
+        if v.get("albedo") is not None:
+            os.makedirs(os.path.join(out_dir, "albedo"), exist_ok=True)
+            cv2.imwrite(os.path.join(out_dir, "albedo", "%03d.png" % i), np.ascontiguousarray(v["albedo"][..., [2, 1, 0]]))
     np.savez(os.path.join(out_dir, "cameras.npz"), **cams)
 
 
-def run_pipeline(name, inp, out, iters, res, timeout, rec):
-    pipe = os.path.join(ROOT, "oracle/_ref/pipeline")
-    env = dict(os.environ); env["PYTHONPATH"] = os.path.join(ROOT, "tests/stubs") + os.pathsep + pipe + os.pathsep + env.get("PYTHONPATH", "")
+def run_pipeline(name, inp, out, iters, res, timeout, rec, has_albedo=False):
+    """has_albedo: BASELINE configs[2] — `run_pipeline.py --has-albedo`: phase 1 geometry (--no-albedo, mesh at 512), the albedo-scaling stage, then the two-stage run with
+    albedo (ref:rnb_neus2/pipeline.py:106-175).  The reference's albedo_scaling.py needs trimesh; the staged copy oracle/_ref/pipeline_rnb carries the one-line import
+    change of INTEGRATION.md §7, so the stage is served by rnb-neus2_b200/albedo_scaling.py over the GPU ray / mesh queries."""
+    pipe = os.path.join(ROOT, "oracle/_ref/pipeline_rnb" if has_albedo else "oracle/_ref/pipeline")
+    pylib = os.path.join(rec["dir"], "pylib"); os.makedirs(pylib, exist_ok=True)
+    link = os.path.join(pylib, "rnb_neus2_b200")
+    if not os.path.exists(link):
+        os.symlink(os.path.join(ROOT, "rnb-neus2_b200"), link)
+    env = dict(os.environ); env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests/stubs"), pipe, pylib, env.get("PYTHONPATH", "")])
     cmd = [sys.executable, os.path.join(pipe, "run_pipeline.py"), "--input", inp, "--testbed", BIN[name], "--output", out, "--max-steps", str(iters), "--mesh-resolution", str(res),
-           "--scaling-mode", "none"]
-    log = os.path.join(rec["dir"], name + "_pipeline.log")
+           "--scaling-mode", "none"] + (["--has-albedo", "--n-samples", "2000"] if has_albedo else [])
+    log = os.path.join(rec["dir"], name + ("_pipeline_albedo.log" if has_albedo else "_pipeline.log"))
     rc, wall = run(cmd, log, timeout, env)
     txt = open(log, errors="replace").read()
     r = dict(argv=cmd[1:], rc=rc, wall_s=round(wall, 2), complete="=== Pipeline complete ===" in txt, mesh_exists=os.path.exists(os.path.join(out, "mesh.obj")),
-             stage_lines=[line.strip()[:160] for line in txt.split("\n") if re.search(r"Stage \d|completed|Pipeline complete|Mesh exported|failed", line)][:20],
+             stage_lines=[line.strip()[:160] for line in txt.split("\n") if re.search(r"Stage \d|Phase \d|completed|Pipeline complete|Mesh exported|failed|Albedo|scale ratio|Scale", line)][:40],
              note="postprocess_mesh imports trimesh, which is not in this image: tests/stubs/trimesh is a stand-in that keeps the mesh as it is (load / split / fix_normals / export)")
     return r
 
@@ -155,6 +165,7 @@ def main():
     ap.add_argument("out"); ap.add_argument("--iters", type=int, default=3000); ap.add_argument("--res", type=int, default=256); ap.add_argument("--views", type=int, default=24)
     ap.add_argument("--width", type=int, default=400); ap.add_argument("--height", type=int, default=300)
     ap.add_argument("--albedo", action="store_true"); ap.add_argument("--pipeline", action="store_true"); ap.add_argument("--only", default="")
+    ap.add_argument("--pipeline-albedo", action="store_true", help="run_pipeline.py --has-albedo (two-phase with albedo scaling) against testbed_rnb"); ap.add_argument("--skip-two-stage", action="store_true")
     ap.add_argument("--timeout", type=int, default=600)
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
@@ -167,7 +178,7 @@ def main():
     except Exception:      # noqa: BLE001
         pass
     meshes = {}
-    for name in names:
+    for name in ([] if a.skip_two_stage else names):
         sd = os.path.join(a.out, "scene_" + name)
         ref_scene.write_scene(sd, views, workers=8)
         r = two_stage(name, sd, a.iters, a.res, a.albedo, a.timeout, rec)
@@ -203,6 +214,21 @@ def main():
             if os.path.exists(mp):
                 rec["run_pipeline"][name]["mesh"], _ = mesh_stats(mp, scene)
             print("run_pipeline.py via", name, {k: rec["run_pipeline"][name][k] for k in ("rc", "wall_s", "complete", "mesh_exists")}, flush=True)
+    if a.pipeline_albedo and os.path.exists(os.path.join(ROOT, "oracle/_ref/pipeline_rnb/run_pipeline.py")):
+        views_a = scene.make_scene(a.views, a.width, a.height, with_albedo=True)
+        # per-view gains on the albedo maps (what the scaling stage is there to undo): the stage must come back with ratios ~ 1 / gain
+        gains = 0.7 + 0.6 * np.random.RandomState(3).rand(a.views)
+        for v, gn in zip(views_a, gains):
+            al = v["albedo"].astype(np.float64); al[..., :3] = np.clip(al[..., :3] * gn, 0, 65535); v["albedo"] = al.astype(np.uint16)
+        inp = os.path.join(a.out, "rnb_input_albedo"); write_rnb_input(inp, views_a)
+        out = os.path.join(a.out, "pipeline_albedo_rnb")
+        r = run_pipeline("rnb", inp, out, a.iters, a.res, a.timeout * 3, rec, has_albedo=True)
+        mp = os.path.join(out, "mesh.obj")
+        if os.path.exists(mp):
+            r["mesh"], _ = mesh_stats(mp, scene)
+        r["albedo_gains_applied"] = [round(float(x), 4) for x in gains]
+        rec["run_pipeline_has_albedo"] = r
+        print("run_pipeline.py --has-albedo via rnb", {k: r[k] for k in ("rc", "wall_s", "complete", "mesh_exists")}, r.get("mesh", {}).get("dist_to_analytic_surface_mean"), flush=True)
     json.dump(rec, open(os.path.join(a.out, "dropin_record.json"), "w"), indent=1)
     print("record:", os.path.join(a.out, "dropin_record.json"))
 
