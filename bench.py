@@ -347,10 +347,12 @@ def main():
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         l0 = tb.launch_count()
         e0.record(tstream)
-        last = None; rays = 0
+        last = None; rays = 0; acc = [0, 0]
         for _ in range(k):
             last = tb.train(stream=sh, want_stats=want_stats)
-            if want_stats: rays += int(last.n_rays)
+            if want_stats:
+                rays += int(last.n_rays); acc[0] += int(last.n_samples); acc[1] += int(last.n_samples_trained)
+        timed.mean_counts = (acc[0] / k, acc[1] / k) if want_stats else None
         e1.record(tstream)
         torch.cuda.synchronize()
         if dist: dist.barrier()
@@ -377,13 +379,14 @@ def main():
     t.checkpoint_restore()
     t.profile_enable(True)                                     # per-stage device timing for the roofline (events on the launching stream; separate pass so that `value` is undisturbed)
     timed(t, args.steps, True)
+    mean_ns, mean_nc = timed.mean_counts          # samples before / after compaction, averaged over the SAME steps the stage times are averaged over
     prof = t.profile_read(); t.profile_enable(False)
 
     value = R * args.steps / (ms * 1e-3)
     e2e = R * args.steps / (ms_e2e * 1e-3)
     hbm_peak, peak_src, tf_peak = peaks()
     per_stage = {k: v[0] / max(v[1], 1) for k, v in prof.items()}
-    ns, nc = last.n_samples, last.n_samples_trained
+    ns, nc = mean_ns, mean_nc
     ts_now = t.get_train_state()[0]
     L = live_levels(ts_now)
     alg, flops = algorithmic_work(L, ns, nc, t.n_params)
@@ -408,7 +411,7 @@ def main():
         par = "single GPU"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "rays_per_step_global": R, "pretrain_steps": args.pretrain, "training_step_at_end": int(ts_now), "samples_per_step": int(ns), "compacted_samples_per_step": int(nc),
+            "config": {"workload": WORKLOADS[args.workload], "rays_per_step_global": R, "pretrain_steps": args.pretrain, "training_step_at_end": int(ts_now), "samples_per_step": int(ns), "compacted_samples_per_step": int(nc), "counts_note": "mean over the timed window",
                        "live_hash_levels": L,
                        "cache": "working set (hash table 21 MB + gradients 42 MB + optimizer state 170 MB + %.1f GB images) exceeds L2; no flush needed" % (dataset_bytes / 1e9),
                        "parallelism": par, "network_path": _network_path(), "stream": "caller's stream with priority -1 (library side stream: lowest priority)" if sh is not None else "legacy default stream",

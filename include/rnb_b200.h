@@ -192,9 +192,10 @@ int rnb_train_step_end(rnb_ctx* ctx, void* stream, rnb_step_stats* stats);
 int rnb_grad_buffer(rnb_ctx* ctx, float** grads_dev, uint64_t* n);
 /* Data parallelism behind the boundary (new; the reference is single-GPU, its gradient buffer between backward and optimizer_step is one contiguous
  * binary16 array: trainer.h:78-84, src/testbed_nerf.cu:4068 -> :3624).  With a communicator installed and rnb_config.world_size > 1,
- * rnb_train_step / rnb_train do the exchange themselves on the caller's stream: the fp32 accumulators are rounded to binary16 once, summed
- * with ONE ncclAllReduce (21 MB at the default configuration) grouped with the 8 floats of loss sums / counts, and Adam / EMA consume the sum.
- * Environment RNB_DP=sharded selects reduce-scatter -> optimizer on 1 / world of the parameters -> all-gather of the binary16 parameters.
+ * rnb_train_step / rnb_train do the exchange themselves on the caller's stream: the fp32 accumulators are rounded to binary16 once (21 MB at the
+ * default configuration), reduce-scattered (grouped with the 8 floats of loss sums / counts), Adam / EMA run on this rank's 1 / world of the parameters
+ * and the binary16 training parameters are all-gathered (sharded optimizer, the measured default; the EMA copy is per shard until rnb_comm_sync_ema).
+ * Environment RNB_DP=allreduce selects ONE ncclAllReduce of the binary16 buffer with replicated Adam / EMA instead.
  * NCCL is opened at run time (dlopen of libnccl.so.2), so single-GPU users have no dependency on it.
  *   rnb_comm_unique_id: ncclGetUniqueId on one rank; the caller's launcher carries the 128 bytes to the other ranks (file, socket, MPI, torchrun store)
  *   rnb_comm_init:      ncclCommInitRank(world_size, id, rank) on the current device, communicator owned by the context

@@ -22,7 +22,7 @@ namespace rnb {
 // rnb_march.cu
 void launch_march(cudaStream_t, uint32_t, uint32_t, uint32_t, uint32_t, Pcg32, const ViewDev*, uint32_t, const uint8_t*, uint32_t*, float*, float*, uint32_t = 0);
 void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t = 1, uint32_t = 0);
-void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, const float*, const float*, float4*);
+void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, const float*, const float*, float4*, float* = nullptr);
 // rnb_network_simt.cu
 void launch_forward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, int, const float4*, const uint32_t*, uint32_t, const float*, __half*, float*, float*, float*);
 void launch_backward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, float*, __half*, float*);
@@ -716,21 +716,22 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt) {
 		drop_prelaunch(c);
 		KT("march", 1, launch_march(st, R, G, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts));
 	}
-	KT("scan_emit", 3, (launch_scan_rays(st, R, max_inference, c->counters + 5, c->ray_n, c->ray_indices, c->numsteps, c->counters, G, c->cfg.rank),
-	                   launch_emit(st, R, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4),
-	                   launch_ray_dirw(st, R, c->counters, c->ray_indices, c->ray_geom, c->ray_dirw)));
+	KT("scan_emit", 2, (launch_scan_rays(st, R, max_inference, c->counters + 5, c->ray_n, c->ray_indices, c->numsteps, c->counters, G, c->cfg.rank),
+	                   launch_emit(st, (R + G - 1) / G, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4, c->ray_dirw)));
 	if (c->pre_armed && c->pre_at == 3) CU(cudaEventRecord(c->ev_bwd, st));      // ray_n / ray_geom / ts have been consumed: the next march may overwrite them
 	// weight blobs for this step's kernels: the mma.sync panel copy only when one of its kernels runs in the step (cross-check paths)
 	const bool all_tc = c->use_tc && c->use_tc_bwd;
 	KT("pass_a_sdf_normal", all_tc ? 2 : 3, ((all_tc ? (void)launch_tc(0, st, c->M, c->params, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm) : net_pack(c, st, c->params)),
 	                                         net_pass_a(c, st, vl, c->pos4, c->counters + 6, max_inference)));
 	if (c->pre_armed && c->pre_at == 2) CU(cudaEventRecord(c->ev_bwd, st));
-	KT("compact", 3, (launch_compact_count(st, R, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd),
+	KT("compact", 3, (launch_compact_count(st, (R + G - 1) / G, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd),
 	                 launch_scan_compact(st, c->counters, local_target, c->n_fwd, c->cbase, c->n_emit, c->stats),
-	                 launch_gather_compacted(st, R, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4)));
+	                 launch_gather_compacted(st, (R + G - 1) / G, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4)));
 	KT("pass_b_forward", 1, net_pass_b(c, st, c->params, vl, c->cpos4, c->counters + 4, c->cap_compact, c->ray_dirw));
-	KT("loss", 2, launch_loss(st, R, c->flags, R, nrt, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
-	            c->out16, c->dout16, c->loss_out, c->stats));
+	// the per-ray loss terms are summed only when somebody will read the sums: the caller (stats), the adaptive controller's host path, or the other ranks
+	const bool want_sums = c->step_waits || G > 1 || c->prof;
+	KT("loss", want_sums ? 2 : 1, launch_loss(st, (R + G - 1) / G, c->flags, R, nrt, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
+	            c->out16, c->dout16, c->loss_out, want_sums ? c->stats : nullptr));
 	if (c->pre_armed && c->pre_at == 1) CU(cudaEventRecord(c->ev_bwd, st));
 	KT("backward", c->use_mma ? 1 : 9, net_backward(c, st, vl, c->counters + 3, local_target, local_target, c->counters + 3));
 	CU(cudaGetLastError());

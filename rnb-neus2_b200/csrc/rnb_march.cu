@@ -194,13 +194,15 @@ __global__ void __launch_bounds__(1024) k_scan_rays(uint32_t n_rays, uint32_t ma
 }
 
 // One warp per kept ray: pos4[base + j] = { o + t*dir , ray slot }.
+// Also writes the ray's warped direction (dir + 1) / 2 (warp_direction, testbed_nerf.cu:413-415) when ray_dirw is given (one launch less per step).
 __global__ void __launch_bounds__(256) k_emit(const uint32_t* __restrict__ counters, uint32_t world, const uint32_t* __restrict__ ray_indices, const uint32_t* __restrict__ numsteps,
-                                              const float* __restrict__ ray_geom, const float* __restrict__ ts, float4* __restrict__ pos4) {
+                                              const float* __restrict__ ray_geom, const float* __restrict__ ts, float4* __restrict__ pos4, float* __restrict__ ray_dirw) {
 	const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (k >= counters[0]) return;
 	const uint32_t i = ray_indices[k], n = numsteps[2 * k], base = numsteps[2 * k + 1];
 	const float* g = ray_geom + (size_t)i * 9;
 	const float ox = g[0], oy = g[1], oz = g[2], dx = g[6], dy = g[7], dz = g[8];
+	if (ray_dirw && lane < 3) ray_dirw[3 * k + lane] = (g[6 + lane] + 1.0f) * 0.5f;
 	const float* tin = ts + (size_t)(i / world) * MAX_STEPS;
 	for (uint32_t j = lane; j < n; j += 32) {
 		const float t = tin[j];
@@ -219,9 +221,9 @@ void launch_march(cudaStream_t st, uint32_t n_rays, uint32_t world, uint32_t ran
 void launch_scan_rays(cudaStream_t st, uint32_t n_rays, uint32_t max_samples, const uint32_t* prev, const uint32_t* ray_n, uint32_t* ray_indices, uint32_t* numsteps, uint32_t* counters, uint32_t world, uint32_t rank) {
 	k_scan_rays<<<1, 1024, 0, st>>>(n_rays, max_samples, prev, ray_n, ray_indices, numsteps, counters, world ? world : 1u, rank);
 }
-void launch_emit(cudaStream_t st, uint32_t n_rays_upper, const uint32_t* counters, uint32_t world, const uint32_t* ray_indices, const uint32_t* numsteps, const float* ray_geom, const float* ts, float4* pos4) {
+void launch_emit(cudaStream_t st, uint32_t n_rays_upper, const uint32_t* counters, uint32_t world, const uint32_t* ray_indices, const uint32_t* numsteps, const float* ray_geom, const float* ts, float4* pos4, float* ray_dirw) {
 	if (!n_rays_upper) return;
-	k_emit<<<(n_rays_upper * 32 + 255) / 256, 256, 0, st>>>(counters, world, ray_indices, numsteps, ray_geom, ts, pos4);
+	k_emit<<<(n_rays_upper * 32 + 255) / 256, 256, 0, st>>>(counters, world, ray_indices, numsteps, ray_geom, ts, pos4, ray_dirw);
 }
 
 } // namespace rnb

@@ -24,6 +24,10 @@
 // rounding at every layer output, dy/dx and the normal in fp32.
 #include "rnb_encode.cuh"
 
+#ifndef RNB_GATHER_PIPE_DEFAULT
+#define RNB_GATHER_PIPE_DEFAULT 0      /* software-pipelined level gather in pass A (A/B: profiles/r02_ab_gather_pipe.txt) */
+#endif
+
 namespace rnb {
 
 namespace tc {
@@ -209,6 +213,52 @@ __device__ __forceinline__ void gather_row_to_tmem(const ModelDev& M, const __ha
 	}
 }
 
+// Software-pipelined variant (RNB_GATHER_PIPE=1): the levels go in pairs; the 16 corner loads of pair p + 1 are issued BEFORE pair p is finished, so a warp's own
+// arithmetic (~270 instructions per pair) covers the L2 round trip of its next loads instead of relying on the other three warps of its scheduler.
+// Same registers as the batch of four (two pairs of LevelLoads in flight), same arithmetic, same order of the dy/dx stores.
+template <bool WITH_DY>
+__device__ __forceinline__ void gather_row_to_tmem_pipe(const ModelDev& M, const __half* __restrict__ P, uint32_t valid_level, float x, float y, float z, uint32_t tcol, float* __restrict__ dyS, int tid,
+                                                        const uint32_t* __restrict__ stab = nullptr, uint32_t n_stage_levels = 0) {
+	const uint32_t L = M.n_levels;
+	const uint32_t n_live = min(L, valid_level + 1u);
+	const __half2 exy = __halves2half2(__hsub(__float2half_rn(x), __float2half_rn(0.5f)), __hsub(__float2half_rn(y), __float2half_rn(0.5f)));
+	const __half2 ez = __halves2half2(__hsub(__float2half_rn(z), __float2half_rn(0.5f)), __float2half_rn(0.f));
+	LevelLoads Qa[2], Qb[2];
+	auto issue2 = [&](uint32_t l0, LevelLoads (&Q)[2]) {
+		#pragma unroll
+		for (uint32_t i = 0; i < 2; ++i) if (l0 + i < n_live) level_issue(M, P, l0 + i, x, y, z, Q[i], stab, n_stage_levels);
+	};
+	auto finish2 = [&](uint32_t l0, const LevelLoads (&Q)[2], uint32_t& w0, uint32_t& w1) {
+		#pragma unroll
+		for (uint32_t i = 0; i < 2; ++i) {
+			if (l0 + i < n_live) {
+				float dy[6];
+				const __half2 e = level_finish(M.scale[l0 + i], Q[i], WITH_DY ? dy : nullptr);
+				(i ? w1 : w0) = *reinterpret_cast<const uint32_t*>(&e);
+				if (WITH_DY) {
+					#pragma unroll
+					for (int q = 0; q < 6; ++q) dyS[((l0 + i) * 6 + q) * TILE + tid] = dy[q];
+				}
+			}
+		}
+	};
+	issue2(0, Qa);
+	#pragma unroll 1
+	for (uint32_t b = 0; b < 16; b += 4) {
+		uint32_t w[4] = {0u, 0u, 0u, 0u};
+		issue2(b + 2, Qb);
+		finish2(b, Qa, w[0], w[1]);
+		if (b + 4 < 16) issue2(b + 4, Qa);
+		finish2(b + 2, Qb, w[2], w[3]);
+		#pragma unroll
+		for (uint32_t i = 0; i < 4; ++i) {
+			if (b + i == L) w[i] = *reinterpret_cast<const uint32_t*>(&exy);
+			else if (b + i == L + 1) w[i] = *reinterpret_cast<const uint32_t*>(&ez);
+		}
+		tmem_st4(tcol + b, w[0], w[1], w[2], w[3]);
+	}
+}
+
 // lattice of Testbed::get_density_on_grid (generate_grid_samples_nerf_uniform, testbed_nerf.cu:541-553): point (x, y, z) of a
 // res^3 lattice sits at idx / res * (aabb.max - aabb.min) + aabb.min (no half-cell offset); the last multiply-add is fused as nvcc
 // contracts it in the reference build
@@ -221,7 +271,7 @@ struct GridSpec { uint32_t rx, ry, rz; float inv[3], ext[3], mn[3]; };
 // Activations are TMEM resident: every thread writes its input row / its tm row straight into its TMEM lane (tcgen05.st) and
 // the MMAs read the A operand from TMEM; shared memory only holds the weights and (pass A) the dy/dx scratch.
 // TMEM columns: [0,64) layer accumulator | [64,80) input row, then [64,96) tm row | [96,128) d sdf / d u'
-template <int SW, int MODE>
+template <int SW, int MODE, bool PIPE = false>
 __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
                                                     const float4* __restrict__ pos4, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
                                                     __half* __restrict__ outA, float* __restrict__ sdf_out, float* __restrict__ dens_out, GridSpec gs, uint32_t n_stage_levels) {
@@ -272,7 +322,8 @@ __global__ void __launch_bounds__(TILE, 4) k_sdf_tc(ModelDev M, const __half* __
 			p = make_float4(__fmaf_rn(__fmul_rn((float)ix, gs.inv[0]), gs.ext[0], gs.mn[0]), __fmaf_rn(__fmul_rn((float)iy, gs.inv[1]), gs.ext[1], gs.mn[1]),
 			                __fmaf_rn(__fmul_rn((float)iz, gs.inv[2]), gs.ext[2], gs.mn[2]), 0.f);
 		} else p = pos4[min(row, n - 1)];
-		gather_row_to_tmem<NORMAL>(M, P, valid_level, p.x, p.y, p.z, trow + C_IN, dyS, tid, stab, n_stage_levels);
+		if (PIPE) gather_row_to_tmem_pipe<NORMAL>(M, P, valid_level, p.x, p.y, p.z, trow + C_IN, dyS, tid, stab, n_stage_levels);
+		else gather_row_to_tmem<NORMAL>(M, P, valid_level, p.x, p.y, p.z, trow + C_IN, dyS, tid, stab, n_stage_levels);
 		tmem_st_wait();
 		tc_fence_before();
 		__syncthreads();
@@ -1068,6 +1119,13 @@ static void launch_tc_sw(int what, cudaStream_t st, const ModelDev& M, const __h
 		if (attr < smem) { cudaFuncSetAttribute(k_sdf_tc<SW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
 		static uint32_t ctas = 0; static size_t ctas_for = ~(size_t)0;
 		if (ctas_for != smem) { ctas = resident_ctas(k_sdf_tc<SW, 0>, TILE, smem, n_sm, 4); ctas_for = smem; }
+		static int pipe = -1;
+		if (pipe < 0) { const char* e = getenv("RNB_GATHER_PIPE"); pipe = e ? (atoi(e) != 0) : RNB_GATHER_PIPE_DEFAULT; }
+		if (pipe) {
+			static size_t attr_p = 0;
+			if (attr_p < smem) { cudaFuncSetAttribute(k_sdf_tc<SW, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_p = smem; }
+			k_sdf_tc<SW, 0, true><<<std::min<uint32_t>(tiles, ctas), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr, GridSpec{}, nst);
+		} else
 		k_sdf_tc<SW, 0><<<std::min<uint32_t>(tiles, ctas), TILE, smem, st>>>(M, P, wtc, vl, pos4, n_ptr, n_max, outA, nullptr, nullptr, GridSpec{}, nst);
 	} else if (what == 3) {
 		const size_t smem = ((B::END + 127u) & ~127u) + 84 * TILE * 4;
