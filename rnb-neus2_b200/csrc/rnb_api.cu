@@ -52,6 +52,7 @@ struct AdamParams {
 	uint32_t shard_begin, shard_end; const float* gsrc;      // data-parallel optimizer shard (rnb_optim.cu)
 	const __half* gsrc16;                                   // binary16 gradient exchange (rnb_optim.cu)
 	uint32_t first, last;                                   // parameter range of this launch
+	int lr_cache;
 };
 void launch_pack_grads(cudaStream_t, uint32_t, float*, __half*);
 void launch_adam_ema(cudaStream_t, const AdamParams&, float*, __half*, __half*, float*, float*, float*, uint32_t*);
@@ -204,6 +205,8 @@ struct NvtxRange { explicit NvtxRange(const char* n) { char b[64]; snprintf(b, s
 #define KT(name, nk, call) do { NvtxRange nvtx_(name); prof_begin(c, st, name); call; prof_end(c, st); c->launches += (nk); } while (0)
 
 static uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
+// a pair of timing events that is released on every return path
+struct EventPair { cudaEvent_t e[2] = {nullptr, nullptr}; ~EventPair() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); } cudaEvent_t& operator[](int i) { return e[i]; } };
 
 // a pre-launched march is only usable if nothing it depends on changed: drop it (after it has drained) otherwise
 static void drop_prelaunch(rnb_ctx* c) { if (c->pre_valid) { cudaStreamSynchronize(c->side); c->pre_valid = false; } }
@@ -753,6 +756,7 @@ static int optimizer_step(rnb_ctx* c, cudaStream_t st, const __half* gsrc16 = nu
 	if (gsrc16 && sh_end) { A.shard_begin = sh_begin; A.shard_end = std::min(sh_end, c->M.n_params); A.gsrc = nullptr; }      // sharded optimizer on the library's own communicator
 	A.gsrc16 = gsrc16;
 	A.first = 0; A.last = c->M.n_params;
+	{ static int lrc = -1; if (lrc < 0) { const char* e = getenv("RNB_ADAM_LRCACHE"); lrc = e ? (atoi(e) != 0) : 1; } A.lr_cache = lrc; }
 	if (c->xch_chunks > 1) {
 		// chunked exchange: the all-reduce of chunk k + 1 (communication stream) runs under Adam / EMA of chunk k (this stream)
 		NvtxRange nvtx_("adam_ema_pipelined"); prof_begin(c, st, "adam_ema");
@@ -1176,14 +1180,14 @@ int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const 
 	const size_t nvp = std::max<uint32_t>(m.n_verts_padded, 1);
 	CU(cudaMalloc(&m.colors, nvp * 12));
 	CU(cudaMemsetAsync(m.colors, 0, nvp * 12, st));
-	cudaEvent_t ec[2];
+	EventPair ec;
 	CU(cudaEventCreate(&ec[0])); CU(cudaEventCreate(&ec[1]));
 	CU(cudaEventRecord(ec[0], st));
 	if (with_colors && m.n_verts_padded) {
 		// the padding vertices (zeros) go through the network as well, as in the reference
 		const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
-	RNB_EMA_READY(c, use_ema);
-	const __half* P = use_ema ? c->ema : c->params;
+		RNB_EMA_READY(c, use_ema);
+		const __half* P = use_ema ? c->ema : c->params;
 		const uint32_t CH = c->cap_compact;
 		float* dirw = nullptr;
 		CU(cudaMalloc(&dirw, (size_t)std::min(CH, m.n_verts_padded) * 12));
@@ -1203,7 +1207,6 @@ int rnb_marching_cubes_from_density(rnb_ctx* c, const float* density_dev, const 
 	CU(cudaStreamSynchronize(st));
 	CU(cudaGetLastError());
 	cudaEventElapsedTime(&m.ms[3], ec[0], ec[1]);
-	cudaEventDestroy(ec[0]); cudaEventDestroy(ec[1]);
 	if (info) {
 		info->n_verts = m.n_verts; info->n_verts_padded = m.n_verts_padded; info->n_indices = m.n_indices; info->res[0] = res[0]; info->res[1] = res[1]; info->res[2] = res[2];
 		for (int k = 0; k < 4; ++k) info->stage_ms[k] = m.ms[k];
@@ -1218,7 +1221,7 @@ int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_mi
 	const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
 	if (n == 0 || n > 0xFFFFFFFFull) return fail(RNB_ERR_INVALID, "lattice empty or larger than 2^32 points");
 	if (c->mesh_density_bytes < n * 4) { cudaFree(c->mesh_density); c->mesh_density = nullptr; c->mesh_density_bytes = 0; CU(cudaMalloc(&c->mesh_density, n * 4)); c->mesh_density_bytes = n * 4; }
-	cudaEvent_t es[2];
+	EventPair es;
 	CU(cudaEventCreate(&es[0])); CU(cudaEventCreate(&es[1]));
 	CU(cudaEventRecord(es[0], (cudaStream_t)stream));
 	int rc = rnb_sdf_on_grid(c, res, aabb_min, aabb_max, c->mesh_density, use_ema, stream);
@@ -1226,7 +1229,6 @@ int rnb_marching_cubes(rnb_ctx* c, const uint32_t res_in[3], const float aabb_mi
 	c->launches += 2;
 	if (rc == RNB_OK) rc = rnb_marching_cubes_from_density(c, c->mesh_density, res, aabb_min, aabb_max, thresh, 1, use_ema, stream, info);
 	if (rc == RNB_OK) { cudaEventElapsedTime(&c->mesh.ms[0], es[0], es[1]); if (info) info->stage_ms[0] = c->mesh.ms[0]; }
-	cudaEventDestroy(es[0]); cudaEventDestroy(es[1]);
 	return rc;
 } RNB_API_CATCH
 

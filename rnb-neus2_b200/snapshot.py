@@ -61,8 +61,10 @@ def _pack_into(o, out):
             out.append(b"\xd3" + struct.pack(">q", o))
     elif isinstance(o, (float, np.floating)):
         o = float(o)
-        f32 = struct.unpack(">f", struct.pack(">f", o))[0] if abs(o) <= 3.4028234663852886e38 or o != o else None
-        if f32 is not None and (f32 == o or o != o):          # exactly a binary32: nlohmann writes the short form
+        # nlohmann::json::write_compact_float: the short form only for values inside the binary32 range that survive the round trip; NaN fails every
+        # comparison and infinity the range check, so both are written as binary64 (0xcb)
+        f32 = struct.unpack(">f", struct.pack(">f", o))[0] if abs(o) <= 3.4028234663852886e38 else None
+        if f32 is not None and f32 == o:
             out.append(b"\xca" + struct.pack(">f", o))
         else:
             out.append(b"\xcb" + struct.pack(">d", o))

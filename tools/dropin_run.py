@@ -178,9 +178,18 @@ def main():
     except Exception:      # noqa: BLE001
         pass
     meshes = {}
+    first_sd = None
     for name in ([] if a.skip_two_stage else names):
         sd = os.path.join(a.out, "scene_" + name)
-        ref_scene.write_scene(sd, views, workers=8)
+        if first_sd is None:
+            t0 = time.time(); ref_scene.write_scene(sd, views, workers=min(16, os.cpu_count() or 8)); rec["scene_write_s"] = round(time.time() - t0, 1); first_sd = sd
+        else:      # same images (symlinked), own transform.json and output/
+            os.makedirs(os.path.join(sd, "output"), exist_ok=True)
+            for sub in ("normals", "albedos"):
+                if not os.path.exists(os.path.join(sd, sub)):
+                    os.symlink(os.path.abspath(os.path.join(first_sd, sub)), os.path.join(sd, sub))
+            import shutil
+            shutil.copyfile(os.path.join(first_sd, "transform.json"), os.path.join(sd, "transform.json"))
         r = two_stage(name, sd, a.iters, a.res, a.albedo, a.timeout, rec)
         m = glob.glob(os.path.join(sd, "output", "mesh_*.obj"))
         if m:
