@@ -52,7 +52,6 @@ struct AdamParams {
 	uint32_t shard_begin, shard_end; const float* gsrc;      // data-parallel optimizer shard (rnb_optim.cu)
 	const __half* gsrc16;                                   // binary16 gradient exchange (rnb_optim.cu)
 	uint32_t first, last;                                   // parameter range of this launch
-	int lr_cache;
 };
 void launch_pack_grads(cudaStream_t, uint32_t, float*, __half*);
 void launch_adam_ema(cudaStream_t, const AdamParams&, float*, __half*, __half*, float*, float*, float*, uint32_t*);
@@ -756,7 +755,6 @@ static int optimizer_step(rnb_ctx* c, cudaStream_t st, const __half* gsrc16 = nu
 	if (gsrc16 && sh_end) { A.shard_begin = sh_begin; A.shard_end = std::min(sh_end, c->M.n_params); A.gsrc = nullptr; }      // sharded optimizer on the library's own communicator
 	A.gsrc16 = gsrc16;
 	A.first = 0; A.last = c->M.n_params;
-	{ static int lrc = -1; if (lrc < 0) { const char* e = getenv("RNB_ADAM_LRCACHE"); lrc = e ? (atoi(e) != 0) : 1; } A.lr_cache = lrc; }
 	if (c->xch_chunks > 1) {
 		// chunked exchange: the all-reduce of chunk k + 1 (communication stream) runs under Adam / EMA of chunk k (this stream)
 		NvtxRange nvtx_("adam_ema_pipelined"); prof_begin(c, st, "adam_ema");
@@ -975,12 +973,13 @@ static int exchange_gradients(rnb_ctx* c, cudaStream_t st) {
 }
 
 int rnb_train_step(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
+	// refused before anything is queued: a data-parallel step whose gradients nobody exchanges would silently train on 1 / world of the rays
+	if (c && c->cfg.world_size > 1 && !c->comm) return fail(RNB_ERR_STATE, "world_size > 1: call rnb_comm_init / rnb_comm_adopt first, or drive rnb_train_step_begin / _end with your own collective");
 	if (c) c->step_waits = stats != nullptr || !c->cfg.pin_rays_per_batch || !c->async_end;
 	int rc = rnb_train_step_begin(c, stream);
 	if (c) c->step_waits = true;
 	if (rc) return rc;
 	if (c->cfg.world_size > 1) {
-		if (!c->comm) { c->in_step = false; return fail(RNB_ERR_STATE, "world_size > 1: call rnb_comm_init / rnb_comm_adopt first, or drive rnb_train_step_begin / _end with your own collective"); }
 		rc = exchange_gradients(c, (cudaStream_t)stream); if (rc) { c->in_step = false; return rc; }
 	}
 	return rnb_train_step_end(c, stream, stats);
@@ -988,6 +987,7 @@ int rnb_train_step(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 
 int rnb_train(rnb_ctx* c, void* stream, rnb_step_stats* stats) try {
 	if (!c) return fail(RNB_ERR_INVALID, "null ctx");
+	if (c->cfg.world_size > 1 && !c->comm) return fail(RNB_ERR_STATE, "world_size > 1: call rnb_comm_init / rnb_comm_adopt first, or drive rnb_train_step_begin / _end with your own collective");
 	NvtxRange nvtx_("train");
 	const uint32_t skip = std::min(std::max(c->canonical_step / 16u, 1u), 16u);    // src/testbed.cu:2805-2806
 	uint32_t updated = 0;

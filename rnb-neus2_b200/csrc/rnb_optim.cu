@@ -24,7 +24,6 @@ struct AdamParams {
 	const __half* gsrc16;
 	// this launch covers parameters [first, last) only (chunked exchange: Adam on chunk k runs while chunk k + 1 is still being all-reduced); multiples of 4
 	uint32_t first, last;
-	int lr_cache;      // 1: the bias-corrected learning rate is computed once per run of equal step counts inside a quad (A/B knob RNB_ADAM_LRCACHE)
 };
 
 // One thread owns 4 consecutive parameters: every array is moved with one 128-bit (fp32 / u32) or 64-bit (binary16) access.
@@ -32,13 +31,14 @@ struct AdamParams {
 // nothing to write (the EMA update (ema*d*old + w*(1-d))*new is a fixed point at ema == w because d*old + 1 - d == 1/new).
 struct AdamLane { float w, m1, m2; uint32_t step; };
 
-// bias-corrected learning rate of a parameter that has taken `cs` steps (adam.h:189-190); the four parameters of a quad almost always share `cs`
-// (two hash entries touched together), so the caller caches it: ncu r02 showed the optimizer at 58 % issue utilisation, two exp2f + sqrt + divide per parameter
+// bias-corrected learning rate of a parameter that has taken `cs` steps (adam.h:189-190).  Computed per parameter: caching it across the four parameters of a
+// quad (they almost always share `cs`) was measured SLOWER (0.091 -> 0.104 ms: the compare-and-branch chain costs the instruction-level parallelism of four
+// independent evaluations; sessions r2j / r2k)
 __device__ __forceinline__ float adam_lr(const AdamParams& A, uint32_t cs) {
 	return A.base_lr * (sqrtf(1 - exp2f((float)cs * A.log2_beta2)) / (1 - exp2f((float)cs * A.log2_beta1)));
 }
 
-__device__ __forceinline__ bool adam_one(const AdamParams& A, uint32_t i, float g32, AdamLane& S, __half& wh, uint32_t& cs_cached, float& lr_cached) {
+__device__ __forceinline__ bool adam_one(const AdamParams& A, uint32_t i, float g32, AdamLane& S, __half& wh) {
 	float gradient = hq(g32) / A.loss_scale;
 	const bool is_mat = i < A.n_matrix;
 	bool update = is_mat || gradient != 0.f;
@@ -49,8 +49,7 @@ __device__ __forceinline__ bool adam_one(const AdamParams& A, uint32_t i, float 
 	const float fm = S.m1 = A.beta1 * S.m1 + (1 - A.beta1) * gradient;
 	const float sm = S.m2 = A.beta2 * S.m2 + (1 - A.beta2) * (gradient * gradient);
 	const uint32_t cs = ++S.step;
-	if (!A.lr_cache || cs != cs_cached) { lr_cached = adam_lr(A, cs); cs_cached = cs; }
-	const float lr = lr_cached;
+	const float lr = adam_lr(A, cs);
 	const float eff = fminf(fmaxf(lr / (sqrtf(sm) + A.eps), 0.f), 3.402823466e+38f);
 	const float nw = w - eff * fm;
 	S.w = nw;
@@ -123,9 +122,8 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 				AdamLane S[4] = {{w4[u].x, a4[u].x, b4[u].x, s4[u].x}, {w4[u].y, a4[u].y, b4[u].y, s4[u].y}, {w4[u].z, a4[u].z, b4[u].z, s4[u].z}, {w4[u].w, a4[u].w, b4[u].w, s4[u].w}};
 				const float gg[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
 				bool any = false;
-				uint32_t cs_c = 0; float lr_c = 0.f;
 				#pragma unroll
-				for (int q = 0; q < 4; ++q) any |= adam_one(A, i0 + q, gg[q], S[q], wh[q], cs_c, lr_c);
+				for (int q = 0; q < 4; ++q) any |= adam_one(A, i0 + q, gg[q], S[q], wh[q]);
 				if (any) {
 					*reinterpret_cast<float4*>(master + i0) = make_float4(S[0].w, S[1].w, S[2].w, S[3].w);
 					*reinterpret_cast<float4*>(m1 + i0) = make_float4(S[0].m1, S[1].m1, S[2].m1, S[3].m1);
@@ -143,8 +141,7 @@ __global__ void __launch_bounds__(256) k_adam_ema(AdamParams A, float* __restric
 				if (!A.gsrc16) grads[i] = 0.f;
 				__half wh = params[i];
 				AdamLane S{master[i], m1[i], m2[i], steps[i]};
-				uint32_t cs_c = 0; float lr_c = 0.f;
-				if (adam_one(A, i, g32, S, wh, cs_c, lr_c)) { master[i] = S.w; m1[i] = S.m1; m2[i] = S.m2; steps[i] = S.step; }
+				if (adam_one(A, i, g32, S, wh)) { master[i] = S.w; m1[i] = S.m1; m2[i] = S.m2; steps[i] = S.step; }
 				params[i] = wh;
 				ema[i] = __float2half_rn((__half2float(ema[i]) * A.ema_decay * A.ema_debias_old + __half2float(wh) * (1 - A.ema_decay)) * A.ema_debias_new);
 			}

@@ -41,3 +41,19 @@ def test_misuse_returns_status_and_message(pkg, tmp_path):
     info = t.marching_cubes_from_density(torch.full((16 * 16 * 16,), 1.0, device="cuda").data_ptr(), (16, 16, 16), with_colors=False)
     assert info["n_verts"] == 0 and info["n_indices"] == 0
     t.close()
+
+
+def test_data_parallel_context_without_communicator_fails_loudly(pkg, scene_mod):
+    """world_size > 1: rnb_train refuses to run a step whose gradients nobody would exchange (no silent single-rank training); the split entry points
+    (the caller's own collective) keep working, and the stale-EMA guard of the sharded optimizer is not armed without a communicator"""
+    views = scene_mod.make_scene(4, 64, 64, with_albedo=False)
+    t = pkg.Testbed(pkg.default_config(n_levels=8, log2_hashmap_size=14, sdf_n_neurons=32, rgb_n_neurons=32, rgb_n_hidden_layers=1, rays_per_batch=256, world_size=2, rank=0))
+    t.init_params(); t.load_training_data(views)
+    with pytest.raises(pkg.RnbError, match="rnb_comm_init"):
+        t.train()
+    assert t.comm_info() == dict(installed=False, nccl_version=t.comm_info()["nccl_version"], sharded=False, world_size=2)
+    t.training_prep_nerf()
+    t.train_step_begin()
+    st = t.train_step_end()                      # this rank's half of the rays, unreduced: the caller would have all-reduced rnb_grad_buffer in between
+    assert st.training_step == 1 and st.n_rays == 256 and st.n_rays_kept <= 128
+    t.export_params_fp16(use_ema=True)           # no communicator, no sharded optimizer: the inference parameters are readable

@@ -17,7 +17,7 @@ def test_default_kernels_use_tcgen05_and_vector_reductions(capsys):
     counts, pretty = sass_evidence.main()
     capsys.readouterr()
     by_name = {pretty[k]: v for k, v in counts.items()}
-    for name in ("tc::k_sdf_tc<64, 0>", "tc::k_full_tc<64, true>", "tc::k_backward_tc<64, true, 1>", "tc::k_sdf_tc<64, 2>", "tc::k_backward_tc<32, false, 1>", "tc::k_backward_tc<64, true, 2>"):
+    for name in ("tc::k_sdf_tc<64, 0, false>", "tc::k_full_tc<64, true>", "tc::k_backward_tc<64, true, 1>", "tc::k_sdf_tc<64, 2, false>", "tc::k_backward_tc<32, false, 1>", "tc::k_backward_tc<64, true, 2>"):
         c = by_name[name]
         assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["STTM"] > 0 and c["UTCBAR"] > 0, (name, dict(c))
         assert c["HMMA"] == 0, name
