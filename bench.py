@@ -398,7 +398,7 @@ def main():
         if k in flops:
             row["TFLOPs"] = round(flops[k] / (msk * 1e-3) / 1e12, 2); row["tensor_frac"] = round(flops[k] / (msk * 1e-3) / 1e12 / tf_peak, 5)
         stages[k] = row
-    comm_stages = ("grid_update", "grad_pack", "grad_exchange", "param_allgather")
+    comm_stages = ("grid_update", "grad_pack", "grad_exchange", "param_allgather", "prefix_exchange")
     dom = max((k for k in per_stage if k not in comm_stages), key=lambda k: per_stage[k])
     ach = alg.get(dom, 0.0) / (per_stage[dom] * 1e-3) / 1e9
     traffic, traffic_src = _traffic(dom)

@@ -200,9 +200,12 @@ int rnb_grad_buffer(rnb_ctx* ctx, float** grads_dev, uint64_t* n);
  *   rnb_comm_unique_id: ncclGetUniqueId on one rank; the caller's launcher carries the 128 bytes to the other ranks (file, socket, MPI, torchrun store)
  *   rnb_comm_init:      ncclCommInitRank(world_size, id, rank) on the current device, communicator owned by the context
  *   rnb_comm_adopt:     use a caller-owned ncclComm_t (its size and rank must equal rnb_config's)
- *   rnb_comm_info:      out = { communicator installed, NCCL version code, sharded optimizer, world_size }
- * Approximation kept from round 1: the 2^18-sample truncation and the roll-over multiplicity are applied per rank on target / world samples (the exact
- * global prefix over interleaved rays would need two more small collectives per step); with the adaptive controller the budget is met, not exceeded. */
+ *   rnb_comm_info:      out = { communicator installed, NCCL version code, bit 0: sharded optimizer | bit 1: one sample order, world_size }
+ * One sample order: with a communicator installed the ranks also exchange two per-ray prefix tables per step (ncclAllGather, 4 bytes per ray), so that the
+ * slot guard, the 2^18-sample truncation and the roll-over multiplicity are those of the batch ONE GPU would have built from the same rays: the data-parallel
+ * run reproduces the single-GPU run.  Environment RNB_DP_EXACT=0 (read by rnb_comm_init / rnb_comm_adopt), or driving
+ * rnb_train_step_begin / _end with an external collective and no communicator, applies those rules per rank against target / world instead (3-6 % faster, the
+ * trajectories drift apart by a few per cent; with the adaptive controller the budget is met, not exceeded). */
 #define RNB_COMM_ID_BYTES 128
 int rnb_comm_unique_id(uint8_t id_out[RNB_COMM_ID_BYTES]);
 int rnb_comm_init(rnb_ctx* ctx, const uint8_t id[RNB_COMM_ID_BYTES]);

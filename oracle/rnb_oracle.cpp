@@ -49,6 +49,11 @@ struct Oracle {
 	std::vector<float> last_loss, last_ek, last_mask;   // per kept ray, in ray_indices order
 	// data-parallel restatement: rank r of `world` marches rays i == r (mod world); sums[] are all-reduced with the gradients
 	uint32_t world = 1, rank = 0; bool in_step = false; uint32_t step_R = 0;
+	// dp_exact: the shards share ONE sample order — every clamp, truncation and roll-over multiplicity is taken at the sample's index in the
+	// GLOBAL batch (the order a single process would have produced), so that the sum of the shard gradients IS the single-process gradient.
+	// The restatement gets there by marching / compacting the whole batch on every rank and keeping loss + backward of its own rays only
+	// (the product exchanges two per-ray prefix tables instead).  false: every rank clamps / truncates / pads its own shard (target / world).
+	bool dp_exact = false;
 	size_t shard_begin = 0, shard_end = 0;      // data-parallel optimizer shard (end == 0: all parameters)
 	double sums[4] = {0, 0, 0, 0};   // loss, ek, mask, compacted samples
 	uint32_t cnt_kept = 0, cnt_samples = 0, cnt_total = 0, cnt_trained = 0;
@@ -158,6 +163,7 @@ void orc_set_train_state(Oracle* o, uint32_t training_step, uint32_t rays_per_ba
 // the two members Testbed::load_snapshot does not restore (src/testbed.cu:3333-3390)
 void orc_set_canonical_state(Oracle* o, uint32_t canonical_step, uint32_t n_images_prev) { o->canonical_step = canonical_step; o->n_images_prev = n_images_prev; }
 void orc_set_world(Oracle* o, uint32_t world, uint32_t rank) { o->world = world ? world : 1; o->rank = rank; }
+void orc_set_dp_exact(Oracle* o, int on) { o->dp_exact = on != 0; }
 // data-parallel restatement of the sharded optimizer: Adam/EMA on [begin, end) only; the binary16 training weights of the other
 // shards are installed by the caller from the all-gather (orc_set_half_params)
 void orc_set_opt_shard(Oracle* o, uint64_t begin, uint64_t end) { o->shard_begin = (size_t)begin; o->shard_end = (size_t)end; }
@@ -179,7 +185,7 @@ void orc_generate_samples(Oracle* o, uint32_t n_rays, uint32_t n_rays_total, uin
 	std::vector<RayGen> rg(n_rays);
 	parallel_for(o->threads, n_rays, [&](int, size_t b, size_t e) {
 		for (size_t i = b; i < e; ++i) {
-			if (i % o->world != o->rank) { rg[i].valid = false; continue; }      // ray shard of this rank
+			if (!o->dp_exact && i % o->world != o->rank) { rg[i].valid = false; continue; }      // ray shard of this rank
 			ray_setup((uint32_t)i, n_rays, n_rays_total, o->rng, o->views.data(), (uint32_t)o->views.size(), o->bitfield.data(), rg[i]);
 		}
 	});
@@ -272,6 +278,7 @@ void orc_loss(Oracle* o, const float* out_c, const uint32_t* ray_indices, const 
 		for (size_t k = b; k < e; ++k) {
 			loss[k] = ek_loss[k] = mask_loss[k] = 0.f;
 			if (n_emit[k] == 0) continue;
+			if (o->dp_exact && ray_indices[k] % o->world != o->rank) continue;      // another rank's ray: its dL/d(out) stays zero here
 			RayTarget T; ray_target(ray_indices[k], n_rays, n_rays_total, o->rng, o->views.data(), (uint32_t)o->views.size(), o->flags, step, T);
 			RayLoss RL;
 			ray_loss(out_c + (size_t)cbase[k] * 16, n_fwd[k], n_emit[k], T, o->flags, dt, n_rays, o->loss_scale, dout + (size_t)cbase[k] * 16, RL);
@@ -288,12 +295,13 @@ float orc_rollover_weight(uint32_t s, uint32_t n_in, uint32_t n_batch) {
 }
 
 // Stage: network forward + backward (first and second order) on n compacted samples; accumulates into o->grads (overwrites).
-static void network_backward_impl(Oracle* o, const float* coords, const float* dout, uint64_t n, uint32_t n_in_for_rollover, uint32_t n_roll, uint32_t n_batch, uint32_t valid_level);
+static void network_backward_impl(Oracle* o, const float* coords, const float* dout, uint64_t n, uint32_t n_in_for_rollover, uint32_t n_roll, uint32_t n_batch, uint32_t valid_level, const uint8_t* foreign = nullptr);
 void orc_network_backward(Oracle* o, const float* coords, const float* dout, uint64_t n, uint32_t n_in_for_rollover, uint32_t n_batch, uint32_t valid_level) {
 	network_backward_impl(o, coords, dout, n, n_in_for_rollover, n_batch, n_batch, valid_level);
 }
 // n_roll: size the compacted batch is padded to by roll-over (per rank: target / world); n_batch: global Eikonal divisor
-static void network_backward_impl(Oracle* o, const float* coords, const float* dout, uint64_t n, uint32_t n_in_for_rollover, uint32_t n_roll, uint32_t n_batch, uint32_t valid_level) {
+// foreign (dp_exact): samples of other ranks' rays — they hold their place in the global order (roll-over index) and are skipped
+static void network_backward_impl(Oracle* o, const float* coords, const float* dout, uint64_t n, uint32_t n_in_for_rollover, uint32_t n_roll, uint32_t n_batch, uint32_t valid_level, const uint8_t* foreign) {
 	const size_t n_mlp = o->m.off_grid;
 	std::fill(o->grads.begin(), o->grads.end(), 0.f);
 	const int T = o->threads;
@@ -305,6 +313,7 @@ static void network_backward_impl(Oracle* o, const float* coords, const float* d
 		float* Gm = T > 1 ? mlp_g[t].data() : G;     // MLP gradients: thread-private, folded below; hash gradients: shared + atomic
 		float gvar = 0.f;
 		for (size_t i = b; i < e; ++i) {
+			if (foreign && foreign[i]) continue;
 			net.forward(coords + i * 7, c, true);
 			float w = orc_rollover_weight((uint32_t)i, n_in_for_rollover, n_roll);
 			net.backward(c, dout + i * 16, w, n_batch, Gm, G, &gvar, T > 1);
@@ -431,7 +440,8 @@ void orc_train_step_begin(Oracle* o) {
 	const uint32_t vl = valid_level_for_step(o->m, (int)o->training_step);
 	const uint32_t R = o->rays_per_batch;
 	const uint32_t max_samples = o->target_batch * 16;
-	const uint32_t local_target = o->target_batch / o->world;
+	const bool exact = o->dp_exact && o->world > 1;
+	const uint32_t local_target = exact ? o->target_batch : o->target_batch / o->world;
 	uint32_t max_inference;
 	if (o->measured_before == 0) { o->measured_before = max_inference = max_samples; }
 	else max_inference = next_multiple(std::min(o->measured_before, max_samples), 128u);
@@ -456,10 +466,19 @@ void orc_train_step_begin(Oracle* o) {
 	orc_loss(o, oc.data(), o->ray_indices.data(), n_fwd.data(), cbase.data(), n_emit.data(), K, R, nrt, o->training_step, dout.data(), loss.data(), ek.data(), ml.data());
 	o->last_loss = loss; o->last_ek = ek; o->last_mask = ml; o->ray_indices.resize(K);
 	const uint32_t n_in = std::min(total, local_target);
-	network_backward_impl(o, cc.data(), dout.data(), n_in, n_in, local_target, o->target_batch, vl);
+	std::vector<uint8_t> foreign;
+	uint32_t total_own = total;
+	if (exact) {
+		foreign.assign(total, 0); total_own = 0;
+		for (uint32_t k = 0; k < K; ++k) {
+			if (o->ray_indices[k] % o->world == o->rank) total_own += n_fwd[k];
+			else std::fill(foreign.begin() + cbase[k], foreign.begin() + cbase[k] + n_fwd[k], (uint8_t)1);
+		}
+	}
+	network_backward_impl(o, cc.data(), dout.data(), n_in, n_in, local_target, o->target_batch, vl, exact ? foreign.data() : nullptr);
 	o->rng.advance();
 	double sl = 0, se = 0, sm = 0; for (uint32_t k = 0; k < K; ++k) { sl += loss[k]; se += ek[k]; sm += ml[k]; }
-	o->sums[0] = sl; o->sums[1] = se; o->sums[2] = sm; o->sums[3] = (double)total;
+	o->sums[0] = sl; o->sums[1] = se; o->sums[2] = sm; o->sums[3] = (double)total_own;      // all-reduced: the global compacted count either way
 	o->cnt_kept = K; o->cnt_samples = counters[1]; o->cnt_total = total; o->cnt_trained = n_in; o->step_R = R;
 	o->in_step = true;
 }

@@ -368,7 +368,7 @@ class Testbed:
 
     def comm_info(self):
         o = (C.c_uint32 * 4)(); self._chk(self.L.rnb_comm_info(self.h, o))
-        return dict(installed=bool(o[0]), nccl_version=int(o[1]), sharded=bool(o[2]), world_size=int(o[3]))
+        return dict(installed=bool(o[0]), nccl_version=int(o[1]), sharded=bool(o[2] & 1), one_sample_order=bool(o[2] & 2), world_size=int(o[3]))
 
     def grad_buffer(self):
         p = C.POINTER(C.c_float)(); n = C.c_uint64()

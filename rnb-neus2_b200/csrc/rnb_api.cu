@@ -21,7 +21,8 @@
 namespace rnb {
 // rnb_march.cu
 void launch_march(cudaStream_t, uint32_t, uint32_t, uint32_t, uint32_t, Pcg32, const ViewDev*, uint32_t, const uint8_t*, uint32_t*, float*, float*, uint32_t = 0);
-void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t = 1, uint32_t = 0);
+void launch_scan_rays(cudaStream_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t = 1, uint32_t = 0, const uint32_t* = nullptr, uint32_t* = nullptr);
+void launch_prefix_positions(cudaStream_t, uint32_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint32_t*);
 void launch_emit(cudaStream_t, uint32_t, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, const float*, const float*, float4*, float* = nullptr);
 // rnb_network_simt.cu
 void launch_forward_simt(cudaStream_t, const ModelDev&, const __half*, uint32_t, int, const float4*, const uint32_t*, uint32_t, const float*, __half*, float*, float*, float*);
@@ -35,13 +36,13 @@ bool tc_supported(const ModelDev&);
 void set_bw_debug(int);
 void set_bw_scatter_groups(int);
 void launch_tc_sdf_grid(cudaStream_t, const ModelDev&, const __half*, const uint8_t*, uint32_t, const uint32_t[3], const float[3], const float[3], float*, int);
-void launch_tc_backward(cudaStream_t, const ModelDev&, const __half*, const uint8_t*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, float*, int);
+void launch_tc_backward(cudaStream_t, const ModelDev&, const __half*, const uint8_t*, uint32_t, const float4*, const __half*, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, float*, int, const uint32_t* = nullptr);
 size_t tc_blob_bytes(const ModelDev&);
 void launch_tc(int, cudaStream_t, const ModelDev&, const __half*, uint8_t*, uint32_t, const float4*, const uint32_t*, uint32_t, __half*, float*, float*, int, const float* = nullptr);
 // rnb_loss.cu
 void launch_ray_dirw(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const float*, float*);
 void launch_compact_count(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const __half*, const float*, const __half*, uint32_t, float, uint32_t*);
-void launch_scan_compact(cudaStream_t, uint32_t*, uint32_t, const uint32_t*, uint32_t*, uint32_t*, float*);
+void launch_scan_compact(cudaStream_t, uint32_t*, uint32_t, const uint32_t*, uint32_t*, uint32_t*, float*, const uint32_t* = nullptr, uint32_t = 0, uint32_t = 1, uint32_t = 0, const uint32_t* = nullptr, uint32_t* = nullptr);
 void launch_gather_compacted(cudaStream_t, uint32_t, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const float4*, float4*);
 void launch_loss(cudaStream_t, uint32_t, const rnb_flags&, uint32_t, uint32_t, uint32_t, float, const uint32_t*, Pcg32, const ViewDev*, uint32_t, const uint32_t*, const float*,
                  const uint32_t*, const uint32_t*, const uint32_t*, const __half*, __half*, float*, float*);
@@ -140,6 +141,9 @@ struct rnb_ctx {
 	cudaEvent_t ev_counters = nullptr; bool counters_pending = false; bool async_end = true;      // RNB_ASYNC_END=0: wait for every step even without stats (A/B)  // asynchronous read-back of the step counters (rnb_train_step_end without stats)
 	// data parallelism behind the boundary (rnb_comm_*): one NCCL communicator per context, binary16 gradient exchange buffer
 	ncclComm_t comm = nullptr; bool comm_owned = false; __half* grads16 = nullptr; int dp_sharded = 0;
+	// one sample order over all ranks (dp_exact; RNB_DP_EXACT=0 selects per-rank clamp / truncation / roll-over): per step two all-gathers of a per-ray-position
+	// prefix table (marched samples before scan/emit, compacted samples before the truncation) give every ray its place in the batch a single GPU would have built
+	bool dp_exact = false; uint32_t *dp_xg = nullptr, *slot_of_pos = nullptr, *goff = nullptr;
 	bool ema_stale = false;      // sharded optimizer: the EMA copy of the other ranks' shards is out of date until rnb_comm_sync_ema
 	const __half* xch16 = nullptr; uint32_t xch_begin = 0, xch_end = 0;      // result of this step's gradient exchange, consumed by rnb_train_step_end
 	// chunked all-reduce on a communication stream, pipelined with Adam / EMA on the caller's stream (RNB_DP_CHUNKS; default 1 = one all-reduce on the caller's stream: at N = 2 four chunks cost 0.898 ms per step against 0.835, profiles/r02_dp_n2.txt)
@@ -212,7 +216,8 @@ static void drop_prelaunch(rnb_ctx* c) { if (c->pre_valid) { cudaStreamSynchroni
 
 // host mirror of the step counters.  update_after_training's rule (:3540-3545): both measured sizes are zeroed by a step without samples
 static void apply_counters(rnb_ctx* c) {
-	const uint32_t before = c->counters_host[1], total = c->counters_host[2];
+	// counters[5] is the device's copy of the rule (k_scan_compact): marched samples of the step — of all ranks when they share one sample order — or 0
+	const uint32_t before = c->counters_host[5], total = c->counters_host[2];
 	if (before == 0 || total == 0) { c->measured_before = 0; c->measured = 0; } else { c->measured_before = before; c->measured = total; }
 }
 // rnb_train_step_end without stats leaves the read-back of the counters in flight: whoever needs the host copy waits for it here
@@ -241,6 +246,10 @@ static int ensure_ray_capacity(rnb_ctx* c, uint32_t R) {
 	uint32_t cap = std::min(std::max(R + R / 2, 4096u), 1u << 18);
 	cudaFree(c->ray_n); cudaFree(c->ray_indices); cudaFree(c->numsteps); cudaFree(c->n_fwd); cudaFree(c->cbase); cudaFree(c->n_emit);
 	cudaFree(c->ray_geom); cudaFree(c->ts); cudaFree(c->ray_dirw); cudaFree(c->loss_out);
+	cudaFree(c->dp_xg); cudaFree(c->slot_of_pos); cudaFree(c->goff); c->dp_xg = c->slot_of_pos = c->goff = nullptr;
+	if (c->cfg.world_size > 1) {      // two tables of world x ceil(R / world) prefixes, the slot of every ray position, the global offset of every kept ray
+		CU(cudaMalloc(&c->dp_xg, (size_t)2 * (cap + c->cfg.world_size) * 4)); CU(cudaMalloc(&c->slot_of_pos, cap * 4)); CU(cudaMalloc(&c->goff, cap * 4));
+	}
 	CU(cudaMalloc(&c->ray_n, cap * 4)); CU(cudaMalloc(&c->ray_indices, cap * 4)); CU(cudaMalloc(&c->numsteps, cap * 8));
 	CU(cudaMalloc(&c->n_fwd, cap * 4)); CU(cudaMalloc(&c->cbase, cap * 4)); CU(cudaMalloc(&c->n_emit, cap * 4));
 	CU(cudaMalloc(&c->ray_geom, (size_t)cap * 9 * 4));
@@ -405,7 +414,7 @@ int rnb_destroy(rnb_ctx* c) try {
 	if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
 	if (c->ev_march) cudaEventDestroy(c->ev_march);
 	if (c->ev_counters) cudaEventDestroy(c->ev_counters);
-	cudaFree(c->grads16);
+	cudaFree(c->grads16); cudaFree(c->dp_xg); cudaFree(c->slot_of_pos); cudaFree(c->goff);
 	if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
 	if (c->ev_pack) cudaEventDestroy(c->ev_pack);
 	for (cudaEvent_t e : c->ev_chunk) if (e) cudaEventDestroy(e);
@@ -697,8 +706,8 @@ static void net_pass_b(rnb_ctx* c, cudaStream_t st, const __half* P, uint32_t vl
 	else if (c->use_mma) launch_mma(2, st, c->M, P, c->wpack, vl, pos, n_ptr, n_max, dirw, c->out16, nullptr, 0, 0, nullptr, nullptr, c->n_sm);
 	else launch_forward_simt(st, c->M, P, vl, 1, pos, n_ptr, n_max, dirw, c->out16, nullptr, nullptr, nullptr);
 }
-static void net_backward(rnb_ctx* c, cudaStream_t st, uint32_t vl, const uint32_t* n_ptr, uint32_t n_max, uint32_t n_roll, const uint32_t* n_in_ptr) {
-	if (c->use_tc_bwd) launch_tc_backward(st, c->M, c->params, c->wtc, vl, c->cpos4, c->dout16, n_ptr, n_max, n_roll, c->cfg.target_batch_size, n_in_ptr, c->grads, c->n_sm);
+static void net_backward(rnb_ctx* c, cudaStream_t st, uint32_t vl, const uint32_t* n_ptr, uint32_t n_max, uint32_t n_roll, const uint32_t* n_in_ptr, const uint32_t* goff = nullptr) {
+	if (c->use_tc_bwd) launch_tc_backward(st, c->M, c->params, c->wtc, vl, c->cpos4, c->dout16, n_ptr, n_max, n_roll, c->cfg.target_batch_size, n_in_ptr, c->grads, c->n_sm, goff);
 	else if (c->use_mma) launch_mma(3, st, c->M, c->params, c->wpack, vl, c->cpos4, n_ptr, n_max, nullptr, nullptr, c->dout16, n_roll, c->cfg.target_batch_size, n_in_ptr, c->grads, c->n_sm);
 	else launch_backward_simt(st, c->M, c->params, vl, c->cpos4, c->dout16, n_ptr, n_max, n_roll, c->cfg.target_batch_size, n_in_ptr, nullptr, c->grads, c->bw_scratch, c->bw_front);
 }
@@ -710,7 +719,14 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt) {
 	const uint32_t max_inference = c->max_samples;      // capacity; the clamp to last step's sample count happens on the device (k_scan_rays, counters[5] -> counters[6])
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
 	const ModelDev& M = c->M;
-	const uint32_t G = c->cfg.world_size, local_target = c->cfg.target_batch_size / G;
+	const uint32_t G = c->cfg.world_size;
+	// data parallel: either every rank clamps / truncates / pads its own shard against target / world, or (exact: library communicator + tcgen05 backward) all
+	// ranks share the sample order of the single-GPU batch
+	const bool exact = c->dp_exact && G > 1 && c->comm && c->use_tc_bwd;
+	const uint32_t local_target = exact ? c->cfg.target_batch_size : c->cfg.target_batch_size / G;
+	const uint32_t L = (R + G - 1) / G;
+	uint32_t* xg_march = exact ? c->dp_xg : nullptr; uint32_t* xg_comp = exact ? c->dp_xg + (size_t)G * L : nullptr;
+	NcclApi* N = exact ? nccl_api() : nullptr;
 	if (c->pre_valid && c->pre_R == R && c->pre_nrt == nrt && c->pre_rng_state == c->rng.state && c->pre_rng_inc == c->rng.inc) {
 		CU(cudaStreamWaitEvent(st, c->ev_march, 0));            // this step's march already ran in the shadow of the previous optimizer step
 		c->pre_valid = false;
@@ -718,7 +734,13 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt) {
 		drop_prelaunch(c);
 		KT("march", 1, launch_march(st, R, G, c->cfg.rank, nrt, c->rng, c->views_dev, c->n_views, c->bitfield, c->ray_n, c->ray_geom, c->ts));
 	}
-	KT("scan_emit", 2, (launch_scan_rays(st, R, max_inference, c->counters + 5, c->ray_n, c->ray_indices, c->numsteps, c->counters, G, c->cfg.rank),
+	if (exact) {
+		int nrc = 0;
+		KT("prefix_exchange", 2, (launch_prefix_positions(st, R, G, c->cfg.rank, c->ray_n, nullptr, xg_march + (size_t)c->cfg.rank * L),
+		                         nrc = (int)N->AllGather(xg_march + (size_t)c->cfg.rank * L, xg_march, L, ncclUint32, c->comm, st)));
+		if (nrc) return fail(RNB_ERR_CUDA, std::string("ncclAllGather: ") + N->GetErrorString((ncclResult_t)nrc));
+	}
+	KT("scan_emit", 2, (launch_scan_rays(st, R, max_inference, c->counters + 5, c->ray_n, c->ray_indices, c->numsteps, c->counters, G, c->cfg.rank, xg_march, exact ? c->slot_of_pos : nullptr),
 	                   launch_emit(st, (R + G - 1) / G, c->counters, G, c->ray_indices, c->numsteps, c->ray_geom, c->ts, c->pos4, c->ray_dirw)));
 	if (c->pre_armed && c->pre_at == 3) CU(cudaEventRecord(c->ev_bwd, st));      // ray_n / ray_geom / ts have been consumed: the next march may overwrite them
 	// weight blobs for this step's kernels: the mma.sync panel copy only when one of its kernels runs in the step (cross-check paths)
@@ -726,6 +748,15 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt) {
 	KT("pass_a_sdf_normal", all_tc ? 2 : 3, ((all_tc ? (void)launch_tc(0, st, c->M, c->params, c->wtc, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, c->n_sm) : net_pack(c, st, c->params)),
 	                                         net_pass_a(c, st, vl, c->pos4, c->counters + 6, max_inference)));
 	if (c->pre_armed && c->pre_at == 2) CU(cudaEventRecord(c->ev_bwd, st));
+	if (exact) {
+		int nrc = 0;
+		KT("compact_count", 1, launch_compact_count(st, L, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd));
+		KT("prefix_exchange", 2, (launch_prefix_positions(st, R, G, c->cfg.rank, c->n_fwd, c->slot_of_pos, xg_comp + (size_t)c->cfg.rank * L),
+		                         nrc = (int)N->AllGather(xg_comp + (size_t)c->cfg.rank * L, xg_comp, L, ncclUint32, c->comm, st)));
+		if (nrc) return fail(RNB_ERR_CUDA, std::string("ncclAllGather: ") + N->GetErrorString((ncclResult_t)nrc));
+		KT("compact", 2, (launch_scan_compact(st, c->counters, local_target, c->n_fwd, c->cbase, c->n_emit, c->stats, xg_comp, L, G, c->cfg.rank, c->ray_indices, c->goff),
+		                 launch_gather_compacted(st, L, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4)));
+	} else
 	KT("compact", 3, (launch_compact_count(st, (R + G - 1) / G, c->counters, c->numsteps, c->outA, c->ray_dirw, c->params, M.off_var, c->flags.cos_anneal_ratio, c->n_fwd),
 	                 launch_scan_compact(st, c->counters, local_target, c->n_fwd, c->cbase, c->n_emit, c->stats),
 	                 launch_gather_compacted(st, (R + G - 1) / G, c->counters, c->numsteps, c->n_fwd, c->cbase, c->n_emit, c->pos4, c->cpos4)));
@@ -735,7 +766,8 @@ static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt) {
 	KT("loss", want_sums ? 2 : 1, launch_loss(st, (R + G - 1) / G, c->flags, R, nrt, c->training_step, c->cfg.loss_scale, c->counters, c->rng, c->views_dev, c->n_views, c->ray_indices, c->ray_dirw, c->n_fwd, c->cbase, c->n_emit,
 	            c->out16, c->dout16, c->loss_out, want_sums ? c->stats : nullptr));
 	if (c->pre_armed && c->pre_at == 1) CU(cudaEventRecord(c->ev_bwd, st));
-	KT("backward", c->use_mma ? 1 : 9, net_backward(c, st, vl, c->counters + 3, local_target, local_target, c->counters + 3));
+	if (exact) KT("backward", 1, net_backward(c, st, vl, c->counters + 3, c->cap_compact, local_target, c->counters + 8, c->goff));
+	else KT("backward", c->use_mma ? 1 : 9, net_backward(c, st, vl, c->counters + 3, local_target, local_target, c->counters + 3));
 	CU(cudaGetLastError());
 	return RNB_OK;
 }
@@ -878,6 +910,7 @@ static int comm_buffers(rnb_ctx* c) {
 	// step at N = 2 and 0.857 vs 0.929 ms at N = 8 against the single all-reduce (profiles/r02_dp_n2.txt, r02_dp_n8.txt).  RNB_DP=allreduce selects the latter.
 	const char* e = getenv("RNB_DP");
 	c->dp_sharded = (!(e && std::string(e) == "allreduce") && c->np_padded % ((size_t)c->cfg.world_size * 8) == 0) ? 1 : 0;
+	{ const char* x = getenv("RNB_DP_EXACT"); c->dp_exact = !(x && atoi(x) == 0); }
 	if (const char* d = getenv("RNB_DP_CHUNKS")) c->dp_chunks = (uint32_t)std::min<int>(std::max(atoi(d), 1), (int)rnb_ctx::MAX_CHUNKS);
 	if (!c->comm_stream) {
 		int prio_lo = 0, prio_hi = 0; CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -927,7 +960,7 @@ int rnb_comm_sync_ema(rnb_ctx* c, void* stream) try {
 int rnb_comm_info(rnb_ctx* c, uint32_t out[4]) try {
 	if (!c || !out) return fail(RNB_ERR_INVALID, "null argument");
 	NcclApi* N = nccl_api(); int v = 0; if (N) N->GetVersion(&v);
-	out[0] = c->comm ? 1u : 0u; out[1] = (uint32_t)v; out[2] = (uint32_t)c->dp_sharded; out[3] = c->cfg.world_size;
+	out[0] = c->comm ? 1u : 0u; out[1] = (uint32_t)v; out[2] = (uint32_t)c->dp_sharded | ((c->comm && c->dp_exact && c->use_tc_bwd) ? 2u : 0u); out[3] = c->cfg.world_size;
 	return RNB_OK;
 } RNB_API_CATCH
 

@@ -139,6 +139,20 @@ __host__ __device__ inline uint32_t hashed_light(uint32_t ray_idx, uint32_t step
 	return h % 3u;
 }
 
+// Data parallel with ONE sample order (rnb_api.cu, dp_exact): xg is the all-gathered table of every rank's inclusive per-position prefix
+// (k_prefix_positions; position m of rank q = global ray m * world + q, L positions per rank).  The samples in front of global ray (m, rank) are
+// those of positions <= m on the ranks before this one and of positions < m on the ranks behind it, plus this rank's own exclusive prefix.
+__device__ __forceinline__ uint32_t foreign_prefix(const uint32_t* __restrict__ xg, uint32_t L, uint32_t world, uint32_t rank, uint32_t m) {
+	uint32_t s = 0;
+	for (uint32_t q = 0; q < rank; ++q) s += xg[q * L + m];
+	if (m) for (uint32_t q = rank + 1; q < world; ++q) s += xg[q * L + m - 1];
+	return s;
+}
+__device__ __forceinline__ uint32_t global_total(const uint32_t* __restrict__ xg, uint32_t L, uint32_t world) {
+	uint32_t s = 0;
+	for (uint32_t q = 0; q < world; ++q) s += xg[q * L + L - 1];
+	return s;
+}
 __host__ __device__ inline float rollover_weight(uint32_t s, uint32_t n_in, uint32_t n_batch) {
 	if (n_in == 0 || n_in >= n_batch) return 1.0f;
 	uint32_t c = (n_batch - 1 - s) / n_in;

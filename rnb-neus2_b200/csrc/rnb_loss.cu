@@ -65,14 +65,17 @@ __global__ void __launch_bounds__(256) k_compact_count(const uint32_t* __restric
 
 // Ordered scan over kept rays: compacted base (untruncated prefix), emitted count (truncated at max_compacted, :1722-1728),
 // totals.  counters: [2] = compacted total (untruncated), [3] = trained samples min(total, max), [4] = samples to forward.
-// ext_base (optional, data-parallel): global compacted index of each kept ray's first sample.
+// Data parallel with one sample order (xg != nullptr; foreign_prefix, rnb_common.cuh): max_compacted is the GLOBAL target and every ray is cut where the
+// single-process batch would cut it; goff[k] = (index of the ray's first sample in the global batch) - cbase[k] for the roll-over multiplicities;
+// counters[3] = this rank's samples inside the target, counters[8] = min(samples of all ranks, target), counters[9] = marched samples of all ranks.
 __global__ void __launch_bounds__(1024) k_scan_compact(uint32_t* __restrict__ counters, uint32_t max_compacted, const uint32_t* __restrict__ n_fwd,
-                                                       uint32_t* __restrict__ cbase, uint32_t* __restrict__ n_emit, float* __restrict__ stats) {
+                                                       uint32_t* __restrict__ cbase, uint32_t* __restrict__ n_emit, float* __restrict__ stats,
+                                                       const uint32_t* __restrict__ xg, uint32_t L, uint32_t world, uint32_t rank, const uint32_t* __restrict__ ray_indices, uint32_t* __restrict__ goff) {
 	__shared__ uint32_t s_a[32];
-	__shared__ uint32_t carry, fwd_end;
+	__shared__ uint32_t carry, fwd_end, trained;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const uint32_t K = counters[0];
-	if (tid == 0) { carry = 0; fwd_end = 0; }
+	if (tid == 0) { carry = 0; fwd_end = 0; trained = 0; }
 	__syncthreads();
 	for (uint32_t c0 = 0; c0 < K; c0 += 1024) {
 		const uint32_t k = c0 + tid;
@@ -88,17 +91,21 @@ __global__ void __launch_bounds__(1024) k_scan_compact(uint32_t* __restrict__ co
 		const uint32_t base = incl - n;
 		if (k < K) {
 			cbase[k] = base;
-			const uint32_t e = min(max_compacted - min(max_compacted, base), n);
+			uint32_t gbase = base;
+			if (xg) { const uint32_t f = foreign_prefix(xg, L, world, rank, ray_indices[k] / world); gbase += f; goff[k] = f; }
+			const uint32_t e = min(max_compacted - min(max_compacted, gbase), n);
 			n_emit[k] = e;
-			if (e > 0) atomicMax(&fwd_end, incl);
+			if (e > 0) { atomicMax(&fwd_end, incl); if (xg) atomicAdd(&trained, e); }
 		}
 		__syncthreads();
 		if (tid == 1023) carry = incl;
 		__syncthreads();
 	}
 	if (tid == 0) {
-		counters[2] = carry; counters[3] = min(carry, max_compacted); counters[4] = fwd_end;
-		counters[5] = (carry == 0u || counters[1] == 0u) ? 0u : counters[1];      // measured_batch_size_before_compaction for the next step's clamp (Counters::update_after_training :3540-3545)
+		const uint32_t total_all = xg ? global_total(xg, L, world) : carry, marched_all = xg ? counters[9] : counters[1];
+		counters[2] = carry; counters[3] = xg ? trained : min(carry, max_compacted); counters[4] = fwd_end;
+		counters[5] = (total_all == 0u || marched_all == 0u) ? 0u : marched_all;      // measured_batch_size_before_compaction for the next step's clamp (Counters::update_after_training :3540-3545)
+		counters[8] = min(total_all, max_compacted);
 		if (stats) { stats[3] = (float)carry; stats[4] = (float)counters[1]; stats[5] = (float)K; }   // float copies: summed across ranks with the losses
 	}
 }
@@ -365,8 +372,9 @@ void launch_ray_dirw(cudaStream_t st, uint32_t n_upper, const uint32_t* counters
 void launch_compact_count(cudaStream_t st, uint32_t n_upper, const uint32_t* counters, const uint32_t* numsteps, const __half* outA, const float* ray_dirw, const __half* P, uint32_t off_var, float car, uint32_t* n_fwd) {
 	if (n_upper) k_compact_count<<<(n_upper * 32 + 255) / 256, 256, 0, st>>>(counters, numsteps, outA, ray_dirw, P, off_var, car, n_fwd);
 }
-void launch_scan_compact(cudaStream_t st, uint32_t* counters, uint32_t max_compacted, const uint32_t* n_fwd, uint32_t* cbase, uint32_t* n_emit, float* stats) {
-	k_scan_compact<<<1, 1024, 0, st>>>(counters, max_compacted, n_fwd, cbase, n_emit, stats);
+void launch_scan_compact(cudaStream_t st, uint32_t* counters, uint32_t max_compacted, const uint32_t* n_fwd, uint32_t* cbase, uint32_t* n_emit, float* stats,
+                         const uint32_t* xg, uint32_t L, uint32_t world, uint32_t rank, const uint32_t* ray_indices, uint32_t* goff) {
+	k_scan_compact<<<1, 1024, 0, st>>>(counters, max_compacted, n_fwd, cbase, n_emit, stats, xg, L, world ? world : 1u, rank, ray_indices, goff);
 }
 void launch_gather_compacted(cudaStream_t st, uint32_t n_upper, const uint32_t* counters, const uint32_t* numsteps, const uint32_t* n_fwd, const uint32_t* cbase, const uint32_t* n_emit, const float4* pos4, float4* cpos4) {
 	if (n_upper) k_gather_compacted<<<(n_upper * 32 + 255) / 256, 256, 0, st>>>(counters, numsteps, n_fwd, cbase, n_emit, pos4, cpos4);

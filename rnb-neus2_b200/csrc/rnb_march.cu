@@ -154,9 +154,39 @@ __global__ void __launch_bounds__(256) k_march(uint32_t n_rays, uint32_t world, 
 // (max_inference, testbed_nerf.cu:3891-3896): 0 -> the whole buffer, else next_multiple(min(prev, capacity), 128).  Keeping the clamp on the device
 // means no step ever needs last step's counters on the host.
 // Data parallel: only rays i = rank (mod world) were marched by this rank; the scan walks those (in ray order), not the global ray array.
+// out[m] = inclusive prefix over this rank's ray positions of val: val[ray] (slot_of_pos == nullptr) or val[slot_of_pos[m]] (0 for dropped rays)
+__global__ void __launch_bounds__(1024) k_prefix_positions(uint32_t n_rays, uint32_t world, uint32_t rank, uint32_t L, const uint32_t* __restrict__ val,
+                                                           const uint32_t* __restrict__ slot_of_pos, uint32_t* __restrict__ out) {
+	__shared__ uint32_t s_a[32];
+	__shared__ uint32_t carry;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) carry = 0;
+	__syncthreads();
+	for (uint32_t c0 = 0; c0 < L; c0 += 1024) {
+		const uint32_t m = c0 + tid, i = m * world + rank;
+		uint32_t n = 0;
+		if (m < L && i < n_rays) {
+			if (slot_of_pos) { const uint32_t k = slot_of_pos[m]; n = k != 0xFFFFFFFFu ? val[k] : 0u; }
+			else n = val[i];
+		}
+		uint32_t a = n;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, a, o); if ((int)lane >= o) a += v; }
+		if (lane == 31) s_a[wid] = a;
+		__syncthreads();
+		if (wid == 0) { uint32_t v = s_a[lane]; for (int o = 1; o < 32; o <<= 1) { uint32_t w = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += w; } s_a[lane] = v; }
+		__syncthreads();
+		const uint32_t incl = a + (wid ? s_a[wid - 1] : 0) + carry;
+		if (m < L) out[m] = incl;
+		__syncthreads();
+		if (tid == 1023) carry = incl;
+		__syncthreads();
+	}
+}
+
 __global__ void __launch_bounds__(1024) k_scan_rays(uint32_t n_rays, uint32_t max_samples, const uint32_t* __restrict__ prev, const uint32_t* __restrict__ ray_n,
-                                                    uint32_t* __restrict__ ray_indices, uint32_t* __restrict__ numsteps /*2 per kept ray*/, uint32_t* __restrict__ counters /*[0]=kept,[1]=samples,[6]=samples to forward*/,
-                                                    uint32_t world, uint32_t rank) {
+                                                    uint32_t* __restrict__ ray_indices, uint32_t* __restrict__ numsteps /*2 per kept ray*/, uint32_t* __restrict__ counters /*[0]=kept,[1]=samples,[6]=samples to forward,[9]=samples of all ranks*/,
+                                                    uint32_t world, uint32_t rank, const uint32_t* __restrict__ xg, uint32_t L, uint32_t* __restrict__ slot_of_pos) {
 	__shared__ uint32_t s_a[32], s_b[32];
 	__shared__ uint32_t carry_n, carry_k;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -176,7 +206,9 @@ __global__ void __launch_bounds__(1024) k_scan_rays(uint32_t n_rays, uint32_t ma
 		__syncthreads();
 		const uint32_t incl = a + (wid ? s_a[wid - 1] : 0) + carry_n;
 		const uint32_t base = incl - n;
-		const uint32_t kept = (n > 0 && base + n <= max_samples) ? 1u : 0u;
+		// the guard of the reference's slot counter (:1346-1350) looks at the ray's place in the whole batch
+		const uint32_t gbase = base + ((xg && n > 0) ? foreign_prefix(xg, L, world, rank, li) : 0u);
+		const uint32_t kept = (n > 0 && gbase + n <= max_samples) ? 1u : 0u;
 		uint32_t b = kept;
 		#pragma unroll
 		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, b, o); if ((int)lane >= o) b += v; }
@@ -186,11 +218,12 @@ __global__ void __launch_bounds__(1024) k_scan_rays(uint32_t n_rays, uint32_t ma
 		__syncthreads();
 		const uint32_t kincl = b + (wid ? s_b[wid - 1] : 0) + carry_k;
 		if (kept) { const uint32_t k = kincl - 1; ray_indices[k] = i; numsteps[2 * k] = n; numsteps[2 * k + 1] = base; }
+		if (slot_of_pos && li < L) slot_of_pos[li] = kept ? kincl - 1 : 0xFFFFFFFFu;
 		__syncthreads();
 		if (tid == 1023) { carry_n = incl; carry_k = kincl; }
 		__syncthreads();
 	}
-	if (tid == 0) { counters[0] = carry_k; counters[1] = carry_n; counters[6] = min(carry_n, max_samples); }
+	if (tid == 0) { counters[0] = carry_k; counters[1] = carry_n; counters[6] = min(carry_n, max_samples); counters[9] = xg ? global_total(xg, L, world) : carry_n; }
 }
 
 // One warp per kept ray: pos4[base + j] = { o + t*dir , ray slot }.
@@ -218,8 +251,14 @@ void launch_march(cudaStream_t st, uint32_t n_rays, uint32_t world, uint32_t ran
 	if (max_ctas) grid = std::min(grid, max_ctas);
 	k_march<<<grid, 256, 0, st>>>(n_rays, world, rank, n_rays_total, rng, views, n_views, bitfield, ray_n, ray_geom, ts);
 }
-void launch_scan_rays(cudaStream_t st, uint32_t n_rays, uint32_t max_samples, const uint32_t* prev, const uint32_t* ray_n, uint32_t* ray_indices, uint32_t* numsteps, uint32_t* counters, uint32_t world, uint32_t rank) {
-	k_scan_rays<<<1, 1024, 0, st>>>(n_rays, max_samples, prev, ray_n, ray_indices, numsteps, counters, world ? world : 1u, rank);
+void launch_scan_rays(cudaStream_t st, uint32_t n_rays, uint32_t max_samples, const uint32_t* prev, const uint32_t* ray_n, uint32_t* ray_indices, uint32_t* numsteps, uint32_t* counters, uint32_t world, uint32_t rank,
+                      const uint32_t* xg, uint32_t* slot_of_pos) {
+	if (!world) world = 1;
+	k_scan_rays<<<1, 1024, 0, st>>>(n_rays, max_samples, prev, ray_n, ray_indices, numsteps, counters, world, rank, xg, (n_rays + world - 1) / world, slot_of_pos);
+}
+void launch_prefix_positions(cudaStream_t st, uint32_t n_rays, uint32_t world, uint32_t rank, const uint32_t* val, const uint32_t* slot_of_pos, uint32_t* out) {
+	const uint32_t L = (n_rays + world - 1) / world;
+	if (L) k_prefix_positions<<<1, 1024, 0, st>>>(n_rays, world, rank, L, val, slot_of_pos, out);
 }
 void launch_emit(cudaStream_t st, uint32_t n_rays_upper, const uint32_t* counters, uint32_t world, const uint32_t* ray_indices, const uint32_t* numsteps, const float* ray_geom, const float* ts, float4* pos4, float* ray_dirw) {
 	if (!n_rays_upper) return;

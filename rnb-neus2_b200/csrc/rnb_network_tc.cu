@@ -673,7 +673,7 @@ static_assert(2 * (BwRegs<2>::LAUNCH - BwRegs<2>::SCAT) >= 2 * (BwRegs<2>::CHAIN
 template <int SW, bool RGB3, int NSC>
 __global__ void __launch_bounds__((2 + NSC) * TILE, 1) k_backward_tc(ModelDev M, const __half* __restrict__ P, const uint8_t* __restrict__ wtc, uint32_t valid_level,
                                                              const float4* __restrict__ pos4, const __half* __restrict__ dout16, const uint32_t* __restrict__ n_ptr, uint32_t n_max,
-                                                             uint32_t n_roll, uint32_t n_batch, const uint32_t* __restrict__ n_in_ptr, float* __restrict__ G) {
+                                                             uint32_t n_roll, uint32_t n_batch, const uint32_t* __restrict__ n_in_ptr, float* __restrict__ G, const uint32_t* __restrict__ goff) {
 	using B = Blob<SW>;
 	constexpr uint32_t T32 = TILE * 64, TW = TILE * SW * 2, T16 = TILE * 32;        // tile bytes: 32-, SW-, 16-wide
 	constexpr uint32_t XB = (B::END + 127u) & ~127u, VB = XB + T32, RB = VB + T32, HB = RB + T32, TMB = HB + TW, DHB = TMB + TW, F1B = DHB + TW,
@@ -797,7 +797,9 @@ __global__ void __launch_bounds__((2 + NSC) * TILE, 1) k_backward_tc(ModelDev M,
 		{
 			const uint4* dp = reinterpret_cast<const uint4*>(dout16 + (size_t)min(row, n - 1) * 16);
 			const uint4 lo = __ldg(dp), hi = __ldg(dp + 1);
-			const float w = live ? rollover_weight(row, min(n_in, n_roll), n_roll) : 0.f;
+			// data parallel with one sample order: the multiplicity is the one of the sample's index in the batch of all ranks (goff per ray slot, k_scan_compact)
+			const uint32_t s_idx = row + (goff ? __ldg(goff + __float_as_uint(p.w)) : 0u);
+			const float w = live ? rollover_weight(s_idx, min(n_in, n_roll), n_roll) : 0.f;
 			const uint32_t u[6] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y};
 			#pragma unroll
 			for (int i = 0; i < 11; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i >> 1])); d[i] = hq(((i & 1) ? f.y : f.x) * w); }
@@ -1157,7 +1159,7 @@ void set_bw_scatter_groups(int n) { g_bw_scatter_groups = n == 1 ? 1 : 2; }
 
 template <int SW, bool RGB3, int NSC>
 static void launch_tc_backward_cfg(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
-                                   uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
+                                   uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm, const uint32_t* goff) {
 	using namespace tc;
 	using B = Blob<SW>;
 	const size_t smem = ((B::END + 127u) & ~127u) + 3 * (TILE * 64) + 8 * (TILE * SW * 2) + 3 * (TILE * 32) + TILE * 32 /* pair exchange */ + TILE * 32 /* scatter hand-off */
@@ -1165,26 +1167,26 @@ static void launch_tc_backward_cfg(cudaStream_t st, const ModelDev& M, const __h
 	const uint32_t grid = std::min<uint32_t>((n_max + TILE - 1) / TILE, (uint32_t)n_sm);
 	static bool attr = false;
 	if (!attr) { cudaFuncSetAttribute(k_backward_tc<SW, RGB3, NSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-	k_backward_tc<SW, RGB3, NSC><<<grid, (2 + NSC) * TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G);
+	k_backward_tc<SW, RGB3, NSC><<<grid, (2 + NSC) * TILE, smem, st>>>(M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, goff);
 }
 
 template <int SW>
 static void launch_tc_backward_sw(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
-                                  uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
+                                  uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm, const uint32_t* goff) {
 	if (!n_max) return;
 	const bool rgb3 = M.n_rgb_layers == 3;
 	if (g_bw_scatter_groups == 2) {
-		if (rgb3) launch_tc_backward_cfg<SW, true, 2>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
-		else launch_tc_backward_cfg<SW, false, 2>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
+		if (rgb3) launch_tc_backward_cfg<SW, true, 2>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm, goff);
+		else launch_tc_backward_cfg<SW, false, 2>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm, goff);
 	} else {
-		if (rgb3) launch_tc_backward_cfg<SW, true, 1>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
-		else launch_tc_backward_cfg<SW, false, 1>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
+		if (rgb3) launch_tc_backward_cfg<SW, true, 1>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm, goff);
+		else launch_tc_backward_cfg<SW, false, 1>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm, goff);
 	}
 }
 void launch_tc_backward(cudaStream_t st, const ModelDev& M, const __half* P, const uint8_t* wtc, uint32_t vl, const float4* pos4, const __half* dout16, const uint32_t* n_ptr, uint32_t n_max,
-                        uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm) {
-	if (M.sdf_width == 64) launch_tc_backward_sw<64>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
-	else launch_tc_backward_sw<32>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm);
+                        uint32_t n_roll, uint32_t n_batch, const uint32_t* n_in_ptr, float* G, int n_sm, const uint32_t* goff) {
+	if (M.sdf_width == 64) launch_tc_backward_sw<64>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm, goff);
+	else launch_tc_backward_sw<32>(st, M, P, wtc, vl, pos4, dout16, n_ptr, n_max, n_roll, n_batch, n_in_ptr, G, n_sm, goff);
 }
 
 // SDF on a res[0] x res[1] x res[2] lattice (Testbed::get_density_on_grid, testbed_nerf.cu:4218-4269); the weight blob must be packed

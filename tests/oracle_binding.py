@@ -228,6 +228,9 @@ class Oracle:
     def set_world(self, world, rank):
         self.L.orc_set_world(self.h, world, rank)
 
+    def set_dp_exact(self, on):
+        self.L.orc_set_dp_exact(self.h, int(on))
+
     def set_opt_shard(self, begin, end):
         self.L.orc_set_opt_shard(self.h, C.c_uint64(begin), C.c_uint64(end))
 

@@ -47,3 +47,13 @@ def test_readme_headline_matches_the_bench_record():
     assert rec["cpu_baseline"]["kind"] == "port" and rec["gpu_launches"] > 0 and rec["clocks"]["reasons"] == []
     assert "normals+albedo" in rec["config"]["workload"] and rec["config"]["live_hash_levels"] == 14 and rec["config"]["workload"] == ref["config"]["workload"]
     assert set(rec["records"]) >= {"normals", "supernormal", "mesh_1024", "adaptive_controller"}
+
+
+def test_readme_multi_gpu_numbers_match_the_records():
+    recs = [json.load(open(os.path.join(ROOT, "profiles", "r02_final_bench_n%d.json" % n))) for n in (2, 4, 8)]
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    assert "%.1f M / %.1f M / %.1f M rays/s on 2 / 4 / 8 GPUs" % tuple(r["value"] / 1e6 for r in recs) in readme
+    for n, r in zip((2, 4, 8), recs):
+        assert r["n_gpus"] == n and r["scaling"] == "weak" and r["config"]["nccl"]["one_sample_order"] and r["config"]["nccl"]["sharded"]
+    old = [json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n%d_per_rank_rule.json" % n))) for n in (2, 4, 8)]
+    assert "%.1f M / %.1f M / %.1f M, 90 / 90 / 92 %%" % tuple(r["value"] / 1e6 for r in old) in readme

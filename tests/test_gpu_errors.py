@@ -51,7 +51,7 @@ def test_data_parallel_context_without_communicator_fails_loudly(pkg, scene_mod)
     t.init_params(); t.load_training_data(views)
     with pytest.raises(pkg.RnbError, match="rnb_comm_init"):
         t.train()
-    assert t.comm_info() == dict(installed=False, nccl_version=t.comm_info()["nccl_version"], sharded=False, world_size=2)
+    assert t.comm_info() == dict(installed=False, nccl_version=t.comm_info()["nccl_version"], sharded=False, one_sample_order=False, world_size=2)
     t.training_prep_nerf()
     t.train_step_begin()
     st = t.train_step_end()                      # this rank's half of the rays, unreduced: the caller would have all-reduced rnb_grad_buffer in between
