@@ -43,11 +43,15 @@ __global__ void __launch_bounds__(256) k_compact_count(const uint32_t* __restric
 	float dx, dy, dz; bent_dir(ray_dirw + 3 * k, dx, dy, dz);
 	const __half var_h = __ldg(P + off_var);
 	float T = 1.0f; uint32_t count = n;
+	// the chunk loop is a chain (load -> alpha -> ordered product): the next chunk's load is issued before this chunk's arithmetic
+	const uint2* src = reinterpret_cast<const uint2*>(outA) + base;
+	uint2 raw_next = lane < n ? __ldg(src + lane) : make_uint2(0u, 0u);
 	for (uint32_t c0 = 0; c0 < n; c0 += 32) {
 		const uint32_t j = c0 + lane;
+		const uint2 raw = raw_next;
+		if (j + 32 < n) raw_next = __ldg(src + j + 32);
 		float om = 1.0f;
 		if (j < n) {
-			const uint2 raw = __ldg(reinterpret_cast<const uint2*>(outA) + base + j);
 			const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
 			om = 1.0f - neus_alpha(a.x, a.y, b.x, b.y, var_h, dx, dy, dz, car).alpha;
 		}
@@ -130,12 +134,10 @@ __device__ __forceinline__ void albedo4(const float* o, const rnb_flags& F, floa
 	if (F.apply_rgbplus) a[3] = F.apply_L2 ? sqrtf(fmaxf(0.0f, 3 - a[0] * a[0] - a[1] * a[1] - a[2] * a[2])) : 3 - fabsf(a[0]) - fabsf(a[1]) - fabsf(a[2]);
 }
 
-__device__ __forceinline__ void load_out16(const __half* p, float* o) {
-	__align__(16) __half h[16];
-	reinterpret_cast<uint4*>(h)[0] = __ldg(reinterpret_cast<const uint4*>(p));
-	reinterpret_cast<uint4*>(h)[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+__device__ __forceinline__ void unpack_out16(const uint4& lo, const uint4& hi, float* o) {
+	const uint32_t u[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 	#pragma unroll
-	for (int i = 0; i < 16; ++i) o[i] = __half2float(h[i]);
+	for (int i = 0; i < 8; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i])); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
 }
 
 __device__ __forceinline__ float warp_scan_add(float v, int lane) {
@@ -168,6 +170,11 @@ __global__ void __launch_bounds__(256) k_loss(LossParams LP, const uint32_t* __r
 	const uint32_t nf = n_fwd[k], cb = cbase[k];
 	const rnb_flags& F = LP.F;
 	const uint32_t ray_idx = ray_indices[k];
+	// every chunk loop below is a chain (load -> alpha -> warp scans -> carries): the next chunk's rows are requested before this chunk's arithmetic,
+	// the first chunk's before the per-ray target is fetched
+	const uint4* rows = reinterpret_cast<const uint4*>(out16 + (size_t)cb * 16);
+	uint4 lo_next = make_uint4(0u, 0u, 0u, 0u), hi_next = lo_next;
+	if ((uint32_t)lane < nf) { lo_next = __ldg(rows + 2 * lane); hi_next = __ldg(rows + 2 * lane + 1); }
 	// ---- per-ray target and light (testbed_nerf.cu:1485-1593) ----
 	rng.advance((int64_t)ray_idx * RNG_PER_RAY);
 	const uint32_t img = image_idx(ray_idx, LP.n_rays, LP.n_rays_total, n_views);
@@ -212,14 +219,15 @@ __global__ void __launch_bounds__(256) k_loss(LossParams LP, const uint32_t* __r
 
 	float dx, dy, dz; bent_dir(ray_dirw + 3 * k, dx, dy, dz);
 	const float car = F.cos_anneal_ratio;
-	const __half* op = out16 + (size_t)cb * 16;
 	// ---- sweep 1: composite (testbed_nerf.cu:1608-1697) ----
 	float rgb_ray[4] = {0, 0, 0, 0}, weight_sum = 0.f, Tc = 1.f;
 	for (uint32_t c0 = 0; c0 < nf; c0 += 32) {
 		const uint32_t j = c0 + lane;
+		const uint4 lo = lo_next, hi = hi_next;
+		if (j + 32 < nf) { lo_next = __ldg(rows + 2 * (j + 32)); hi_next = __ldg(rows + 2 * (j + 32) + 1); }
 		float om = 1.f, w = 0.f, alb[4] = {0, 0, 0, 0}, sh = 0.f, alpha = 0.f;
 		if (j < nf) {
-			float o[16]; load_out16(op + (size_t)j * 16, o);
+			float o[16]; unpack_out16(lo, hi, o);
 			const AlphaTerms A = neus_alpha(o[3], o[4], o[5], o[6], __float2half_rn(o[7]), dx, dy, dz, car);
 			albedo4(o, F, alb);
 			sh = A.nx * light[0] + A.ny * light[1] + A.nz * light[2];
@@ -234,6 +242,8 @@ __global__ void __launch_bounds__(256) k_loss(LossParams LP, const uint32_t* __r
 		weight_sum += w;
 		Tc *= __shfl_sync(0xffffffffu, incl, 31);
 	}
+	lo_next = hi_next = make_uint4(0u, 0u, 0u, 0u);      // first chunk of sweep 2, requested before the reductions and the loss terms
+	if ((uint32_t)lane < ne) { lo_next = __ldg(rows + 2 * lane); hi_next = __ldg(rows + 2 * lane + 1); }
 	#pragma unroll
 	for (int c = 0; c < 4; ++c) rgb_ray[c] = warp_sum(rgb_ray[c]);
 	weight_sum = warp_sum(weight_sum);
@@ -263,10 +273,11 @@ __global__ void __launch_bounds__(256) k_loss(LossParams LP, const uint32_t* __r
 	for (uint32_t c0 = 0; c0 < ne; c0 += 32) {
 		const uint32_t j = c0 + lane;
 		const bool valid = j < ne;
+		const uint4 lo = lo_next, hi = hi_next;          // all-zero rows (binary16 0) for lanes past the end
+		lo_next = hi_next = make_uint4(0u, 0u, 0u, 0u);
+		if (j + 32 < ne) { lo_next = __ldg(rows + 2 * (j + 32)); hi_next = __ldg(rows + 2 * (j + 32) + 1); }
 		float o[16];
-		#pragma unroll
-		for (int c = 0; c < 16; ++c) o[c] = 0.f;
-		if (valid) load_out16(op + (size_t)j * 16, o);
+		unpack_out16(lo, hi, o);
 		const AlphaTerms A = neus_alpha(o[3], o[4], o[5], o[6], __float2half_rn(o[7]), dx, dy, dz, car);
 		float alb[4]; albedo4(o, F, alb);
 		const float alpha = valid ? A.alpha : 0.f;
