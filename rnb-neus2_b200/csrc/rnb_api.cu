@@ -714,7 +714,9 @@ static void net_backward(rnb_ctx* c, cudaStream_t st, uint32_t vl, const uint32_
 
 // ---- one training step ----------------------------------------------------------------------------------------------
 // counters (device, uint32): [0] kept rays  [1] samples before compaction  [2] compacted (untruncated)  [3] trained = min([2], target)
-//                            [4] samples forwarded in pass B  [5] samples before compaction of the previous step
+//                            [4] samples forwarded in pass B  [5] samples before compaction of the previous step (0: no clamp)  [6] sample slots pass A forwards
+//                            data parallel with one sample order: [1]-[4], [6] are this rank's; [3] = this rank's samples inside the global target,
+//                            [8] = min(compacted samples of all ranks, target) (roll-over), [9] = samples of all ranks before compaction ([5] is taken from it)
 static int step_front(rnb_ctx* c, cudaStream_t st, uint32_t R, uint32_t nrt) {
 	const uint32_t max_inference = c->max_samples;      // capacity; the clamp to last step's sample count happens on the device (k_scan_rays, counters[5] -> counters[6])
 	const uint32_t vl = valid_level_for_step(c, (int)c->training_step);
