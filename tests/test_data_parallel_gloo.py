@@ -196,3 +196,53 @@ def test_one_sample_order_reproduces_the_single_process_step():
     assert int(se.n_compacted) == int(s1.n_compacted) and int(se.n_samples) == int(s1.n_samples)
     assert rel(ga, g1) > 10 * rel(ge, g1)                 # the per-rank rule is an approximation (and measurably so)
     assert np.isfinite(pa).all() and rel(pa, p1) < 0.1
+
+
+# ---- the prefix-table exchange behind "one sample order" (rnb_common.cuh: foreign_prefix / global_total; rnb_march.cu: k_prefix_positions) ----------
+def _prefix_worker(rank, world, port, n_rays, seed, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    counts = np.random.default_rng(seed).integers(0, 1025, size=n_rays).astype(np.int64)      # per-ray sample counts of the GLOBAL batch (0 = ray misses the grid)
+    L = (n_rays + world - 1) // world
+    mine = np.zeros(L, np.int64)                                                              # position m of this rank = global ray m * world + rank
+    own = counts[rank::world]; mine[:own.size] = own
+    incl = np.cumsum(mine)                                                                    # k_prefix_positions
+    table = [torch.zeros(L, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(table, torch.from_numpy(incl))                                            # ncclAllGather in the product
+    xg = np.stack([t.numpy() for t in table])
+    base = np.zeros(L, np.int64)
+    for m in range(L):                                                                        # foreign_prefix + the rank's own exclusive prefix
+        s = sum(xg[r][m] for r in range(rank))
+        if m:
+            s += sum(xg[r][m - 1] for r in range(rank + 1, world))
+        base[m] = s + incl[m] - mine[m]
+    total = int(sum(xg[r][L - 1] for r in range(world)))                                      # global_total
+    q.put((rank, base[:own.size].copy(), total))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_rays", [(2, 257), (3, 1000), (3, 2)])
+def test_prefix_table_exchange_gives_every_ray_its_place_in_the_global_batch(world, n_rays):
+    """Interleaved rays, one all-gather of per-position inclusive prefixes: rank r's ray at position m starts at the exclusive prefix of the GLOBAL ray order
+    (what one GPU's ordered scan hands out) — for any world size, with ragged shards (n_rays % world != 0) and with fewer rays than ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() + 7 * world + n_rays) % 2000)
+    procs = [ctx.Process(target=_prefix_worker, args=(r, world, port, n_rays, 1234, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, base, total = q.get(timeout=120)
+        res[r] = (base, total)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    counts = np.random.default_rng(1234).integers(0, 1025, size=n_rays).astype(np.int64)
+    excl = np.cumsum(counts) - counts
+    for r in range(world):
+        assert np.array_equal(res[r][0], excl[r::world]), r
+        assert res[r][1] == int(counts.sum())
