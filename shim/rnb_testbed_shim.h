@@ -15,7 +15,8 @@
 // Design: the library owns the training state while training runs; `push_state` copies it into the reference's own objects (trainer
 // parameters, density grid + bitfield, step counters) so that EVERY stock consumer — snapshot writer, renderer, the stock marching
 // cubes — keeps working on trained weights without knowing about the library; `pull_state` goes the other way after a snapshot load.
-// One Testbed per process (./build/testbed), hence one context.
+// One Testbed per process (./build/testbed), hence one context.  Data parallel: N processes, one per GPU, RNB_WORLD_SIZE / RNB_RANK / RNB_COMM_ID_FILE
+// (install_communicator below; run on 2 B200s: profiles/r02_shim_dp_record.json).
 #pragma once
 #ifdef NGP_USE_RNB_B200
 
@@ -24,10 +25,14 @@
 #include <neural-graphics-primitives/nerf_network.h>
 #include <tiny-cuda-nn/common.h>
 #include <tiny-cuda-nn/trainer.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace rnb_shim {
@@ -40,6 +45,42 @@ inline void check(int rc) {      // CUDA_CHECK_THROW behaviour: a failing call e
 }
 
 inline uint32_t grid_cells() { return ngp::NERF_GRIDSIZE() * ngp::NERF_GRIDSIZE() * ngp::NERF_GRIDSIZE(); }
+
+// --- data parallel: N copies of ./build/testbed, one per GPU (CUDA_VISIBLE_DEVICES), same command line, each with its own output directory ----------
+//   RNB_WORLD_SIZE=N RNB_RANK=r RNB_COMM_ID_FILE=/shared/path ./build/testbed --scene ... (rank r marches rays i = r mod N of the SAME global batch,
+//   gradients are exchanged inside rnb_train; with one sample order the N-GPU run reproduces the single-GPU run)
+// The 128-byte NCCL id travels through a file: rank 0 writes <file>.<generation> (temporary name + rename), the others wait for it.  The generation
+// counts the networks this process has created (load_snapshot -> reset_network creates a second one), the same on every rank.
+inline uint32_t env_u32(const char* name, uint32_t dflt) { const char* v = std::getenv(name); return v && *v ? (uint32_t)std::strtoul(v, nullptr, 10) : dflt; }
+inline uint32_t world_size() { static const uint32_t w = std::max(env_u32("RNB_WORLD_SIZE", 1u), 1u); return w; }
+inline uint32_t world_rank() { static const uint32_t r = env_u32("RNB_RANK", 0u); return r; }
+inline void install_communicator() {
+	static uint32_t generation = 0;
+	const char* base = std::getenv("RNB_COMM_ID_FILE");
+	if (!base || !*base) throw std::runtime_error{"rnb_b200: RNB_WORLD_SIZE > 1 needs RNB_COMM_ID_FILE (a path every rank can read)"};
+	const std::string path = std::string{base} + "." + std::to_string(generation++);
+	uint8_t id[RNB_COMM_ID_BYTES];
+	if (world_rank() == 0) {
+		check(rnb_comm_unique_id(id));
+		const std::string tmp = path + ".tmp";
+		FILE* f = std::fopen(tmp.c_str(), "wb");
+		if (!f || std::fwrite(id, 1, sizeof(id), f) != sizeof(id)) { if (f) std::fclose(f); throw std::runtime_error{"rnb_b200: cannot write " + tmp}; }
+		std::fclose(f);
+		if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error{"rnb_b200: cannot publish " + path};
+	} else {
+		const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(env_u32("RNB_COMM_TIMEOUT_S", 120u));
+		for (;;) {
+			if (FILE* f = std::fopen(path.c_str(), "rb")) {
+				const size_t got = std::fread(id, 1, sizeof(id), f);
+				std::fclose(f);
+				if (got == sizeof(id)) break;
+			}
+			if (std::chrono::steady_clock::now() > deadline) throw std::runtime_error{"rnb_b200: rank 0 did not publish " + path};
+			std::this_thread::sleep_for(std::chrono::milliseconds(20));
+		}
+	}
+	check(rnb_comm_init(ctx(), id));
+}
 
 // --- dataset: device pointers stay owned by the reference's loader (metadata_normal / metadata_albedo, nerf_loader.h:88-89) -----------
 inline void on_dataset(ngp::Testbed& t) {
@@ -101,8 +142,11 @@ inline void on_reset_network(ngp::Testbed& t) {
 	cfg.rays_per_batch = t.m_nerf.training.counters_rgb.rays_per_batch;
 	cfg.pin_rays_per_batch = 0;                                    // the reference's adaptive controller stays in charge
 	cfg.density_grid_decay = t.m_nerf.training.density_grid_decay;
+	cfg.world_size = world_size(); cfg.rank = world_rank();      // the global batch (rays per step, 2^18-sample budget) is the reference's; the ranks share it
+	if (cfg.rank >= cfg.world_size) throw std::runtime_error{"rnb_b200: RNB_RANK must be below RNB_WORLD_SIZE"};
 	if (ctx()) { rnb_destroy(ctx()); ctx() = nullptr; }
 	check(rnb_create(&cfg, &ctx()));
+	if (cfg.world_size > 1) install_communicator();
 	// initial parameters: whatever the reference's Trainer just initialised (fp32 master copy), in the same order (nerf_network.h:539-583)
 	uint64_t layout[5]; check(rnb_param_layout(ctx(), layout));
 	const size_t n = t.m_network->n_params();
@@ -147,7 +191,7 @@ inline bool train(ngp::Testbed& t) {
 	c.measured_batch_size = st.n_samples_compacted;
 	c.measured_batch_size_before_compaction = st.n_samples;
 	c.n_rays_total += st.n_rays;
-	if (st.n_samples_compacted == 0) {
+	if (st.n_samples_compacted == 0 && world_size() == 1) {      // data parallel: the count is this rank's; a rank must not leave the collective on its own
 		tlog::warning() << "Nerf training generated 0 samples. Aborting training.";
 		t.m_train = false;
 	}
@@ -161,6 +205,9 @@ inline void push_state(ngp::Testbed& t) {
 	static_assert(sizeof(precision_t) == 2, "the library exchanges binary16 parameters");
 	const size_t n = t.m_network->n_params();
 	std::vector<uint16_t> h(n);
+	if (world_size() > 1) {      // sharded optimizer: gather the per-shard EMA copy (collective: every rank saves at the same point)
+		check(rnb_comm_sync_ema(ctx(), t.m_training_stream)); CUDA_CHECK_THROW(cudaStreamSynchronize(t.m_training_stream));
+	}
 	check(rnb_export_params_fp16(ctx(), h.data(), n, /*use_ema=*/1));
 	CUDA_CHECK_THROW(cudaMemcpy(t.m_trainer->params_inference(), h.data(), n * 2, cudaMemcpyHostToDevice));
 	check(rnb_export_params_fp16(ctx(), h.data(), n, /*use_ema=*/0));
@@ -210,6 +257,7 @@ inline bool compute_and_save_mesh(ngp::Testbed& t, const char* filename, Eigen::
 	if (thresh == std::numeric_limits<float>::max()) thresh = t.m_mesh.thresh;
 	const uint32_t r[3] = {(uint32_t)res3d.x(), (uint32_t)res3d.y(), (uint32_t)res3d.z()};      // rounded up to multiples of 16 inside, like :4298-4300
 	rnb_mesh_info mi;
+	if (world_size() > 1) { check(rnb_comm_sync_ema(ctx(), t.m_training_stream)); CUDA_CHECK_THROW(cudaStreamSynchronize(t.m_training_stream)); }
 	check(rnb_marching_cubes(ctx(), r, aabb.min.data(), aabb.max.data(), thresh, /*use_ema=*/1, t.m_inference_stream, &mi));
 	float *v = nullptr, *nrm = nullptr, *col = nullptr; uint32_t* idx = nullptr;
 	check(rnb_mesh_buffers(ctx(), &v, &nrm, &col, &idx, nullptr));
