@@ -50,7 +50,8 @@ inline uint32_t grid_cells() { return ngp::NERF_GRIDSIZE() * ngp::NERF_GRIDSIZE(
 //   RNB_WORLD_SIZE=N RNB_RANK=r RNB_COMM_ID_FILE=/shared/path ./build/testbed --scene ... (rank r marches rays i = r mod N of the SAME global batch,
 //   gradients are exchanged inside rnb_train; with one sample order the N-GPU run reproduces the single-GPU run)
 // The 128-byte NCCL id travels through a file: rank 0 writes <file>.<generation> (temporary name + rename), the others wait for it.  The generation
-// counts the networks this process has created (load_snapshot -> reset_network creates a second one), the same on every rank.
+// counts the networks this process has created (load_snapshot -> reset_network creates a second one), the same on every rank.  The launcher removes
+// <file>.* of an earlier run before it starts the ranks (a stale id file would be read as it is).
 inline uint32_t env_u32(const char* name, uint32_t dflt) { const char* v = std::getenv(name); return v && *v ? (uint32_t)std::strtoul(v, nullptr, 10) : dflt; }
 inline uint32_t world_size() { static const uint32_t w = std::max(env_u32("RNB_WORLD_SIZE", 1u), 1u); return w; }
 inline uint32_t world_rank() { static const uint32_t r = env_u32("RNB_RANK", 0u); return r; }
