@@ -49,12 +49,17 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons during the timed region.  The sampler is started ahead of the region (on a box with 8 GPUs nvidia-smi needs longer
+    to deliver its first row than 200 steps take) and every row carries its arrival time: `mark_begin()` opens the region, `stop()` closes it and keeps
+    the rows inside; when the region is shorter than one sample, the rows of the warm-up steps right before it (the same kernels, the GPU never idles
+    in between) stand in and `window` says so."""
 
-    def __init__(self, index=0):
-        self.rows = []; self.p = None; self.index = index
+    def __init__(self, index=0, enabled=True):
+        self.rows = []; self.p = None; self.index = index; self.enabled = enabled; self.t_begin = None
 
     def start(self):
+        if not self.enabled:
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -64,18 +69,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.time()
         time.sleep(0.15)
         self.p.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        rows = [r for ts, r in self.rows if t0 <= ts <= t_end + 0.15]; window = None
+        if not rows:
+            rows = [r for ts, r in self.rows if ts >= t0 - 1.0]; window = "warm-up steps + timed region (the region is shorter than one nvidia-smi sample)"
+        if not rows:
+            rows = [r for _, r in self.rows]; window = "pretraining + warm-up + timed region (no later sample arrived)"
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+        if window and sm:
+            out["window"] = window
+        return out
 
 
 def build_views(n_views, w, h, with_albedo):
@@ -365,13 +383,14 @@ def main():
     # is a global cap; leaving it at 2^18 for N GPUs would shrink every rank's network passes by N and read as super-linear scaling)
     R = RAYS_PER_STEP * n_gpus
     t, upload_s = make_testbed(R, (1 << 18) * n_gpus)
+    clocks = ClockSampler(local_rank, enabled=rank == 0); clocks.start()      # rank 0's line is the one printed; started here so that rows are flowing when the timed region opens
     for _ in range(args.pretrain + args.warmup):
         t.train(stream=sh, want_stats=False)
     torch.cuda.synchronize()
     # value, e2e and the per-stage pass are all taken on the SAME training steps: the state after warm-up is checkpointed on the device
     # and restored between the passes (the cost of a step changes with the training step: live hash levels, samples per ray)
     t.checkpoint_save()
-    clocks = ClockSampler(local_rank); clocks.start()
+    clocks.mark_begin()
     ms, launches, _, _ = timed(t, args.steps, False)          # no per-step read-back: rnb_train returns without host synchronisation
     clk = clocks.stop()
     t.checkpoint_restore()
