@@ -117,6 +117,8 @@ typedef struct rnb_step_stats {
 	uint32_t density_grid_updated;  /* 1 if training_prep_nerf ran inside this call */
 } rnb_step_stats;
 
+/* error reporting: every entry point returns an RNB_* code; the message of the last failure on the calling thread is kept here.  Replaces the reference's
+ * CUDA_CHECK_THROW -> std::runtime_error (tiny-cuda-nn/common.h:202-208): the caller converts a non-zero code into its own throw (shim: rnb_shim::check). */
 const char* rnb_last_error(void);
 uint32_t    rnb_abi_version(void);
 
@@ -172,6 +174,7 @@ int  rnb_load_png_rgba16(const char* path, uint32_t* w, uint32_t* h, uint16_t** 
 void rnb_free_host(void* p);
 int  rnb_load_dataset_images(rnb_ctx* ctx, const rnb_view* meta, uint32_t n_views, const char* const* normal_paths, const char* const* albedo_paths /* NULL or entries NULL: no albedo */,
                              uint32_t threads, void* stream);
+/* replaces the Testbed members the CLI sets (testbed.h:503-521) and train_nerf_step passes by value to the loss kernel every step (src/testbed_nerf.cu:4030-4039) */
 int rnb_set_flags(rnb_ctx* ctx, const rnb_flags* flags);
 
 /* replaces Testbed::training_prep_nerf (src/testbed_nerf.cu:4125-4138): one occupancy-grid refresh. */
@@ -238,7 +241,8 @@ int rnb_checkpoint_save(rnb_ctx* ctx);
 int rnb_checkpoint_restore(rnb_ctx* ctx);
 
 /* instrumentation for bench.py: per-stage CUDA-event timing (events recorded on the caller's stream around each stage of
- * the step; resolved at the end of rnb_train_step_end) and a count of kernels launched by this ctx. */
+ * the step; resolved at the end of rnb_train_step_end) and a count of kernels launched by this ctx.  The reference's counterpart are the wall-clock
+ * EMAs m_training_prep_ms / m_training_ms (testbed.h:863-864, fed by ScopeGuards at src/testbed.cu:2807-2810,2853-2856). */
 int rnb_profile_enable(rnb_ctx* ctx, int on);
 int rnb_profile_read(rnb_ctx* ctx, char* names_buf, size_t names_cap, double* ms, uint64_t* calls, uint32_t* n);
 int rnb_launch_count(rnb_ctx* ctx, uint64_t* out);
@@ -269,7 +273,8 @@ int rnb_marching_cubes(rnb_ctx* ctx, const uint32_t res[3], const float aabb_min
  * density_dev[x + y res[0] + z res[0] res[1]] (res[0] a multiple of 16, as every lattice the reference builds); with_colors != 0 also runs the colour network at the vertices */
 int rnb_marching_cubes_from_density(rnb_ctx* ctx, const float* density_dev, const uint32_t res[3], const float aabb_min[3], const float aabb_max[3], float thresh,
                                     int with_colors, int use_ema, void* stream, rnb_mesh_info* info);
-/* device pointers of the current mesh (valid until the next extraction or rnb_destroy); any out pointer may be NULL */
+/* device pointers of the current mesh = MeshState::verts / vert_normals / vert_colors / indices (testbed.h:418-447); valid until the next extraction or
+ * rnb_destroy; any out pointer may be NULL */
 int rnb_mesh_buffers(rnb_ctx* ctx, float** verts_dev, float** normals_dev, float** colors_dev, uint32_t** indices_dev, rnb_mesh_info* info);
 /* replaces the copies of Testbed::compute_marching_cubes_mesh (src/python_api.cu:99-130): host arrays of n_verts_padded x 3 floats and
  * n_indices uint32; any pointer may be NULL */
