@@ -452,9 +452,9 @@ def main():
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         t.checkpoint_restore()
         threads = os.cpu_count() or 1
-        cs, cr = 6, 2048
+        cs, cr = 8, RAYS_PER_STEP      # ~10 s on 16 cores: whole steps of the workload, not a sub-sampled batch
         v, info = cpu_baseline_from_state(t, views, flags_kw, threads, cs, cr)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": "%d steps x %d rays (of 4096 rays/step) from the same trained state (%s)" % (cs, cr, json.dumps(info))}
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": "%d steps x %d rays (whole steps of the workload) from the same trained state (%s)" % (cs, cr, json.dumps(info))}
 
     # ---- further operating points (shorter windows) ------------------------------------------------------------------------------
     if not args.no_records:
