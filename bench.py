@@ -382,8 +382,8 @@ def main():
     # ---- headline: weak scaling with the per-GPU work fixed: 4096 rays AND a 2^18-sample training batch per GPU (the reference's target_batch_size
     # is a global cap; leaving it at 2^18 for N GPUs would shrink every rank's network passes by N and read as super-linear scaling)
     R = RAYS_PER_STEP * n_gpus
+    clocks = ClockSampler(local_rank, enabled=rank == 0); clocks.start()      # rank 0's line is the one printed; started here (before the upload, the communicator and the pretraining steps) so that rows are flowing when the timed region opens
     t, upload_s = make_testbed(R, (1 << 18) * n_gpus)
-    clocks = ClockSampler(local_rank, enabled=rank == 0); clocks.start()      # rank 0's line is the one printed; started here so that rows are flowing when the timed region opens
     for _ in range(args.pretrain + args.warmup):
         t.train(stream=sh, want_stats=False)
     torch.cuda.synchronize()
