@@ -502,6 +502,25 @@ def main():
             m4, _, _, _ = timed(tsx, k2, False)
             records["strong_16384_rays"] = {"workload": WORKLOADS[args.workload].replace("4096 rays/step pinned", "16384 rays/step in total, ray-sharded over %d GPUs" % n_gpus), "scaling": "strong",
                                             "value": 16384 * k2 / (m4 * 1e-3), "unit": UNIT, "ms_per_step": m4 / k2, "steps": k2}
+            # (4) the headline workload with the per-rank clamp / truncation / roll-over of round 1 (RNB_DP_EXACT=0, read when the communicator is installed):
+            # what the two prefix all-gathers of the default — ONE sample order over all ranks, the single-GPU batch — cost
+            prev = os.environ.get("RNB_DP_EXACT")
+            os.environ["RNB_DP_EXACT"] = "0"
+            try:
+                tpr, _ = make_testbed(R, (1 << 18) * n_gpus)
+            finally:
+                if prev is None:
+                    os.environ.pop("RNB_DP_EXACT", None)
+                else:
+                    os.environ["RNB_DP_EXACT"] = prev
+            try:
+                for _ in range(args.pretrain + args.warmup):
+                    tpr.train(stream=sh, want_stats=False)
+                m6, _, _, _ = timed(tpr, k2, False)
+                records["per_rank_rule"] = {"workload": WORKLOADS[args.workload], "value": R * k2 / (m6 * 1e-3), "unit": UNIT, "ms_per_step": m6 / k2, "steps": k2, "nccl": tpr.comm_info(),
+                                            "note": "RNB_DP_EXACT=0: every rank clamps / truncates / pads its own shard against target / world (not the single-GPU batch)"}
+            except Exception as ex:      # noqa: BLE001  (a side record must not cost the headline line)
+                records["per_rank_rule"] = {"error": str(ex)[:200]}
         line["records"] = records
     sys.stdout.flush(); os.dup2(_saved_stdout, 1)
     if rank == 0:
